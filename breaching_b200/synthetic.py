@@ -1,0 +1,150 @@
+"""Synthetic federated-learning cases for tests and benchmarks.
+
+The reference's case machinery (``breaching/cases``) needs dataset downloads and hydra; what the
+attack actually consumes is the pair ``server_payload`` / ``shared_data`` whose layout is fixed by
+``cases/servers.py:138-147`` and ``cases/users.py:176-186`` (and shown literally in
+``minimal_example.py:52-66``).  This module builds exactly those dictionaries from random-init models
+and random user data, for the BASELINE.json configurations.
+"""
+from collections import OrderedDict
+
+import torch
+
+
+class DataConfig:
+    """Stand-in for the hydra ``cfg.case.data`` node: attribute *and* item access (base_attack.py:51-62)."""
+
+    def __init__(self, **kwargs):
+        self.__dict__.update(kwargs)
+
+    def __getitem__(self, key):
+        return self.__dict__[key]
+
+    def __contains__(self, key):
+        return key in self.__dict__
+
+
+IMAGENET = dict(  # config/case/data/ImageNet.yaml:1-22 (397-class subset used by the benchmark)
+    name="ImageNet", modality="vision", task="classification", classes=397, shape=(3, 224, 224),
+    mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), normalize=True,
+)
+CIFAR10 = dict(  # config/case/data/CIFAR10.yaml:1-22
+    name="CIFAR10", modality="vision", task="classification", classes=10, shape=(3, 32, 32),
+    mean=(0.4914672374725342, 0.4822617471218109, 0.4467701315879822),
+    std=(0.24703224003314972, 0.24348513782024384, 0.26158785820007324), normalize=True,
+)
+
+
+def convnet(width=64, num_classes=10, num_channels=3):
+    """Architecture of the reference's ``ConvNet`` (cases/models/model_preparation.py:437-479):
+    eight conv3x3(+bias)-BN-ReLU stages, MaxPool2d(3) after stages 5 and 7, then a linear head."""
+    chans = [num_channels, width, 2 * width, 2 * width, 4 * width, 4 * width, 4 * width, 4 * width, 4 * width]
+    layers = []
+    for i in range(8):
+        layers.append((f"conv{i}", torch.nn.Conv2d(chans[i], chans[i + 1], kernel_size=3, padding=1)))
+        layers.append((f"bn{i}", torch.nn.BatchNorm2d(chans[i + 1])))
+        layers.append((f"relu{i}", torch.nn.ReLU()))
+        if i == 5:
+            layers.append(("pool0", torch.nn.MaxPool2d(3)))
+        if i == 7:
+            layers.append(("pool1", torch.nn.MaxPool2d(3)))
+    layers.append(("flatten", torch.nn.Flatten()))
+    layers.append(("linear", torch.nn.Linear(36 * width, num_classes)))
+
+    class ConvNet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.Sequential(OrderedDict(layers))
+
+        def forward(self, inputs):
+            return self.model(inputs)
+
+    return ConvNet()
+
+
+def build_model(name, classes, seed=0):
+    """Random-init model of the requested architecture (no checkpoints: there is no network)."""
+    import torchvision
+
+    torch.manual_seed(seed)
+    if name == "convnet":
+        model = convnet(width=64, num_classes=classes)
+    elif name == "convnet-tiny":
+        model = convnet(width=8, num_classes=classes)
+    elif name in ("resnet18", "resnet34", "resnet50", "resnet101"):
+        model = getattr(torchvision.models, name)(weights=None)
+        model.fc = torch.nn.Linear(model.fc.in_features, classes)  # cases/models/model_preparation.py:172-177
+    else:
+        raise ValueError(name)
+    return model
+
+
+def randomize_bn(model, seed=1):
+    """Give BN layers non-trivial affine parameters and running statistics so that parity tests
+    exercise every term (random init has gamma=1, beta=0, mean=0, var=1)."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=gen))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=gen))
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=gen))
+                m.running_var.copy_(1.0 + 0.3 * torch.rand(m.running_var.shape, generator=gen))
+    return model
+
+
+def make_case(model_name="resnet18", data="imagenet", batch=1, seed=233, provide_labels=False,
+              user_buffers=False, bn_random=False, image_size=None, classes=None, unique_labels=True):
+    """Return ``(model, loss_fn, server_payload, shared_data, true_user_data)`` with CPU tensors.
+
+    Single local step (``local_hyperparams=None``); honest server with public buffers (eval-mode BN) or,
+    with ``user_buffers=True``, the see-through-gradients setting where the user computes its update in
+    train mode with ``momentum=None`` and ships the buffers (cases/users.py:140-143,174).
+    """
+    base = dict(IMAGENET if data == "imagenet" else CIFAR10)
+    if image_size is not None:
+        base["shape"] = (3, image_size, image_size)
+    if classes is not None:
+        base["classes"] = classes
+    meta = DataConfig(**base)
+    model = build_model(model_name, meta.classes, seed=seed)
+    if bn_random:
+        randomize_bn(model, seed + 1)
+    loss_fn = torch.nn.CrossEntropyLoss()
+
+    gen = torch.Generator().manual_seed(seed + 7)
+    x = torch.randn((batch, *meta.shape), generator=gen)
+    if unique_labels and batch <= meta.classes:
+        y = torch.randperm(meta.classes, generator=gen)[:batch].sort()[0]
+    else:
+        y = torch.randint(0, meta.classes, (batch,), generator=gen).sort()[0]
+
+    params = [p for p in model.parameters()]
+    if user_buffers:
+        model.train()
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.momentum = None
+                m.reset_running_stats()
+        loss = loss_fn(model(x), y)
+        grads = torch.autograd.grad(loss, params)
+        model.eval()
+        shared_buffers = [b.clone().detach() for b in model.buffers()]
+        payload_buffers = None
+    else:
+        model.eval()
+        loss = loss_fn(model(x), y)
+        grads = torch.autograd.grad(loss, params)
+        shared_buffers = None
+        payload_buffers = [b for b in model.buffers()]
+
+    server_payload = [dict(parameters=params, buffers=payload_buffers, metadata=meta)]
+    shared_data = [
+        dict(
+            gradients=[g.detach().clone() for g in grads],
+            buffers=shared_buffers,
+            metadata=dict(num_data_points=batch, labels=y.clone() if provide_labels else None, local_hyperparams=None),
+        )
+    ]
+    true_user_data = dict(data=x, labels=y)
+    return model, loss_fn, server_payload, shared_data, true_user_data
