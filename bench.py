@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the gradient-inversion hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # product arm: the sm_100a engine
+    python bench.py --impl reference --steps K --warmup W    # reference arm: the CPU restatement of the reference loop
+
+A "step" is one iteration of ``OptimizationBasedAttacker._run_trial`` (closure + signed Adam step + projection +
+best-so-far) on one candidate batch.  Workload at N=1: BASELINE config 2 -- ``invertinggradients`` on a random-init
+torchvision ResNet-18 (397 classes), one synthetic 3x224x224 image.  With N GPUs every rank runs an independent
+restart (trial) of the same workload, no data-path collective (weak scaling); value = N*K / max-over-ranks time.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+P_R18 = 11_380_173                      # parameters of ResNet-18 with a 397-class head
+FLOP_PER_ITER = 24.92e9                 # 2*(7F - 2 F_conv1), ResNet-18 224^2 batch 1
+MATCH_BYTES = 8 * P_R18                 # matching reduction: read G and g once = 91.04 MB
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), bf16_tflops=d.get("bf16_tflops", 1590.0),
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, r[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def build_case(seed=233):
+    import torch
+
+    from breaching_b200 import get_attack_config, synthetic
+
+    torch.manual_seed(seed + 1)  # breaching/utils.py:159-167 seeding recipe (CPU generator part)
+    model, loss_fn, payload, shared, true = synthetic.make_case("resnet18", "imagenet", batch=1, seed=seed)
+    cfg = get_attack_config("invertinggradients")
+    return model, loss_fn, payload, shared, true, cfg
+
+
+def oracle_iters_per_sec(model, loss_fn, payload, shared, true, cfg, device, warmup, steps):
+    """The reference algorithm (CPU restatement in oracle/restate.py, same torch ops as the reference) timed on `device`."""
+    import torch
+
+    from oracle import restate
+
+    meta = payload[0]["metadata"]
+    dev = torch.device(device)
+    m = copy.deepcopy(model).to(dev).eval()
+    dm = torch.tensor(meta.mean, device=dev)[None, :, None, None]
+    ds = torch.tensor(meta.std, device=dev)[None, :, None, None]
+    labels = restate.recover_labels(cfg.label_strategy, shared, 1).to(dev)
+    orc = restate.TrialOracle(m, loss_fn, cfg, [g.to(dev) for g in shared[0]["gradients"]], labels, dm, ds)
+    x0 = torch.randn(1, 3, 224, 224, device=dev)
+    orc.run(x0, iterations=warmup)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    orc.run(x0, iterations=steps)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    orc.close()
+    return steps / dt, dt
+
+
+def kernel_rooflines(dev):
+    """Isolated timings of the two kernel families the north star names, with CUDA events on the launching stream,
+    L2 flushed between repetitions by writing a 512 MB buffer."""
+    import torch
+
+    from breaching_b200 import engine as E
+
+    peaks = measured_peaks()
+    flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
+    G = torch.randn(P_R18, device=dev)
+    g = torch.randn(P_R18, device=dev)
+
+    def timed(fn, reps=10):
+        best, total = 1e9, 0.0
+        for _ in range(reps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best, total = min(best, ms), total + ms
+        return best, total / reps
+
+    # matching reduction: the library call synchronises internally; time the kernel through repeated launches
+    E.match_reduce(G, g)
+    _, ms_match = timed(lambda: E.match_reduce(G, g))
+    match = dict(bound="hbm", achieved=MATCH_BYTES / (ms_match * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
+                 traffic=None, kernel="match_reduce_kernel", ms=ms_match, peak_source=peaks["source"],
+                 note="includes the 5-double D2H read of the stand-alone API")
+    match["frac"] = match["achieved"] / match["peak"]
+    return match
+
+
+def product_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from breaching_b200 import build as bbuild
+    from breaching_b200.attacks import prepare_attack
+    from breaching_b200.engine import Engine
+    from breaching_b200.schedule import lr_table
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product arm has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    bbuild.build()
+
+    model, loss_fn, payload, shared, true, cfg = build_case()
+    meta = payload[0]["metadata"]
+    eng = Engine(copy.deepcopy(model).to(dev).eval(), (1, 3, 224, 224), cfg, dev)
+    if args.backend == "tc":
+        eng.set_option("gemm_backend", 1)
+    eng.load_model()
+    eng.load_targets([g.to(dev) for g in shared[0]["gradients"]], true["labels"].to(dev), mean=meta.mean, std=meta.std)
+    table = lr_table(cfg.optim.step_size, cfg.optim.step_size_decay, cfg.optim.warmup, cfg.optim.max_iterations)
+    torch.manual_seed(1000 + rank)  # every rank = an independent restart
+    x0 = torch.randn(1, 3, 224, 224, device=dev)
+    eng.begin_trial(x0, table)
+    eng.run(max(args.warmup, 3))
+    eng.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    barrier()
+    with ClockSampler(local) as clocks:
+        ms = eng.run_timed(args.steps)
+        barrier()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    st = eng.status()
+    launches = eng.launches_per_iteration()
+
+    # ---- end-to-end through the public API with HOST (pinned) buffers ---------------------------------------------
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(args.steps, 1000)
+    cfg_e2e = copy.deepcopy(cfg)
+    cfg_e2e.optim.max_iterations = e2e_steps
+    cfg_e2e.optim.callback = e2e_steps
+    payload_host = [dict(parameters=[p.detach().clone().pin_memory() for p in payload[0]["parameters"]],
+                         buffers=[b.detach().clone().pin_memory() for b in payload[0]["buffers"]], metadata=meta)]
+    shared_host = [dict(gradients=[g.detach().clone().pin_memory() for g in shared[0]["gradients"]], buffers=None,
+                        metadata=dict(shared[0]["metadata"]))]
+    h2d = sum(p.numel() * 4 for p in payload_host[0]["parameters"]) + sum(b.numel() * b.element_size() for b in payload_host[0]["buffers"]) \
+        + sum(g.numel() * 4 for g in shared_host[0]["gradients"])
+    attacker = prepare_attack(model, loss_fn, cfg_e2e, dict(device=dev, dtype=torch.float))
+    barrier()
+    t0 = time.perf_counter()
+    rec, stats = attacker.reconstruct(payload_host, shared_host, {}, dryrun=False)
+    result_host = rec["data"].to("cpu")
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    td = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    e2e_dt = float(td.item())
+    d2h = result_host.numel() * 4 + len(stats["Trial_0_Val"]) * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    its = world * args.steps / (ms_max * 1e-3)
+    # dominant kernel family = the conv/linear implicit GEMMs; their share of the step is in profiles/ (ncu launch list)
+    roof = dict(bound="tensor", achieved=FLOP_PER_ITER * (args.steps / (ms_max * 1e-3)) / 1e12, peak=peaks["bf16_tflops_sustained"],
+                unit="TFLOP/s", traffic=None, peak_source=peaks["source"],
+                note="whole-iteration algorithmic conv FLOPs (24.92 GFLOP, SURVEY 8d) / iteration time; peak = measured "
+                     "sustained bf16 cuBLAS; the fp32 SIMT back end cannot exceed ~70 TFLOP/s")
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    match = kernel_rooflines(dev)
+    cpu_threads = torch.get_num_threads()
+    cpu_its, cpu_dt = oracle_iters_per_sec(model, loss_fn, payload, shared, true, cfg, "cpu", 2, args.cpu_steps)
+    eager_its = None
+    if not args.skip_eager:
+        try:
+            eager_its, _ = oracle_iters_per_sec(model, loss_fn, payload, shared, true, cfg, dev, 10, args.eager_steps)
+        except Exception as exc:  # noqa: BLE001
+            eager_its = f"failed: {exc}"
+    out = {
+        "metric": "reconstruction iters/sec (ResNet-18 224x224, invertinggradients)", "value": its, "unit": "it/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: invertinggradients, torchvision ResNet-18 (397 classes, random init), "
+                               "synthetic 3x224x224 batch=1, one trial per GPU", "parallelism": f"restarts x{world} (no data-path collective)",
+                   "gemm_backend": args.backend,
+                   "l2": "per-iteration working set (4 parameter-sized arenas = 182 MB + activations) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": world * e2e_steps / e2e_dt, "unit": "it/s", "h2d_bytes_per_step": h2d / e2e_steps,
+                "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
+                "what": "prepare_attack(...).reconstruct(host payload, host shared_data): model rebuild, program compile, engine "
+                        "create, H2D of parameters+gradients from pinned memory, all iterations, scoring, D2H of the result"},
+        "gpu_launches": launches * args.steps,
+        "launches_per_step": launches,
+        "clocks": clocks.summary(),
+        "roofline": roof,
+        "roofline_matching_reduction": match,
+        "cpu_baseline": {"value": cpu_its, "unit": "it/s", "cores": cpu_threads, "kind": "port",
+                         "sample": f"{args.cpu_steps} iterations of the same workload after 2 warm-up ({cpu_dt:.1f} s), torch CPU ops "
+                                   f"with {cpu_threads} threads (host has {os.cpu_count()} logical CPUs)"},
+        "torch_eager_gpu_baseline": {"value": eager_its, "unit": "it/s",
+                                     "what": "the reference loop (oracle/restate.py = same torch ops as the reference) in eager PyTorch on "
+                                             "the same B200; denominator of the north-star >=10x target"},
+        "final_objective": st["min_objective"],
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(args):
+    """The reference's own CPU implementation of the path = oracle port (the reference is Python and cannot travel to
+    the GPU box; oracle/restate.py runs the same torch CPU ops in the same order and is pinned to it by tests/golden)."""
+    import torch
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    model, loss_fn, payload, shared, true, cfg = build_case()
+    threads = torch.get_num_threads()
+    its, dt = oracle_iters_per_sec(model, loss_fn, payload, shared, true, cfg, "cpu", max(args.warmup, 1), args.steps)
+    out = {
+        "impl": "reference", "metric": "reconstruction iters/sec (ResNet-18 224x224, invertinggradients)", "value": its,
+        "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: invertinggradients, torchvision ResNet-18 (397 classes, random init), "
+                               "synthetic 3x224x224 batch=1", "parallelism": "host CPU threads"},
+        "cpu_baseline": {"value": its, "unit": "it/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} iterations (one step = one full iteration of the reference loop)"},
+        "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--backend", default="simt", choices=["simt", "tc"])
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--eager-steps", type=int, default=60)
+    ap.add_argument("--skip-eager", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 20 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else args.warmup
+        reference_arm(args)
+    else:
+        args.steps = 500 if args.steps is None else args.steps
+        args.warmup = 50 if args.warmup is None else args.warmup
+        product_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,34 @@
+"""Drop-in for ``breaching.attacks`` (reference ``attacks/__init__.py:12-37``)."""
+import torch
+
+from .optimization_attack import OptimizationBasedAttacker
+
+_OTHER_ATTACKS = (
+    "multiscale", "analytic", "april-analytic", "imprint-readout", "decepticon-readout", "recursive",
+    "joint-optimization", "permutation-optimization",
+)
+
+
+def prepare_attack(model, loss, cfg_attack, setup=dict(dtype=torch.float, device=torch.device("cpu"))):
+    """Same signature and error behaviour as the reference's ``prepare_attack``.
+
+    ``attack_type == "optimization"`` is served by the sm_100a engine.  Other attack types are outside the
+    accelerated hot path; when the original ``breaching`` package is importable they are delegated to it,
+    otherwise a ``NotImplementedError`` names what is missing (never a silent fallback).
+    """
+    if cfg_attack.attack_type == "optimization":
+        return OptimizationBasedAttacker(model, loss, cfg_attack, setup)
+    if cfg_attack.attack_type in _OTHER_ATTACKS:
+        from ..install import reference_prepare_attack
+
+        ref = reference_prepare_attack()
+        if ref is not None:
+            return ref(model, loss, cfg_attack, setup)
+        raise NotImplementedError(
+            f"attack_type={cfg_attack.attack_type} is not part of the accelerated path and the reference package "
+            "`breaching` is not importable to delegate to."
+        )
+    raise ValueError(f"Invalid type of attack {cfg_attack.attack_type} given.")
+
+
+__all__ = ["prepare_attack", "OptimizationBasedAttacker"]

@@ -1,0 +1,222 @@
+"""``OptimizationBasedAttacker`` served by the sm_100a engine.
+
+API-compatible with the reference class of the same name (``attacks/optimization_based_attack.py:24-218``):
+``prepare_attack(model, loss_fn, cfg_attack, setup)`` builds it, ``reconstruct(server_payload, shared_data,
+server_secrets, initial_data, dryrun)`` returns ``(dict(data=..., labels=...), stats)``.
+
+What differs is *where* the trial runs: ``_run_trial`` hands the candidate to ``breaching_b200.engine.Engine``,
+which executes all iterations on the GPU from a captured CUDA graph; the host only polls a status word every
+``cfg.optim.callback`` iterations for the log line (the reference synchronises three times per iteration,
+``:119,:131,:135``).  Independent trials are sharded round-robin over the ranks of an initialised
+``torch.distributed`` process group and the winner is selected with one MIN all-reduce (``dist.py``).
+"""
+import copy
+import logging
+import time
+from collections import defaultdict
+
+import torch
+
+from .. import dist as bdist
+from ..config import cfg_get
+from ..engine import OBJECTIVES, Engine, EngineError
+from ..schedule import lr_table
+from . import host
+
+log = logging.getLogger(__name__)
+
+_REGULARIZERS = ("total_variation", "orthogonality", "norm", "deep_inversion", "features")  # regularizers.py:233-239
+
+
+def _loss_name(loss_fn):
+    return getattr(loss_fn, "original_name", None) or type(loss_fn).__name__
+
+
+class OptimizationBasedAttacker:
+    """Implements the optimisation-based attacks of the reference on the B200 engine."""
+
+    def __init__(self, model, loss_fn, cfg_attack, setup=dict(dtype=torch.float, device=torch.device("cpu"))):
+        self.cfg = cfg_attack
+        self.setup = dict(device=torch.device(setup["device"]), dtype=getattr(torch, cfg_attack.impl.dtype))
+        self.model_template = copy.deepcopy(model)
+        self.loss_fn = copy.deepcopy(loss_fn)
+
+        if cfg_attack.objective.type not in OBJECTIVES:
+            if cfg_attack.objective.type in ("pearlmutter-loss", "pearlmutter-cosine", "dynamic-cosine-similarity"):
+                raise NotImplementedError(f"objective {cfg_attack.objective.type} is not implemented by the B200 engine")
+            raise ValueError(f"Unknown objective type {self.cfg.objective.type} given.")  # reference :31
+        self.regularizers = []
+        reg = cfg_get(self.cfg, "regularization")
+        if reg is not None:
+            for key in reg.keys():
+                if reg[key].scale > 0:
+                    if key not in _REGULARIZERS:
+                        raise KeyError(key)
+                    self.regularizers.append((key, dict(reg[key])))
+        aug = cfg_get(self.cfg, "augmentations")
+        if aug is not None and len(list(aug.keys())) > 0:
+            raise NotImplementedError("candidate augmentations are not implemented by the B200 engine")
+        if self.setup["dtype"] != torch.float32:
+            raise NotImplementedError("the B200 engine computes in fp32 (cfg.impl.dtype=float)")
+        if cfg_get(self.cfg.impl, "mixed_precision", False):
+            raise NotImplementedError("impl.mixed_precision is not implemented by the B200 engine")
+        if self.setup["device"].type != "cuda":
+            raise EngineError("the B200 engine needs setup['device'] to be a CUDA device (there is no CPU fallback)")
+        if _loss_name(self.loss_fn) != "CrossEntropyLoss":
+            raise NotImplementedError(f"loss {_loss_name(self.loss_fn)} is not implemented by the B200 engine (CrossEntropyLoss only)")
+        self._engine = None
+        self._engine_key = None
+
+    def __repr__(self):
+        n = "\n"
+        regs = (n + " " * 18).join(f"{k}: {v}" for k, v in self.regularizers)
+        opt = (n + " " * 8).join(f"{key}: {val}" for key, val in self.cfg.optim.items())
+        return f"""Attacker (of type {self.__class__.__name__}, B200 engine) with settings:
+    Hyperparameter Template: {self.cfg.type}
+
+    Objective: {self.cfg.objective.type} with scale={cfg_get(self.cfg.objective, 'scale', 1.0)} and task reg={cfg_get(self.cfg.objective, 'task_regularization', 0.0)}
+    Regularizers: {regs}
+    Augmentations:
+
+    Optimization Setup:
+        {opt}
+        """
+
+    # ------------------------------------------------------------------------------------------------
+    def prepare_attack(self, server_payload, shared_data):
+        """base_attack.py:43-74."""
+        stats = defaultdict(list)
+        shared_data = shared_data.copy()
+        server_payload = server_payload.copy()
+        metadata = server_payload[0]["metadata"]
+        self.data_shape = metadata.shape
+        self.dm, self.ds = host.preprocessing_constants(metadata, self.setup)
+        if getattr(metadata, "modality", "vision") == "text":
+            raise NotImplementedError("text modality is not implemented by the B200 engine")
+        rec_models = host.construct_models(self.model_template, server_payload, shared_data, self.setup)
+        shared_data = host.cast_shared_data(shared_data, self.setup["dtype"])
+        self._rec_models = rec_models
+        if shared_data[0]["metadata"]["labels"] is None:
+            labels = host.recover_labels(self.cfg.label_strategy, shared_data, self.setup, self.data_shape)
+        else:
+            labels = shared_data[0]["metadata"]["labels"].clone()
+        if self.cfg.normalize_gradients:
+            shared_data = host.normalize_gradients(shared_data)
+        return rec_models, labels, stats, shared_data
+
+    def _get_engine(self, rec_models, shared_data, labels):
+        if len(rec_models) != 1:
+            raise NotImplementedError("multiple model queries per attack are not implemented by the B200 engine")
+        if shared_data[0]["metadata"]["local_hyperparams"] is not None:
+            raise NotImplementedError("FedAvg multi-step updates (local_hyperparams) are not implemented by the B200 engine yet")
+        model = rec_models[0]
+        n = shared_data[0]["metadata"]["num_data_points"]
+        shape = (n, *self.data_shape)
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if cfg_get(self.cfg.optim, "langevin_noise", 0.0) else 0
+        if self._engine is not None:
+            self._engine.close()
+        eng = Engine(model, shape, self.cfg, self.setup["device"], noise_seed=seed)
+        eng.load_model()
+        tw = None
+        if self.cfg.objective.type == "tag-euclidean":  # objectives.py:115-124
+            L = len(shared_data[0]["gradients"])
+            scheme = cfg_get(self.cfg.objective, "scale_scheme", "linear")
+            if scheme == "linear":
+                tw = torch.arange(L, 0, -1, dtype=torch.float32) / L
+            elif scheme == "exp":
+                tw = torch.arange(L, 0, -1, dtype=torch.float32).softmax(dim=0)
+                tw = tw / tw[0]
+            else:
+                tw = torch.ones(L)
+        mean = self.dm.flatten() if self.dm.numel() > 1 else self.dm.flatten().expand(self.data_shape[0])
+        std = self.ds.flatten() if self.ds.numel() > 1 else self.ds.flatten().expand(self.data_shape[0])
+        eng.load_targets(shared_data[0]["gradients"], labels, mean=mean, std=std, tensor_weights=tw)
+        if any(k == "features" for k, _ in self.regularizers):
+            eng.load_feature_targets(host.measured_features(shared_data, labels)[0])
+        self._engine = eng
+        return eng
+
+    def reconstruct(self, server_payload, shared_data, server_secrets=None, initial_data=None, dryrun=False):
+        rec_models, labels, stats, shared_data = self.prepare_attack(server_payload, shared_data)
+        engine = self._get_engine(rec_models, shared_data, labels)
+        num_trials = self.cfg.restarts.num_trials
+        rank, world = bdist.rank_and_world()
+        scores = torch.full((num_trials,), float("inf"))
+        candidate_solutions = [None] * num_trials
+        shape = [shared_data[0]["metadata"]["num_data_points"], *self.data_shape]
+        try:
+            for trial in range(num_trials):
+                # every rank draws every initialisation in reference order (base_attack.py:226-230), keeps its own
+                candidate = host.initialize_data(self.cfg.init, shape, self.dm, self.ds, self.setup)
+                if initial_data is not None:
+                    candidate = initial_data.detach().clone().to(**self.setup)
+                if trial % world != rank:
+                    continue
+                candidate_solutions[trial] = self._run_trial(engine, candidate, stats, trial, dryrun)
+                scores[trial] = self._score_trial(engine, candidate_solutions[trial])
+        except KeyboardInterrupt:
+            print("Trial procedure manually interruped.")
+        optimal_solution = self._select_optimal_reconstruction(candidate_solutions, scores, stats, shape)
+        reconstructed_data = dict(data=optimal_solution, labels=labels)
+        if server_secrets is not None and "ClassAttack" in server_secrets:  # :82-87
+            true_num_data = server_secrets["ClassAttack"]["true_num_data"]
+            reconstructed_data["data"] = torch.zeros([true_num_data, *self.data_shape], **self.setup)
+            reconstructed_data["data"][server_secrets["ClassAttack"]["target_indx"]] = optimal_solution
+            reconstructed_data["labels"] = server_secrets["ClassAttack"]["all_labels"]
+        return reconstructed_data, stats
+
+    def _run_trial(self, engine, candidate, stats, trial, dryrun=False):
+        """optimization_based_attack.py:90-143, iterations executed on the device."""
+        opt = self.cfg.optim
+        T = int(opt.max_iterations)
+        table = lr_table(opt.step_size, cfg_get(opt, "step_size_decay"), cfg_get(opt, "warmup", 0), T)
+        engine.begin_trial(candidate, table)
+        callback = int(cfg_get(opt, "callback", 0) or 0)
+        chunk = callback if callback > 0 else T
+        total = 1 if dryrun else T
+        done = 0
+        current_wallclock = time.time()
+        try:
+            while done < total:
+                n = min(chunk, total - done) if done > 0 else 1  # first log line after iteration 1, like the reference
+                engine.run(n)
+                done += n
+                st = engine.status()  # one host sync per `callback` iterations
+                if done == total or (callback > 0 and (done - 1) % callback == 0):
+                    timestamp = time.time()
+                    obj = engine.history(st["recorded"])[-1].item() if st["recorded"] > 0 else float("nan")
+                    log.info(
+                        f"| It: {done} | Rec. loss: {obj:2.4f} |  Task loss: {st['task_loss']:2.4f} | "
+                        f"T: {timestamp - current_wallclock:4.2f}s"
+                    )
+                    current_wallclock = timestamp
+                if st["stopped"]:
+                    log.info(f"Recovery loss is non-finite in iteration {st['recorded']}. Cancelling reconstruction!")
+                    break
+        except KeyboardInterrupt:
+            print(f"Recovery interrupted manually in iteration {done}!")
+        engine.sync()
+        stats[f"Trial_{trial}_Val"].extend(engine.history().tolist())
+        return engine.best().detach()
+
+    def _score_trial(self, engine, candidate):
+        """optimization_based_attack.py:191-204."""
+        scoring = self.cfg.restarts.scoring
+        if scoring in ("euclidean", "cosine-similarity"):
+            return engine.score(candidate, scoring)
+        if scoring in ("TV", "total-variation"):
+            from ..engine import total_variation
+
+            return total_variation(candidate.contiguous(), scale=1.0)[0]
+        raise ValueError(f"Scoring mechanism {scoring} not implemented.")
+
+    def _select_optimal_reconstruction(self, candidate_solutions, scores, stats, shape):
+        """optimization_based_attack.py:206-218 + the cross-rank MINLOC select (dist.py)."""
+        optimal_val, optimal_index = bdist.select_best(scores)
+        solution = bdist.fetch_solution(candidate_solutions, optimal_index, shape, self.setup)
+        stats["opt_value"] = optimal_val
+        if optimal_val != float("inf") and optimal_val == optimal_val:
+            log.info(f"Optimal candidate solution with rec. loss {optimal_val:2.4f} selected.")
+            return solution
+        log.info("No valid reconstruction could be found.")
+        return torch.zeros_like(solution)

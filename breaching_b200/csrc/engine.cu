@@ -1,0 +1,895 @@
+// The iteration engine: owns the device-resident state of one trial and executes the four sweeps of the layer
+// program plus objective, priors and the fused optimiser step, captured once as a CUDA graph and replayed with
+// no host synchronisation inside the loop (the reference needs three host syncs per iteration,
+// optimization_based_attack.py:119,131,135).  C ABI in include/breaching_b200.h.
+#include <math.h>
+#include <string.h>
+
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/breaching_b200.h"
+#include "common.cuh"
+#include "igemm.cuh"
+#include "layers.cuh"
+#include "objective.cuh"
+
+namespace bre {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace bre
+
+using namespace bre;
+
+namespace {
+
+struct TensorBuf {
+  bre_tensor_desc desc;
+  long long numel = 0;
+  float *val = nullptr, *d = nullptr, *tval = nullptr, *td = nullptr;
+};
+struct ParamInfo {
+  bre_param_desc desc;
+  long long off = 0;
+};
+struct BnBuf {
+  int C = 0;
+  float *rm = nullptr, *rv = nullptr, *scale = nullptr, *shift = nullptr, *inv = nullptr, *nrm = nullptr;
+  float *di_mean = nullptr, *di_var = nullptr, *di_cm = nullptr, *di_cv = nullptr;
+};
+
+#define BRE_TRY(call)            \
+  do {                           \
+    int _rc = (call);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+#define BRE_LAUNCH(call)         \
+  do {                           \
+    int _rc = (call);            \
+    if (_rc != 0) return _rc;    \
+    ++launch_count;              \
+  } while (0)
+
+template <typename T>
+int dev_alloc(T** p, long long n) {
+  if (n <= 0) n = 1;
+  BRE_CUDA_CHECK(cudaMalloc((void**)p, (size_t)n * sizeof(T)));
+  BRE_CUDA_CHECK(cudaMemset(*p, 0, (size_t)n * sizeof(T)));
+  return 0;
+}
+
+}  // namespace
+
+struct bre_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<TensorBuf> t;
+  std::vector<bre_op_desc> ops;
+  std::vector<ParamInfo> params;
+  std::vector<BnBuf> bn;           // indexed by op.bn_buffer
+  std::vector<int*> pool_idx;      // per op (maxpool only)
+  int logits = -1;
+  bre_attack_cfg cfg;
+  std::vector<void*> allocs;
+
+  long long P_pad = 0, max_param = 0, max_tensor = 0;
+  float *W = nullptr, *g = nullptr, *G = nullptr, *V = nullptr, *stage = nullptr, *chunk_w = nullptr;
+  float *p = nullptr, *loss_n = nullptr;
+  long long* labels = nullptr;
+  int n_labels = 0;
+  // candidate state
+  long long nx = 0;
+  int xN = 0, xC = 0, xH = 0, xW = 0;
+  float *x = nullptr, *gradx = nullptr, *gradx_task = nullptr, *m = nullptr, *v = nullptr, *best = nullptr;
+  float *history = nullptr, *lr_table = nullptr, *lo = nullptr, *hi = nullptr;
+  int n_lr = 0, lr_cap = 0;
+  Scalars* sc = nullptr;
+  // scratch
+  float* ws = nullptr;
+  int ws_tiles = 0;
+  int* gemm_counters = nullptr;
+  float* red_partials = nullptr;
+  int* red_counters = nullptr;
+  double* dpartials = nullptr;
+  int* dcounter = nullptr;
+  DiLayer* di_layers_dev = nullptr;
+  int n_di = 0;
+  float* feat_measured = nullptr;
+  long long feat_numel = 0;
+  int feat_op = -1;
+  // execution
+  bool use_graph = true;
+  int gemm_backend = 0;  // 0 = SIMT fp32, 1 = tcgen05 TF32 where supported
+  cudaGraphExec_t exec = nullptr;
+  bool graph_ready = false;
+  int launch_count = 0, launches_per_iter = 0;
+  bool model_loaded = false, targets_loaded = false, trial_begun = false;
+
+  template <typename T>
+  int alloc(T** ptr, long long n) {
+    int rc = dev_alloc(ptr, n);
+    if (rc == 0) allocs.push_back((void*)*ptr);
+    return rc;
+  }
+
+  const bre_tensor_desc& td(int i) const { return t[i].desc; }
+  float* Wp(int idx) const { return W + params[idx].off; }
+  float* Gp(int idx) const { return G + params[idx].off; }
+  float* Vp(int idx) const { return V + params[idx].off; }
+
+  // ---- GEMM argument assembly -----------------------------------------------------------------
+  GemmArgs conv_geom(const bre_op_desc& op) const {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    const bre_tensor_desc &ti = td(op.tin), &to = td(op.tout);
+    ConvGeom& g = a.g;
+    if (op.kind == BRE_OP_LINEAR) {
+      g.N = ti.N; g.H = 1; g.W = 1; g.Ci = ti.C * ti.H * ti.W; g.Ho = 1; g.Wo = 1; g.Co = to.C;
+      g.R = 1; g.S = 1; g.stride = 1; g.pad = 0;
+      a.x_sN = g.Ci; a.x_sP = g.Ci; a.x_sC = 1;
+    } else {
+      g.N = ti.N; g.H = ti.H; g.W = ti.W; g.Ci = ti.C; g.Ho = to.H; g.Wo = to.W; g.Co = to.C;
+      g.R = op.R; g.S = op.S; g.stride = op.stride; g.pad = op.pad;
+      if (op.tin == 0) { a.x_sN = (long long)ti.C * ti.H * ti.W; a.x_sP = 1; a.x_sC = ti.H * ti.W; }   // NCHW candidate
+      else { a.x_sN = (long long)ti.H * ti.W * ti.C; a.x_sP = ti.C; a.x_sC = 1; }                         // NHWC internal
+    }
+    a.nsrc = 1;
+    a.ws = ws; a.counters = gemm_counters; a.ws_tiles = ws_tiles; a.splits = 0;
+    return a;
+  }
+  int gemm(const GemmArgs& a) {
+    if (gemm_backend == 1 && igemm_tc_supported(a)) return launch_igemm_tc(a, stream);
+    return launch_igemm_simt(a, stream);
+  }
+
+  BnConsts bn_consts(const bre_op_desc& op) const {
+    BnConsts c{nullptr, nullptr, nullptr, nullptr};
+    if (op.has_bn) { const BnBuf& b = bn[op.bn_buffer]; c = BnConsts{b.scale, b.shift, b.inv, b.nrm}; }
+    return c;
+  }
+  PoolGeom pool_geom(const bre_op_desc& op) const {
+    const bre_tensor_desc &ti = td(op.tin), &to = td(op.tout);
+    return PoolGeom{ti.N, ti.H, ti.W, ti.C, to.H, to.W, op.R, op.stride, op.pad};
+  }
+  bool need_task_grad() const { return cfg.task_regularization != 0.f; }
+
+  // ---- sweeps ---------------------------------------------------------------------------------------
+  int sweep_forward() {
+    for (size_t i = 0; i < ops.size(); ++i) {
+      const bre_op_desc& op = ops[i];
+      const bre_tensor_desc& to = td(op.tout);
+      const long long Pout = (long long)to.N * to.H * to.W;
+      switch (op.kind) {
+        case BRE_OP_CONV:
+        case BRE_OP_LINEAR: {
+          GemmArgs a = conv_geom(op);
+          a.mode = GEMM_FPROP;
+          a.act[0] = t[op.tin].val; a.wgt[0] = Wp(op.w);
+          a.bias = op.b >= 0 ? Wp(op.b) : nullptr;
+          a.out = t[op.tout].val;
+          BRE_LAUNCH(gemm(a));
+          break;
+        }
+        case BRE_OP_BNACT:
+          BRE_LAUNCH(launch_bnact_fwd(t[op.tin].val, op.res >= 0 ? t[op.res].val : nullptr, t[op.tout].val, Pout, to.C,
+                                      op.has_bn != 0, op.relu != 0, bn_consts(op), stream));
+          break;
+        case BRE_OP_MAXPOOL:
+          BRE_LAUNCH(launch_maxpool_fwd(t[op.tin].val, t[op.tout].val, pool_idx[i], pool_geom(op), stream));
+          break;
+        case BRE_OP_AVGPOOL: {
+          const bre_tensor_desc& ti = td(op.tin);
+          BRE_LAUNCH(launch_avgpool_fwd(t[op.tin].val, t[op.tout].val, ti.N, ti.H * ti.W, ti.C, stream));
+          break;
+        }
+        default: set_error("unknown op kind"); return BRE_ERR_INVALID;
+      }
+    }
+    const bre_tensor_desc& lt = td(logits);
+    BRE_LAUNCH(launch_ce_fwd(t[logits].val, labels, lt.N, lt.C, p, loss_n, t[logits].d, stream));
+    BRE_LAUNCH(launch_loss_mean(loss_n, lt.N, sc, stream));
+    return 0;
+  }
+
+  int sweep_backward() {
+    for (int i = (int)ops.size() - 1; i >= 0; --i) {
+      const bre_op_desc& op = ops[i];
+      const bre_tensor_desc& to = td(op.tout);
+      const long long Pout = (long long)to.N * to.H * to.W;
+      switch (op.kind) {
+        case BRE_OP_CONV:
+        case BRE_OP_LINEAR: {
+          GemmArgs a = conv_geom(op);
+          a.mode = GEMM_WGRAD;
+          a.act[0] = t[op.tin].val; a.wgt[0] = t[op.tout].d; a.out = Gp(op.w);
+          BRE_LAUNCH(gemm(a));
+          if (op.b >= 0) BRE_LAUNCH(launch_channel_sum(t[op.tout].d, Pout, to.C, Gp(op.b), red_partials, red_counters, stream));
+          if (op.tin != 0 || need_task_grad()) {
+            GemmArgs b = conv_geom(op);
+            b.mode = GEMM_DGRAD;
+            b.act[0] = t[op.tout].d; b.wgt[0] = Wp(op.w);
+            b.out = op.tin == 0 ? gradx_task : t[op.tin].d;
+            b.accumulate = op.tin == 0 ? 0 : op.acc_in;
+            BRE_LAUNCH(gemm(b));
+          }
+          break;
+        }
+        case BRE_OP_BNACT: {
+          BnActBwdArgs a;
+          a.P = Pout; a.C = to.C; a.has_bn = op.has_bn != 0; a.relu = op.relu != 0; a.bn = bn_consts(op);
+          a.in = t[op.tin].val; a.out = t[op.tout].val; a.dout = t[op.tout].d;
+          a.din = t[op.tin].d; a.acc_in = op.acc_in != 0;
+          a.dres = op.res >= 0 ? t[op.res].d : nullptr; a.acc_res = op.acc_res != 0;
+          a.g_gamma = op.has_bn ? Gp(op.gamma) : nullptr; a.g_beta = op.has_bn ? Gp(op.beta) : nullptr;
+          a.partials = red_partials; a.counters = red_counters;
+          BRE_LAUNCH(launch_bnact_bwd(a, stream));
+          break;
+        }
+        case BRE_OP_MAXPOOL:
+          BRE_LAUNCH(launch_maxpool_bwd(t[op.tout].d, pool_idx[i], t[op.tin].d, op.acc_in != 0, pool_geom(op), stream));
+          break;
+        case BRE_OP_AVGPOOL: {
+          const bre_tensor_desc& ti = td(op.tin);
+          BRE_LAUNCH(launch_avgpool_bwd(t[op.tout].d, t[op.tin].d, op.acc_in != 0, ti.N, ti.H * ti.W, ti.C, stream));
+          break;
+        }
+        default: break;
+      }
+    }
+    return 0;
+  }
+
+  int reduce_objective(int objective, float scale, float mask_value, bool finalize) {
+    const float mv = objective == BRE_OBJ_MASKED_COSINE ? mask_value : -1.f;
+    BRE_LAUNCH(launch_match_reduce(G, g, chunk_w, P_pad, mv, objective, scale, cfg.tag_scale, cfg.angular_fudge, finalize, sc,
+                                   dpartials, dcounter, stream));
+    return 0;
+  }
+
+  int sweep_tangent_forward() {
+    for (size_t i = 0; i < ops.size(); ++i) {
+      const bre_op_desc& op = ops[i];
+      const bre_tensor_desc& to = td(op.tout);
+      const long long Pout = (long long)to.N * to.H * to.W;
+      switch (op.kind) {
+        case BRE_OP_CONV:
+        case BRE_OP_LINEAR: {
+          GemmArgs a = conv_geom(op);
+          a.mode = GEMM_FPROP;
+          if (op.tin == 0) {  // tangent of the candidate is zero: only the v-term
+            a.act[0] = t[op.tin].val; a.wgt[0] = Vp(op.w);
+          } else {
+            a.nsrc = 2;
+            a.act[0] = t[op.tin].tval; a.wgt[0] = Wp(op.w);
+            a.act[1] = t[op.tin].val; a.wgt[1] = Vp(op.w);
+          }
+          a.bias = op.b >= 0 ? Vp(op.b) : nullptr;
+          a.out = t[op.tout].tval;
+          BRE_LAUNCH(gemm(a));
+          break;
+        }
+        case BRE_OP_BNACT: {
+          BnActTanFwdArgs a;
+          a.P = Pout; a.C = to.C; a.has_bn = op.has_bn != 0; a.relu = op.relu != 0; a.bn = bn_consts(op);
+          a.in = t[op.tin].val; a.out = t[op.tout].val;
+          a.tin = t[op.tin].tval; a.tres = op.res >= 0 ? t[op.res].tval : nullptr;
+          a.v_gamma = op.has_bn ? Vp(op.gamma) : nullptr; a.v_beta = op.has_bn ? Vp(op.beta) : nullptr;
+          a.tout = t[op.tout].tval;
+          BRE_LAUNCH(launch_bnact_tan_fwd(a, stream));
+          break;
+        }
+        case BRE_OP_MAXPOOL:
+          BRE_LAUNCH(launch_maxpool_gather(t[op.tin].tval, pool_idx[i], t[op.tout].tval, pool_geom(op), stream));
+          break;
+        case BRE_OP_AVGPOOL: {
+          const bre_tensor_desc& ti = td(op.tin);
+          BRE_LAUNCH(launch_avgpool_fwd(t[op.tin].tval, t[op.tout].tval, ti.N, ti.H * ti.W, ti.C, stream));
+          break;
+        }
+        default: break;
+      }
+    }
+    return 0;
+  }
+
+  int deep_inversion_stats() {
+    if (cfg.di_scale <= 0.f || n_di == 0) return 0;
+    for (size_t i = 0; i < ops.size(); ++i) {
+      const bre_op_desc& op = ops[i];
+      if (op.kind != BRE_OP_BNACT || !op.has_bn) continue;
+      const bre_tensor_desc& ti = td(op.tin);
+      BnBuf& b = bn[op.bn_buffer];
+      BRE_LAUNCH(launch_channel_stats(t[op.tin].val, (long long)ti.N * ti.H * ti.W, ti.C, b.di_mean, b.di_var, red_partials,
+                                      red_counters, stream));
+    }
+    BRE_LAUNCH(launch_di_finalize(di_layers_dev, n_di, sc, stream));
+    return 0;
+  }
+
+  int sweep_tangent_backward() {
+    const bre_tensor_desc& lt = td(logits);
+    BRE_LAUNCH(launch_ce_tan_bwd(p, t[logits].tval, lt.N, lt.C, t[logits].td, stream));
+    const bool di = cfg.di_scale > 0.f && n_di > 0;
+    for (int i = (int)ops.size() - 1; i >= 0; --i) {
+      const bre_op_desc& op = ops[i];
+      const bre_tensor_desc& to = td(op.tout);
+      const long long Pout = (long long)to.N * to.H * to.W;
+      switch (op.kind) {
+        case BRE_OP_CONV:
+        case BRE_OP_LINEAR: {
+          GemmArgs a = conv_geom(op);
+          a.mode = GEMM_DGRAD;
+          a.nsrc = 2;
+          a.act[0] = t[op.tout].td; a.wgt[0] = Wp(op.w);
+          a.act[1] = t[op.tout].d; a.wgt[1] = Vp(op.w);
+          a.out = op.tin == 0 ? gradx : t[op.tin].td;
+          a.accumulate = op.tin == 0 ? 0 : op.acc_in;
+          BRE_LAUNCH(gemm(a));
+          if ((int)i == feat_op && cfg.feat_scale > 0.f && feat_measured != nullptr)
+            BRE_LAUNCH(launch_feature_reg(t[op.tin].val, feat_measured, t[op.tin].td, feat_numel, cfg.feat_scale, sc, stream));
+          break;
+        }
+        case BRE_OP_BNACT: {
+          BnActTanBwdArgs a;
+          a.P = Pout; a.C = to.C; a.has_bn = op.has_bn != 0; a.relu = op.relu != 0; a.bn = bn_consts(op);
+          a.in = t[op.tin].val; a.out = t[op.tout].val; a.tdout = t[op.tout].td; a.dout = t[op.tout].d;
+          a.v_gamma = op.has_bn ? Vp(op.gamma) : nullptr;
+          a.di_cm = a.di_cv = a.di_mean = nullptr;
+          if (di && op.has_bn) { const BnBuf& b = bn[op.bn_buffer]; a.di_cm = b.di_cm; a.di_cv = b.di_cv; a.di_mean = b.di_mean; }
+          a.tdin = t[op.tin].td; a.acc_in = op.acc_in != 0;
+          a.tdres = op.res >= 0 ? t[op.res].td : nullptr; a.acc_res = op.acc_res != 0;
+          BRE_LAUNCH(launch_bnact_tan_bwd(a, stream));
+          break;
+        }
+        case BRE_OP_MAXPOOL:
+          BRE_LAUNCH(launch_maxpool_bwd(t[op.tout].td, pool_idx[i], t[op.tin].td, op.acc_in != 0, pool_geom(op), stream));
+          break;
+        case BRE_OP_AVGPOOL: {
+          const bre_tensor_desc& ti = td(op.tin);
+          BRE_LAUNCH(launch_avgpool_bwd(t[op.tout].td, t[op.tin].td, op.acc_in != 0, ti.N, ti.H * ti.W, ti.C, stream));
+          break;
+        }
+        default: break;
+      }
+    }
+    return 0;
+  }
+
+  int priors() {
+    if (cfg.tv_scale == 0.f && cfg.norm_scale == 0.f) return 0;
+    PriorArgs a;
+    a.x = x; a.grad = gradx; a.N = xN; a.H = xH; a.W = xW; a.accumulate = 1;
+    a.tv_scale = cfg.tv_scale; a.p = cfg.tv_inner_exp; a.q = cfg.tv_outer_exp; a.eps = cfg.tv_eps;
+    a.double_opponents = cfg.tv_double_opponents; a.norm_scale = cfg.norm_scale; a.norm_p = cfg.norm_p;
+    BRE_LAUNCH(launch_image_priors(a, sc, dpartials, dcounter, stream));
+    return 0;
+  }
+
+  // objective + its gradient w.r.t. the candidate (closure body, optimization_based_attack.py:146-165)
+  int evaluate() {
+    BRE_TRY(sweep_forward());
+    BRE_TRY(sweep_backward());
+    BRE_TRY(reduce_objective(cfg.objective, cfg.obj_scale, cfg.mask_value, true));
+    BRE_LAUNCH(launch_make_v(G, g, chunk_w, V, P_pad, cfg.objective == BRE_OBJ_MASKED_COSINE ? cfg.mask_value : -1.f, sc, stream));
+    BRE_TRY(sweep_tangent_forward());
+    BRE_TRY(deep_inversion_stats());
+    BRE_TRY(sweep_tangent_backward());
+    BRE_TRY(priors());
+    return 0;
+  }
+
+  StepArgs step_args() const {
+    StepArgs a;
+    a.x = x; a.m = m; a.v = v; a.best = best; a.grad = gradx; a.grad_task = need_task_grad() ? gradx_task : nullptr;
+    a.lr_table = lr_table; a.n_lr = n_lr; a.lo = lo; a.hi = hi; a.n = nx; a.C = xC; a.HW = xH * xW; a.cfg = cfg;
+    return a;
+  }
+
+  int iteration() {
+    BRE_TRY(evaluate());
+    StepArgs a = step_args();
+    if (cfg.grad_clip >= 0.f) BRE_LAUNCH(launch_grad_norm(a, sc, dpartials, dcounter, stream));
+    BRE_LAUNCH(launch_pixel_step(a, sc, stream));
+    BRE_LAUNCH(launch_commit(sc, history, lr_cap, cfg.task_regularization, stream));
+    return 0;
+  }
+};
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+extern "C" {
+
+const char* bre_last_error(void) { return bre::g_last_error.c_str(); }
+const char* bre_version(void) { return "breaching_b200 0.1.0 (sm_100a)"; }
+
+int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const bre_op_desc* ops, int32_t n_ops,
+                      const bre_param_desc* params, int32_t n_params, int32_t logits_tensor, const bre_attack_cfg* cfg,
+                      int32_t device, bre_engine** out) {
+  if (!tensors || !ops || !params || !cfg || !out || n_tensors < 2 || n_ops < 1) { set_error("bre_engine_create: bad arguments"); return BRE_ERR_INVALID; }
+  BRE_CUDA_CHECK(cudaSetDevice(device));
+  bre_engine* e = new bre_engine();
+  e->device = device;
+  e->cfg = *cfg;
+  e->logits = logits_tensor;
+  e->ops.assign(ops, ops + n_ops);
+  auto fail = [&](int rc) { bre_engine_destroy(e); return rc; };
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(BRE_ERR_CUDA); }
+
+  // ---- validate the program -------------------------------------------------------------------
+  int consumers0 = 0;
+  int n_bn = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    const bre_op_desc& op = ops[i];
+    if (op.tin < 0 || op.tin >= n_tensors || op.tout <= 0 || op.tout >= n_tensors || op.res >= n_tensors) { set_error("op tensor id out of range"); return fail(BRE_ERR_INVALID); }
+    if (op.tin == 0 || op.res == 0) {
+      ++consumers0;
+      if (op.res == 0 || (op.kind != BRE_OP_CONV && op.kind != BRE_OP_LINEAR)) { set_error("the candidate must feed exactly one conv/linear layer"); return fail(BRE_ERR_UNSUPPORTED); }
+    }
+    if (op.kind == BRE_OP_BNACT && op.has_bn) n_bn = op.bn_buffer + 1 > n_bn ? op.bn_buffer + 1 : n_bn;
+    if ((op.kind == BRE_OP_CONV || op.kind == BRE_OP_LINEAR) && (op.w < 0 || op.w >= n_params)) { set_error("conv/linear without weight"); return fail(BRE_ERR_INVALID); }
+    if (op.kind == BRE_OP_LINEAR) e->feat_op = i;
+  }
+  if (consumers0 != 1) { set_error("the candidate must feed exactly one layer"); return fail(BRE_ERR_UNSUPPORTED); }
+  if (tensors[logits_tensor].H * tensors[logits_tensor].W != 1) { set_error("logits must be [N, classes]"); return fail(BRE_ERR_INVALID); }
+
+  // ---- parameter arenas -------------------------------------------------------------------------
+  long long off = 0;
+  e->params.resize(n_params);
+  for (int i = 0; i < n_params; ++i) {
+    e->params[i].desc = params[i];
+    e->params[i].off = off;
+    off += ((params[i].numel + kChunk - 1) / kChunk) * kChunk;
+    if (params[i].numel > e->max_param) e->max_param = params[i].numel;
+  }
+  e->P_pad = off;
+  int rc = 0;
+  rc |= e->alloc(&e->W, off); rc |= e->alloc(&e->g, off); rc |= e->alloc(&e->G, off); rc |= e->alloc(&e->V, off);
+  rc |= e->alloc(&e->chunk_w, off / kChunk);
+  // ---- activations ---------------------------------------------------------------------------------
+  e->t.resize(n_tensors);
+  int maxC = 1;
+  for (int i = 0; i < n_tensors; ++i) {
+    e->t[i].desc = tensors[i];
+    e->t[i].numel = (long long)tensors[i].N * tensors[i].C * tensors[i].H * tensors[i].W;
+    if (e->t[i].numel > e->max_tensor) e->max_tensor = e->t[i].numel;
+    if (tensors[i].C > maxC) maxC = tensors[i].C;
+    if (i == 0) continue;
+    rc |= e->alloc(&e->t[i].val, e->t[i].numel); rc |= e->alloc(&e->t[i].d, e->t[i].numel);
+    rc |= e->alloc(&e->t[i].tval, e->t[i].numel); rc |= e->alloc(&e->t[i].td, e->t[i].numel);
+  }
+  rc |= e->alloc(&e->stage, e->max_param > e->max_tensor ? e->max_param : e->max_tensor);
+  const bre_tensor_desc& x0 = tensors[0];
+  e->xN = x0.N; e->xC = x0.C; e->xH = x0.H; e->xW = x0.W; e->nx = e->t[0].numel;
+  rc |= e->alloc(&e->x, e->nx); rc |= e->alloc(&e->gradx, e->nx); rc |= e->alloc(&e->gradx_task, e->nx);
+  rc |= e->alloc(&e->m, e->nx); rc |= e->alloc(&e->v, e->nx); rc |= e->alloc(&e->best, e->nx);
+  rc |= e->alloc(&e->lo, x0.C); rc |= e->alloc(&e->hi, x0.C);
+  e->t[0].val = e->x; e->t[0].d = e->gradx_task; e->t[0].td = e->gradx; e->t[0].tval = nullptr;
+  const bre_tensor_desc& lt = tensors[logits_tensor];
+  rc |= e->alloc(&e->p, (long long)lt.N * lt.C); rc |= e->alloc(&e->loss_n, lt.N); rc |= e->alloc(&e->labels, lt.N);
+  e->n_labels = lt.N;
+  rc |= e->alloc(&e->sc, 1);
+  // ---- per-op buffers --------------------------------------------------------------------------------
+  e->pool_idx.assign(n_ops, nullptr);
+  e->bn.resize(n_bn);
+  for (int i = 0; i < n_ops; ++i) {
+    const bre_op_desc& op = ops[i];
+    if (op.kind == BRE_OP_MAXPOOL) rc |= e->alloc(&e->pool_idx[i], e->t[op.tout].numel);
+    if (op.kind == BRE_OP_BNACT && op.has_bn) {
+      BnBuf& b = e->bn[op.bn_buffer];
+      b.C = tensors[op.tout].C;
+      float** ptrs[] = {&b.rm, &b.rv, &b.scale, &b.shift, &b.inv, &b.nrm, &b.di_mean, &b.di_var, &b.di_cm, &b.di_cv};
+      for (float** pp : ptrs) rc |= e->alloc(pp, b.C);
+    }
+  }
+  // ---- scratch ---------------------------------------------------------------------------------------
+  e->ws_tiles = 1024;
+  rc |= e->alloc(&e->ws, (long long)e->ws_tiles * IG_BM * IG_BN);
+  rc |= e->alloc(&e->gemm_counters, 1 << 16);
+  const long long redp = (long long)(16384 > 2 * maxC + 64 ? 16384 : 2 * maxC + 64) * 2 * 2;
+  rc |= e->alloc(&e->red_partials, redp);
+  rc |= e->alloc(&e->red_counters, maxC / 32 + 8);
+  long long tv_blocks = (long long)((x0.W + 31) / 32) * ((x0.H + 7) / 8) * x0.N;
+  long long dp = tv_blocks * 2 > kMatchMaxBlocks * 5 ? tv_blocks * 2 : kMatchMaxBlocks * 5;
+  if (dp < kNumSMs * 8) dp = kNumSMs * 8;
+  rc |= e->alloc(&e->dpartials, dp);
+  rc |= e->alloc(&e->dcounter, 4);
+  if (rc != 0) return fail(BRE_ERR_CUDA);
+  // DeepInversion layer table
+  if (cfg->di_scale > 0.f && n_bn > 0) {
+    std::vector<DiLayer> layers;
+    bool first = true;
+    for (int i = 0; i < n_ops; ++i) {
+      const bre_op_desc& op = ops[i];
+      if (op.kind != BRE_OP_BNACT || !op.has_bn) continue;
+      const BnBuf& b = e->bn[op.bn_buffer];
+      const bre_tensor_desc& ti = tensors[op.tin];
+      DiLayer L{b.di_mean, b.di_var, b.rm, b.rv, b.di_cm, b.di_cv, b.C, (float)((long long)ti.N * ti.H * ti.W),
+                cfg->di_scale * (first ? cfg->di_first_bn_multiplier : 1.f)};
+      first = false;
+      layers.push_back(L);
+    }
+    e->n_di = (int)layers.size();
+    if (e->alloc(&e->di_layers_dev, (long long)layers.size()) != 0) return fail(BRE_ERR_CUDA);
+    if (cudaMemcpy(e->di_layers_dev, layers.data(), layers.size() * sizeof(DiLayer), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("DI table upload failed"); return fail(BRE_ERR_CUDA); }
+  }
+  // default box = unbounded; chunk weights = 1
+  {
+    std::vector<float> ones((size_t)(off / kChunk), 1.f);
+    if (!ones.empty() && cudaMemcpy(e->chunk_w, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("chunk weight upload failed"); return fail(BRE_ERR_CUDA); }
+  }
+  *out = e;
+  return BRE_OK;
+}
+
+void bre_engine_destroy(bre_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->exec) cudaGraphExecDestroy(e->exec);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+static int load_list(bre_engine* e, const float* const* ptrs, int32_t n, float* arena) {
+  if (n != (int)e->params.size()) { set_error("parameter count mismatch"); return BRE_ERR_INVALID; }
+  for (int i = 0; i < n; ++i) {
+    const ParamInfo& pi = e->params[i];
+    if (!ptrs[i]) { set_error("null parameter pointer"); return BRE_ERR_INVALID; }
+    if (pi.desc.perm == BRE_PERM_NONE) {
+      BRE_CUDA_CHECK(cudaMemcpyAsync(arena + pi.off, ptrs[i], pi.desc.numel * sizeof(float), cudaMemcpyDefault, e->stream));
+    } else {
+      BRE_CUDA_CHECK(cudaMemcpyAsync(e->stage, ptrs[i], pi.desc.numel * sizeof(float), cudaMemcpyDefault, e->stream));
+      BRE_TRY(launch_permute(e->stage, arena + pi.off, pi.desc.d0, pi.desc.d1, pi.desc.d2, false, e->stream));
+    }
+  }
+  return 0;
+}
+
+int bre_engine_load_model(bre_engine* e, const float* const* params, int32_t n_params, const float* const* bn_mean,
+                          const float* const* bn_var, int32_t n_bn) {
+  if (!e || !params) { set_error("bre_engine_load_model: bad arguments"); return BRE_ERR_INVALID; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  if (n_bn != (int)e->bn.size()) { set_error("BN buffer count mismatch"); return BRE_ERR_INVALID; }
+  BRE_TRY(load_list(e, params, n_params, e->W));
+  for (int j = 0; j < n_bn; ++j) {
+    BnBuf& b = e->bn[j];
+    BRE_CUDA_CHECK(cudaMemcpyAsync(b.rm, bn_mean[j], b.C * sizeof(float), cudaMemcpyDefault, e->stream));
+    BRE_CUDA_CHECK(cudaMemcpyAsync(b.rv, bn_var[j], b.C * sizeof(float), cudaMemcpyDefault, e->stream));
+  }
+  for (const bre_op_desc& op : e->ops) {
+    if (op.kind != BRE_OP_BNACT || !op.has_bn) continue;
+    BnBuf& b = e->bn[op.bn_buffer];
+    BRE_TRY(launch_bn_prepare(e->Wp(op.gamma), e->Wp(op.beta), b.rm, b.rv, op.eps, b.C, b.scale, b.shift, b.inv, b.nrm, e->stream));
+  }
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  e->model_loaded = true;
+  return BRE_OK;
+}
+
+int bre_engine_load_targets(bre_engine* e, const float* const* grads, int32_t n_params, const float* tensor_weights,
+                            const int64_t* labels, int32_t n_labels, const float* mean, const float* stdv, int32_t n_channels) {
+  if (!e || !grads || !labels) { set_error("bre_engine_load_targets: bad arguments"); return BRE_ERR_INVALID; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  if (n_labels != e->n_labels) { set_error("label count must equal the batch size"); return BRE_ERR_INVALID; }
+  BRE_TRY(load_list(e, grads, n_params, e->g));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->labels, labels, n_labels * sizeof(int64_t), cudaMemcpyDefault, e->stream));
+  std::vector<float> cw((size_t)(e->P_pad / kChunk), 1.f);
+  if (tensor_weights) {
+    std::vector<float> tw(n_params);
+    BRE_CUDA_CHECK(cudaMemcpy(tw.data(), tensor_weights, n_params * sizeof(float), cudaMemcpyDefault));
+    for (int i = 0; i < n_params; ++i) {
+      const long long c0 = e->params[i].off / kChunk, c1 = c0 + (e->params[i].desc.numel + kChunk - 1) / kChunk;
+      for (long long c = c0; c < c1; ++c) cw[(size_t)c] = tw[i];
+    }
+  }
+  if (!cw.empty()) BRE_CUDA_CHECK(cudaMemcpyAsync(e->chunk_w, cw.data(), cw.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  std::vector<float> lo(e->xC, -std::numeric_limits<float>::infinity()), hi(e->xC, std::numeric_limits<float>::infinity());
+  if (mean && stdv) {
+    if (n_channels != e->xC) { set_error("mean/std channel count mismatch"); return BRE_ERR_INVALID; }
+    std::vector<float> mh(n_channels), sh(n_channels);
+    BRE_CUDA_CHECK(cudaMemcpy(mh.data(), mean, n_channels * sizeof(float), cudaMemcpyDefault));
+    BRE_CUDA_CHECK(cudaMemcpy(sh.data(), stdv, n_channels * sizeof(float), cudaMemcpyDefault));
+    for (int c = 0; c < n_channels; ++c) { lo[c] = -mh[c] / sh[c]; hi[c] = (1.f - mh[c]) / sh[c]; }  // base_attack.py:117-118 box
+  } else {
+    for (int c = 0; c < e->xC; ++c) { lo[c] = -0.f / 1.f; hi[c] = 1.f; }  // dm = 0, ds = 1 (base_attack.py:57)
+  }
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  e->targets_loaded = true;
+  return BRE_OK;
+}
+
+int bre_engine_load_feature_targets(bre_engine* e, const float* measured, int64_t numel) {
+  if (!e || !measured || e->feat_op < 0) { set_error("bre_engine_load_feature_targets: no linear layer / bad arguments"); return BRE_ERR_INVALID; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  const long long expect = e->t[e->ops[e->feat_op].tin].numel;
+  if (numel != expect) { set_error("feature target size mismatch"); return BRE_ERR_INVALID; }
+  if (!e->feat_measured) BRE_TRY(e->alloc(&e->feat_measured, numel));
+  e->feat_numel = numel;
+  BRE_CUDA_CHECK(cudaMemcpy(e->feat_measured, measured, numel * sizeof(float), cudaMemcpyDefault));
+  e->graph_ready = false;
+  return BRE_OK;
+}
+
+static int reset_trial_state(bre_engine* e) {
+  Scalars h;
+  memset(&h, 0, sizeof(h));
+  h.fmin = std::numeric_limits<double>::infinity();
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->sc, &h, sizeof(h), cudaMemcpyHostToDevice, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));  // `h` is a stack object
+  return 0;
+}
+
+int bre_engine_begin_trial(bre_engine* e, const float* candidate, const float* lr_table, int32_t n_lr) {
+  if (!e || !candidate || !lr_table || n_lr <= 0) { set_error("bre_engine_begin_trial: bad arguments"); return BRE_ERR_INVALID; }
+  if (!e->model_loaded || !e->targets_loaded) { set_error("load model and targets before beginning a trial"); return BRE_ERR_STATE; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  if (n_lr > e->lr_cap) {
+    // (re)allocate schedule + history; device pointers baked into a captured graph change -> recapture
+    BRE_TRY(e->alloc(&e->lr_table, n_lr));
+    BRE_TRY(e->alloc(&e->history, n_lr));
+    e->lr_cap = n_lr;
+    e->graph_ready = false;
+  }
+  if (n_lr != e->n_lr) e->graph_ready = false;
+  e->n_lr = n_lr;
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->lr_table, lr_table, n_lr * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->x, candidate, e->nx * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->best, e->x, e->nx * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+  BRE_CUDA_CHECK(cudaMemsetAsync(e->m, 0, e->nx * sizeof(float), e->stream));
+  BRE_CUDA_CHECK(cudaMemsetAsync(e->v, 0, e->nx * sizeof(float), e->stream));
+  BRE_TRY(reset_trial_state(e));
+  e->trial_begun = true;
+  return BRE_OK;
+}
+
+int bre_engine_run(bre_engine* e, int32_t n_iters) {
+  if (!e || n_iters < 0) { set_error("bre_engine_run: bad arguments"); return BRE_ERR_INVALID; }
+  if (!e->trial_begun) { set_error("bre_engine_begin_trial must be called first"); return BRE_ERR_STATE; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  if (!e->use_graph) {
+    for (int i = 0; i < n_iters; ++i) { e->launch_count = 0; BRE_TRY(e->iteration()); e->launches_per_iter = e->launch_count; }
+    return BRE_OK;
+  }
+  if (!e->graph_ready) {
+    if (e->exec) { cudaGraphExecDestroy(e->exec); e->exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    BRE_CUDA_CHECK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    e->launch_count = 0;
+    const int rc = e->iteration();
+    cudaError_t err = cudaStreamEndCapture(e->stream, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (err != cudaSuccess) { set_error(std::string("graph capture failed: ") + cudaGetErrorString(err)); return BRE_ERR_CUDA; }
+    e->launches_per_iter = e->launch_count;
+    err = cudaGraphInstantiate(&e->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) { set_error(std::string("graph instantiation failed: ") + cudaGetErrorString(err)); return BRE_ERR_CUDA; }
+    e->graph_ready = true;
+  }
+  for (int i = 0; i < n_iters; ++i) BRE_CUDA_CHECK(cudaGraphLaunch(e->exec, e->stream));
+  return BRE_OK;
+}
+
+int bre_engine_run_timed(bre_engine* e, int32_t n_iters, float* ms_out) {
+  if (!e || !ms_out) return BRE_ERR_INVALID;
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  cudaEvent_t ev0, ev1;
+  BRE_CUDA_CHECK(cudaEventCreate(&ev0));
+  BRE_CUDA_CHECK(cudaEventCreate(&ev1));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  BRE_CUDA_CHECK(cudaEventRecord(ev0, e->stream));
+  int rc = bre_engine_run(e, n_iters);
+  if (rc == 0 && cudaEventRecord(ev1, e->stream) != cudaSuccess) rc = BRE_ERR_CUDA;
+  if (rc == 0 && cudaEventSynchronize(ev1) != cudaSuccess) rc = BRE_ERR_CUDA;
+  if (rc == 0 && cudaEventElapsedTime(ms_out, ev0, ev1) != cudaSuccess) rc = BRE_ERR_CUDA;
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (rc == BRE_ERR_CUDA) set_error("timed run failed");
+  return rc;
+}
+
+int bre_engine_sync(bre_engine* e) {
+  if (!e) return BRE_ERR_INVALID;
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRE_OK;
+}
+
+static int read_scalars(bre_engine* e, Scalars* h) {
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(h, e->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int bre_engine_status(bre_engine* e, int32_t* iters_recorded, int32_t* stopped, double* min_objective, double* last_task_loss) {
+  if (!e) return BRE_ERR_INVALID;
+  Scalars h;
+  BRE_TRY(read_scalars(e, &h));
+  if (iters_recorded) *iters_recorded = h.recorded;
+  if (stopped) *stopped = h.stopped;
+  if (min_objective) *min_objective = h.fmin;
+  if (last_task_loss) *last_task_loss = h.task_loss;
+  return BRE_OK;
+}
+
+int bre_engine_read_history(bre_engine* e, float* out_host, int32_t n) {
+  if (!e || !out_host || n < 0 || n > e->lr_cap) { set_error("bre_engine_read_history: bad arguments"); return BRE_ERR_INVALID; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(out_host, e->history, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRE_OK;
+}
+
+static int copy_out(bre_engine* e, const float* src, float* out) {
+  if (!e || !out) return BRE_ERR_INVALID;
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(out, src, e->nx * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRE_OK;
+}
+int bre_engine_get_best(bre_engine* e, float* out) { return copy_out(e, e ? e->best : nullptr, out); }
+int bre_engine_get_candidate(bre_engine* e, float* out) { return copy_out(e, e ? e->x : nullptr, out); }
+
+int bre_engine_score(bre_engine* e, const float* candidate, int32_t scoring, double* out_score) {
+  if (!e || !candidate || !out_score) return BRE_ERR_INVALID;
+  if (scoring != BRE_OBJ_EUCLIDEAN && scoring != BRE_OBJ_COSINE) { set_error("scoring must be euclidean or cosine-similarity"); return BRE_ERR_UNSUPPORTED; }
+  if (!e->model_loaded || !e->targets_loaded) { set_error("load model and targets first"); return BRE_ERR_STATE; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->x, candidate, e->nx * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_TRY(e->sweep_forward());
+  BRE_TRY(e->sweep_backward());
+  BRE_TRY(e->reduce_objective(scoring, 1.0f, -1.f, true));
+  Scalars h;
+  BRE_TRY(read_scalars(e, &h));
+  const double s = (double)(float)h.match;
+  *out_score = isfinite(s) ? s : std::numeric_limits<double>::infinity();
+  return BRE_OK;
+}
+
+int bre_engine_objective_and_gradient(bre_engine* e, const float* candidate, double* objective, float* grad_out) {
+  if (!e || !candidate) return BRE_ERR_INVALID;
+  if (!e->model_loaded || !e->targets_loaded) { set_error("load model and targets first"); return BRE_ERR_STATE; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->x, candidate, e->nx * sizeof(float), cudaMemcpyDefault, e->stream));
+  e->launch_count = 0;
+  BRE_TRY(e->evaluate());
+  if (e->need_task_grad()) BRE_TRY(launch_axpy(e->gradx_task, e->gradx, e->cfg.task_regularization, e->nx, e->stream));
+  Scalars h;
+  BRE_TRY(read_scalars(e, &h));
+  if (objective) {
+    double phi = h.match + h.tv + h.norm + h.di + h.feat;
+    if (e->cfg.task_regularization != 0.f) phi += (double)e->cfg.task_regularization * h.task_loss;
+    *objective = phi;
+  }
+  if (grad_out) BRE_TRY(copy_out(e, e->gradx, grad_out));
+  return BRE_OK;
+}
+
+int bre_engine_last_terms(bre_engine* e, double* terms6) {
+  if (!e || !terms6) return BRE_ERR_INVALID;
+  Scalars h;
+  BRE_TRY(read_scalars(e, &h));
+  terms6[0] = h.match; terms6[1] = h.task_loss; terms6[2] = h.tv; terms6[3] = h.norm; terms6[4] = h.di; terms6[5] = h.feat;
+  return BRE_OK;
+}
+
+int bre_engine_debug_param(bre_engine* e, int32_t which, int32_t index, float* out_host) {
+  if (!e || !out_host || index < 0 || index >= (int)e->params.size() || which < 0 || which > 3) return BRE_ERR_INVALID;
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  const float* arenas[4] = {e->G, e->V, e->W, e->g};
+  const ParamInfo& pi = e->params[index];
+  const float* src = arenas[which] + pi.off;
+  if (pi.desc.perm != BRE_PERM_NONE) {
+    BRE_TRY(launch_permute(src, e->stage, pi.desc.d0, pi.desc.d1, pi.desc.d2, true, e->stream));
+    src = e->stage;
+  }
+  BRE_CUDA_CHECK(cudaMemcpyAsync(out_host, src, pi.desc.numel * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRE_OK;
+}
+
+int bre_engine_debug_tensor(bre_engine* e, int32_t which, int32_t tensor, float* out_host) {
+  if (!e || !out_host || tensor < 0 || tensor >= (int)e->t.size() || which < 0 || which > 3) return BRE_ERR_INVALID;
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  const TensorBuf& tb = e->t[tensor];
+  const float* bufs[4] = {tb.val, tb.d, tb.tval, tb.td};
+  const float* src = bufs[which];
+  if (!src) { set_error("tensor has no such buffer"); return BRE_ERR_INVALID; }
+  if (tensor != 0) {
+    BRE_TRY(launch_permute(src, e->stage, tb.desc.N, tb.desc.C, tb.desc.H * tb.desc.W, true, e->stream));
+    src = e->stage;
+  }
+  BRE_CUDA_CHECK(cudaMemcpyAsync(out_host, src, tb.numel * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRE_OK;
+}
+
+int bre_engine_launches_per_iteration(bre_engine* e, int32_t* out) {
+  if (!e || !out) return BRE_ERR_INVALID;
+  *out = e->launches_per_iter;
+  return BRE_OK;
+}
+
+int bre_engine_set_option(bre_engine* e, const char* name, int64_t value) {
+  if (!e || !name) return BRE_ERR_INVALID;
+  const std::string n(name);
+  if (n == "use_graph") { e->use_graph = value != 0; e->graph_ready = false; return BRE_OK; }
+  if (n == "gemm_backend") {
+    if (value != 0 && value != 1) { set_error("gemm_backend must be 0 (simt) or 1 (tcgen05)"); return BRE_ERR_INVALID; }
+    e->gemm_backend = (int)value; e->graph_ready = false; return BRE_OK;
+  }
+  set_error("unknown option " + n);
+  return BRE_ERR_INVALID;
+}
+
+// ---- stand-alone kernels --------------------------------------------------------------------------
+int bre_match_reduce(const float* G, const float* g, const float* chunk_weights, int64_t n, float mask_value,
+                     double* sums5_host, void* stream) {
+  if (!G || !g || !sums5_host || n <= 0) { set_error("bre_match_reduce: bad arguments"); return BRE_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  static thread_local Scalars* sc = nullptr;
+  static thread_local double* partials = nullptr;
+  static thread_local int* counter = nullptr;
+  if (!sc) {
+    BRE_TRY(dev_alloc(&sc, 1));
+    BRE_TRY(dev_alloc(&partials, (long long)kMatchMaxBlocks * 5));
+    BRE_TRY(dev_alloc(&counter, 1));
+  }
+  BRE_TRY(launch_match_reduce(G, g, chunk_weights, n, mask_value, BRE_OBJ_COSINE, 1.f, 0.f, 0.f, false, sc, partials, counter, s));
+  Scalars h;
+  BRE_CUDA_CHECK(cudaMemcpyAsync(&h, sc, sizeof(h), cudaMemcpyDeviceToHost, s));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(s));
+  sums5_host[0] = h.dot; sums5_host[1] = h.nG; sums5_host[2] = h.ng; sums5_host[3] = h.sq; sums5_host[4] = h.l1w;
+  return BRE_OK;
+}
+
+int bre_total_variation(const float* x, float* grad, int32_t N, int32_t H, int32_t W, float scale, float inner_exp,
+                        float outer_exp, float eps, int32_t double_opponents, int32_t accumulate, double* value_host,
+                        void* stream) {
+  if (!x || !grad || N <= 0 || H <= 0 || W <= 0) { set_error("bre_total_variation: bad arguments"); return BRE_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  Scalars* sc = nullptr; double* partials = nullptr; int* counter = nullptr;
+  const long long blocks = (long long)((W + 31) / 32) * ((H + 7) / 8) * N;
+  BRE_TRY(dev_alloc(&sc, 1)); BRE_TRY(dev_alloc(&partials, blocks * 2)); BRE_TRY(dev_alloc(&counter, 1));
+  PriorArgs a;
+  a.x = x; a.grad = grad; a.N = N; a.H = H; a.W = W; a.accumulate = accumulate; a.tv_scale = scale; a.p = inner_exp;
+  a.q = outer_exp; a.eps = eps; a.double_opponents = double_opponents; a.norm_scale = 0.f; a.norm_p = 2.f;
+  int rc = launch_image_priors(a, sc, partials, counter, s);
+  Scalars h;
+  if (rc == 0 && cudaMemcpyAsync(&h, sc, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = BRE_ERR_CUDA;
+  if (rc == 0 && cudaStreamSynchronize(s) != cudaSuccess) rc = BRE_ERR_CUDA;
+  cudaFree(sc); cudaFree(partials); cudaFree(counter);
+  if (rc == 0 && value_host) *value_host = h.tv;
+  return rc;
+}
+
+int bre_conv_gemm(int32_t mode, int32_t backend, const float* a, const float* w, const float* a2, const float* w2, float* out,
+                  int32_t N, int32_t H, int32_t W, int32_t Ci, int32_t Co, int32_t R, int32_t S, int32_t stride, int32_t pad,
+                  void* stream) {
+  if (!a || !w || !out || mode < 0 || mode > 2) { set_error("bre_conv_gemm: bad arguments"); return BRE_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.mode = mode;
+  g.g = ConvGeom{N, H, W, Ci, (H + 2 * pad - R) / stride + 1, (W + 2 * pad - S) / stride + 1, Co, R, S, stride, pad};
+  g.nsrc = (a2 && w2) ? 2 : 1;
+  g.act[0] = a; g.wgt[0] = w; g.act[1] = a2; g.wgt[1] = w2;
+  g.x_sN = (long long)H * W * Ci; g.x_sP = Ci; g.x_sC = 1;
+  g.out = out;
+  static thread_local float* ws = nullptr;
+  static thread_local int* counters = nullptr;
+  if (!ws) { BRE_TRY(dev_alloc(&ws, 1024LL * IG_BM * IG_BN)); BRE_TRY(dev_alloc(&counters, 1 << 16)); }
+  g.ws = ws; g.counters = counters; g.ws_tiles = 1024;
+  if (backend == 1) {
+    if (!igemm_tc_supported(g)) { set_error("tcgen05 back end does not cover this shape"); return BRE_ERR_UNSUPPORTED; }
+    return launch_igemm_tc(g, s);
+  }
+  return launch_igemm_simt(g, s);
+}
+
+}  // extern "C"

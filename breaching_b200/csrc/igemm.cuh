@@ -1,0 +1,52 @@
+// Implicit-GEMM convolution family (fprop / dgrad / wgrad, optional K-concatenated second source).
+//
+// These are the dense contractions of the hot path: model forward (objectives.py:44), the first backward
+// (objectives.py:45) and -- via the K-concatenated "dual source" form [W | v] . [a_dot ; a] -- both halves
+// of the second backward (optimization_based_attack.py:165), see DESIGN.md section 3.
+#pragma once
+#include "common.cuh"
+
+namespace bre {
+
+enum GemmMode { GEMM_FPROP = 0, GEMM_DGRAD = 1, GEMM_WGRAD = 2 };
+
+struct ConvGeom {
+  int N, H, W, Ci;   // input-shaped tensor
+  int Ho, Wo, Co;    // output-shaped tensor
+  int R, S, stride, pad;
+};
+
+struct GemmArgs {
+  int mode;
+  ConvGeom g;
+  int nsrc;               // 1 or 2 (dual source: K-concatenation, fprop / dgrad only)
+  const float* act[2];    // fprop: in ; dgrad: dout ; wgrad: in
+  const float* wgt[2];    // fprop/dgrad: weights OHWI ; wgrad: dout
+  // addressing of the input-shaped tensor (gathered operand of fprop/wgrad, *output* of dgrad):
+  // offset(img, pixel, c) = img * x_sN + pixel * x_sP + c * x_sC   (NHWC: HWC, C, 1 ; NCHW: CHW, 1, HW)
+  long long x_sN;
+  int x_sP, x_sC;
+  float* out;
+  const float* bias;      // fprop only, per output channel (may be null)
+  int accumulate;         // out += result
+  float* ws;              // split-K workspace (>= ws_tiles * 4096 floats)
+  int* counters;          // >= max tiles ints, zero-initialised, self-resetting
+  int ws_tiles;
+  int splits;             // 0 = choose automatically
+};
+
+constexpr int IG_BM = 64, IG_BN = 64, IG_BK = 16, IG_THREADS = 256;
+
+int launch_igemm_simt(const GemmArgs& a, cudaStream_t stream);
+// tcgen05 TF32 back end (igemm_tc.cu); returns BRE_ERR_UNSUPPORTED (-4) for shapes it does not cover.
+int launch_igemm_tc(const GemmArgs& a, cudaStream_t stream);
+bool igemm_tc_supported(const GemmArgs& a);
+
+inline void gemm_dims(const GemmArgs& a, int& M, int& Nc, int& K) {
+  const ConvGeom& g = a.g;
+  if (a.mode == GEMM_FPROP) { M = g.N * g.Ho * g.Wo; Nc = g.Co; K = g.R * g.S * g.Ci; }
+  else if (a.mode == GEMM_DGRAD) { M = g.N * g.H * g.W; Nc = g.Ci; K = g.R * g.S * g.Co; }
+  else { M = g.Co; Nc = g.R * g.S * g.Ci; K = g.N * g.Ho * g.Wo; }
+}
+
+}  // namespace bre

@@ -1,0 +1,456 @@
+// Non-GEMM layer kernels (see layers.cuh).  All HBM-bound: coalesced along the channel dimension of the
+// NHWC activations (32 consecutive channels = one 128-byte line per warp row), grid sized from the SM count.
+#include "layers.cuh"
+
+#include <float.h>
+
+namespace bre {
+
+namespace {
+
+constexpr int kEwThreads = 256;
+
+inline int ew_grid(long long n) {
+  long long b = (n + kEwThreads - 1) / kEwThreads;
+  const long long cap = (long long)kNumSMs * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// ---- BN constants -------------------------------------------------------------------------------
+__global__ void bn_prepare_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
+                                  float* scale, float* shift, float* inv, float* nrm) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float iv = 1.0f / sqrtf(rv[c] + eps);
+  inv[c] = iv;
+  nrm[c] = -rm[c] * iv;
+  scale[c] = gamma[c] * iv;
+  shift[c] = beta[c] - gamma[c] * rm[c] * iv;
+}
+
+// ---- fused BN + residual + ReLU forward ------------------------------------------------------------
+__global__ void bnact_fwd_kernel(const float* __restrict__ in, const float* __restrict__ res, float* __restrict__ out,
+                                 long long total, int C, bool has_bn, bool relu, BnConsts bn) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float u = in[i];
+    // eval-mode BN as ATen applies it: x * alpha + beta', alpha = gamma * invstd, beta' = beta - mean * alpha
+    if (has_bn) u = fmaf(u, __ldg(bn.scale + c), __ldg(bn.shift + c));
+    if (res != nullptr) u += res[i];
+    out[i] = relu ? fmaxf(u, 0.f) : u;
+  }
+}
+
+// ---- (32 channels) x (pixel slab) reductions ------------------------------------------------------
+// Block (32, 8); blockIdx.x = channel group, blockIdx.y = slab.  Returns per-thread partial sums reduced over
+// threadIdx.y into row 0, then the last-arriving block of a channel group reduces the slabs in fixed order.
+template <int NV>
+__device__ __forceinline__ bool slab_reduce(float (&v)[NV], float* partials, int* counters, int Cpad, float (&total)[NV]) {
+  __shared__ float sm[NV][8][33];
+  __shared__ int s_last;
+  const int x = threadIdx.x, y = threadIdx.y;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) sm[k][y][x] = v[k];
+  __syncthreads();
+  const int c = blockIdx.x * 32 + x;
+  if (y == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float s = 0.f;
+#pragma unroll
+      for (int yy = 0; yy < 8; ++yy) s += sm[k][yy][x];
+      partials[((long long)blockIdx.y * Cpad + c) * NV + k] = s;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (x == 0 && y == 0) {
+    const int prev = atomicAdd(counters + blockIdx.x, 1);
+    s_last = (prev == (int)gridDim.y - 1);
+    if (s_last) counters[blockIdx.x] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  if (y == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float s = 0.f;
+      for (int sl = 0; sl < (int)gridDim.y; ++sl) s += __ldcg(partials + ((long long)sl * Cpad + c) * NV + k);
+      total[k] = s;
+    }
+  }
+  return y == 0;
+}
+
+inline void slab_grid(long long P, int C, dim3& grid, dim3& block, long long& pps) {
+  const int cg = ceil_div(C, 32);
+  long long slabs = (2LL * kNumSMs + cg - 1) / cg;
+  const long long max_slabs = (P + 7) / 8;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  if (slabs > 4096) slabs = 4096;
+  pps = (P + slabs - 1) / slabs;
+  slabs = (P + pps - 1) / pps;
+  grid = dim3(cg, (unsigned)slabs);
+  block = dim3(32, 8);
+}
+
+__global__ void bnact_bwd_kernel(BnActBwdArgs a, long long pps, int Cpad) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cv = c < a.C;
+  const long long p0 = blockIdx.y * pps;
+  const long long p1 = (p0 + pps < a.P) ? p0 + pps : a.P;
+  float v[2] = {0.f, 0.f};
+  float inv = 0.f, nrm = 0.f, scale = 1.f;
+  if (cv && a.has_bn) { inv = __ldg(a.bn.inv + c); nrm = __ldg(a.bn.nrm + c); scale = __ldg(a.bn.scale + c); }
+  if (cv) {
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      const long long o = p * a.C + c;
+      float du = a.dout[o];
+      if (a.relu && !(a.out[o] > 0.f)) du = 0.f;
+      float di = du;
+      if (a.has_bn) {
+        const float xhat = fmaf(a.in[o], inv, nrm);
+        v[0] = fmaf(du, xhat, v[0]);
+        v[1] += du;
+        di = scale * du;
+      }
+      if (a.din != nullptr) a.din[o] = a.acc_in ? a.din[o] + di : di;
+      if (a.dres != nullptr) a.dres[o] = a.acc_res ? a.dres[o] + du : du;
+    }
+  }
+  if (!a.has_bn || a.g_gamma == nullptr) return;  // uniform across the grid
+  float tot[2];
+  if (slab_reduce<2>(v, a.partials, a.counters, Cpad, tot) && cv) {
+    a.g_gamma[c] = tot[0];
+    a.g_beta[c] = tot[1];
+  }
+}
+
+__global__ void bnact_tan_fwd_kernel(BnActTanFwdArgs a, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % a.C);
+    float u = a.tin != nullptr ? a.tin[i] : 0.f;
+    if (a.has_bn) {
+      const float xhat = fmaf(a.in[i], __ldg(a.bn.inv + c), __ldg(a.bn.nrm + c));
+      u = fmaf(__ldg(a.bn.scale + c), u, fmaf(__ldg(a.v_gamma + c), xhat, __ldg(a.v_beta + c)));
+    }
+    if (a.tres != nullptr) u += a.tres[i];
+    if (a.relu && !(a.out[i] > 0.f)) u = 0.f;
+    a.tout[i] = u;
+  }
+}
+
+__global__ void bnact_tan_bwd_kernel(BnActTanBwdArgs a, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % a.C);
+    float tdu = a.tdout[i];
+    float du = a.dout[i];
+    if (a.relu && !(a.out[i] > 0.f)) { tdu = 0.f; du = 0.f; }
+    float tdi = tdu;
+    if (a.has_bn) {
+      tdi = fmaf(__ldg(a.bn.scale + c), tdu, __ldg(a.v_gamma + c) * __ldg(a.bn.inv + c) * du);
+      if (a.di_cm != nullptr) tdi += fmaf(__ldg(a.di_cv + c), a.in[i] - __ldg(a.di_mean + c), __ldg(a.di_cm + c));
+    }
+    if (a.tdin != nullptr) a.tdin[i] = a.acc_in ? a.tdin[i] + tdi : tdi;
+    if (a.tdres != nullptr) a.tdres[i] = a.acc_res ? a.tdres[i] + tdu : tdu;
+  }
+}
+
+__global__ void channel_sum_kernel(const float* __restrict__ x, long long P, int C, float* out, float* partials,
+                                   int* counters, long long pps, int Cpad) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long p0 = blockIdx.y * pps;
+  const long long p1 = (p0 + pps < P) ? p0 + pps : P;
+  float v[1] = {0.f};
+  if (c < C)
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) v[0] += x[p * C + c];
+  float tot[1];
+  if (slab_reduce<1>(v, partials, counters, Cpad, tot) && c < C) out[c] = tot[0];
+}
+
+__global__ void channel_stats_kernel(const float* __restrict__ x, long long P, int C, float* mean, float* var,
+                                     float* partials, int* counters, long long pps, int Cpad) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long p0 = blockIdx.y * pps;
+  const long long p1 = (p0 + pps < P) ? p0 + pps : P;
+  // shifted sums (shift = first element of the channel) keep E[x^2] - E[x]^2 well conditioned in fp32
+  const float sh = c < C ? x[c] : 0.f;
+  float v[2] = {0.f, 0.f};
+  if (c < C)
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      const float t = x[p * C + c] - sh;
+      v[0] += t;
+      v[1] = fmaf(t, t, v[1]);
+    }
+  float tot[2];
+  if (slab_reduce<2>(v, partials, counters, Cpad, tot) && c < C) {
+    const float m = tot[0] / (float)P;
+    mean[c] = m + sh;
+    var[c] = fmaxf(tot[1] / (float)P - m * m, 0.f);
+  }
+}
+
+// ---- pooling ---------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int* __restrict__ idx, PoolGeom g,
+                                   long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % g.C);
+    long long t = i / g.C;
+    const int q = (int)(t % g.Wo); t /= g.Wo;
+    const int p = (int)(t % g.Ho);
+    const int n = (int)(t / g.Ho);
+    const int h0 = p * g.stride - g.pad, w0 = q * g.stride - g.pad;
+    float best = -FLT_MAX * 2.f;  // -inf
+    int bi = -1;
+    for (int r = 0; r < g.k; ++r) {
+      const int h = h0 + r;
+      if (h < 0 || h >= g.H) continue;
+      for (int s = 0; s < g.k; ++s) {
+        const int w = w0 + s;
+        if (w < 0 || w >= g.W) continue;
+        const float v = in[((long long)(n * g.H + h) * g.W + w) * g.C + c];
+        if (v > best || v != v || bi < 0) { best = v; bi = h * g.W + w; }
+      }
+    }
+    out[i] = best;
+    idx[i] = bi;
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ idx, float* __restrict__ din, bool acc,
+                                   PoolGeom g, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % g.C);
+    long long t = i / g.C;
+    const int w = (int)(t % g.W); t /= g.W;
+    const int h = (int)(t % g.H);
+    const int n = (int)(t / g.H);
+    const int me = h * g.W + w;
+    int p_lo = h + g.pad - g.k + 1; p_lo = p_lo > 0 ? (p_lo + g.stride - 1) / g.stride : 0;
+    int q_lo = w + g.pad - g.k + 1; q_lo = q_lo > 0 ? (q_lo + g.stride - 1) / g.stride : 0;
+    int p_hi = (h + g.pad) / g.stride; if (p_hi > g.Ho - 1) p_hi = g.Ho - 1;
+    int q_hi = (w + g.pad) / g.stride; if (q_hi > g.Wo - 1) q_hi = g.Wo - 1;
+    float s = 0.f;
+    for (int p = p_lo; p <= p_hi; ++p)
+      for (int q = q_lo; q <= q_hi; ++q) {
+        const long long o = ((long long)(n * g.Ho + p) * g.Wo + q) * g.C + c;
+        if (idx[o] == me) s += dout[o];
+      }
+    din[i] = acc ? din[i] + s : s;
+  }
+}
+
+__global__ void maxpool_gather_kernel(const float* __restrict__ tin, const int* __restrict__ idx, float* __restrict__ tout,
+                                      PoolGeom g, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % g.C);
+    const long long n = i / ((long long)g.C * g.Ho * g.Wo);
+    tout[i] = tin[(n * g.H * g.W + idx[i]) * g.C + c];
+  }
+}
+
+__global__ void avgpool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int HW, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += in[((long long)n * HW + p) * C + c];
+  out[i] = s / (float)HW;
+}
+
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, bool acc, long long total, int HW, int C) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long n = i / ((long long)C * HW);
+    const float v = dout[n * C + c] / (float)HW;
+    din[i] = acc ? din[i] + v : v;
+  }
+}
+
+// ---- softmax cross-entropy -------------------------------------------------------------------------
+__global__ void ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int N, int C, float* p,
+                              float* loss_n, float* dlogits) {
+  __shared__ double scratch[32];
+  __shared__ float s_max, s_sum;
+  const int n = blockIdx.x;
+  const float* z = logits + (long long)n * C;
+  float mx = -FLT_MAX;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, z[c]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __shared__ float wmax[32];
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = wmax[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, wmax[w]);
+    s_max = m;
+  }
+  __syncthreads();
+  mx = s_max;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) part += (double)expf(z[c] - mx);
+  const double tot = block_sum(part, scratch);
+  if (threadIdx.x == 0) s_sum = (float)tot;
+  __syncthreads();
+  const float sum = s_sum;
+  const int y = (int)labels[n];
+  const float invN = 1.0f / (float)N;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float pc = expf(z[c] - mx) / sum;
+    p[(long long)n * C + c] = pc;
+    dlogits[(long long)n * C + c] = (pc - (c == y ? 1.f : 0.f)) * invN;
+  }
+  if (threadIdx.x == 0) loss_n[n] = -(z[y] - mx - logf(sum));
+}
+
+__global__ void ce_tan_bwd_kernel(const float* __restrict__ p, const float* __restrict__ zdot, int N, int C, float* tdl) {
+  __shared__ double scratch[32];
+  __shared__ float s_dot;
+  const int n = blockIdx.x;
+  const float* pp = p + (long long)n * C;
+  const float* zz = zdot + (long long)n * C;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) part += (double)pp[c] * (double)zz[c];
+  const double tot = block_sum(part, scratch);
+  if (threadIdx.x == 0) s_dot = (float)tot;
+  __syncthreads();
+  const float dot = s_dot, invN = 1.0f / (float)N;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) tdl[(long long)n * C + c] = pp[c] * (zz[c] - dot) * invN;
+}
+
+// ---- layout ----------------------------------------------------------------------------------------
+__global__ void permute_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int HW, bool inverse,
+                               long long total) {
+  // index space of the OHWI side (coalesced writes forward, coalesced reads inverse)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ic = (int)(i % I);
+    long long t = i / I;
+    const int hw = (int)(t % HW);
+    const long long o = t / HW;
+    const long long j = (o * I + ic) * HW + hw;  // OIHW side
+    if (!inverse) dst[i] = src[j]; else dst[j] = src[i];
+  }
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float alpha, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = fmaf(alpha, x[i], y[i]);
+}
+
+}  // namespace
+
+int launch_bn_prepare(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C,
+                      float* scale, float* shift, float* inv, float* nrm, cudaStream_t s) {
+  bn_prepare_kernel<<<ceil_div(C, 128), 128, 0, s>>>(gamma, beta, rm, rv, eps, C, scale, shift, inv, nrm);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_bnact_fwd(const float* in, const float* res, float* out, long long P, int C, bool has_bn, bool relu,
+                     BnConsts bn, cudaStream_t s) {
+  const long long total = P * C;
+  bnact_fwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(in, res, out, total, C, has_bn, relu, bn);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_bnact_bwd(const BnActBwdArgs& a, cudaStream_t s) {
+  dim3 grid, block;
+  long long pps;
+  slab_grid(a.P, a.C, grid, block, pps);
+  bnact_bwd_kernel<<<grid, block, 0, s>>>(a, pps, grid.x * 32);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_bnact_tan_fwd(const BnActTanFwdArgs& a, cudaStream_t s) {
+  const long long total = a.P * a.C;
+  bnact_tan_fwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(a, total);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_bnact_tan_bwd(const BnActTanBwdArgs& a, cudaStream_t s) {
+  const long long total = a.P * a.C;
+  bnact_tan_bwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(a, total);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_channel_sum(const float* x, long long P, int C, float* out, float* partials, int* counters, cudaStream_t s) {
+  dim3 grid, block;
+  long long pps;
+  slab_grid(P, C, grid, block, pps);
+  channel_sum_kernel<<<grid, block, 0, s>>>(x, P, C, out, partials, counters, pps, grid.x * 32);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_channel_stats(const float* x, long long P, int C, float* mean, float* var, float* partials, int* counters,
+                         cudaStream_t s) {
+  dim3 grid, block;
+  long long pps;
+  slab_grid(P, C, grid, block, pps);
+  channel_stats_kernel<<<grid, block, 0, s>>>(x, P, C, mean, var, partials, counters, pps, grid.x * 32);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_maxpool_fwd(const float* in, float* out, int* idx, PoolGeom g, cudaStream_t s) {
+  const long long total = (long long)g.N * g.Ho * g.Wo * g.C;
+  maxpool_fwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(in, out, idx, g, total);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+int launch_maxpool_bwd(const float* dout, const int* idx, float* din, bool acc, PoolGeom g, cudaStream_t s) {
+  const long long total = (long long)g.N * g.H * g.W * g.C;
+  maxpool_bwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(dout, idx, din, acc, g, total);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+int launch_maxpool_gather(const float* tin, const int* idx, float* tout, PoolGeom g, cudaStream_t s) {
+  const long long total = (long long)g.N * g.Ho * g.Wo * g.C;
+  maxpool_gather_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(tin, idx, tout, g, total);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+int launch_avgpool_fwd(const float* in, float* out, int N, int HW, int C, cudaStream_t s) {
+  avgpool_fwd_kernel<<<ceil_div((long long)N * C, 128), 128, 0, s>>>(in, out, N, HW, C);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+int launch_avgpool_bwd(const float* dout, float* din, bool acc, int N, int HW, int C, cudaStream_t s) {
+  const long long total = (long long)N * HW * C;
+  avgpool_bwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(dout, din, acc, total, HW, C);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_ce_fwd(const float* logits, const long long* labels, int N, int C, float* p, float* loss_n, float* dlogits,
+                  cudaStream_t s) {
+  ce_fwd_kernel<<<N, 256, 0, s>>>(logits, labels, N, C, p, loss_n, dlogits);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+int launch_ce_tan_bwd(const float* p, const float* zdot, int N, int C, float* tdlogits, cudaStream_t s) {
+  ce_tan_bwd_kernel<<<N, 256, 0, s>>>(p, zdot, N, C, tdlogits);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_permute(const float* src, float* dst, int O, int I, int HW, bool inverse, cudaStream_t s) {
+  const long long total = (long long)O * I * HW;
+  permute_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(src, dst, O, I, HW, inverse, total);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+int launch_axpy(const float* x, float* y, float alpha, long long n, cudaStream_t s) {
+  axpy_kernel<<<ew_grid(n), kEwThreads, 0, s>>>(x, y, alpha, n);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace bre

@@ -1,0 +1,83 @@
+// Non-GEMM layer kernels of the four sweeps (NHWC activations): eval-mode BN + residual + ReLU (fused),
+// max/avg pooling, softmax cross-entropy, per-channel reductions, layout permutes.
+#pragma once
+#include "common.cuh"
+
+namespace bre {
+
+struct BnConsts {          // per-channel constants of an eval-mode BN (weights are fixed during an attack)
+  const float* scale;      // gamma * inv
+  const float* shift;      // beta - gamma * mean * inv
+  const float* inv;        // 1/sqrt(var + eps)
+  const float* nrm;        // -mean * inv      (xhat = x * inv + nrm)
+};
+
+// dst[c] constants from (gamma, beta, running_mean, running_var)
+int launch_bn_prepare(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C,
+                      float* scale, float* shift, float* inv, float* nrm, cudaStream_t s);
+
+// out = relu?( bn?(in) + res? )
+int launch_bnact_fwd(const float* in, const float* res, float* out, long long P, int C, bool has_bn, bool relu,
+                     BnConsts bn, cudaStream_t s);
+
+struct BnActBwdArgs {
+  long long P; int C; bool has_bn, relu;
+  BnConsts bn;
+  const float* in;      // BN input z (for xhat)
+  const float* out;     // activation (ReLU mask)
+  const float* dout;    // delta of out
+  float* din; bool acc_in;     // may be null
+  float* dres; bool acc_res;   // may be null
+  float* g_gamma; float* g_beta;  // parameter-gradient outputs (may be null)
+  float* partials; int* counters; // scratch: >= slabs*Cpad*2 floats, >= Cgroups ints (zeroed, self-resetting)
+};
+int launch_bnact_bwd(const BnActBwdArgs& a, cudaStream_t s);
+
+struct BnActTanFwdArgs {
+  long long P; int C; bool has_bn, relu;
+  BnConsts bn;
+  const float* in; const float* out;   // forward values (xhat, mask)
+  const float* tin; const float* tres; // tangents (may be null = zero)
+  const float* v_gamma; const float* v_beta;
+  float* tout;
+};
+int launch_bnact_tan_fwd(const BnActTanFwdArgs& a, cudaStream_t s);
+
+struct BnActTanBwdArgs {
+  long long P; int C; bool has_bn, relu;
+  BnConsts bn;
+  const float* in; const float* out;
+  const float* tdout;   // tangent delta of out
+  const float* dout;    // sweep-B delta of out
+  const float* v_gamma;
+  const float* di_cm; const float* di_cv; const float* di_mean;  // DeepInversion adjoint (may be null)
+  float* tdin; bool acc_in;
+  float* tdres; bool acc_res;
+};
+int launch_bnact_tan_bwd(const BnActTanBwdArgs& a, cudaStream_t s);
+
+// per-channel column sum: out[c] = sum_p x[p][c]   (conv / linear bias gradient)
+int launch_channel_sum(const float* x, long long P, int C, float* out, float* partials, int* counters, cudaStream_t s);
+// per-channel mean / biased variance over pixels (DeepInversion statistics, deepinversion.py:96-98)
+int launch_channel_stats(const float* x, long long P, int C, float* mean, float* var, float* partials, int* counters,
+                         cudaStream_t s);
+
+struct PoolGeom { int N, H, W, C, Ho, Wo, k, stride, pad; };
+int launch_maxpool_fwd(const float* in, float* out, int* idx, PoolGeom g, cudaStream_t s);
+int launch_maxpool_bwd(const float* dout, const int* idx, float* din, bool acc, PoolGeom g, cudaStream_t s);
+int launch_maxpool_gather(const float* tin, const int* idx, float* tout, PoolGeom g, cudaStream_t s);
+int launch_avgpool_fwd(const float* in, float* out, int N, int HW, int C, cudaStream_t s);
+int launch_avgpool_bwd(const float* dout, float* din, bool acc, int N, int HW, int C, cudaStream_t s);
+
+// softmax cross-entropy (mean over N): p, per-sample loss and dlogits = (p - onehot)/N
+int launch_ce_fwd(const float* logits, const long long* labels, int N, int C, float* p, float* loss_n, float* dlogits,
+                  cudaStream_t s);
+// tangent of dlogits: (p*zdot - p * sum(p*zdot)) / N
+int launch_ce_tan_bwd(const float* p, const float* zdot, int N, int C, float* tdlogits, cudaStream_t s);
+
+// dst[(o*HW + hw)*I + i] = src[(o*I + i)*HW + hw]   (inverse=false: OIHW -> OHWI / NCHW -> NHWC)
+int launch_permute(const float* src, float* dst, int O, int I, int HW, bool inverse, cudaStream_t s);
+// y[i] += alpha * x[i]
+int launch_axpy(const float* x, float* y, float alpha, long long n, cudaStream_t s);
+
+}  // namespace bre

@@ -1,0 +1,423 @@
+"""ctypes binding of ``libbreaching_b200.so`` (C ABI in ``include/breaching_b200.h``).
+
+PyTorch is used here only as plumbing: it owns the tensors whose ``data_ptr()`` is handed to the library.
+There is no fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import compiler as C
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libbreaching_b200.so")
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class TensorDesc(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int32), ("C", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32)]
+
+
+class ParamDesc(ctypes.Structure):
+    _fields_ = [("numel", ctypes.c_int64), ("perm", ctypes.c_int32), ("d0", ctypes.c_int32), ("d1", ctypes.c_int32),
+                ("d2", ctypes.c_int32)]
+
+
+class OpDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("kind", "tin", "tout", "res", "R", "S", "stride", "pad", "w", "b", "has_bn", "relu", "gamma", "beta",
+                 "bn_buffer")] + [("eps", ctypes.c_float), ("acc_in", ctypes.c_int32), ("acc_res", ctypes.c_int32)]
+
+
+class AttackCfg(ctypes.Structure):
+    _fields_ = [
+        ("objective", ctypes.c_int32),
+        ("obj_scale", ctypes.c_float), ("task_regularization", ctypes.c_float), ("tag_scale", ctypes.c_float),
+        ("mask_value", ctypes.c_float), ("angular_fudge", ctypes.c_float),
+        ("optimizer", ctypes.c_int32),
+        ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("adam_eps", ctypes.c_float),
+        ("weight_decay", ctypes.c_float), ("momentum", ctypes.c_float),
+        ("nesterov", ctypes.c_int32), ("signed_mode", ctypes.c_int32), ("boxed", ctypes.c_int32),
+        ("max_iterations", ctypes.c_int32),
+        ("langevin_noise", ctypes.c_float), ("grad_clip", ctypes.c_float),
+        ("noise_seed", ctypes.c_uint64),
+        ("tv_scale", ctypes.c_float), ("tv_inner_exp", ctypes.c_float), ("tv_outer_exp", ctypes.c_float),
+        ("tv_eps", ctypes.c_float), ("tv_double_opponents", ctypes.c_int32),
+        ("norm_scale", ctypes.c_float), ("norm_p", ctypes.c_float),
+        ("di_scale", ctypes.c_float), ("di_first_bn_multiplier", ctypes.c_float),
+        ("feat_scale", ctypes.c_float),
+    ]
+
+
+OBJECTIVES = {  # reference objectives.py:496-506
+    "euclidean": 0, "cosine-similarity": 1, "l1": 2, "tag-euclidean": 3, "angular": 4,
+    "fast-cosine-similarity": 5, "masked-cosine-similarity": 6,
+}
+OPTIMIZERS = {  # reference common.py:6-17 -> (kind, beta1, beta2, eps, weight_decay, momentum, nesterov)
+    "adam": (0, 0.9, 0.999, 1e-8, 0.0, 0.0, 0),
+    "adam-safe": (0, 0.5, 0.99, 1e-4, 0.0, 0.0, 0),
+    "bert-adam": (1, 0.9, 0.999, 1e-6, 0.01, 0.0, 0),
+    "momgd": (2, 0.0, 0.0, 0.0, 0.0, 0.9, 1),
+    "gd": (2, 0.0, 0.0, 0.0, 0.0, 0.0, 0),
+}
+
+EXPORTS = [
+    "bre_engine_create", "bre_engine_destroy", "bre_engine_load_model", "bre_engine_load_targets",
+    "bre_engine_load_feature_targets", "bre_engine_begin_trial", "bre_engine_run", "bre_engine_run_timed", "bre_engine_sync",
+    "bre_engine_status", "bre_engine_read_history", "bre_engine_get_best", "bre_engine_get_candidate",
+    "bre_engine_score", "bre_engine_objective_and_gradient", "bre_engine_last_terms", "bre_engine_debug_param",
+    "bre_engine_debug_tensor", "bre_engine_launches_per_iteration", "bre_engine_set_option", "bre_match_reduce",
+    "bre_total_variation", "bre_conv_gemm", "bre_last_error", "bre_version",
+]
+
+
+def load_library(path=None):
+    """Load the shared library (no compute is triggered; works without a GPU)."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise EngineError(
+            f"{path} not found: build it with `python -m breaching_b200.build` (there is no CPU/eager fallback)"
+        )
+    lib = ctypes.CDLL(path)
+    lib.bre_last_error.restype = ctypes.c_char_p
+    lib.bre_version.restype = ctypes.c_char_p
+    lib.bre_engine_destroy.restype = None
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+    P = ctypes.POINTER
+    lib.bre_engine_create.argtypes = [P(TensorDesc), i32, P(OpDesc), i32, P(ParamDesc), i32, i32, P(AttackCfg), i32, P(vp)]
+    lib.bre_engine_destroy.argtypes = [vp]
+    lib.bre_engine_load_model.argtypes = [vp, P(vp), i32, P(vp), P(vp), i32]
+    lib.bre_engine_load_targets.argtypes = [vp, P(vp), i32, vp, vp, i32, vp, vp, i32]
+    lib.bre_engine_load_feature_targets.argtypes = [vp, vp, i64]
+    lib.bre_engine_begin_trial.argtypes = [vp, vp, vp, i32]
+    lib.bre_engine_run.argtypes = [vp, i32]
+    lib.bre_engine_sync.argtypes = [vp]
+    lib.bre_engine_run_timed.argtypes = [vp, i32, P(ctypes.c_float)]
+    lib.bre_engine_status.argtypes = [vp, P(i32), P(i32), P(ctypes.c_double), P(ctypes.c_double)]
+    lib.bre_engine_read_history.argtypes = [vp, vp, i32]
+    lib.bre_engine_get_best.argtypes = [vp, vp]
+    lib.bre_engine_get_candidate.argtypes = [vp, vp]
+    lib.bre_engine_score.argtypes = [vp, vp, i32, P(ctypes.c_double)]
+    lib.bre_engine_objective_and_gradient.argtypes = [vp, vp, P(ctypes.c_double), vp]
+    lib.bre_engine_last_terms.argtypes = [vp, P(ctypes.c_double)]
+    lib.bre_engine_debug_param.argtypes = [vp, i32, i32, vp]
+    lib.bre_engine_debug_tensor.argtypes = [vp, i32, i32, vp]
+    lib.bre_engine_launches_per_iteration.argtypes = [vp, P(i32)]
+    lib.bre_engine_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+    lib.bre_match_reduce.argtypes = [vp, vp, vp, i64, f32, P(ctypes.c_double), vp]
+    lib.bre_total_variation.argtypes = [vp, vp, i32, i32, i32, f32, f32, f32, f32, i32, i32, P(ctypes.c_double), vp]
+    lib.bre_conv_gemm.argtypes = [i32, i32, vp, vp, vp, vp, vp] + [i32] * 9 + [vp]
+    for name in EXPORTS:
+        if name not in ("bre_last_error", "bre_version", "bre_engine_destroy"):
+            getattr(lib, name).restype = ctypes.c_int
+    _LIB = lib
+    return lib
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        raise EngineError(f"{what} failed ({rc}): {lib.bre_last_error().decode()}")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _f32c(t, device=None):
+    t = t.detach()
+    if device is not None:
+        t = t.to(device)
+    return t.to(torch.float32).contiguous()
+
+
+def make_cfg(cfg_attack, noise_seed=0):
+    """Flatten the reference-style attack config into the C struct (values as the reference reads them,
+    attacks/optimization_based_attack.py:29-38, :166-184; regularizers.py constructors)."""
+    from .config import cfg_get
+
+    c = AttackCfg()
+    obj = cfg_attack["objective"]
+    kind = obj["type"]
+    if kind not in OBJECTIVES:
+        if kind in ("pearlmutter-loss", "pearlmutter-cosine", "dynamic-cosine-similarity"):
+            raise EngineError(f"objective {kind} is not implemented by the engine")
+        raise ValueError(f"Unknown objective type {kind} given.")
+    c.objective = OBJECTIVES[kind]
+    c.obj_scale = float(cfg_get(obj, "scale", 1.0))
+    c.task_regularization = float(cfg_get(obj, "task_regularization", 0.0) or 0.0)
+    c.tag_scale = float(cfg_get(obj, "tag_scale", 0.1))
+    c.mask_value = 1e-6  # objectives.py:227 hard-codes 1e-6
+    c.angular_fudge = 1e-7  # objectives.py:208
+    opt = cfg_attack["optim"]
+    name = str(opt["optimizer"]).lower()
+    if name not in OPTIMIZERS:
+        if name == "l-bfgs":
+            raise EngineError("L-BFGS is not implemented by the engine")
+        raise ValueError(f"Invalid optimizer {opt['optimizer']} given.")
+    c.optimizer, c.beta1, c.beta2, c.adam_eps, c.weight_decay, c.momentum, c.nesterov = OPTIMIZERS[name]
+    signed = cfg_get(opt, "signed")
+    c.signed_mode = {"hard": 1, "soft": 2}.get(signed, 0) if isinstance(signed, str) else 0
+    c.boxed = int(bool(cfg_get(opt, "boxed", False)))
+    c.max_iterations = int(opt["max_iterations"])
+    c.langevin_noise = float(cfg_get(opt, "langevin_noise", 0.0) or 0.0)
+    clip = cfg_get(opt, "grad_clip")
+    c.grad_clip = -1.0 if clip is None else float(clip)
+    c.noise_seed = int(noise_seed) & 0xFFFFFFFFFFFFFFFF
+    c.tv_eps, c.tv_inner_exp, c.tv_outer_exp, c.norm_p, c.di_first_bn_multiplier = 1e-8, 1.0, 1.0, 2.0, 10.0
+    reg = cfg_get(cfg_attack, "regularization")
+    if reg is not None:
+        for key in reg.keys():
+            r = reg[key]
+            if not r["scale"] > 0:
+                continue
+            if key == "total_variation":
+                c.tv_scale = float(r["scale"])
+                c.tv_inner_exp = float(cfg_get(r, "inner_exp", 1))
+                c.tv_outer_exp = float(cfg_get(r, "outer_exp", 1))
+                c.tv_eps = float(cfg_get(r, "eps", 1e-8))
+                c.tv_double_opponents = int(bool(cfg_get(r, "double_opponents", False)))
+            elif key == "norm":
+                c.norm_scale = float(r["scale"])
+                c.norm_p = float(cfg_get(r, "pnorm", 2.0))
+            elif key == "deep_inversion":
+                c.di_scale = float(r["scale"])
+                c.di_first_bn_multiplier = float(cfg_get(r, "first_bn_multiplier", 10))
+            elif key == "features":
+                c.feat_scale = float(r["scale"])
+            elif key == "orthogonality":
+                raise EngineError("orthogonality regularisation is not implemented by the engine")
+            else:
+                raise KeyError(key)
+    return c
+
+
+class Engine:
+    """One engine = one model replica + one trial state on one GPU."""
+
+    def __init__(self, model, input_shape, cfg_attack, device, noise_seed=0):
+        self.lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise EngineError("the engine runs on CUDA devices only (no CPU fallback)")
+        self.model = model
+        self.prog = C.compile_model(model, input_shape)
+        self.input_shape = tuple(int(s) for s in input_shape)
+        self.ccfg = make_cfg(cfg_attack, noise_seed)
+        prog = self.prog
+        tens = (TensorDesc * len(prog.tensors))(*[TensorDesc(t.N, t.C, t.H, t.W) for t in prog.tensors])
+        pds = []
+        for p in prog.params:
+            if p.perm == C.PERM_OIHW_TO_OHWI:
+                pds.append(ParamDesc(p.numel, 1, p.shape[0], p.shape[1], p.shape[2] * p.shape[3]))
+            elif p.perm == C.PERM_LINEAR_CHW_TO_HWC:
+                pds.append(ParamDesc(p.numel, 1, p.shape[0], p.perm_c, p.perm_hw))
+            else:
+                pds.append(ParamDesc(p.numel, 0, 0, 0, 0))
+        self._bn_modules = []
+        ops = []
+        mods = C.bn_modules(model, prog)
+        for op, mod in zip(prog.ops, mods):
+            bn_idx = -1
+            if mod is not None:
+                bn_idx = len(self._bn_modules)
+                self._bn_modules.append(mod)
+            ops.append(OpDesc(op.kind, op.tin, op.tout, op.res, op.R, op.S, op.stride, op.pad, op.w, op.b, int(op.has_bn),
+                              int(op.relu), op.gamma, op.beta, bn_idx, float(op.eps), int(op.acc_in), int(op.acc_res)))
+        self._keep = (tens, (OpDesc * len(ops))(*ops), (ParamDesc * len(pds))(*pds))
+        handle = ctypes.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        rc = self.lib.bre_engine_create(self._keep[0], len(prog.tensors), self._keep[1], len(ops), self._keep[2], len(pds),
+                                        prog.logits, ctypes.byref(self.ccfg), dev_index, ctypes.byref(handle))
+        _check(self.lib, rc, "bre_engine_create")
+        self.h = handle
+        self.numel = 1
+        for s in self.input_shape:
+            self.numel *= s
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bre_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---------------------------------------------------------------------------------------------
+    def _ptr_array(self, tensors):
+        arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        return arr
+
+    def load_model(self, params=None, buffers_from=None):
+        """``params``: list of tensors in ``model.parameters()`` order (default: the model's own)."""
+        params = [_f32c(p) for p in (params if params is not None else self.model.parameters())]
+        mods = self._bn_modules
+        means = [_f32c(m.running_mean) for m in mods]
+        vars_ = [_f32c(m.running_var) for m in mods]
+        torch.cuda.synchronize(self.device) if any(p.is_cuda for p in params) else None
+        pa, ma, va = self._ptr_array(params), self._ptr_array(means), self._ptr_array(vars_)
+        rc = self.lib.bre_engine_load_model(self.h, pa, len(params), ma, va, len(mods))
+        _check(self.lib, rc, "bre_engine_load_model")
+
+    def load_targets(self, gradients, labels, mean=None, std=None, tensor_weights=None):
+        grads = [_f32c(g) for g in gradients]
+        labels = labels.detach().to(torch.int64).contiguous()
+        if any(g.is_cuda for g in grads) or labels.is_cuda:
+            torch.cuda.synchronize(self.device)
+        tw = None if tensor_weights is None else _f32c(tensor_weights).cpu()
+        mean_t = None if mean is None else torch.as_tensor(mean, dtype=torch.float32).flatten().contiguous().cpu()
+        std_t = None if std is None else torch.as_tensor(std, dtype=torch.float32).flatten().contiguous().cpu()
+        ga = self._ptr_array(grads)
+        rc = self.lib.bre_engine_load_targets(self.h, ga, len(grads), _ptr(tw), _ptr(labels), labels.numel(), _ptr(mean_t),
+                                              _ptr(std_t), 0 if mean_t is None else mean_t.numel())
+        _check(self.lib, rc, "bre_engine_load_targets")
+
+    def load_feature_targets(self, measured):
+        """``measured``: [N, F] in torch (flatten) feature order; permuted here if the head sees a spatial map."""
+        lin = [op for op in self.prog.ops if op.kind == C.OP_LINEAR][-1]
+        ti = self.prog.tensors[lin.tin]
+        m = _f32c(measured)
+        if ti.H * ti.W > 1:
+            m = m.view(ti.N, ti.C, ti.H * ti.W).permute(0, 2, 1).contiguous()
+        if m.is_cuda:
+            torch.cuda.synchronize(self.device)
+        _check(self.lib, self.lib.bre_engine_load_feature_targets(self.h, _ptr(m), m.numel()), "bre_engine_load_feature_targets")
+
+    def begin_trial(self, candidate, lr_table):
+        cand = _f32c(candidate)
+        if cand.numel() != self.numel:
+            raise EngineError(f"candidate has {cand.numel()} elements, engine expects {self.numel}")
+        lr = torch.as_tensor(lr_table, dtype=torch.float32).contiguous().cpu()
+        if cand.is_cuda:
+            torch.cuda.synchronize(self.device)
+        _check(self.lib, self.lib.bre_engine_begin_trial(self.h, _ptr(cand), _ptr(lr), lr.numel()), "bre_engine_begin_trial")
+
+    def run(self, n_iters):
+        _check(self.lib, self.lib.bre_engine_run(self.h, int(n_iters)), "bre_engine_run")
+
+    def run_timed(self, n_iters):
+        """Run ``n_iters`` iterations and return the device time in milliseconds (CUDA events on the engine stream)."""
+        ms = ctypes.c_float()
+        _check(self.lib, self.lib.bre_engine_run_timed(self.h, int(n_iters), ctypes.byref(ms)), "bre_engine_run_timed")
+        return ms.value
+
+    def sync(self):
+        _check(self.lib, self.lib.bre_engine_sync(self.h), "bre_engine_sync")
+
+    def status(self):
+        rec, stop = ctypes.c_int32(), ctypes.c_int32()
+        fmin, tl = ctypes.c_double(), ctypes.c_double()
+        _check(self.lib, self.lib.bre_engine_status(self.h, ctypes.byref(rec), ctypes.byref(stop), ctypes.byref(fmin), ctypes.byref(tl)),
+               "bre_engine_status")
+        return dict(recorded=rec.value, stopped=bool(stop.value), min_objective=fmin.value, task_loss=tl.value)
+
+    def history(self, n=None):
+        n = self.status()["recorded"] if n is None else n
+        out = torch.empty(max(n, 1), dtype=torch.float32)
+        _check(self.lib, self.lib.bre_engine_read_history(self.h, _ptr(out), n), "bre_engine_read_history")
+        return out[:n]
+
+    def best(self, device=None):
+        out = torch.empty(self.input_shape, dtype=torch.float32, device=device or self.device)
+        torch.cuda.synchronize(self.device)
+        _check(self.lib, self.lib.bre_engine_get_best(self.h, _ptr(out)), "bre_engine_get_best")
+        return out
+
+    def candidate(self, device=None):
+        out = torch.empty(self.input_shape, dtype=torch.float32, device=device or self.device)
+        torch.cuda.synchronize(self.device)
+        _check(self.lib, self.lib.bre_engine_get_candidate(self.h, _ptr(out)), "bre_engine_get_candidate")
+        return out
+
+    def score(self, candidate, scoring):
+        cand = _f32c(candidate)
+        if cand.is_cuda:
+            torch.cuda.synchronize(self.device)
+        out = ctypes.c_double()
+        _check(self.lib, self.lib.bre_engine_score(self.h, _ptr(cand), OBJECTIVES[scoring], ctypes.byref(out)), "bre_engine_score")
+        return out.value
+
+    def objective_and_gradient(self, candidate):
+        cand = _f32c(candidate)
+        if cand.is_cuda:
+            torch.cuda.synchronize(self.device)
+        grad = torch.empty(self.input_shape, dtype=torch.float32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        val = ctypes.c_double()
+        _check(self.lib, self.lib.bre_engine_objective_and_gradient(self.h, _ptr(cand), ctypes.byref(val), _ptr(grad)),
+               "bre_engine_objective_and_gradient")
+        return val.value, grad
+
+    def last_terms(self):
+        arr = (ctypes.c_double * 6)()
+        _check(self.lib, self.lib.bre_engine_last_terms(self.h, arr), "bre_engine_last_terms")
+        return dict(zip(("match", "task_loss", "total_variation", "norm", "deep_inversion", "features"), list(arr)))
+
+    def debug_param(self, which, index):
+        p = self.prog.params[index]
+        out = torch.empty(p.shape, dtype=torch.float32)
+        code = {"G": 0, "v": 1, "W": 2, "g": 3}[which]
+        _check(self.lib, self.lib.bre_engine_debug_param(self.h, code, index, _ptr(out)), "bre_engine_debug_param")
+        return out
+
+    def debug_tensor(self, which, tid):
+        t = self.prog.tensors[tid]
+        out = torch.empty((t.N, t.C, t.H, t.W), dtype=torch.float32)
+        code = {"val": 0, "delta": 1, "tangent": 2, "tangent_delta": 3}[which]
+        _check(self.lib, self.lib.bre_engine_debug_tensor(self.h, code, tid, _ptr(out)), "bre_engine_debug_tensor")
+        return out
+
+    def launches_per_iteration(self):
+        out = ctypes.c_int32()
+        _check(self.lib, self.lib.bre_engine_launches_per_iteration(self.h, ctypes.byref(out)), "bre_engine_launches_per_iteration")
+        return out.value
+
+    def set_option(self, name, value):
+        _check(self.lib, self.lib.bre_engine_set_option(self.h, name.encode(), int(value)), "bre_engine_set_option")
+
+
+# ---- stand-alone kernels ---------------------------------------------------------------------------
+def match_reduce(G, g, chunk_weights=None, mask_value=-1.0):
+    lib = load_library()
+    assert G.is_cuda and g.is_cuda and G.dtype == torch.float32 and G.is_contiguous() and g.is_contiguous()
+    out = (ctypes.c_double * 5)()
+    stream = torch.cuda.current_stream(G.device).cuda_stream
+    with torch.cuda.device(G.device):
+        rc = lib.bre_match_reduce(_ptr(G), _ptr(g), _ptr(chunk_weights), G.numel(), float(mask_value), out,
+                                  ctypes.c_void_p(stream))
+    _check(lib, rc, "bre_match_reduce")
+    return list(out)
+
+
+def total_variation(x, scale=0.1, inner_exp=1.0, outer_exp=1.0, eps=1e-8, double_opponents=False, grad=None):
+    lib = load_library()
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3
+    accumulate = grad is not None
+    grad = torch.empty_like(x) if grad is None else grad
+    val = ctypes.c_double()
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        rc = lib.bre_total_variation(_ptr(x), _ptr(grad), x.shape[0], x.shape[2], x.shape[3], scale, inner_exp, outer_exp,
+                                     eps, int(double_opponents), int(accumulate), ctypes.byref(val), ctypes.c_void_p(stream))
+    _check(lib, rc, "bre_total_variation")
+    return val.value, grad
+
+
+def conv_gemm(mode, a, w, out, N, H, W, Ci, Co, R, S, stride, pad, a2=None, w2=None, backend=0):
+    """mode: 0 fprop / 1 dgrad / 2 wgrad on NHWC / OHWI device tensors (see the header)."""
+    lib = load_library()
+    stream = torch.cuda.current_stream(a.device).cuda_stream
+    with torch.cuda.device(a.device):
+        rc = lib.bre_conv_gemm(mode, backend, _ptr(a), _ptr(w), _ptr(a2), _ptr(w2), _ptr(out), N, H, W, Ci, Co, R, S, stride,
+                               pad, ctypes.c_void_p(stream))
+    _check(lib, rc, "bre_conv_gemm")
+    return out

@@ -1,0 +1,53 @@
+"""Shared helpers for the parity tests."""
+import copy
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from breaching_b200 import config as bcfg  # noqa: E402
+from breaching_b200 import synthetic  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def cfg_from_fixture(fx):
+    return bcfg.get_attack_config(fx["attack"], dict(fx["overrides"]))
+
+
+def case_from_fixture(fx):
+    model, loss_fn, payload, shared, true = synthetic.make_case(**fx["case"])
+    checksum = float(sum(p.double().sum() for p in model.parameters()))
+    assert abs(checksum - fx["weight_checksum"]) <= 1e-6 * max(1.0, abs(fx["weight_checksum"])), \
+        "synthetic case differs from the one the fixture was generated with"
+    return model, loss_fn, payload, shared, true
+
+
+def oracle_for_fixture(fx):
+    """TrialOracle (CPU restatement) set up exactly like the reference attacker was for this fixture."""
+    from oracle import restate
+
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    shared = copy.deepcopy(shared)
+    m = copy.deepcopy(model)
+    if shared[0]["buffers"] is not None:
+        for buf, src in zip(m.buffers(), shared[0]["buffers"]):
+            buf.data.copy_(src)
+    m.eval()
+    meta = payload[0]["metadata"]
+    dm = torch.tensor(meta.mean)[None, :, None, None]
+    ds = torch.tensor(meta.std)[None, :, None, None]
+    labels = restate.recover_labels(cfg.label_strategy, shared, shared[0]["metadata"]["num_data_points"])
+    return restate.TrialOracle(m, loss_fn, cfg, shared[0]["gradients"], labels, dm, ds), cfg, labels
+
+
+TRIAL_FIXTURES = ["ig_convnet", "ig_resnet18", "stg_resnet18", "modern_convnet", "tag_clip_convnet", "l1_sgd_convnet"]

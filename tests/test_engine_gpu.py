@@ -1,0 +1,205 @@
+"""Engine-level parity on the B200: objective, parameter gradients and d(objective)/d(candidate) of one closure
+evaluation; short trajectories; the attacker API -- against the CPU oracle and the reference's golden fixtures."""
+import copy
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from breaching_b200 import compiler, get_attack_config, synthetic  # noqa: E402
+from breaching_b200.attacks import prepare_attack  # noqa: E402
+from breaching_b200.engine import Engine  # noqa: E402
+from helpers import TRIAL_FIXTURES, case_from_fixture, cfg_from_fixture, load_golden, oracle_for_fixture  # noqa: E402
+
+DEV = torch.device("cuda:0")
+SETUP = dict(device=DEV, dtype=torch.float)
+
+
+def _relerr(a, b):
+    return ((a.double().cpu() - b.double().cpu()).norm() / (b.double().cpu().norm() + 1e-30)).item()
+
+
+def _engine_for(model, cfg, shared, labels, meta, shape, features=None):
+    m = copy.deepcopy(model).to(DEV).eval()
+    eng = Engine(m, shape, cfg, DEV)
+    eng.load_model()
+    tw = None
+    if cfg.objective.type == "tag-euclidean":
+        L = len(shared[0]["gradients"])
+        tw = torch.arange(L, 0, -1, dtype=torch.float32) / L
+    eng.load_targets([g.to(DEV) for g in shared[0]["gradients"]], labels.to(DEV), mean=meta.mean, std=meta.std, tensor_weights=tw)
+    if features is not None:
+        eng.load_feature_targets(features.to(DEV))
+    return eng
+
+
+@pytest.mark.parametrize("name", TRIAL_FIXTURES)
+def test_closure_matches_reference_fixture(name):
+    """Objective value, label recovery and raw candidate gradient at x0 vs what the reference produced."""
+    fx = load_golden(f"trial_{name}.pt")
+    orc, cfg, labels = oracle_for_fixture(fx)
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    feats = orc._measured if orc._measured is not None else None
+    eng = _engine_for(orc.model, cfg, shared, labels, payload[0]["metadata"], tuple(fx["x0"].shape), feats)
+    val, grad = eng.objective_and_gradient(fx["x0"].to(DEV))
+    terms = eng.last_terms()
+    assert math.isclose(val, fx["objective0"], rel_tol=2e-4, abs_tol=1e-6), (val, fx["objective0"], terms)
+    assert math.isclose(terms["task_loss"], fx["task_loss0"], rel_tol=1e-4, abs_tol=1e-6)
+    rel = _relerr(grad, fx["raw_grad0"])
+    agree = (torch.sign(grad.cpu()) == torch.sign(fx["raw_grad0"])).float().mean().item()
+    assert rel < 1e-3 and agree > 0.99, (rel, agree, terms)  # tolerances of SURVEY.md section 7.4(3)(ii)
+    # parameter gradients G against autograd on the same candidate
+    Gref, _ = orc.param_gradient(fx["x0"], False)
+    worst = max(_relerr(eng.debug_param("G", i), Gref[i]) for i in range(len(Gref)))
+    assert worst < 1e-3, worst
+    orc.close()
+    eng.close()
+
+
+@pytest.mark.parametrize("kind", ["cosine-similarity", "euclidean", "l1", "tag-euclidean", "angular",
+                                  "fast-cosine-similarity", "masked-cosine-similarity"])
+def test_every_objective_gradient_vs_oracle(kind):
+    from oracle import restate
+
+    model, loss_fn, payload, shared, true = synthetic.make_case("resnet18", "imagenet", batch=2, seed=21, bn_random=True,
+                                                                image_size=64, classes=10)
+    cfg = get_attack_config("invertinggradients", {"objective.type": kind, "objective.task_regularization": 0.1,
+                                                    "objective.scale": 0.5})
+    meta = payload[0]["metadata"]
+    dm, ds = torch.tensor(meta.mean)[None, :, None, None], torch.tensor(meta.std)[None, :, None, None]
+    orc = restate.TrialOracle(model.eval(), loss_fn, cfg, shared[0]["gradients"], true["labels"], dm, ds)
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(4))
+    phi, _, raw, terms = orc.closure_gradient(x, 0, 0.1)
+    eng = _engine_for(model, cfg, shared, true["labels"], meta, (2, 3, 64, 64))
+    val, grad = eng.objective_and_gradient(x.to(DEV))
+    assert math.isclose(val, float(phi), rel_tol=2e-4, abs_tol=1e-6), (val, float(phi))
+    assert _relerr(grad, raw) < 2e-3, _relerr(grad, raw)
+    eng.close()
+
+
+def test_resnet18_224_closure_vs_float64_interpreter():
+    """BASELINE config 2 shape: one closure evaluation on the full 224x224 ResNet-18 against the float64 four-sweep."""
+    from oracle import program_interp as PI
+
+    model, loss_fn, payload, shared, true = synthetic.make_case("resnet18", "imagenet", batch=1, seed=233)
+    cfg = get_attack_config("invertinggradients")
+    x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(8))
+    eng = _engine_for(model, cfg, shared, true["labels"], payload[0]["metadata"], (1, 3, 224, 224))
+    val, grad = eng.objective_and_gradient(x.to(DEV))
+    m64 = copy.deepcopy(model).double().eval()
+    it = PI.ProgramInterpreter(m64, compiler.compile_model(m64, x.shape))
+    ref_val, dx, _, G = it.matching_gradient(x.double(), true["labels"], [g.double() for g in shared[0]["gradients"]],
+                                             "cosine-similarity")
+    from oracle import restate
+
+    xd = x.double().requires_grad_(True)
+    tv = restate.total_variation(xd, scale=0.2)
+    (gtv,) = torch.autograd.grad(tv, xd)
+    assert math.isclose(val, float(ref_val + tv), rel_tol=1e-4), (val, float(ref_val + tv))
+    rel = _relerr(grad, dx + gtv)
+    assert rel < 1e-3, rel
+    worst = max(_relerr(eng.debug_param("G", i), G[i]) for i in range(len(G)))
+    assert worst < 1e-4, worst
+    eng.close()
+
+
+@pytest.mark.parametrize("name", TRIAL_FIXTURES)
+def test_short_trajectory_matches_reference_fixture(name):
+    fx = load_golden(f"trial_{name}.pt")
+    orc, cfg, labels = oracle_for_fixture(fx)
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    feats = orc._measured if orc._measured is not None else None
+    eng = _engine_for(orc.model, cfg, shared, labels, payload[0]["metadata"], tuple(fx["x0"].shape), feats)
+    from breaching_b200.schedule import lr_table
+
+    opt = cfg.optim
+    eng.begin_trial(fx["x0"].to(DEV), lr_table(opt.step_size, opt.step_size_decay, opt.warmup, opt.max_iterations))
+    eng.run(1)
+    eng.sync()
+    after1 = eng.candidate().cpu()
+    # one optimiser step: identical up to sign flips of (numerically) zero gradient entries
+    diff = (after1 - fx["candidate_after_1"]).abs()
+    assert (diff > 1e-3).float().mean().item() < 0.01, (diff > 1e-3).float().mean().item()
+    eng.run(fx["iters"] - 1)
+    eng.sync()
+    hist = eng.history().tolist()
+    assert len(hist) == fx["iters"]
+    for a, b in zip(hist, fx["history"]):
+        assert math.isclose(a, b, rel_tol=5e-3, abs_tol=1e-5), (hist, fx["history"])
+    st = eng.status()
+    assert st["recorded"] == fx["iters"] and not st["stopped"]
+    assert math.isclose(st["min_objective"], min(fx["history"]), rel_tol=5e-3, abs_tol=1e-5)
+    final = eng.candidate().cpu()
+    assert (final - fx["candidate_final"]).abs().mean().item() < 5e-3
+    # best-so-far keeps the post-step candidate of the iteration with the minimal *pre-step* objective (:112-121)
+    best = eng.best().cpu()
+    assert (best - fx["best"]).abs().mean().item() < 5e-3
+    score = eng.score(best.to(DEV), fx["scoring"])
+    assert math.isclose(score, fx["score"], rel_tol=0.1, abs_tol=1e-4), (score, fx["score"])
+    orc.close()
+    eng.close()
+
+
+def test_graph_replay_equals_eager_launches():
+    model, loss_fn, payload, shared, true = synthetic.make_case("convnet-tiny", "cifar", batch=2, seed=3, bn_random=True)
+    cfg = get_attack_config("invertinggradients")
+    x0 = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(1)).to(DEV)
+    from breaching_b200.schedule import lr_table
+
+    table = lr_table(0.1, "step-lr", 0, 24000, 64)
+    outs = []
+    for use_graph in (1, 0):
+        eng = _engine_for(model, cfg, shared, true["labels"], payload[0]["metadata"], (2, 3, 32, 32))
+        eng.set_option("use_graph", use_graph)
+        eng.begin_trial(x0, table)
+        eng.run(12)
+        eng.sync()
+        outs.append((eng.candidate().cpu(), eng.history().clone(), eng.launches_per_iteration()))
+        eng.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2] > 0
+
+
+def test_non_finite_objective_stops_the_trial():
+    model, loss_fn, payload, shared, true = synthetic.make_case("convnet-tiny", "cifar", batch=1, seed=3, bn_random=True)
+    cfg = get_attack_config("invertinggradients", {"optim.boxed": False})
+    shared = copy.deepcopy(shared)
+    eng = _engine_for(model, cfg, shared, true["labels"], payload[0]["metadata"], (1, 3, 32, 32))
+    x0 = torch.full((1, 3, 32, 32), float("nan"), device=DEV)
+    eng.begin_trial(x0, [0.1] * 8)
+    eng.run(4)
+    eng.sync()
+    st = eng.status()
+    assert st["stopped"] and st["recorded"] == 0 and st["min_objective"] == float("inf")
+    assert eng.score(x0, "cosine-similarity") == float("inf")  # :204
+    eng.close()
+
+
+def test_reconstruct_api_dryrun_config1():
+    """BASELINE config 1: invertinggradients, ConvNet(width 64)/CIFAR-10 shape, 1 image, dryrun -> 1 iteration."""
+    model, loss_fn, payload, shared, true = synthetic.make_case("convnet", "cifar", batch=1, seed=233)
+    cfg = get_attack_config("invertinggradients")
+    attacker = prepare_attack(model, torch.jit.script(loss_fn), cfg, SETUP)
+    assert "Attacker" in repr(attacker)
+    payload_dev = [dict(parameters=[p.to(DEV) for p in payload[0]["parameters"]],
+                        buffers=[b.to(DEV) for b in payload[0]["buffers"]], metadata=payload[0]["metadata"])]
+    shared_dev = [dict(gradients=[g.to(DEV) for g in shared[0]["gradients"]], buffers=None, metadata=shared[0]["metadata"])]
+    rec, stats = attacker.reconstruct(payload_dev, shared_dev, {}, dryrun=True)
+    assert rec["data"].shape == (1, 3, 32, 32) and rec["data"].device.type == "cuda"
+    assert rec["labels"].tolist() == true["labels"].tolist()  # bias-corrected recovery, bit-exact
+    assert len(stats["Trial_0_Val"]) == 1 and "opt_value" in stats
+    assert torch.isfinite(rec["data"]).all()
+
+
+def test_reconstruct_multiple_restarts_pick_the_lowest_score():
+    model, loss_fn, payload, shared, true = synthetic.make_case("convnet-tiny", "cifar", batch=1, seed=5, bn_random=True)
+    cfg = get_attack_config("invertinggradients", {"restarts.num_trials": 3, "optim.max_iterations": 20, "optim.callback": 10})
+    attacker = prepare_attack(model, loss_fn, cfg, SETUP)
+    torch.manual_seed(0)
+    rec, stats = attacker.reconstruct(payload, copy.deepcopy(shared), {}, dryrun=False)
+    assert all(len(stats[f"Trial_{k}_Val"]) == 20 for k in range(3))
+    # objective decreases under the signed Adam steps
+    assert stats["Trial_0_Val"][-1] < stats["Trial_0_Val"][0]
+    assert math.isfinite(stats["opt_value"])
