@@ -339,7 +339,85 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_simt_kernel(GemmArgs a, Dims
   }
 }
 
+// ---- dgrad onto a tensor with very few channels (the 3-channel candidate behind the stem conv) ----------------
+// The GEMM formulation would run an N=64-wide tile for Ci=3 columns and multiply stride^2-1 out of stride^2 taps by
+// structural zeros.  Here one thread owns one input pixel and all CI channels, walks only the taps that hit the
+// output grid, and streams dout with 128-bit loads; lanes of a warp are mapped to pixels of the same stride-parity
+// class so the tap loop is warp-uniform and the weight loads are broadcasts.
+template <int CI>
+__global__ void __launch_bounds__(128) dgrad_small_ci_kernel(GemmArgs a, int vec) {
+  const ConvGeom g = a.g;
+  const int img = blockIdx.z, h = blockIdx.y;
+  const int Wc = (g.W + g.stride - 1) / g.stride;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cls = slot / Wc, w = (slot - cls * Wc) * g.stride + cls;
+  if (cls >= g.stride || w >= g.W) return;
+  float acc[CI];
+#pragma unroll
+  for (int c = 0; c < CI; ++c) acc[c] = 0.f;
+  const int RS = g.R * g.S;
+  for (int src = 0; src < a.nsrc; ++src) {
+    const float* __restrict__ dout = a.act[src];
+    const float* __restrict__ wgt = a.wgt[src];
+    for (int r = 0; r < g.R; ++r) {
+      const int hp = h + g.pad - r;
+      if (hp < 0) break;
+      const int p = hp / g.stride;
+      if (p * g.stride != hp || p >= g.Ho) continue;
+      for (int s = 0; s < g.S; ++s) {
+        const int wp = w + g.pad - s;
+        if (wp < 0) break;
+        const int q = wp / g.stride;
+        if (q * g.stride != wp || q >= g.Wo) continue;
+        const float* dp = dout + ((long long)(img * g.Ho + p) * g.Wo + q) * g.Co;
+        const float* wq = wgt + (long long)(r * g.S + s) * g.Ci;
+        if (vec) {
+          for (int ko = 0; ko < g.Co; ko += 4) {
+            const float4 dv = __ldg(reinterpret_cast<const float4*>(dp + ko));
+            const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float* wj = wq + (long long)(ko + j) * RS * g.Ci;
+#pragma unroll
+              for (int c = 0; c < CI; ++c) acc[c] = fmaf(dd[j], __ldg(wj + c), acc[c]);
+            }
+          }
+        } else {
+          for (int ko = 0; ko < g.Co; ++ko) {
+            const float dd = __ldg(dp + ko);
+            const float* wj = wq + (long long)ko * RS * g.Ci;
+#pragma unroll
+            for (int c = 0; c < CI; ++c) acc[c] = fmaf(dd, __ldg(wj + c), acc[c]);
+          }
+        }
+      }
+    }
+  }
+  float* op = a.out + img * a.x_sN + (long long)(h * g.W + w) * a.x_sP;
+#pragma unroll
+  for (int c = 0; c < CI; ++c) {
+    float* q = op + (long long)c * a.x_sC;
+    *q = a.accumulate ? *q + acc[c] : acc[c];
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int launch_dgrad_small_ci(const GemmArgs& a, cudaStream_t stream) {
+  const ConvGeom& g = a.g;
+  bool vec = g.Co % 4 == 0;
+  for (int s = 0; s < a.nsrc; ++s) vec = vec && aligned16(a.act[s]);
+  const int Wc = (g.W + g.stride - 1) / g.stride;
+  dim3 grid(ceil_div((long long)Wc * g.stride, 128), g.H, g.N), block(128);
+  switch (g.Ci) {
+    case 1: dgrad_small_ci_kernel<1><<<grid, block, 0, stream>>>(a, vec); break;
+    case 2: dgrad_small_ci_kernel<2><<<grid, block, 0, stream>>>(a, vec); break;
+    case 3: dgrad_small_ci_kernel<3><<<grid, block, 0, stream>>>(a, vec); break;
+    default: dgrad_small_ci_kernel<4><<<grid, block, 0, stream>>>(a, vec); break;
+  }
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
 
 }  // namespace
 
@@ -349,6 +427,7 @@ int launch_igemm_simt(const GemmArgs& a, cudaStream_t stream) {
   const ConvGeom& g = a.g;
   if (d.M <= 0 || d.Nc <= 0 || d.K <= 0) { set_error("igemm: empty problem"); return -1; }
   if (a.nsrc < 1 || a.nsrc > 2 || (a.nsrc == 2 && a.mode == GEMM_WGRAD)) { set_error("igemm: bad nsrc"); return -1; }
+  if (a.mode == GEMM_DGRAD && g.Ci <= 4 && g.H <= 65535 && g.N <= 65535) return launch_dgrad_small_ci(a, stream);
   d.steps_per_src = ceil_div(d.K, IG_BK);
   d.total_steps = d.steps_per_src * a.nsrc;
 

@@ -60,28 +60,39 @@ __global__ void __launch_bounds__(256) match_reduce_kernel(const float* __restri
   __shared__ int s_last;
   double acc[5] = {0, 0, 0, 0, 0};
   const bool masked = mask_value >= 0.f;
-  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const long long i = ch * kChunk + threadIdx.x * 4;
-    float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-    if (i + 3 < n) {
-      const float4 va = __ldg(reinterpret_cast<const float4*>(G + i));
-      const float4 vb = __ldg(reinterpret_cast<const float4*>(g + i));
-      a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
-      b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
-    } else {
-      for (int j = 0; j < 4; ++j)
-        if (i + j < n) { a[j] = G[i + j]; b[j] = g[i + j]; }
-    }
-    const float w = chunk_w != nullptr ? __ldg(chunk_w + ch) : 1.f;
-    float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+  constexpr int U = 4;  // chunks in flight per block iteration: 8 independent 128-bit loads per thread
+  for (long long base = (long long)blockIdx.x * U; base < nchunks; base += (long long)gridDim.x * U) {
+    float a[U][4], b[U][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float x = a[j], y = b[j];
-      if (masked && !(fabsf(y) > mask_value)) { x = 0.f; y = 0.f; }
-      const float df = x - y;
-      s0 = fmaf(x, y, s0); s1 = fmaf(x, x, s1); s2 = fmaf(y, y, s2); s3 = fmaf(df, df, s3); s4 += fabsf(df);
+    for (int u = 0; u < U; ++u) {
+      const long long i = (base + u) * kChunk + threadIdx.x * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[u][j] = 0.f; b[u][j] = 0.f; }
+      if (base + u < nchunks) {
+        if (i + 3 < n) {
+          const float4 va = __ldg(reinterpret_cast<const float4*>(G + i));
+          const float4 vb = __ldg(reinterpret_cast<const float4*>(g + i));
+          a[u][0] = va.x; a[u][1] = va.y; a[u][2] = va.z; a[u][3] = va.w;
+          b[u][0] = vb.x; b[u][1] = vb.y; b[u][2] = vb.z; b[u][3] = vb.w;
+        } else {
+          for (int j = 0; j < 4; ++j)
+            if (i + j < n) { a[u][j] = G[i + j]; b[u][j] = g[i + j]; }
+        }
+      }
     }
-    acc[0] += s0; acc[1] += s1; acc[2] += s2; acc[3] += s3; acc[4] += (double)w * s4;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float w = (chunk_w != nullptr && base + u < nchunks) ? __ldg(chunk_w + base + u) : 1.f;
+      float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x = a[u][j], y = b[u][j];
+        if (masked && !(fabsf(y) > mask_value)) { x = 0.f; y = 0.f; }
+        const float df = x - y;
+        s0 = fmaf(x, y, s0); s1 = fmaf(x, x, s1); s2 = fmaf(y, y, s2); s3 = fmaf(df, df, s3); s4 += fabsf(df);
+      }
+      acc[0] += s0; acc[1] += s1; acc[2] += s2; acc[3] += s3; acc[4] += (double)w * s4;
+    }
   }
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
@@ -456,7 +467,8 @@ int launch_match_reduce(const float* G, const float* g, const float* chunk_w, lo
                         int objective, float scale, float tag_scale, float fudge, bool finalize, Scalars* sc,
                         double* partials, int* counter, cudaStream_t s) {
   const long long nchunks = (n + kChunk - 1) / kChunk;
-  const int grid = (int)(nchunks < kMatchMaxBlocks ? (nchunks > 0 ? nchunks : 1) : kMatchMaxBlocks);
+  const long long groups = (nchunks + 3) / 4;
+  const int grid = (int)(groups < kMatchMaxBlocks ? (groups > 0 ? groups : 1) : kMatchMaxBlocks);
   match_reduce_kernel<<<grid, 256, 0, s>>>(G, g, chunk_w, n, nchunks, mask_value, objective, scale, tag_scale, fudge,
                                            finalize, sc, partials, counter);
   BRE_CHECK_LAUNCH();

@@ -24,6 +24,9 @@ CONV_SHAPES = [
     (1, 7, 7, 512, 512, 3, 1, 1),     # tiny-M, split-K heavy
     (2, 14, 14, 256, 1024, 1, 1, 0),  # bottleneck 1x1 expansions
     (2, 28, 28, 512, 128, 1, 1, 0),
+    (2, 32, 32, 3, 64, 3, 1, 1),      # ConvNet stem (small-Ci dgrad kernel, stride 1)
+    (2, 12, 13, 1, 8, 3, 2, 1),       # single input channel, stride 2, odd sizes
+    (1, 9, 9, 4, 6, 5, 3, 2),         # 5x5 stride 3
     (3, 9, 11, 5, 7, 3, 1, 1),        # ragged everything
     (2, 10, 10, 6, 10, 3, 3, 0),
     (1, 1, 1, 512, 397, 1, 1, 0),     # the linear head as a 1x1 conv
@@ -120,6 +123,41 @@ def test_total_variation_value_and_gradient(p, q, dbl, shape):
     (gref,) = torch.autograd.grad(ref, xd)
     assert math.isclose(val, ref.item(), rel_tol=2e-5), (val, ref.item())
     assert _relerr(grad.cpu(), gref) < 5e-5
-    base = torch.ones_like(x)
+    base = grad.clone()  # accumulate on top of an existing gradient: result must be exactly doubled
     _, acc = E.total_variation(x, scale=0.2, inner_exp=p, outer_exp=q, double_opponents=dbl, grad=base)
-    assert _relerr((acc - 1).cpu(), gref) < 5e-4
+    assert _relerr(acc.cpu(), 2 * gref) < 5e-5
+
+
+TC_SHAPES = [s for s in CONV_SHAPES if s[3] % 32 == 0 and s[4] % 64 == 0] + [(1, 56, 56, 64, 64, 3, 1, 1), (8, 14, 14, 128, 256, 3, 2, 1)]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_tcgen05_tf32_backend(shape):
+    """tcgen05 TF32 back end (tensor cores, TMEM accumulators): TF32 products (10-bit mantissa), fp32 accumulation,
+    tolerance 2e-3 relative l2 -- the precision of the reference's default cuDNN TF32 conv path."""
+    N, H, W, Ci, Co, R, st, pd = shape
+    x = _rand(N, Ci, H, W, seed=1)
+    w = _rand(Co, Ci, R, R, seed=2) * 0.1
+    Ho, Wo = (H + 2 * pd - R) // st + 1, (W + 2 * pd - R) // st + 1
+    dy = _rand(N, Co, Ho, Wo, seed=3)
+    x2, w2, dy2 = _rand(N, Ci, H, W, seed=4), _rand(Co, Ci, R, R, seed=5) * 0.1, _rand(N, Co, Ho, Wo, seed=6)
+    w_ohwi, w2_ohwi = w.permute(0, 2, 3, 1).contiguous(), w2.permute(0, 2, 3, 1).contiguous()
+    tol = 2e-3
+    out = torch.empty(N, Ho, Wo, Co, device=DEV)
+    E.conv_gemm(0, _nhwc(x), w_ohwi, out, N, H, W, Ci, Co, R, R, st, pd, a2=_nhwc(x2), w2=w2_ohwi, backend=1)
+    ref = F.conv2d(x.double(), w.double(), stride=st, padding=pd) + F.conv2d(x2.double(), w2.double(), stride=st, padding=pd)
+    assert _relerr(out.permute(0, 3, 1, 2), ref) < tol, "fprop dual"
+    again = torch.empty_like(out)
+    E.conv_gemm(0, _nhwc(x), w_ohwi, again, N, H, W, Ci, Co, R, R, st, pd, a2=_nhwc(x2), w2=w2_ohwi, backend=1)
+    assert torch.equal(out, again)
+    if Ci % 64 == 0:
+        din = torch.empty(N, H, W, Ci, device=DEV)
+        E.conv_gemm(1, _nhwc(dy), w_ohwi, din, N, H, W, Ci, Co, R, R, st, pd, a2=_nhwc(dy2), w2=w2_ohwi, backend=1)
+        refd = torch.nn.grad.conv2d_input((N, Ci, H, W), w.double(), dy.double(), stride=st, padding=pd) + \
+            torch.nn.grad.conv2d_input((N, Ci, H, W), w2.double(), dy2.double(), stride=st, padding=pd)
+        assert _relerr(din.permute(0, 3, 1, 2), refd) < tol, "dgrad dual"
+    if Co % 128 == 0 and (R * R * Ci) % 64 == 0:
+        dw = torch.empty(Co, R, R, Ci, device=DEV)
+        E.conv_gemm(2, _nhwc(x), _nhwc(dy), dw, N, H, W, Ci, Co, R, R, st, pd, backend=1)
+        refw = torch.nn.grad.conv2d_weight(x.double(), (Co, Ci, R, R), dy.double(), stride=st, padding=pd)
+        assert _relerr(dw.permute(0, 3, 1, 2), refw) < tol, "wgrad"
