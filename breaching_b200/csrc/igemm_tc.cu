@@ -10,6 +10,9 @@
 //
 // fp32 storage everywhere; TF32 (10-bit mantissa) multiplies with fp32 accumulation -- the numeric mode cuDNN uses
 // for the reference's GPU path by default (torch.backends.cudnn.allow_tf32).
+#include <stdlib.h>
+#include <string.h>
+
 #include "igemm.cuh"
 
 namespace bre {
@@ -18,8 +21,9 @@ namespace {
 
 constexpr int TC_BM = 128;      // UMMA M
 constexpr int TC_BK = 32;       // k-block per pipeline stage (4 MMAs of K = 8)
-constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 128;
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 128;       // loader / epilogue threads (warps 0-3 <-> TMEM lane quadrants)
+constexpr int TC_BLOCK = TC_THREADS + 32;  // + one MMA-issuer warp
 
 struct TcDims {
   int M, Nc, K;
@@ -98,34 +102,61 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 // Shared-memory layouts of a [ROWS x 32] fp32 operand tile (ROWS = extent along M or N), as the tensor core reads them.
 // Both were verified on the B200 with profiles/experiments/umma_layout_probe.cu (one-hot probing of every byte offset):
-//   K-major, no swizzle (layout type 0), core matrix = 8 rows x 16 B:
-//       byte(row, k) = (k/4) * (ROWS*16) + row * 16 + (k%4) * 4
-//       MMA covering k in [8j, 8j+8): start + 2j*LBO, LBO = ROWS*16, SBO = 128
+//   K-major, SWIZZLE_128B (layout type 2): one 128-byte smem row per operand row = the whole 32-wide k-block, its eight
+//   16-byte granules XOR-swizzled with (row % 8), 8-row groups at SBO = 1024:
+//       byte(row, k) = (row/8) * 1024 + (row%8) * 128 + (((k/4) ^ (row%8)) * 16) + (k%4) * 4
+//       MMA covering k in [8j, 8j+8): start + 32 j (the swizzle is a function of the absolute address), LBO = 16
+//   (the no-swizzle K-major layout also works -- first version of this kernel -- but forces either uncoalesced global
+//   reads or 8-way conflicting shared stores; 128B swizzle gives coalesced 128-byte reads AND conflict-free stores)
 //   MN-major for 32-bit operands only exists as SWIZZLE_128B_BASE32B (layout type 1; the plain / 16-byte-atom MN-major
 //   layouts produce zeros for kind::tf32): 32 elements (128 B) contiguous along MN, rows of 128 B along k, the four
 //   32-byte chunks of a row XOR-swizzled with (k % 4), k-groups of 4 at SBO, MN-groups of 32 at LBO:
 //       byte(row, k) = (row/32) * 4096 + (k/4) * 512 + (k%4) * 128 + ((((row%32)/8) ^ (k%4)) * 32) + (row%8) * 4
 //       MMA covering k in [8j, 8j+8): start + j*1024, LBO = 4096, SBO = 512
-template <int ROWS>
-__device__ __forceinline__ uint32_t off_kmajor(int row, int k) { return (uint32_t)((k >> 2) * (ROWS * 16) + row * 16 + (k & 3) * 4); }
+// K-major SWIZZLE_128B: granule = 16 bytes (4 k), `g` = granule column 0..7 of the 32-wide k-block
+__device__ __forceinline__ uint32_t off_k128(int row, int g) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((g ^ (row & 7)) << 4));
+}
 template <int ROWS>
 __device__ __forceinline__ uint32_t off_mnmajor(int row, int k) {
   return (uint32_t)((row >> 5) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + ((((row >> 3) & 3) ^ (k & 3)) << 5) + (row & 7) * 4);
 }
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ void sts4(uint8_t* base, uint32_t off, float4 v) { *reinterpret_cast<float4*>(base + off) = v; }
+// 16-byte asynchronous global -> shared copy; src_bytes = 0 zero-fills the destination (padding, out-of-range taps)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const float* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// arrive on `bar` once all cp.async issued so far by this thread have landed (counts against the barrier's init count)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void loader_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16-byte load from the shared memory of CTA `rank` of this cluster at the same offset as local address `saddr`
+__device__ __forceinline__ float4 ld_dsmem4(uint32_t saddr, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(saddr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raddr) : "memory");
+  return v;
+}
 
 template <int MODE, int BN>
-__global__ void __launch_bounds__(TC_THREADS) igemm_tc_kernel(GemmArgs a, TcDims d) {
+__global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d, int proxy_fence) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;                                  // [STAGES][A_BYTES]
   uint8_t* sB = smem + TC_STAGES * A_BYTES;            // [STAGES][B_BYTES]
-  __shared__ __align__(8) uint64_t bar_stage[TC_STAGES];
+  __shared__ __align__(8) uint64_t bar_full[TC_STAGES];   // loaders -> MMA issuer (cp.async completion, 128 arrivals)
+  __shared__ __align__(8) uint64_t bar_empty[TC_STAGES];  // MMA issuer -> loaders (tcgen05.commit)
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ uint32_t s_tmem;
-  __shared__ int s_last;
 
   const ConvGeom g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -136,7 +167,7 @@ __global__ void __launch_bounds__(TC_THREADS) igemm_tc_kernel(GemmArgs a, TcDims
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TC_STAGES; ++s) mbar_init(&bar_stage[s], 1);
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], TC_THREADS); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_done, 1);
     fence_barrier_init();
   }
@@ -153,209 +184,227 @@ __global__ void __launch_bounds__(TC_THREADS) igemm_tc_kernel(GemmArgs a, TcDims
                              ((uint32_t)(TC_BM >> 4) << 24);
 
   // ---- per-thread fixed decode of the gathered (activation) operand ----------------------------------------
-  // FPROP / DGRAD: thread `tid` owns A row m0 + tid.   WGRAD: B rows are (r, s, c) columns, decoded below.
-  bool a_valid = false;
-  int a_img = 0, a_y = 0, a_x = 0;
-  if (MODE == GEMM_FPROP) {
-    const int m = m0 + tid;
-    a_valid = m < d.M;
-    if (a_valid) {
-      a_img = m / HoWo;
-      const int rem = m - a_img * HoWo;
-      const int p = rem / g.Wo, q = rem - p * g.Wo;
-      a_y = p * g.stride - g.pad;
-      a_x = q * g.stride - g.pad;
-    }
-  } else if (MODE == GEMM_DGRAD) {
-    const int m = m0 + tid;
-    a_valid = m < d.M;
-    if (a_valid) {
-      a_img = m / HW;
-      const int rem = m - a_img * HW;
-      a_y = rem / g.W;
-      a_x = rem - a_y * g.W;
+  // Loader thread t handles 16-byte granule column (t % 8) of A rows (t / 8) + 16 j, j = 0..7: the eight lanes of a
+  // quarter warp read one full 128-byte line of a pixel row (coalesced) and write one swizzled 128-byte smem row
+  // (conflict-free).  Everything that depends only on the row is computed once: the element offset of the row's
+  // anchor pixel and a bit mask over the R*S filter taps saying which taps land inside the tensor, so that staging a
+  // k-block costs one shift/and + one add + one cp.async per row (the loader warps are issue-latency bound otherwise).
+  constexpr int A_VEC = TC_BM * TC_BK / 4 / TC_THREADS;  // 16-byte granules per thread per stage: 8
+  constexpr int B_VEC = BN * TC_BK / 4 / TC_THREADS;     // 4 (BN = 64)
+  const int gcol = tid & 7, grow = (tid >> 3) & 15;
+  const bool fast = (g.R * g.S <= 64) && (MODE == GEMM_FPROP || (MODE == GEMM_DGRAD && g.stride == 1));
+  int a_off[A_VEC];                  // element offset of the anchor pixel (+ granule column)
+  unsigned long long a_taps[A_VEC];  // bit rs: tap (r, s) of this row reads inside the tensor
+  int a_yx[A_VEC];                   // slow path (strided dgrad): packed (y << 16) | x and image index in a_off
+  if (MODE == GEMM_FPROP || MODE == GEMM_DGRAD) {
+#pragma unroll
+    for (int j = 0; j < A_VEC; ++j) {
+      const int m = m0 + grow + 16 * j;
+      a_off[j] = 0; a_taps[j] = 0ull; a_yx[j] = 0;
+      if (m < d.M) {
+        if (MODE == GEMM_FPROP) {
+          const int img = m / HoWo, rem = m - img * HoWo;
+          const int p = rem / g.Wo, q = rem - p * g.Wo;
+          const int y0 = p * g.stride - g.pad, x0 = q * g.stride - g.pad;
+          a_off[j] = (int)(img * a.x_sN) + (y0 * g.W + x0) * a.x_sP + gcol * 4;
+          for (int r = 0; r < g.R; ++r)
+            for (int s2 = 0; s2 < g.S; ++s2)
+              if (y0 + r >= 0 && y0 + r < g.H && x0 + s2 >= 0 && x0 + s2 < g.W) a_taps[j] |= 1ull << (r * g.S + s2);
+        } else {
+          const int img = m / HW, rem = m - img * HW;
+          const int y = rem / g.W, x = rem - y * g.W;
+          if (fast) {  // stride 1: p = y + pad - r, q = x + pad - s
+            a_off[j] = ((img * g.Ho + y + g.pad) * g.Wo + x + g.pad) * g.Co + gcol * 4;
+            for (int r = 0; r < g.R; ++r)
+              for (int s2 = 0; s2 < g.S; ++s2) {
+                const int pp = y + g.pad - r, qq = x + g.pad - s2;
+                if (pp >= 0 && pp < g.Ho && qq >= 0 && qq < g.Wo) a_taps[j] |= 1ull << (r * g.S + s2);
+              }
+          } else {
+            a_off[j] = img;
+            a_yx[j] = (y << 16) | x;
+            a_taps[j] = 1ull;
+          }
+        }
+      }
     }
   }
+  // running decode of the k-block sequence this CTA walks: (source, filter tap, first channel) advance incrementally
+  int it_src, it_rs, it_c0;
+  {
+    const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
+    it_src = kb_begin / d.kblocks_per_src;
+    const int kbase = (kb_begin - it_src * d.kblocks_per_src) * TC_BK;
+    it_rs = (MODE == GEMM_WGRAD) ? 0 : kbase / kch;
+    it_c0 = (MODE == GEMM_WGRAD) ? kbase : kbase - it_rs * kch;
+  }
 
-  constexpr int A_VEC = TC_BM * TC_BK / 4 / TC_THREADS;  // float4 per thread per stage: 8
-  constexpr int B_VEC = BN * TC_BK / 4 / TC_THREADS;     // 4 (BN = 64) or 8 (BN = 128)
-  float4 ra[A_VEC], rb[B_VEC];
-
-  auto load_block = [&](int kb) {
-    const int src = kb / d.kblocks_per_src;
-    const int kbase = (kb - src * d.kblocks_per_src) * TC_BK;
+  // Stage one k-block: cp.async (LDGSTS, 16 B, zero-fill for padding / out-of-range taps) straight from global memory
+  // into the UMMA operand layouts -- no register staging, so up to TC_STAGES k-blocks of loads stay in flight.
+  auto issue_block = [&](int stage) {
+    const int src = it_src;
+    const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
+    const int kbase = (MODE == GEMM_WGRAD) ? it_c0 : it_rs * kch + it_c0;
     const float* __restrict__ act = a.act[src];
     const float* __restrict__ wgt = a.wgt[src];
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t pa = smem_u32(sA + stage * A_BYTES), pb = smem_u32(sB + stage * B_BYTES);
     if (MODE == GEMM_FPROP) {
-      // A(m, k) = in[img, y + r, x + s, c], k = (r, s, c); the 32-wide k-block lies inside one (r, s) cell (Ci % 32 == 0)
-      const int rs = kbase / g.Ci, c0 = kbase - rs * g.Ci;
-      const int r = rs / g.S, s = rs - r * g.S;
-      const int h = a_y + r, w = a_x + s;
-      const bool ok = a_valid && h >= 0 && h < g.H && w >= 0 && w < g.W;
-      const float* p = act + a_img * a.x_sN + (long long)(h * g.W + w) * a.x_sP + c0;
+      // A(m, k) = in[img, y0 + r, x0 + s, c], k = (r, s, c); the 32-wide k-block lies inside one (r, s) cell (Ci % 32 == 0)
+      const int r = it_rs / g.S, s = it_rs - r * g.S;
+      const int tapoff = (r * g.W + s) * a.x_sP + it_c0;
 #pragma unroll
-      for (int j = 0; j < A_VEC; ++j) ra[j] = ok ? ldg4(p + 4 * j) : zero;
-      // B(n, k) = W[n][k] (row-major [Co][K]): thread -> row tid % BN, k-chunks (tid / BN) * B_VEC ...
-      const int row = tid % BN, kc0 = (tid / BN) * B_VEC;
-      const float* q = wgt + (long long)(n0 + row) * d.K + kbase + kc0 * 4;
+      for (int j = 0; j < A_VEC; ++j) {
+        const bool ok = (a_taps[j] >> it_rs) & 1ull;
+        cp_async16(pa + off_k128(grow + 16 * j, gcol), ok ? act + (a_off[j] + tapoff) : act, ok ? 16u : 0u);
+      }
+      // B(n, k) = W[n][k] (row-major [Co][K])
+      const float* q = wgt + (long long)(n0 + grow) * d.K + kbase + gcol * 4;
 #pragma unroll
-      for (int j = 0; j < B_VEC; ++j) rb[j] = ldg4(q + 4 * j);
+      for (int j = 0; j < B_VEC; ++j) cp_async16(pb + off_k128(grow + 16 * j, gcol), q + (long long)(16 * j) * d.K, 16u);
     } else if (MODE == GEMM_DGRAD) {
       // A(m, k) = dout[img, (y + pad - r)/stride, (x + pad - s)/stride, ko], k = (r, s, ko)   (Co % 32 == 0)
-      const int rs = kbase / g.Co, k0 = kbase - rs * g.Co;
+      const int rs = it_rs, k0 = it_c0;
       const int r = rs / g.S, s = rs - r * g.S;
-      const int hp = a_y + g.pad - r, wp = a_x + g.pad - s;
-      bool ok = a_valid && hp >= 0 && wp >= 0;
-      int p = 0, q = 0;
-      if (ok) {
-        p = hp / g.stride; q = wp / g.stride;
-        ok = (p * g.stride == hp) && (q * g.stride == wp) && p < g.Ho && q < g.Wo;
+      if (fast) {
+        const int tapoff = k0 - (r * g.Wo + s) * g.Co;
+#pragma unroll
+        for (int j = 0; j < A_VEC; ++j) {
+          const bool ok = (a_taps[j] >> rs) & 1ull;
+          cp_async16(pa + off_k128(grow + 16 * j, gcol), ok ? act + (a_off[j] + tapoff) : act, ok ? 16u : 0u);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < A_VEC; ++j) {
+          const int hp = (a_yx[j] >> 16) + g.pad - r, wp = (a_yx[j] & 0xffff) + g.pad - s;
+          bool ok = (a_taps[j] != 0ull) && hp >= 0 && wp >= 0;
+          int p = 0, q = 0;
+          if (ok) {
+            p = hp / g.stride; q = wp / g.stride;
+            ok = (p * g.stride == hp) && (q * g.stride == wp) && p < g.Ho && q < g.Wo;
+          }
+          const float* ga = ok ? act + ((long long)(a_off[j] * g.Ho + p) * g.Wo + q) * g.Co + k0 + gcol * 4 : act;
+          cp_async16(pa + off_k128(grow + 16 * j, gcol), ga, ok ? 16u : 0u);
+        }
       }
-      const float* pa = act + ((long long)(a_img * g.Ho + p) * g.Wo + q) * g.Co + k0;
-#pragma unroll
-      for (int j = 0; j < A_VEC; ++j) ra[j] = ok ? ldg4(pa + 4 * j) : zero;
-      // B(n = ci, k) = W[ko][r][s][ci]  -> contiguous along n: MN-major.  thread -> k = tid % 32, n-chunks (tid / 32) ...
-      const int k = tid & 31, nc0 = (tid >> 5) * B_VEC;
-      const float* pb = wgt + ((long long)(k0 + k) * (g.R * g.S) + rs) * g.Ci + n0 + nc0 * 4;
-#pragma unroll
-      for (int j = 0; j < B_VEC; ++j) rb[j] = ldg4(pb + 4 * j);
-    } else {
-      // WGRAD: k = pixel.  A(m = ko, k) = dout[pixel][ko] (MN-major).  thread -> k = tid % 32, m-chunks (tid / 32) * 8 ...
-      const int k = tid & 31;
-      const int pix = kbase + k;
-      const bool kok = pix < d.K;
-      const int mc0 = (tid >> 5) * A_VEC;
-      const float* pa = wgt + (long long)pix * g.Co + m0 + mc0 * 4;
-#pragma unroll
-      for (int j = 0; j < A_VEC; ++j) ra[j] = kok ? ldg4(pa + 4 * j) : zero;
-      // B(n = (r, s, c), k) = in[img, p*stride - pad + r, q*stride - pad + s, c] (MN-major, Ci % 4 == 0)
-      int img = 0, hb = 0, wb = 0;
-      if (kok) {
-        img = pix / HoWo;
-        const int rem = pix - img * HoWo;
-        const int p = rem / g.Wo, q = rem - p * g.Wo;
-        hb = p * g.stride - g.pad; wb = q * g.stride - g.pad;
-      }
-      const int nc0 = (tid >> 5) * B_VEC;
+      // B(n = ci, k) = W[ko][r][s][ci]: contiguous along n -> MN-major.  lanes along n (16 granules = 64 ci), 8 k per pass
+      const int n4 = tid & 15, kk = tid >> 4;
 #pragma unroll
       for (int j = 0; j < B_VEC; ++j) {
-        const int n = n0 + (nc0 + j) * 4;
+        const int k = kk + 8 * j;
+        const float* gb = wgt + ((long long)(k0 + k) * (g.R * g.S) + rs) * g.Ci + n0 + n4 * 4;
+        cp_async16(pb + off_mnmajor<BN>(4 * n4, k), gb, 16u);
+      }
+    } else {
+      // WGRAD: k = pixel.  A(m = ko, k) = dout[pixel][ko] (MN-major): lanes along m (32 granules = 128 ko), 4 k per pass
+      {
+        const int m4 = tid & 31, kk = tid >> 5;
+#pragma unroll
+        for (int j = 0; j < A_VEC; ++j) {
+          const int k = kk + 4 * j;
+          const int pix = kbase + k;
+          const bool kok = pix < d.K;
+          const float* ga = kok ? wgt + (long long)pix * g.Co + m0 + m4 * 4 : wgt;
+          cp_async16(pa + off_mnmajor<TC_BM>(4 * m4, k), ga, kok ? 16u : 0u);
+        }
+      }
+      // B(n = (r, s, c), k) = in[img, p*stride - pad + r, q*stride - pad + s, c] (MN-major, Ci % 4 == 0)
+      {
+        const int n4 = tid & 15, kk = tid >> 4;
+        const int n = n0 + n4 * 4;
         const int rs = n / g.Ci, c = n - rs * g.Ci;
         const int r = rs / g.S, s = rs - r * g.S;
-        const int h = hb + r, w = wb + s;
-        const bool ok = kok && h >= 0 && h < g.H && w >= 0 && w < g.W;
-        rb[j] = ok ? ldg4(act + img * a.x_sN + (long long)(h * g.W + w) * a.x_sP + c) : zero;
+#pragma unroll
+        for (int j = 0; j < B_VEC; ++j) {
+          const int k = kk + 8 * j;
+          const int pix = kbase + k;
+          bool ok = pix < d.K;
+          const float* gb = act;
+          if (ok) {
+            const int img = pix / HoWo, rem = pix - img * HoWo;
+            const int p = rem / g.Wo, q = rem - p * g.Wo;
+            const int h = p * g.stride - g.pad + r, w = q * g.stride - g.pad + s;
+            ok = h >= 0 && h < g.H && w >= 0 && w < g.W;
+            if (ok) gb = act + img * a.x_sN + (long long)(h * g.W + w) * a.x_sP + c;
+          }
+          cp_async16(pb + off_mnmajor<BN>(4 * n4, k), gb, ok ? 16u : 0u);
+        }
       }
+    }
+    // advance the running (source, tap, channel) decode to the next k-block
+    it_c0 += TC_BK;
+    if (MODE == GEMM_WGRAD) {
+      if (it_c0 >= d.kblocks_per_src * TC_BK) { it_c0 = 0; ++it_src; }
+    } else if (it_c0 >= kch) {
+      it_c0 = 0;
+      if (++it_rs == g.R * g.S) { it_rs = 0; ++it_src; }
     }
   };
 
-  auto store_block = [&](int stage) {
-    uint8_t* pa = sA + stage * A_BYTES;
-    uint8_t* pb = sB + stage * B_BYTES;
-    if (MODE == GEMM_FPROP) {
+  // ---- main loop, warp-specialised: warps 0-3 stream k-blocks into a TC_STAGES-deep ring with cp.async and signal
+  //      "full" through cp.async.mbarrier.arrive; one thread of warp 4 waits for "full", issues the four tcgen05.mma of
+  //      the k-block and lets tcgen05.commit signal "empty" when the tensor core has consumed the stage.  No CTA-wide
+  //      barrier inside the loop.
+  const int nkb = kb_end > kb_begin ? kb_end - kb_begin : 0;  // a trailing split may be empty: it contributes zeros
+  if (warp == TC_THREADS / 32) {
+    if (tid == TC_THREADS) {
+      for (int i = 0; i < nkb; ++i) {
+        const int stage = i % TC_STAGES;
+        mbar_wait(&bar_full[stage], (uint32_t)((i / TC_STAGES) & 1));
+        // The mbarrier phase completes only after every cp.async of this stage has been performed, so the data is in
+        // shared memory when the wait returns; like CUTLASS' sm100 cp.async mainloop no fence.proxy.async is issued
+        // here (measured: it costs ~0.5 us per k-block on the single-thread critical path).  BRE_TC_PROXY_FENCE=1 re-enables it.
+        if (proxy_fence) fence_proxy_async();
+        tc_fence_after();
+        const uint32_t sa = smem_u32(sA + stage * A_BYTES), sb = smem_u32(sB + stage * B_BYTES);
 #pragma unroll
-      for (int j = 0; j < A_VEC; ++j) sts4(pa, off_kmajor<TC_BM>(tid, 4 * j), ra[j]);
-      const int row = tid % BN, kc0 = (tid / BN) * B_VEC;
-#pragma unroll
-      for (int j = 0; j < B_VEC; ++j) sts4(pb, off_kmajor<BN>(row, 4 * (kc0 + j)), rb[j]);
-    } else if (MODE == GEMM_DGRAD) {
-#pragma unroll
-      for (int j = 0; j < A_VEC; ++j) sts4(pa, off_kmajor<TC_BM>(tid, 4 * j), ra[j]);
-      const int k = tid & 31, nc0 = (tid >> 5) * B_VEC;
-#pragma unroll
-      for (int j = 0; j < B_VEC; ++j) sts4(pb, off_mnmajor<BN>(4 * (nc0 + j), k), rb[j]);
-    } else {
-      const int k = tid & 31, mc0 = (tid >> 5) * A_VEC, nc0 = (tid >> 5) * B_VEC;
-#pragma unroll
-      for (int j = 0; j < A_VEC; ++j) sts4(pa, off_mnmajor<TC_BM>(4 * (mc0 + j), k), ra[j]);
-#pragma unroll
-      for (int j = 0; j < B_VEC; ++j) sts4(pb, off_mnmajor<BN>(4 * (nc0 + j), k), rb[j]);
-    }
-  };
-
-  // ---- main loop: 3-stage ring, MMAs are asynchronous, completion frees the stage through its mbarrier ----------
-  const int nkb = kb_end - kb_begin;
-  for (int i = 0; i < nkb; ++i) {
-    const int stage = i % TC_STAGES;
-    load_block(kb_begin + i);                                      // global loads in flight while earlier MMAs run
-    if (i >= TC_STAGES) mbar_wait(&bar_stage[stage], (uint32_t)((i / TC_STAGES - 1) & 1));
-    store_block(stage);
-    fence_proxy_async();                                           // generic-proxy st.shared -> visible to the MMA's async proxy
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t sa = smem_u32(sA + stage * A_BYTES), sb = smem_u32(sB + stage * B_BYTES);
-#pragma unroll
-      for (int j = 0; j < TC_BK / 8; ++j) {
-        const uint64_t adesc = a_mn ? make_desc(sa + j * 1024, 4096, 512, 1) : make_desc(sa + 2 * j * (TC_BM * 16), TC_BM * 16, 128, 0);
-        const uint64_t bdesc = b_mn ? make_desc(sb + j * 1024, 4096, 512, 1) : make_desc(sb + 2 * j * (BN * 16), BN * 16, 128, 0);
-        umma_tf32(tmem_d, adesc, bdesc, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        for (int j = 0; j < TC_BK / 8; ++j) {
+          const uint64_t adesc = a_mn ? make_desc(sa + j * 1024, 4096, 512, 1) : make_desc(sa + j * 32, 16, 1024, 2);
+          const uint64_t bdesc = b_mn ? make_desc(sb + j * 1024, 4096, 512, 1) : make_desc(sb + j * 32, 16, 1024, 2);
+          umma_tf32(tmem_d, adesc, bdesc, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        }
+        umma_commit(&bar_empty[stage]);
       }
-      umma_commit(&bar_stage[stage]);
+      umma_commit(&bar_done);
     }
+    __syncwarp();
+  } else {
+    for (int i = 0; i < nkb; ++i) {
+      const int stage = i % TC_STAGES;
+      if (i >= TC_STAGES) mbar_wait(&bar_empty[stage], (uint32_t)((i / TC_STAGES - 1) & 1));
+      issue_block(stage);
+      cp_async_arrive(&bar_full[stage]);
+    }
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
   }
-  if (tid == 0) umma_commit(&bar_done);
-  mbar_wait(&bar_done, 0);
-  tc_fence_after();
 
   // ---- epilogue: TMEM -> registers; thread `tid` holds row m0 + tid, BN columns in chunks of 32 -----------------
   const int splits = gridDim.z;
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
   const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
   float v[32];
-  if (splits > 1) {
-    float* wsb = a.ws + ((long long)tile * splits + z) * (TC_BM * BN) + (long long)tid * BN;
-#pragma unroll
-    for (int c = 0; c < BN; c += 32) {
-      if (nkb > 0) tmem_ld32(lane_base + c, v);
-      else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(wsb + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const int prev = atomicAdd(a.counters + tile, 1);
-      s_last = (prev == splits - 1);
-      if (s_last) a.counters[tile] = 0;
-    }
-    __syncthreads();
-  }
-  const bool writer = (splits == 1) || s_last;
-  if (writer) {
-    if (splits > 1) __threadfence();
-    const int m = m0 + tid;
-    const bool row_ok = m < d.M;
-    long long row = 0;
-    int cs = 1;
+  const int m = m0 + tid;
+  const bool row_ok = m < d.M;
+  const bool is_loader = warp < TC_THREADS / 32;
+  auto out_row = [&](int mm, long long& row, int& cs) {
     if (MODE == GEMM_DGRAD) {
-      const int img = row_ok ? m / HW : 0;
-      row = img * a.x_sN + (long long)(m - img * HW) * a.x_sP;
+      const int img = mm / HW;
+      row = img * a.x_sN + (long long)(mm - img * HW) * a.x_sP;
       cs = a.x_sC;
     } else {
-      row = (long long)m * d.Nc;
+      row = (long long)mm * d.Nc;
+      cs = 1;
     }
-    const float* wst = a.ws + (long long)tile * splits * (TC_BM * BN) + (long long)tid * BN;
+  };
+  if (!is_loader) {
+    // MMA-issuer warp: nothing to write back
+  } else if (splits == 1) {
+    long long row = 0;
+    int cs = 1;
+    if (row_ok) out_row(m, row, cs);
 #pragma unroll
     for (int c = 0; c < BN; c += 32) {
-      if (splits == 1) {
-        tmem_ld32(lane_base + c, v);  // warp-collective: executed by all lanes, also for rows beyond M
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        for (int zz = 0; zz < splits; ++zz) {
-          const float* p = wst + (long long)zz * (TC_BM * BN) + c;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(p + j));
-            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-          }
-        }
-      }
+      tmem_ld32(lane_base + c, v);  // warp-collective: executed by all lanes, also for rows beyond M
       if (!row_ok) continue;
       const int n = n0 + c;
       if (MODE == GEMM_FPROP && a.bias != nullptr) {
@@ -381,6 +430,67 @@ __global__ void __launch_bounds__(TC_THREADS) igemm_tc_kernel(GemmArgs a, TcDims
         }
       }
     }
+  } else {
+    // split-K inside a thread-block cluster (cluster = the `splits` CTAs of one output tile along z): every CTA parks
+    // its partial accumulator tile in its own shared memory (the operand ring is idle now), one cluster barrier, then
+    // CTA `z` sums rows [z*128/S, (z+1)*128/S) of all S partials straight out of the peers' shared memory (DSMEM,
+    // ld.shared::cluster) in fixed rank order -- deterministic, no global workspace, no atomics, no "last CTA" tail.
+    float* part = reinterpret_cast<float*>(sA);  // [128 rows][BN] fp32, 16-byte chunks XOR-swizzled by (row & 15)
+#pragma unroll
+    for (int c = 0; c < BN; c += 32) {
+      if (nkb > 0) tmem_ld32(lane_base + c, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int chunk = ((c + j) >> 2) ^ (tid & 15);
+        *reinterpret_cast<float4*>(part + tid * BN + chunk * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  if (splits > 1) {
+    cluster_sync_all();   // every thread of every CTA in the cluster (partials visible cluster-wide)
+    if (is_loader) {
+      const int rows_per = TC_BM / splits;
+      constexpr int C4 = BN / 4;
+      const uint32_t part_s = smem_u32(sA);
+      const int nslots = rows_per * C4;
+      for (int slot = tid; slot < nslots; slot += TC_THREADS) {
+        const int r = z * rows_per + slot / C4, c4 = slot % C4;
+        if (m0 + r >= d.M) continue;
+        const uint32_t local = part_s + (uint32_t)(r * BN + ((c4 ^ (r & 15)) << 2)) * 4u;
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < splits; ++q) {
+          const float4 t = ld_dsmem4(local, (uint32_t)q);
+          acc4.x += t.x; acc4.y += t.y; acc4.z += t.z; acc4.w += t.w;
+        }
+        const int n = n0 + c4 * 4;
+        if (MODE == GEMM_FPROP && a.bias != nullptr) {
+          acc4.x += __ldg(a.bias + n); acc4.y += __ldg(a.bias + n + 1); acc4.z += __ldg(a.bias + n + 2); acc4.w += __ldg(a.bias + n + 3);
+        }
+        long long row;
+        int cs;
+        out_row(m0 + r, row, cs);
+        float* op = a.out + row + (long long)n * cs;
+        if (cs == 1) {
+          if (a.accumulate) {
+            const float4 o = *reinterpret_cast<const float4*>(op);
+            acc4.x += o.x; acc4.y += o.y; acc4.z += o.z; acc4.w += o.w;
+          }
+          *reinterpret_cast<float4*>(op) = acc4;
+        } else {
+          const float vv[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float* qq = op + (long long)j * cs;
+            *qq = a.accumulate ? *qq + vv[j] : vv[j];
+          }
+        }
+      }
+    }
+    cluster_sync_all();   // nobody leaves (and frees its shared memory) while a peer may still be reading it
   }
   tc_fence_before();
   __syncthreads();
@@ -394,30 +504,41 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, cudaStream_t stream) {
   TcDims d = d0;
   const int tm = ceil_div(d.M, TC_BM), tn = d.Nc / BN;
   const long long tiles = (long long)tm * tn;
-  const int ws_tiles_tc = a.ws_tiles * (IG_BM * IG_BN) / (TC_BM * BN);  // workspace is sized in 64x64 tiles
+  // split-K factor = cluster size along z: a power of two <= 8 (portable cluster limit) that brings the grid to ~100 CTAs
+  static const int max_splits_env = [] { const char* e = getenv("BRE_TC_MAX_SPLITS"); return e ? atoi(e) : 0; }();
+  static const int target_ctas_env = [] { const char* e = getenv("BRE_TC_TARGET_CTAS"); return e ? atoi(e) : 0; }();
+  const int target = target_ctas_env > 0 ? target_ctas_env : 96;
   int splits = a.splits;
   if (splits <= 0) {
     splits = 1;
-    if (tiles < kNumSMs) {
-      splits = ceil_div(kNumSMs, tiles);
-      const int max_by_k = d.total_kblocks / 2 > 0 ? d.total_kblocks / 2 : 1;
-      if (splits > max_by_k) splits = max_by_k;
-    }
+    while (splits < 8 && tiles * splits < target && d.total_kblocks / (splits * 2) >= 2) splits *= 2;
   }
-  if (splits > d.total_kblocks) splits = d.total_kblocks;
-  if (splits > 1 && (a.ws == nullptr || a.counters == nullptr)) splits = 1;
-  if (splits > 1 && tiles * splits > ws_tiles_tc) splits = (int)(ws_tiles_tc / tiles) > 1 ? (int)(ws_tiles_tc / tiles) : 1;
+  if (max_splits_env > 0 && splits > max_splits_env) splits = max_splits_env;
+  int pow2 = 1;
+  while (pow2 * 2 <= splits && pow2 < 8) pow2 *= 2;
+  splits = pow2;
+  while (splits > 1 && splits > d.total_kblocks) splits /= 2;
   d.kblocks_per_split = ceil_div(d.total_kblocks, splits);
-  splits = ceil_div(d.total_kblocks, d.kblocks_per_split);
-  if (tn > 65535 || splits > 65535) { set_error("igemm_tc: grid too large"); return -1; }
+  if (tn > 65535) { set_error("igemm_tc: grid too large"); return -1; }
   const size_t smem = (size_t)TC_STAGES * (TC_BM + BN) * TC_BK * 4;
   static bool attr_done = false;
   if (!attr_done) {
     BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid(tm, tn, splits), block(TC_THREADS);
-  igemm_tc_kernel<MODE, BN><<<grid, block, smem, stream>>>(a, d);
+  static const int proxy_fence_env = [] { const char* e = getenv("BRE_TC_PROXY_FENCE"); return e ? atoi(e) : 0; }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(tm, tn, splits);
+  cfg.blockDim = dim3(TC_BLOCK);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = splits;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, igemm_tc_kernel<MODE, BN>, a, d, proxy_fence_env));
   BRE_CHECK_LAUNCH();
   return 0;
 }
