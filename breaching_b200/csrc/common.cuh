@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 
 namespace bre {
@@ -30,6 +31,53 @@ void set_error(const std::string& msg);
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// Every kernel of the iteration is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may be
+// scheduled while its predecessor is still draining, runs its private prologue (barrier init, TMEM allocation, index
+// pre-computation) and then blocks in griddepcontrol.wait until the predecessor grid has completed and flushed its
+// memory.  This hides the ~2-3 us launch latency between the ~200 dependent kernels of one iteration; stream capture
+// records the edges as programmatic dependencies of the CUDA graph.  Without the launch attribute both instructions
+// are no-ops.  BRE_PDL=0 disables it.
+bool use_pdl();
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 int cluster_z, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  int n = 0;
+  if (cluster_z > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = 1; attrs[n].val.clusterDim.y = 1; attrs[n].val.clusterDim.z = (unsigned)cluster_z;
+    ++n;
+  }
+  if (use_pdl()) {
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define BRE_KLAUNCH(kernel, grid, block, smem, stream, ...)                                                          \
+  do {                                                                                                                 \
+    cudaError_t _lerr = ::bre::launch_kernel(kernel, dim3(grid), dim3(block), smem, stream, 1, __VA_ARGS__);           \
+    if (_lerr != cudaSuccess) {                                                                                        \
+      ::bre::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_lerr) + " at " + __FILE__ + ":" +  \
+                       std::to_string(__LINE__));                                                                      \
+      return -2;                                                                                                       \
+    }                                                                                                                  \
+  } while (0)
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -3,6 +3,7 @@
 // no host synchronisation inside the loop (the reference needs three host syncs per iteration,
 // optimization_based_attack.py:119,131,135).  C ABI in include/breaching_b200.h.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <limits>
@@ -16,8 +17,18 @@
 #include "objective.cuh"
 
 namespace bre {
+void set_pdl(bool on);
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+static int g_pdl = -1;
+bool use_pdl() {
+  if (g_pdl < 0) {
+    const char* e = getenv("BRE_PDL");
+    g_pdl = e ? (atoi(e) != 0) : 1;
+  }
+  return g_pdl != 0;
+}
+void set_pdl(bool on) { g_pdl = on ? 1 : 0; }
 }  // namespace bre
 
 using namespace bre;
@@ -98,6 +109,16 @@ struct bre_engine {
   float* feat_measured = nullptr;
   long long feat_numel = 0;
   int feat_op = -1;
+  // side stream: weight gradients are off the critical path of the backward sweep (they only feed the matching
+  // reduction), so they run concurrently with the dgrad chain; the side stream has its own split-K / reduction scratch
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev_fork;
+  cudaEvent_t ev_join = nullptr;
+  bool overlap_wgrad = true;
+  float* ws2 = nullptr;
+  int* gemm_counters2 = nullptr;
+  float* red_partials2 = nullptr;
+  int* red_counters2 = nullptr;
   // execution
   bool use_graph = true;
   int gemm_backend = 0;  // 0 = SIMT fp32, 1 = tcgen05 TF32 where supported
@@ -138,9 +159,10 @@ struct bre_engine {
     a.ws = ws; a.counters = gemm_counters; a.ws_tiles = ws_tiles; a.splits = 0;
     return a;
   }
-  int gemm(const GemmArgs& a) {
-    if (gemm_backend == 1 && igemm_tc_supported(a)) return launch_igemm_tc(a, stream);
-    return launch_igemm_simt(a, stream);
+  int gemm(const GemmArgs& a) { return gemm_on(a, stream); }
+  int gemm_on(const GemmArgs& a, cudaStream_t st) {
+    if (gemm_backend == 1 && igemm_tc_supported(a)) return launch_igemm_tc(a, st);
+    return launch_igemm_simt(a, st);
   }
 
   BnConsts bn_consts(const bre_op_desc& op) const {
@@ -193,6 +215,7 @@ struct bre_engine {
   }
 
   int sweep_backward() {
+    bool forked = false;
     for (int i = (int)ops.size() - 1; i >= 0; --i) {
       const bre_op_desc& op = ops[i];
       const bre_tensor_desc& to = td(op.tout);
@@ -203,8 +226,17 @@ struct bre_engine {
           GemmArgs a = conv_geom(op);
           a.mode = GEMM_WGRAD;
           a.act[0] = t[op.tin].val; a.wgt[0] = t[op.tout].d; a.out = Gp(op.w);
-          BRE_LAUNCH(gemm(a));
-          if (op.b >= 0) BRE_LAUNCH(launch_channel_sum(t[op.tout].d, Pout, to.C, Gp(op.b), red_partials, red_counters, stream));
+          if (overlap_wgrad && side != nullptr) {
+            BRE_CUDA_CHECK(cudaEventRecord(ev_fork[i], stream));
+            BRE_CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork[i], 0));
+            a.ws = ws2; a.counters = gemm_counters2;
+            BRE_LAUNCH(gemm_on(a, side));
+            if (op.b >= 0) BRE_LAUNCH(launch_channel_sum(t[op.tout].d, Pout, to.C, Gp(op.b), red_partials2, red_counters2, side));
+            forked = true;
+          } else {
+            BRE_LAUNCH(gemm(a));
+            if (op.b >= 0) BRE_LAUNCH(launch_channel_sum(t[op.tout].d, Pout, to.C, Gp(op.b), red_partials, red_counters, stream));
+          }
           if (op.tin != 0 || need_task_grad()) {
             GemmArgs b = conv_geom(op);
             b.mode = GEMM_DGRAD;
@@ -236,6 +268,10 @@ struct bre_engine {
         }
         default: break;
       }
+    }
+    if (forked) {
+      BRE_CUDA_CHECK(cudaEventRecord(ev_join, side));
+      BRE_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));
     }
     return 0;
   }
@@ -483,6 +519,13 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
       for (float** pp : ptrs) rc |= e->alloc(pp, b.C);
     }
   }
+  // ---- side stream for the weight-gradient GEMMs ----------------------------------------------------------
+  if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(BRE_ERR_CUDA); }
+  e->ev_fork.assign(n_ops, nullptr);
+  for (int i = 0; i < n_ops; ++i)
+    if ((ops[i].kind == BRE_OP_CONV || ops[i].kind == BRE_OP_LINEAR) &&
+        cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(BRE_ERR_CUDA); }
+  if (cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(BRE_ERR_CUDA); }
   // ---- scratch ---------------------------------------------------------------------------------------
   e->ws_tiles = 1024;
   rc |= e->alloc(&e->ws, (long long)e->ws_tiles * IG_BM * IG_BN);
@@ -490,6 +533,10 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
   const long long redp = (long long)(16384 > 2 * maxC + 64 ? 16384 : 2 * maxC + 64) * 2 * 2;
   rc |= e->alloc(&e->red_partials, redp);
   rc |= e->alloc(&e->red_counters, maxC / 32 + 8);
+  rc |= e->alloc(&e->ws2, (long long)e->ws_tiles * IG_BM * IG_BN);
+  rc |= e->alloc(&e->gemm_counters2, 1 << 16);
+  rc |= e->alloc(&e->red_partials2, redp);
+  rc |= e->alloc(&e->red_counters2, maxC / 32 + 8);
   long long tv_blocks = (long long)((x0.W + 31) / 32) * ((x0.H + 7) / 8) * x0.N;
   long long dp = tv_blocks * 2 > kMatchMaxBlocks * 5 ? tv_blocks * 2 : kMatchMaxBlocks * 5;
   if (dp < kNumSMs * 8) dp = kNumSMs * 8;
@@ -527,7 +574,11 @@ void bre_engine_destroy(bre_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->side) cudaStreamSynchronize(e->side);
   if (e->exec) cudaGraphExecDestroy(e->exec);
+  for (cudaEvent_t ev : e->ev_fork) if (ev) cudaEventDestroy(ev);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->side) cudaStreamDestroy(e->side);
   for (void* p : e->allocs) cudaFree(p);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -819,6 +870,8 @@ int bre_engine_set_option(bre_engine* e, const char* name, int64_t value) {
   if (!e || !name) return BRE_ERR_INVALID;
   const std::string n(name);
   if (n == "use_graph") { e->use_graph = value != 0; e->graph_ready = false; return BRE_OK; }
+  if (n == "pdl") { bre::set_pdl(value != 0); e->graph_ready = false; return BRE_OK; }
+  if (n == "overlap_wgrad") { e->overlap_wgrad = value != 0; e->graph_ready = false; return BRE_OK; }
   if (n == "gemm_backend") {
     if (value != 0 && value != 1) { set_error("gemm_backend must be 0 (simt) or 1 (tcgen05)"); return BRE_ERR_INVALID; }
     e->gemm_backend = (int)value; e->graph_ready = false; return BRE_OK;

@@ -20,6 +20,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 template <int MODE>
 __global__ void __launch_bounds__(IG_THREADS) igemm_simt_kernel(GemmArgs a, Dims d) {
+  pdl_prologue();
   __shared__ __align__(16) float As[2][IG_BK][IG_BM + 4];
   __shared__ __align__(16) float Bs[2][IG_BK][IG_BN + 4];
   __shared__ int s_last;
@@ -344,77 +345,161 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_simt_kernel(GemmArgs a, Dims
 // structural zeros.  Here one thread owns one input pixel and all CI channels, walks only the taps that hit the
 // output grid, and streams dout with 128-bit loads; lanes of a warp are mapped to pixels of the same stride-parity
 // class so the tap loop is warp-uniform and the weight loads are broadcasts.
+// Weights of the taps that can hit this block's image row are staged once in shared memory as [src][tap][ko][ci]
+// (12 consecutive floats per 4 output channels -> three broadcast LDS.128 feed 48 FMAs); each thread owns PX pixels of
+// one stride-parity class so every weight fetched from shared memory is reused PX times.
+constexpr int SC_PX = 4;
+constexpr int SC_ROWS = 4;
 template <int CI>
-__global__ void __launch_bounds__(128) dgrad_small_ci_kernel(GemmArgs a, int vec) {
+__global__ void __launch_bounds__(128) dgrad_small_ci_kernel(GemmArgs a, int n_r, int smem_floats) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float wsm[];            // [nsrc][n_r * S][Co][CI], then the reduction scratch
   const ConvGeom g = a.g;
-  const int img = blockIdx.z, h = blockIdx.y;
+  const int img = blockIdx.z;
+  const int lane = threadIdx.x & 31, kq = threadIdx.x >> 5;  // warp = quarter of the output-channel range
   const int Wc = (g.W + g.stride - 1) / g.stride;
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  const int cls = slot / Wc, w = (slot - cls * Wc) * g.stride + cls;
-  if (cls >= g.stride || w >= g.W) return;
-  float acc[CI];
+  // this block owns up to SC_ROWS image rows h = hcls + stride * (hgrp * SC_ROWS + i): they share the set of filter rows
+  // that can hit them (r = r0 + t * stride), so the weight slice is staged once for all of them
+  const int Hc = (g.H + g.stride - 1) / g.stride;
+  const int hgroups = (Hc + SC_ROWS - 1) / SC_ROWS;
+  const int hcls = blockIdx.y / hgroups, hgrp = blockIdx.y - hcls * hgroups;
+  const int r0 = (hcls + g.pad) % g.stride;
+  const int taps = n_r * g.S;
+  for (int e = threadIdx.x; e < g.Co * CI; e += 128) {     // (ko, c) fixed per thread; no divisions in the copy loops
+    const int ko = e / CI, c = e - ko * CI;
+    for (int src = 0; src < a.nsrc; ++src)
+      for (int tr = 0; tr < n_r; ++tr) {
+        const int r = r0 + tr * g.stride;
+        for (int s = 0; s < g.S; ++s)
+          wsm[((src * taps + tr * g.S + s) * g.Co + ko) * CI + c] =
+              r < g.R ? __ldg(a.wgt[src] + ((long long)ko * (g.R * g.S) + r * g.S + s) * g.Ci + c) : 0.f;
+      }
+  }
+  __syncthreads();
+  float* red = wsm + smem_floats;  // reduction scratch behind the weights: [4][32][SC_PX * CI]
+ for (int hi = 0; hi < SC_ROWS; ++hi) {
+  const int h = hcls + g.stride * (hgrp * SC_ROWS + hi);
+  if (h >= g.H) break;   // uniform across the block
+  const int p0 = (h + g.pad) / g.stride;
+  const int Wcp = ((Wc + SC_PX - 1) / SC_PX) * SC_PX;     // per-class slot range padded so that a thread never straddles classes
+  const int slot0 = (blockIdx.x * 32 + lane) * SC_PX;   // SC_PX consecutive slots of one class
+  const int cls = slot0 / Wcp;
+  const int kper = ((g.Co + 15) / 16) * 4;               // output channels per warp, multiple of 4
+  const int ko_lo = kq * kper, ko_hi = min(g.Co, ko_lo + kper);
+  float acc[SC_PX][CI];
 #pragma unroll
-  for (int c = 0; c < CI; ++c) acc[c] = 0.f;
-  const int RS = g.R * g.S;
-  for (int src = 0; src < a.nsrc; ++src) {
-    const float* __restrict__ dout = a.act[src];
-    const float* __restrict__ wgt = a.wgt[src];
-    for (int r = 0; r < g.R; ++r) {
-      const int hp = h + g.pad - r;
-      if (hp < 0) break;
-      const int p = hp / g.stride;
-      if (p * g.stride != hp || p >= g.Ho) continue;
-      for (int s = 0; s < g.S; ++s) {
-        const int wp = w + g.pad - s;
-        if (wp < 0) break;
-        const int q = wp / g.stride;
-        if (q * g.stride != wp || q >= g.Wo) continue;
-        const float* dp = dout + ((long long)(img * g.Ho + p) * g.Wo + q) * g.Co;
-        const float* wq = wgt + (long long)(r * g.S + s) * g.Ci;
-        if (vec) {
-          for (int ko = 0; ko < g.Co; ko += 4) {
-            const float4 dv = __ldg(reinterpret_cast<const float4*>(dp + ko));
-            const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+  for (int px = 0; px < SC_PX; ++px)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float* wj = wq + (long long)(ko + j) * RS * g.Ci;
+    for (int c = 0; c < CI; ++c) acc[px][c] = 0.f;
+  int wpix[SC_PX];
+  bool pvalid[SC_PX];
 #pragma unroll
-              for (int c = 0; c < CI; ++c) acc[c] = fmaf(dd[j], __ldg(wj + c), acc[c]);
-            }
+  for (int px = 0; px < SC_PX; ++px) {
+    const int idx = slot0 + px - cls * Wcp;
+    wpix[px] = idx * g.stride + cls;
+    pvalid[px] = cls < g.stride && idx < Wc && wpix[px] < g.W;
+  }
+  if (cls < g.stride) {
+    const int xb = cls + g.pad;
+    const int s0 = xb % g.stride;                          // valid filter columns: s = s0 + u * stride, same for the whole class
+    for (int src = 0; src < a.nsrc; ++src) {
+      const float* __restrict__ dout = a.act[src];
+      for (int tr = 0; tr < n_r; ++tr) {
+        const int r = r0 + tr * g.stride, p = p0 - tr;
+        if (r >= g.R || p < 0 || p >= g.Ho) continue;
+        for (int s = s0; s < g.S; s += g.stride) {
+          const float* wt = wsm + ((long long)(src * taps + tr * g.S + s) * g.Co) * CI;
+          const float* dp[SC_PX];
+          bool ok[SC_PX];
+#pragma unroll
+          for (int px = 0; px < SC_PX; ++px) {
+            const int wp = wpix[px] + g.pad - s;
+            const int q = wp / g.stride;
+            ok[px] = pvalid[px] && wp >= 0 && q < g.Wo;
+            dp[px] = dout + ((long long)(img * g.Ho + p) * g.Wo + (ok[px] ? q : 0)) * g.Co;
           }
-        } else {
-          for (int ko = 0; ko < g.Co; ++ko) {
-            const float dd = __ldg(dp + ko);
-            const float* wj = wq + (long long)ko * RS * g.Ci;
+          for (int ko = ko_lo; ko < ko_hi; ko += 4) {
+            float wv[4 * CI];
+            if (CI == 3 || CI == 1 || CI == 2 || CI == 4) {
 #pragma unroll
-            for (int c = 0; c < CI; ++c) acc[c] = fmaf(dd, __ldg(wj + c), acc[c]);
+              for (int e = 0; e < 4 * CI; ++e) wv[e] = (ko + e / CI < g.Co) ? wt[ko * CI + e] : 0.f;
+            }
+#pragma unroll
+            for (int px = 0; px < SC_PX; ++px) {
+              if (!ok[px]) continue;
+              float dd[4] = {0.f, 0.f, 0.f, 0.f};
+              if (ko + 3 < g.Co && (g.Co & 3) == 0) {
+                const float4 dv = __ldg(reinterpret_cast<const float4*>(dp[px] + ko));
+                dd[0] = dv.x; dd[1] = dv.y; dd[2] = dv.z; dd[3] = dv.w;
+              } else {
+                for (int j = 0; j < 4; ++j)
+                  if (ko + j < g.Co) dd[j] = __ldg(dp[px] + ko + j);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < CI; ++c) acc[px][c] = fmaf(dd[j], wv[j * CI + c], acc[px][c]);
+            }
           }
         }
       }
     }
   }
-  float* op = a.out + img * a.x_sN + (long long)(h * g.W + w) * a.x_sP;
+  // sum the four output-channel quarters through shared memory
+  __syncthreads();
 #pragma unroll
-  for (int c = 0; c < CI; ++c) {
-    float* q = op + (long long)c * a.x_sC;
-    *q = a.accumulate ? *q + acc[c] : acc[c];
+  for (int px = 0; px < SC_PX; ++px)
+#pragma unroll
+    for (int c = 0; c < CI; ++c) red[(kq * 32 + lane) * (SC_PX * CI) + px * CI + c] = acc[px][c];
+  __syncthreads();
+  if (kq == 0) {
+#pragma unroll
+  for (int px = 0; px < SC_PX; ++px) {
+    if (!pvalid[px]) continue;
+    float* op = a.out + img * a.x_sN + (long long)(h * g.W + wpix[px]) * a.x_sP;
+#pragma unroll
+    for (int c = 0; c < CI; ++c) {
+      const int e = px * CI + c;
+      const float v = ((red[lane * (SC_PX * CI) + e] + red[(32 + lane) * (SC_PX * CI) + e]) + red[(64 + lane) * (SC_PX * CI) + e]) +
+                      red[(96 + lane) * (SC_PX * CI) + e];
+      float* q = op + (long long)c * a.x_sC;
+      *q = a.accumulate ? *q + v : v;
+    }
   }
+  }
+ }  // image rows of this block
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int launch_dgrad_small_ci(const GemmArgs& a, cudaStream_t stream) {
   const ConvGeom& g = a.g;
-  bool vec = g.Co % 4 == 0;
-  for (int s = 0; s < a.nsrc; ++s) vec = vec && aligned16(a.act[s]);
   const int Wc = (g.W + g.stride - 1) / g.stride;
-  dim3 grid(ceil_div((long long)Wc * g.stride, 128), g.H, g.N), block(128);
+  const int n_r = (g.R + g.stride - 1) / g.stride;   // filter rows that can hit one image row
+  const int wfloats = a.nsrc * n_r * g.S * g.Co * g.Ci;
+  const int rfloats = 4 * 32 * SC_PX * g.Ci;
+  const int smem_floats = (wfloats + 3) & ~3;   // weights, then the reduction scratch
+  const size_t smem = (size_t)(smem_floats + rfloats) * sizeof(float);
+  if (smem > 200 * 1024) { set_error("dgrad_small_ci: filter too large for shared memory"); return -4; }
+  const int Wcp = ((Wc + SC_PX - 1) / SC_PX) * SC_PX;
+  const int Hc = (g.H + g.stride - 1) / g.stride;
+  dim3 grid(ceil_div((long long)Wcp * g.stride, 32 * SC_PX), g.stride * ceil_div(Hc, SC_ROWS), g.N), block(128);
+#define BRE_LAUNCH_SC(CI_)                                                                                              \
+  do {                                                                                                                  \
+    static size_t cap = 0;                                                                                              \
+    if (smem > 48 * 1024 && smem > cap) {                                                                               \
+      BRE_CUDA_CHECK(cudaFuncSetAttribute(dgrad_small_ci_kernel<CI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      cap = smem;                                                                                                       \
+    }                                                                                                                   \
+    BRE_KLAUNCH((dgrad_small_ci_kernel<CI_>), grid, block, smem, stream, a, n_r, smem_floats);                                     \
+  } while (0)
   switch (g.Ci) {
-    case 1: dgrad_small_ci_kernel<1><<<grid, block, 0, stream>>>(a, vec); break;
-    case 2: dgrad_small_ci_kernel<2><<<grid, block, 0, stream>>>(a, vec); break;
-    case 3: dgrad_small_ci_kernel<3><<<grid, block, 0, stream>>>(a, vec); break;
-    default: dgrad_small_ci_kernel<4><<<grid, block, 0, stream>>>(a, vec); break;
+    case 1: BRE_LAUNCH_SC(1); break;
+    case 2: BRE_LAUNCH_SC(2); break;
+    case 3: BRE_LAUNCH_SC(3); break;
+    default: BRE_LAUNCH_SC(4); break;
   }
+#undef BRE_LAUNCH_SC
   BRE_CHECK_LAUNCH();
   return 0;
 }
@@ -427,7 +512,9 @@ int launch_igemm_simt(const GemmArgs& a, cudaStream_t stream) {
   const ConvGeom& g = a.g;
   if (d.M <= 0 || d.Nc <= 0 || d.K <= 0) { set_error("igemm: empty problem"); return -1; }
   if (a.nsrc < 1 || a.nsrc > 2 || (a.nsrc == 2 && a.mode == GEMM_WGRAD)) { set_error("igemm: bad nsrc"); return -1; }
-  if (a.mode == GEMM_DGRAD && g.Ci <= 4 && g.H <= 65535 && g.N <= 65535) return launch_dgrad_small_ci(a, stream);
+  if (a.mode == GEMM_DGRAD && g.Ci <= 4 && g.H <= 65535 && g.N <= 65535 &&
+      (size_t)a.nsrc * ((g.R + g.stride - 1) / g.stride) * g.S * g.Co * g.Ci * 4 <= 200 * 1024)
+    return launch_dgrad_small_ci(a, stream);
   d.steps_per_src = ceil_div(d.K, IG_BK);
   d.total_steps = d.steps_per_src * a.nsrc;
 
@@ -467,9 +554,9 @@ int launch_igemm_simt(const GemmArgs& a, cudaStream_t stream) {
   if (tn > 65535 || splits > 65535) { set_error("igemm: grid too large"); return -1; }
 
   dim3 grid(tm, tn, splits), block(IG_THREADS);
-  if (a.mode == GEMM_FPROP) igemm_simt_kernel<GEMM_FPROP><<<grid, block, 0, stream>>>(a, d);
-  else if (a.mode == GEMM_DGRAD) igemm_simt_kernel<GEMM_DGRAD><<<grid, block, 0, stream>>>(a, d);
-  else igemm_simt_kernel<GEMM_WGRAD><<<grid, block, 0, stream>>>(a, d);
+  if (a.mode == GEMM_FPROP) BRE_KLAUNCH((igemm_simt_kernel<GEMM_FPROP>), grid, block, 0, stream, a, d);
+  else if (a.mode == GEMM_DGRAD) BRE_KLAUNCH((igemm_simt_kernel<GEMM_DGRAD>), grid, block, 0, stream, a, d);
+  else BRE_KLAUNCH((igemm_simt_kernel<GEMM_WGRAD>), grid, block, 0, stream, a, d);
   BRE_CHECK_LAUNCH();
   return 0;
 }

@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ uint32_t s_tmem;
 
+  pdl_launch_dependents();   // the successor may start its own prologue; it blocks in its griddepcontrol.wait
   const ConvGeom g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN, z = blockIdx.z;
@@ -192,7 +193,6 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   constexpr int A_VEC = TC_BM * TC_BK / 4 / TC_THREADS;  // 16-byte granules per thread per stage: 8
   constexpr int B_VEC = BN * TC_BK / 4 / TC_THREADS;     // 4 (BN = 64)
   const int gcol = tid & 7, grow = (tid >> 3) & 15;
-  const bool fast = (g.R * g.S <= 64) && (MODE == GEMM_FPROP || (MODE == GEMM_DGRAD && g.stride == 1));
   int a_off[A_VEC];                  // element offset of the anchor pixel (+ granule column)
   unsigned long long a_taps[A_VEC];  // bit rs: tap (r, s) of this row reads inside the tensor
   int a_yx[A_VEC];                   // slow path (strided dgrad): packed (y << 16) | x and image index in a_off
@@ -213,18 +213,16 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
         } else {
           const int img = m / HW, rem = m - img * HW;
           const int y = rem / g.W, x = rem - y * g.W;
-          if (fast) {  // stride 1: p = y + pad - r, q = x + pad - s
-            a_off[j] = ((img * g.Ho + y + g.pad) * g.Wo + x + g.pad) * g.Co + gcol * 4;
-            for (int r = 0; r < g.R; ++r)
-              for (int s2 = 0; s2 < g.S; ++s2) {
-                const int pp = y + g.pad - r, qq = x + g.pad - s2;
-                if (pp >= 0 && pp < g.Ho && qq >= 0 && qq < g.Wo) a_taps[j] |= 1ull << (r * g.S + s2);
-              }
-          } else {
-            a_off[j] = img;
-            a_yx[j] = (y << 16) | x;
-            a_taps[j] = 1ull;
-          }
+          // p = (y + pad - r) / stride must be exact.  With yb = y + pad = stride * py + ey the valid taps are r = ey + stride * t
+          // and p = py - t: anchor the row at (py, qx) and keep (ey, ex) so that a tap costs two shifts/divides and an fma.
+          const int yb = y + g.pad, xb = x + g.pad;
+          const int py = yb / g.stride, qx = xb / g.stride;
+          const int ey = yb - py * g.stride, ex = xb - qx * g.stride;
+          a_off[j] = ((img * g.Ho + py) * g.Wo + qx) * g.Co + gcol * 4;
+          a_yx[j] = (ey << 16) | ex;
+          for (int r = ey, pp = py; r < g.R; r += g.stride, --pp)
+            for (int s2 = ex, qq = qx; s2 < g.S; s2 += g.stride, --qq)
+              if (pp >= 0 && pp < g.Ho && qq >= 0 && qq < g.Wo) a_taps[j] |= 1ull << (r * g.S + s2);
         }
       }
     }
@@ -238,6 +236,10 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
     it_rs = (MODE == GEMM_WGRAD) ? 0 : kbase / kch;
     it_c0 = (MODE == GEMM_WGRAD) ? kbase : kbase - it_rs * kch;
   }
+
+  // Everything above touched only kernel parameters, shared memory and TMEM; from here on global memory written by the
+  // predecessor kernel is read.
+  pdl_wait();
 
   // Stage one k-block: cp.async (LDGSTS, 16 B, zero-fill for padding / out-of-range taps) straight from global memory
   // into the UMMA operand layouts -- no register staging, so up to TC_STAGES k-blocks of loads stay in flight.
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
       // A(m, k) = dout[img, (y + pad - r)/stride, (x + pad - s)/stride, ko], k = (r, s, ko)   (Co % 32 == 0)
       const int rs = it_rs, k0 = it_c0;
       const int r = rs / g.S, s = rs - r * g.S;
-      if (fast) {
+      if (g.stride == 1) {
         const int tapoff = k0 - (r * g.Wo + s) * g.Co;
 #pragma unroll
         for (int j = 0; j < A_VEC; ++j) {
@@ -273,17 +275,13 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
           cp_async16(pa + off_k128(grow + 16 * j, gcol), ok ? act + (a_off[j] + tapoff) : act, ok ? 16u : 0u);
         }
       } else {
+        const bool st2 = g.stride == 2;
 #pragma unroll
         for (int j = 0; j < A_VEC; ++j) {
-          const int hp = (a_yx[j] >> 16) + g.pad - r, wp = (a_yx[j] & 0xffff) + g.pad - s;
-          bool ok = (a_taps[j] != 0ull) && hp >= 0 && wp >= 0;
-          int p = 0, q = 0;
-          if (ok) {
-            p = hp / g.stride; q = wp / g.stride;
-            ok = (p * g.stride == hp) && (q * g.stride == wp) && p < g.Ho && q < g.Wo;
-          }
-          const float* ga = ok ? act + ((long long)(a_off[j] * g.Ho + p) * g.Wo + q) * g.Co + k0 + gcol * 4 : act;
-          cp_async16(pa + off_k128(grow + 16 * j, gcol), ga, ok ? 16u : 0u);
+          const bool ok = (a_taps[j] >> rs) & 1ull;
+          const int dr = r - (a_yx[j] >> 16), ds = s - (a_yx[j] & 0xffff);
+          const int tr = st2 ? dr >> 1 : dr / g.stride, ts = st2 ? ds >> 1 : ds / g.stride;
+          cp_async16(pa + off_k128(grow + 16 * j, gcol), ok ? act + (a_off[j] + k0 - (tr * g.Wo + ts) * g.Co) : act, ok ? 16u : 0u);
         }
       }
       // B(n = ci, k) = W[ko][r][s][ci]: contiguous along n -> MN-major.  lanes along n (16 granules = 64 ci), 8 k per pass
@@ -303,8 +301,9 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
           const int k = kk + 4 * j;
           const int pix = kbase + k;
           const bool kok = pix < d.K;
-          const float* ga = kok ? wgt + (long long)pix * g.Co + m0 + m4 * 4 : wgt;
-          cp_async16(pa + off_mnmajor<TC_BM>(4 * m4, k), ga, kok ? 16u : 0u);
+          const bool mok = kok && (m0 + m4 * 4 < d.M);
+          const float* ga = mok ? wgt + (long long)pix * g.Co + m0 + m4 * 4 : wgt;
+          cp_async16(pa + off_mnmajor<TC_BM>(4 * m4, k), ga, mok ? 16u : 0u);
         }
       }
       // B(n = (r, s, c), k) = in[img, p*stride - pad + r, q*stride - pad + s, c] (MN-major, Ci % 4 == 0)
@@ -508,14 +507,15 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, cudaStream_t stream) {
   static const int max_splits_env = [] { const char* e = getenv("BRE_TC_MAX_SPLITS"); return e ? atoi(e) : 0; }();
   static const int target_ctas_env = [] { const char* e = getenv("BRE_TC_TARGET_CTAS"); return e ? atoi(e) : 0; }();
   const int target = target_ctas_env > 0 ? target_ctas_env : 96;
+  constexpr int kMaxCluster = 16;  // non-portable cluster size (8 is the portable limit); opted in below
   int splits = a.splits;
   if (splits <= 0) {
     splits = 1;
-    while (splits < 8 && tiles * splits < target && d.total_kblocks / (splits * 2) >= 2) splits *= 2;
+    while (splits < kMaxCluster && tiles * splits < target && d.total_kblocks / (splits * 2) >= 2) splits *= 2;
   }
   if (max_splits_env > 0 && splits > max_splits_env) splits = max_splits_env;
   int pow2 = 1;
-  while (pow2 * 2 <= splits && pow2 < 8) pow2 *= 2;
+  while (pow2 * 2 <= splits && pow2 < kMaxCluster) pow2 *= 2;
   splits = pow2;
   while (splits > 1 && splits > d.total_kblocks) splits /= 2;
   d.kblocks_per_split = ceil_div(d.total_kblocks, splits);
@@ -524,21 +524,15 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_done = true;
   }
   static const int proxy_fence_env = [] { const char* e = getenv("BRE_TC_PROXY_FENCE"); return e ? atoi(e) : 0; }();
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(tm, tn, splits);
-  cfg.blockDim = dim3(TC_BLOCK);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = splits;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  BRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, igemm_tc_kernel<MODE, BN>, a, d, proxy_fence_env));
+  {
+    cudaError_t lerr = launch_kernel(igemm_tc_kernel<MODE, BN>, dim3(tm, tn, splits), dim3(TC_BLOCK), smem, stream, splits, a, d,
+                                     proxy_fence_env);
+    if (lerr != cudaSuccess) { set_error(std::string("igemm_tc launch failed: ") + cudaGetErrorString(lerr)); return -2; }
+  }
   BRE_CHECK_LAUNCH();
   return 0;
 }
@@ -555,9 +549,9 @@ bool igemm_tc_supported(const GemmArgs& a) {
   const bool x_nhwc = a.x_sC == 1 && a.x_sP % 4 == 0 && a.x_sN % 4 == 0;
   if (Nc % 64 != 0) return false;
   switch (a.mode) {
-    case GEMM_FPROP: return x_nhwc && g.Ci % TC_BK == 0;                 // k-block inside one (r, s) cell
-    case GEMM_DGRAD: return x_nhwc && g.Co % TC_BK == 0 && g.Ci % 64 == 0;
-    case GEMM_WGRAD: return x_nhwc && g.Co % TC_BM == 0 && g.Ci % 4 == 0 && g.Co % 4 == 0;
+    case GEMM_FPROP: return x_nhwc && g.Ci % TC_BK == 0 && g.R * g.S <= 64;  // k-block inside one (r, s) cell
+    case GEMM_DGRAD: return x_nhwc && g.Co % TC_BK == 0 && g.Ci % 64 == 0 && g.R * g.S <= 64;
+    case GEMM_WGRAD: return x_nhwc && g.Co % 4 == 0 && g.Ci % 4 == 0 && g.R * g.S <= 64;
     default: return false;
   }
 }

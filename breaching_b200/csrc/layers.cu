@@ -20,6 +20,7 @@ inline int ew_grid(long long n) {
 __global__ void bn_prepare_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                   const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
                                   float* scale, float* shift, float* inv, float* nrm) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float iv = 1.0f / sqrtf(rv[c] + eps);
@@ -32,6 +33,7 @@ __global__ void bn_prepare_kernel(const float* __restrict__ gamma, const float* 
 // ---- fused BN + residual + ReLU forward ------------------------------------------------------------
 __global__ void bnact_fwd_kernel(const float* __restrict__ in, const float* __restrict__ res, float* __restrict__ out,
                                  long long total, int C, bool has_bn, bool relu, BnConsts bn) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     float u = in[i];
@@ -98,6 +100,7 @@ inline void slab_grid(long long P, int C, dim3& grid, dim3& block, long long& pp
 }
 
 __global__ void bnact_bwd_kernel(BnActBwdArgs a, long long pps, int Cpad) {
+  pdl_prologue();
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool cv = c < a.C;
   const long long p0 = blockIdx.y * pps;
@@ -130,6 +133,7 @@ __global__ void bnact_bwd_kernel(BnActBwdArgs a, long long pps, int Cpad) {
 }
 
 __global__ void bnact_tan_fwd_kernel(BnActTanFwdArgs a, long long total) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % a.C);
     float u = a.tin != nullptr ? a.tin[i] : 0.f;
@@ -144,6 +148,7 @@ __global__ void bnact_tan_fwd_kernel(BnActTanFwdArgs a, long long total) {
 }
 
 __global__ void bnact_tan_bwd_kernel(BnActTanBwdArgs a, long long total) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % a.C);
     float tdu = a.tdout[i];
@@ -161,6 +166,7 @@ __global__ void bnact_tan_bwd_kernel(BnActTanBwdArgs a, long long total) {
 
 __global__ void channel_sum_kernel(const float* __restrict__ x, long long P, int C, float* out, float* partials,
                                    int* counters, long long pps, int Cpad) {
+  pdl_prologue();
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long p0 = blockIdx.y * pps;
   const long long p1 = (p0 + pps < P) ? p0 + pps : P;
@@ -173,6 +179,7 @@ __global__ void channel_sum_kernel(const float* __restrict__ x, long long P, int
 
 __global__ void channel_stats_kernel(const float* __restrict__ x, long long P, int C, float* mean, float* var,
                                      float* partials, int* counters, long long pps, int Cpad) {
+  pdl_prologue();
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long p0 = blockIdx.y * pps;
   const long long p1 = (p0 + pps < P) ? p0 + pps : P;
@@ -196,6 +203,7 @@ __global__ void channel_stats_kernel(const float* __restrict__ x, long long P, i
 // ---- pooling ---------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int* __restrict__ idx, PoolGeom g,
                                    long long total) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % g.C);
     long long t = i / g.C;
@@ -222,6 +230,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ in, float* __restri
 
 __global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ idx, float* __restrict__ din, bool acc,
                                    PoolGeom g, long long total) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % g.C);
     long long t = i / g.C;
@@ -245,6 +254,7 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int* __
 
 __global__ void maxpool_gather_kernel(const float* __restrict__ tin, const int* __restrict__ idx, float* __restrict__ tout,
                                       PoolGeom g, long long total) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % g.C);
     const long long n = i / ((long long)g.C * g.Ho * g.Wo);
@@ -253,6 +263,7 @@ __global__ void maxpool_gather_kernel(const float* __restrict__ tin, const int* 
 }
 
 __global__ void avgpool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int HW, int C) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i - n * C;
@@ -262,6 +273,7 @@ __global__ void avgpool_fwd_kernel(const float* __restrict__ in, float* __restri
 }
 
 __global__ void avgpool_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, bool acc, long long total, int HW, int C) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long long n = i / ((long long)C * HW);
@@ -273,6 +285,7 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dout, float* __rest
 // ---- softmax cross-entropy -------------------------------------------------------------------------
 __global__ void ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int N, int C, float* p,
                               float* loss_n, float* dlogits) {
+  pdl_prologue();
   __shared__ double scratch[32];
   __shared__ float s_max, s_sum;
   const int n = blockIdx.x;
@@ -307,6 +320,7 @@ __global__ void ce_fwd_kernel(const float* __restrict__ logits, const long long*
 }
 
 __global__ void ce_tan_bwd_kernel(const float* __restrict__ p, const float* __restrict__ zdot, int N, int C, float* tdl) {
+  pdl_prologue();
   __shared__ double scratch[32];
   __shared__ float s_dot;
   const int n = blockIdx.x;
@@ -324,6 +338,7 @@ __global__ void ce_tan_bwd_kernel(const float* __restrict__ p, const float* __re
 // ---- layout ----------------------------------------------------------------------------------------
 __global__ void permute_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int HW, bool inverse,
                                long long total) {
+  pdl_prologue();
   // index space of the OHWI side (coalesced writes forward, coalesced reads inverse)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ic = (int)(i % I);
@@ -336,6 +351,7 @@ __global__ void permute_kernel(const float* __restrict__ src, float* __restrict_
 }
 
 __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float alpha, long long n) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = fmaf(alpha, x[i], y[i]);
 }
@@ -344,7 +360,7 @@ __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, 
 
 int launch_bn_prepare(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C,
                       float* scale, float* shift, float* inv, float* nrm, cudaStream_t s) {
-  bn_prepare_kernel<<<ceil_div(C, 128), 128, 0, s>>>(gamma, beta, rm, rv, eps, C, scale, shift, inv, nrm);
+  BRE_KLAUNCH(bn_prepare_kernel, ceil_div(C, 128), 128, 0, s, gamma, beta, rm, rv, eps, C, scale, shift, inv, nrm);
   BRE_CHECK_LAUNCH();
   return 0;
 }
@@ -352,7 +368,7 @@ int launch_bn_prepare(const float* gamma, const float* beta, const float* rm, co
 int launch_bnact_fwd(const float* in, const float* res, float* out, long long P, int C, bool has_bn, bool relu,
                      BnConsts bn, cudaStream_t s) {
   const long long total = P * C;
-  bnact_fwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(in, res, out, total, C, has_bn, relu, bn);
+  BRE_KLAUNCH(bnact_fwd_kernel, ew_grid(total), kEwThreads, 0, s, in, res, out, total, C, has_bn, relu, bn);
   BRE_CHECK_LAUNCH();
   return 0;
 }
@@ -361,21 +377,21 @@ int launch_bnact_bwd(const BnActBwdArgs& a, cudaStream_t s) {
   dim3 grid, block;
   long long pps;
   slab_grid(a.P, a.C, grid, block, pps);
-  bnact_bwd_kernel<<<grid, block, 0, s>>>(a, pps, grid.x * 32);
+  BRE_KLAUNCH(bnact_bwd_kernel, grid, block, 0, s, a, pps, grid.x * 32);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_bnact_tan_fwd(const BnActTanFwdArgs& a, cudaStream_t s) {
   const long long total = a.P * a.C;
-  bnact_tan_fwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(a, total);
+  BRE_KLAUNCH(bnact_tan_fwd_kernel, ew_grid(total), kEwThreads, 0, s, a, total);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_bnact_tan_bwd(const BnActTanBwdArgs& a, cudaStream_t s) {
   const long long total = a.P * a.C;
-  bnact_tan_bwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(a, total);
+  BRE_KLAUNCH(bnact_tan_bwd_kernel, ew_grid(total), kEwThreads, 0, s, a, total);
   BRE_CHECK_LAUNCH();
   return 0;
 }
@@ -384,7 +400,7 @@ int launch_channel_sum(const float* x, long long P, int C, float* out, float* pa
   dim3 grid, block;
   long long pps;
   slab_grid(P, C, grid, block, pps);
-  channel_sum_kernel<<<grid, block, 0, s>>>(x, P, C, out, partials, counters, pps, grid.x * 32);
+  BRE_KLAUNCH(channel_sum_kernel, grid, block, 0, s, x, P, C, out, partials, counters, pps, grid.x * 32);
   BRE_CHECK_LAUNCH();
   return 0;
 }
@@ -394,61 +410,61 @@ int launch_channel_stats(const float* x, long long P, int C, float* mean, float*
   dim3 grid, block;
   long long pps;
   slab_grid(P, C, grid, block, pps);
-  channel_stats_kernel<<<grid, block, 0, s>>>(x, P, C, mean, var, partials, counters, pps, grid.x * 32);
+  BRE_KLAUNCH(channel_stats_kernel, grid, block, 0, s, x, P, C, mean, var, partials, counters, pps, grid.x * 32);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_maxpool_fwd(const float* in, float* out, int* idx, PoolGeom g, cudaStream_t s) {
   const long long total = (long long)g.N * g.Ho * g.Wo * g.C;
-  maxpool_fwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(in, out, idx, g, total);
+  BRE_KLAUNCH(maxpool_fwd_kernel, ew_grid(total), kEwThreads, 0, s, in, out, idx, g, total);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_maxpool_bwd(const float* dout, const int* idx, float* din, bool acc, PoolGeom g, cudaStream_t s) {
   const long long total = (long long)g.N * g.H * g.W * g.C;
-  maxpool_bwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(dout, idx, din, acc, g, total);
+  BRE_KLAUNCH(maxpool_bwd_kernel, ew_grid(total), kEwThreads, 0, s, dout, idx, din, acc, g, total);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_maxpool_gather(const float* tin, const int* idx, float* tout, PoolGeom g, cudaStream_t s) {
   const long long total = (long long)g.N * g.Ho * g.Wo * g.C;
-  maxpool_gather_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(tin, idx, tout, g, total);
+  BRE_KLAUNCH(maxpool_gather_kernel, ew_grid(total), kEwThreads, 0, s, tin, idx, tout, g, total);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_avgpool_fwd(const float* in, float* out, int N, int HW, int C, cudaStream_t s) {
-  avgpool_fwd_kernel<<<ceil_div((long long)N * C, 128), 128, 0, s>>>(in, out, N, HW, C);
+  BRE_KLAUNCH(avgpool_fwd_kernel, ceil_div((long long)N * C, 128), 128, 0, s, in, out, N, HW, C);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_avgpool_bwd(const float* dout, float* din, bool acc, int N, int HW, int C, cudaStream_t s) {
   const long long total = (long long)N * HW * C;
-  avgpool_bwd_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(dout, din, acc, total, HW, C);
+  BRE_KLAUNCH(avgpool_bwd_kernel, ew_grid(total), kEwThreads, 0, s, dout, din, acc, total, HW, C);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_ce_fwd(const float* logits, const long long* labels, int N, int C, float* p, float* loss_n, float* dlogits,
                   cudaStream_t s) {
-  ce_fwd_kernel<<<N, 256, 0, s>>>(logits, labels, N, C, p, loss_n, dlogits);
+  BRE_KLAUNCH(ce_fwd_kernel, N, 256, 0, s, logits, labels, N, C, p, loss_n, dlogits);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_ce_tan_bwd(const float* p, const float* zdot, int N, int C, float* tdlogits, cudaStream_t s) {
-  ce_tan_bwd_kernel<<<N, 256, 0, s>>>(p, zdot, N, C, tdlogits);
+  BRE_KLAUNCH(ce_tan_bwd_kernel, N, 256, 0, s, p, zdot, N, C, tdlogits);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_permute(const float* src, float* dst, int O, int I, int HW, bool inverse, cudaStream_t s) {
   const long long total = (long long)O * I * HW;
-  permute_kernel<<<ew_grid(total), kEwThreads, 0, s>>>(src, dst, O, I, HW, inverse, total);
+  BRE_KLAUNCH(permute_kernel, ew_grid(total), kEwThreads, 0, s, src, dst, O, I, HW, inverse, total);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_axpy(const float* x, float* y, float alpha, long long n, cudaStream_t s) {
-  axpy_kernel<<<ew_grid(n), kEwThreads, 0, s>>>(x, y, alpha, n);
+  BRE_KLAUNCH(axpy_kernel, ew_grid(n), kEwThreads, 0, s, x, y, alpha, n);
   BRE_CHECK_LAUNCH();
   return 0;
 }

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) match_reduce_kernel(const float* __restri
                                                           float mask_value, int objective, float scale, float tag_scale,
                                                           float fudge, bool finalize, Scalars* sc, double* partials,
                                                           int* counter) {
+  pdl_prologue();
   __shared__ double scratch[32];
   __shared__ int s_last;
   double acc[5] = {0, 0, 0, 0, 0};
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(256) match_reduce_kernel(const float* __restri
 __global__ void __launch_bounds__(256) make_v_kernel(const float* __restrict__ G, const float* __restrict__ g,
                                                     const float* __restrict__ chunk_w, float* __restrict__ v, long long n,
                                                     long long nchunks, float mask_value, const Scalars* sc) {
+  pdl_prologue();
   const float c1 = sc->c1, c2 = sc->c2, c3 = sc->c3;
   const bool masked = mask_value >= 0.f;
   for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
@@ -184,6 +186,7 @@ __device__ __forceinline__ TvD tv_point(float t00, float t10, float t01, float p
 constexpr int TV_TW = 32, TV_TH = 8;
 
 __global__ void __launch_bounds__(TV_TW * TV_TH) image_priors_kernel(PriorArgs a, Scalars* sc, double* partials, int* counter) {
+  pdl_prologue();
   __shared__ float xs[3][TV_TH + 2][TV_TW + 2];
   __shared__ double scratch[32];
   __shared__ int s_last;
@@ -310,6 +313,7 @@ __device__ __forceinline__ float raw_gradient(const StepArgs& a, const Scalars* 
 }
 
 __global__ void __launch_bounds__(256) grad_norm_kernel(StepArgs a, Scalars* sc, double* partials, int* counter) {
+  pdl_prologue();
   __shared__ double scratch[32];
   __shared__ int s_last;
   const int it = sc->it;
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(256) grad_norm_kernel(StepArgs a, Scalars* sc,
 }
 
 __global__ void __launch_bounds__(256) pixel_step_kernel(StepArgs a, Scalars* sc) {
+  pdl_prologue();
   if (sc->stopped) return;
   __shared__ float s_c[8];
   const int it = sc->it;
@@ -400,6 +405,7 @@ __global__ void __launch_bounds__(256) pixel_step_kernel(StepArgs a, Scalars* sc
 }
 
 __global__ void commit_kernel(Scalars* sc, float* history, int max_hist, float task_reg) {
+  pdl_prologue();
   if (sc->stopped) return;
   const float phi = (float)total_objective(sc, task_reg);
   if (phi < (float)sc->fmin) sc->fmin = (double)phi;
@@ -414,12 +420,14 @@ __global__ void commit_kernel(Scalars* sc, float* history, int max_hist, float t
 }
 
 __global__ void loss_mean_kernel(const float* loss_n, int N, Scalars* sc) {
+  pdl_prologue();
   double s = 0.0;
   for (int n = 0; n < N; ++n) s += (double)loss_n[n];
   sc->task_loss = (double)(float)(s / N);
 }
 
 __global__ void __launch_bounds__(256) di_finalize_kernel(const DiLayer* layers, int n_layers, Scalars* sc) {
+  pdl_prologue();
   __shared__ double scratch[32];
   __shared__ double s_n[2];
   double value = 0.0;
@@ -449,6 +457,7 @@ __global__ void __launch_bounds__(256) di_finalize_kernel(const DiLayer* layers,
 
 __global__ void __launch_bounds__(256) feature_reg_kernel(const float* __restrict__ feat, const float* __restrict__ measured,
                                                          float* tdelta, long long n, float scale, Scalars* sc) {
+  pdl_prologue();
   __shared__ double scratch[32];
   double acc = 0.0;
   const float coef = 2.f * scale / (float)n;
@@ -469,7 +478,7 @@ int launch_match_reduce(const float* G, const float* g, const float* chunk_w, lo
   const long long nchunks = (n + kChunk - 1) / kChunk;
   const long long groups = (nchunks + 3) / 4;
   const int grid = (int)(groups < kMatchMaxBlocks ? (groups > 0 ? groups : 1) : kMatchMaxBlocks);
-  match_reduce_kernel<<<grid, 256, 0, s>>>(G, g, chunk_w, n, nchunks, mask_value, objective, scale, tag_scale, fudge,
+  BRE_KLAUNCH(match_reduce_kernel, grid, 256, 0, s, G, g, chunk_w, n, nchunks, mask_value, objective, scale, tag_scale, fudge,
                                            finalize, sc, partials, counter);
   BRE_CHECK_LAUNCH();
   return 0;
@@ -480,14 +489,14 @@ int launch_make_v(const float* G, const float* g, const float* chunk_w, float* v
   const long long nchunks = (n + kChunk - 1) / kChunk;
   const int cap = kNumSMs * 8;
   const int grid = (int)(nchunks < cap ? (nchunks > 0 ? nchunks : 1) : cap);
-  make_v_kernel<<<grid, 256, 0, s>>>(G, g, chunk_w, v, n, nchunks, mask_value, sc);
+  BRE_KLAUNCH(make_v_kernel, grid, 256, 0, s, G, g, chunk_w, v, n, nchunks, mask_value, sc);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_image_priors(const PriorArgs& a, Scalars* sc, double* partials, int* counter, cudaStream_t s) {
   dim3 grid(ceil_div(a.W, TV_TW), ceil_div(a.H, TV_TH), a.N), block(TV_TW, TV_TH);
-  image_priors_kernel<<<grid, block, 0, s>>>(a, sc, partials, counter);
+  BRE_KLAUNCH(image_priors_kernel, grid, block, 0, s, a, sc, partials, counter);
   BRE_CHECK_LAUNCH();
   return 0;
 }
@@ -499,33 +508,33 @@ static inline int step_grid(long long n) {
 }
 
 int launch_grad_norm(const StepArgs& a, Scalars* sc, double* partials, int* counter, cudaStream_t s) {
-  grad_norm_kernel<<<step_grid(a.n), 256, 0, s>>>(a, sc, partials, counter);
+  BRE_KLAUNCH(grad_norm_kernel, step_grid(a.n), 256, 0, s, a, sc, partials, counter);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_pixel_step(const StepArgs& a, Scalars* sc, cudaStream_t s) {
-  pixel_step_kernel<<<step_grid(a.n), 256, 0, s>>>(a, sc);
+  BRE_KLAUNCH(pixel_step_kernel, step_grid(a.n), 256, 0, s, a, sc);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_commit(Scalars* sc, float* history, int max_hist, float task_reg, cudaStream_t s) {
-  commit_kernel<<<1, 1, 0, s>>>(sc, history, max_hist, task_reg);
+  BRE_KLAUNCH(commit_kernel, 1, 1, 0, s, sc, history, max_hist, task_reg);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_loss_mean(const float* loss_n, int N, Scalars* sc, cudaStream_t s) {
-  loss_mean_kernel<<<1, 1, 0, s>>>(loss_n, N, sc);
+  BRE_KLAUNCH(loss_mean_kernel, 1, 1, 0, s, loss_n, N, sc);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_di_finalize(const DiLayer* layers_dev, int n_layers, Scalars* sc, cudaStream_t s) {
-  di_finalize_kernel<<<1, 256, 0, s>>>(layers_dev, n_layers, sc);
+  BRE_KLAUNCH(di_finalize_kernel, 1, 256, 0, s, layers_dev, n_layers, sc);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_feature_reg(const float* feat, const float* measured, float* tdelta, long long n, float scale, Scalars* sc,
                        cudaStream_t s) {
-  feature_reg_kernel<<<1, 256, 0, s>>>(feat, measured, tdelta, n, scale, sc);
+  BRE_KLAUNCH(feature_reg_kernel, 1, 256, 0, s, feat, measured, tdelta, n, scale, sc);
   BRE_CHECK_LAUNCH();
   return 0;
 }
