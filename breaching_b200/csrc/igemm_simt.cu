@@ -349,38 +349,40 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_simt_kernel(GemmArgs a, Dims
 // (12 consecutive floats per 4 output channels -> three broadcast LDS.128 feed 48 FMAs); each thread owns PX pixels of
 // one stride-parity class so every weight fetched from shared memory is reused PX times.
 constexpr int SC_PX = 4;
-constexpr int SC_ROWS = 4;
+constexpr int SC_KCH = 4;   // 16-byte chunks of output channels per warp and tap (Co <= 64)
 template <int CI>
-__global__ void __launch_bounds__(128) dgrad_small_ci_kernel(GemmArgs a, int n_r, int smem_floats) {
+__global__ void __launch_bounds__(128) dgrad_small_ci_kernel(GemmArgs a, int n_r, int smem_floats, int vec) {
   pdl_prologue();
   extern __shared__ __align__(16) float wsm[];            // [nsrc][n_r * S][Co][CI], then the reduction scratch
   const ConvGeom g = a.g;
-  const int img = blockIdx.z;
+  const int img = blockIdx.z, h = blockIdx.y;
   const int lane = threadIdx.x & 31, kq = threadIdx.x >> 5;  // warp = quarter of the output-channel range
   const int Wc = (g.W + g.stride - 1) / g.stride;
-  // this block owns up to SC_ROWS image rows h = hcls + stride * (hgrp * SC_ROWS + i): they share the set of filter rows
-  // that can hit them (r = r0 + t * stride), so the weight slice is staged once for all of them
-  const int Hc = (g.H + g.stride - 1) / g.stride;
-  const int hgroups = (Hc + SC_ROWS - 1) / SC_ROWS;
-  const int hcls = blockIdx.y / hgroups, hgrp = blockIdx.y - hcls * hgroups;
-  const int r0 = (hcls + g.pad) % g.stride;
+  // valid filter rows for this image row: r = r0 + t * stride, p = p0 - t
+  const int hb = h + g.pad;
+  const int r0 = hb % g.stride, p0 = hb / g.stride;
   const int taps = n_r * g.S;
   for (int e = threadIdx.x; e < g.Co * CI; e += 128) {     // (ko, c) fixed per thread; no divisions in the copy loops
     const int ko = e / CI, c = e - ko * CI;
     for (int src = 0; src < a.nsrc; ++src)
       for (int tr = 0; tr < n_r; ++tr) {
         const int r = r0 + tr * g.stride;
-        for (int s = 0; s < g.S; ++s)
-          wsm[((src * taps + tr * g.S + s) * g.Co + ko) * CI + c] =
-              r < g.R ? __ldg(a.wgt[src] + ((long long)ko * (g.R * g.S) + r * g.S + s) * g.Ci + c) : 0.f;
+        for (int s = 0; s < g.S; ++s) {
+          float* dst = wsm + ((src * taps + tr * g.S + s) * g.Co + ko) * CI + c;
+          if (r < g.R) {
+            const float* gp = a.wgt[src] + ((long long)ko * (g.R * g.S) + r * g.S + s) * g.Ci + c;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(gp) : "memory");
+          } else {
+            *dst = 0.f;
+          }
+        }
       }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   float* red = wsm + smem_floats;  // reduction scratch behind the weights: [4][32][SC_PX * CI]
- for (int hi = 0; hi < SC_ROWS; ++hi) {
-  const int h = hcls + g.stride * (hgrp * SC_ROWS + hi);
-  if (h >= g.H) break;   // uniform across the block
-  const int p0 = (h + g.pad) / g.stride;
+  {
   const int Wcp = ((Wc + SC_PX - 1) / SC_PX) * SC_PX;     // per-class slot range padded so that a thread never straddles classes
   const int slot0 = (blockIdx.x * 32 + lane) * SC_PX;   // SC_PX consecutive slots of one class
   const int cls = slot0 / Wcp;
@@ -418,23 +420,35 @@ __global__ void __launch_bounds__(128) dgrad_small_ci_kernel(GemmArgs a, int n_r
             ok[px] = pvalid[px] && wp >= 0 && q < g.Wo;
             dp[px] = dout + ((long long)(img * g.Ho + p) * g.Wo + (ok[px] ? q : 0)) * g.Co;
           }
-          for (int ko = ko_lo; ko < ko_hi; ko += 4) {
-            float wv[4 * CI];
-            if (CI == 3 || CI == 1 || CI == 2 || CI == 4) {
+          // the warp's slice of output channels is at most SC_KCH * 4 wide: issue every dout load of this tap first
+          float4 dv[SC_KCH][SC_PX];
 #pragma unroll
-              for (int e = 0; e < 4 * CI; ++e) wv[e] = (ko + e / CI < g.Co) ? wt[ko * CI + e] : 0.f;
-            }
+          for (int kc = 0; kc < SC_KCH; ++kc) {
+            const int ko = ko_lo + 4 * kc;
 #pragma unroll
             for (int px = 0; px < SC_PX; ++px) {
-              if (!ok[px]) continue;
-              float dd[4] = {0.f, 0.f, 0.f, 0.f};
-              if (ko + 3 < g.Co && (g.Co & 3) == 0) {
-                const float4 dv = __ldg(reinterpret_cast<const float4*>(dp[px] + ko));
-                dd[0] = dv.x; dd[1] = dv.y; dd[2] = dv.z; dd[3] = dv.w;
-              } else {
-                for (int j = 0; j < 4; ++j)
-                  if (ko + j < g.Co) dd[j] = __ldg(dp[px] + ko + j);
+              dv[kc][px] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok[px] && ko < ko_hi) {
+                if (vec) dv[kc][px] = __ldg(reinterpret_cast<const float4*>(dp[px] + ko));
+                else {
+                  float t4[4] = {0.f, 0.f, 0.f, 0.f};
+                  for (int j = 0; j < 4; ++j)
+                    if (ko + j < g.Co) t4[j] = __ldg(dp[px] + ko + j);
+                  dv[kc][px] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                }
               }
+            }
+          }
+#pragma unroll
+          for (int kc = 0; kc < SC_KCH; ++kc) {
+            const int ko = ko_lo + 4 * kc;
+            if (ko >= ko_hi) break;
+            float wv[4 * CI];
+#pragma unroll
+            for (int e = 0; e < 4 * CI; ++e) wv[e] = (ko + e / CI < g.Co) ? wt[ko * CI + e] : 0.f;
+#pragma unroll
+            for (int px = 0; px < SC_PX; ++px) {
+              const float dd[4] = {dv[kc][px].x, dv[kc][px].y, dv[kc][px].z, dv[kc][px].w};
 #pragma unroll
               for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -467,7 +481,7 @@ __global__ void __launch_bounds__(128) dgrad_small_ci_kernel(GemmArgs a, int n_r
     }
   }
   }
- }  // image rows of this block
+ }
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -476,14 +490,16 @@ int launch_dgrad_small_ci(const GemmArgs& a, cudaStream_t stream) {
   const ConvGeom& g = a.g;
   const int Wc = (g.W + g.stride - 1) / g.stride;
   const int n_r = (g.R + g.stride - 1) / g.stride;   // filter rows that can hit one image row
+  bool vecb = (g.Co % 4 == 0);
+  for (int q = 0; q < a.nsrc; ++q) vecb = vecb && aligned16(a.act[q]);
+  const int vec = vecb ? 1 : 0;
   const int wfloats = a.nsrc * n_r * g.S * g.Co * g.Ci;
   const int rfloats = 4 * 32 * SC_PX * g.Ci;
   const int smem_floats = (wfloats + 3) & ~3;   // weights, then the reduction scratch
   const size_t smem = (size_t)(smem_floats + rfloats) * sizeof(float);
   if (smem > 200 * 1024) { set_error("dgrad_small_ci: filter too large for shared memory"); return -4; }
   const int Wcp = ((Wc + SC_PX - 1) / SC_PX) * SC_PX;
-  const int Hc = (g.H + g.stride - 1) / g.stride;
-  dim3 grid(ceil_div((long long)Wcp * g.stride, 32 * SC_PX), g.stride * ceil_div(Hc, SC_ROWS), g.N), block(128);
+  dim3 grid(ceil_div((long long)Wcp * g.stride, 32 * SC_PX), g.H, g.N), block(128);
 #define BRE_LAUNCH_SC(CI_)                                                                                              \
   do {                                                                                                                  \
     static size_t cap = 0;                                                                                              \
@@ -491,7 +507,7 @@ int launch_dgrad_small_ci(const GemmArgs& a, cudaStream_t stream) {
       BRE_CUDA_CHECK(cudaFuncSetAttribute(dgrad_small_ci_kernel<CI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       cap = smem;                                                                                                       \
     }                                                                                                                   \
-    BRE_KLAUNCH((dgrad_small_ci_kernel<CI_>), grid, block, smem, stream, a, n_r, smem_floats);                                     \
+    BRE_KLAUNCH((dgrad_small_ci_kernel<CI_>), grid, block, smem, stream, a, n_r, smem_floats, vec);                                     \
   } while (0)
   switch (g.Ci) {
     case 1: BRE_LAUNCH_SC(1); break;
@@ -512,7 +528,7 @@ int launch_igemm_simt(const GemmArgs& a, cudaStream_t stream) {
   const ConvGeom& g = a.g;
   if (d.M <= 0 || d.Nc <= 0 || d.K <= 0) { set_error("igemm: empty problem"); return -1; }
   if (a.nsrc < 1 || a.nsrc > 2 || (a.nsrc == 2 && a.mode == GEMM_WGRAD)) { set_error("igemm: bad nsrc"); return -1; }
-  if (a.mode == GEMM_DGRAD && g.Ci <= 4 && g.H <= 65535 && g.N <= 65535 &&
+  if (a.mode == GEMM_DGRAD && g.Ci <= 4 && g.Co <= 16 * SC_KCH && g.H <= 65535 && g.N <= 65535 &&
       (size_t)a.nsrc * ((g.R + g.stride - 1) / g.stride) * g.S * g.Co * g.Ci * 4 <= 200 * 1024)
     return launch_dgrad_small_ci(a, stream);
   d.steps_per_src = ceil_div(d.K, IG_BK);
