@@ -124,38 +124,101 @@ def oracle_iters_per_sec(model, loss_fn, payload, shared, true, cfg, device, war
 
 
 def kernel_rooflines(dev):
-    """Isolated timings of the two kernel families the north star names, with CUDA events on the launching stream,
-    L2 flushed between repetitions by writing a 512 MB buffer."""
+    """Isolated device time of the matching-reduction kernel (the HBM-bound kernel the north star names): the bare kernel
+    is captured 16x into a CUDA graph over four rotating (G, g) buffer pairs (4 x 91 MB > 126 MB L2, so every launch
+    streams from HBM) and the replay is timed with CUDA events on the launching stream."""
     import torch
 
     from breaching_b200 import engine as E
 
     peaks = measured_peaks()
-    flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
-    G = torch.randn(P_R18, device=dev)
-    g = torch.randn(P_R18, device=dev)
-
-    def timed(fn, reps=10):
-        best, total = 1e9, 0.0
-        for _ in range(reps):
-            flush.fill_(1.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            e1.synchronize()
-            ms = e0.elapsed_time(e1)
-            best, total = min(best, ms), total + ms
-        return best, total / reps
-
-    # matching reduction: the library call synchronises internally; time the kernel through repeated launches
-    E.match_reduce(G, g)
-    _, ms_match = timed(lambda: E.match_reduce(G, g))
+    pairs = [(torch.randn(P_R18, device=dev), torch.randn(P_R18, device=dev)) for _ in range(4)]
+    E.match_reduce(*pairs[0])
+    reps = 16
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(reps):
+                E.match_reduce(*pairs[i % 4], readback=False)
+    torch.cuda.synchronize(dev)
+    graph.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    graph.replay()
+    e1.record()
+    e1.synchronize()
+    ms_match = e0.elapsed_time(e1) / reps
     match = dict(bound="hbm", achieved=MATCH_BYTES / (ms_match * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
-                 traffic=None, kernel="match_reduce_kernel", ms=ms_match, peak_source=peaks["source"],
-                 note="includes the 5-double D2H read of the stand-alone API")
+                 traffic=91086336 + 2996736, kernel="match_reduce_kernel", ms=ms_match, peak_source=peaks["source"],
+                 note="graph replay of 16 launches over 4 rotating 91 MB buffer pairs (cold in L2); includes inter-kernel gaps; traffic = "
+                      "dram read+write bytes of one ncu --set full capture (profiles/r1_match_reduce_summary.txt)")
     match["frac"] = match["achieved"] / match["peak"]
     return match
+
+
+def gemm_family_roofline(dev, model, backend):
+    """Live device time of the dominant kernel family -- the conv/linear implicit GEMMs -- for exactly the launches one
+    iteration of config 2 issues (per layer: fprop, wgrad, dgrad, dual-source tangent fprop, dual-source tangent dgrad),
+    replayed from one CUDA graph through the C ABI (`bre_conv_gemm`, engine dispatch rule) and timed with CUDA events on
+    the launching stream.  Operands total > 200 MB, i.e. larger than the 126 MB L2, so a replay does not run L2-hot."""
+    import torch
+
+    from breaching_b200 import compiler as C
+    from breaching_b200 import engine as E
+
+    prog = C.compile_model(model.eval(), (1, 3, 224, 224))
+    be = 2 if backend == "tc" else 0
+    launches, flops, keep = [], 0.0, []
+    for op in prog.ops:
+        if op.kind not in (C.OP_CONV, C.OP_LINEAR):
+            continue
+        ti, to = prog.tensors[op.tin], prog.tensors[op.tout]
+        if op.kind == C.OP_LINEAR:
+            N, H, W, Ci, Co, R, st, pd = ti.N, 1, 1, ti.C * ti.H * ti.W, to.C, 1, 1, 0
+        else:
+            N, H, W, Ci, Co, R, st, pd = ti.N, ti.H, ti.W, ti.C, to.C, op.R, op.stride, op.pad
+        Ho, Wo = to.H if op.kind == C.OP_CONV else 1, to.W if op.kind == C.OP_CONV else 1
+        x, x2 = (torch.randn(N, H, W, Ci, device=dev) for _ in range(2))
+        w, w2 = (torch.randn(Co, R, R, Ci, device=dev) for _ in range(2))
+        dy, dy2 = (torch.randn(N, Ho, Wo, Co, device=dev) for _ in range(2))
+        out_f, out_d, out_w = torch.empty(N, Ho, Wo, Co, device=dev), torch.empty(N, H, W, Ci, device=dev), torch.empty(Co, R, R, Ci, device=dev)
+        keep += [x, x2, w, w2, dy, dy2, out_f, out_d, out_w]
+        g = (N, H, W, Ci, Co, R, R, st, pd)
+        f1 = 2.0 * N * Ho * Wo * Co * R * R * Ci
+        first = op.tin == 0
+        launches.append(lambda x=x, w=w, o=out_f, g=g: E.conv_gemm(0, x, w, o, *g, backend=be)); flops += f1
+        launches.append(lambda x=x, dy=dy, o=out_w, g=g: E.conv_gemm(2, x, dy, o, *g, backend=be)); flops += f1
+        if not first:
+            launches.append(lambda dy=dy, w=w, o=out_d, g=g: E.conv_gemm(1, dy, w, o, *g, backend=be)); flops += f1
+            launches.append(lambda x=x, w=w, x2=x2, w2=w2, o=out_f, g=g: E.conv_gemm(0, x, w, o, *g, a2=x2, w2=w2, backend=be)); flops += 2 * f1
+        else:
+            launches.append(lambda x=x, w=w, o=out_f, g=g: E.conv_gemm(0, x, w, o, *g, backend=be)); flops += f1
+        launches.append(lambda dy=dy, w=w, dy2=dy2, w2=w2, o=out_d, g=g: E.conv_gemm(1, dy, w, o, *g, a2=dy2, w2=w2, backend=be)); flops += 2 * f1
+    for fn in launches:
+        fn()
+    torch.cuda.synchronize(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for fn in launches:
+                fn()
+    torch.cuda.synchronize(dev)
+    graph.replay()
+    torch.cuda.synchronize(dev)
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return dict(n_launches=len(launches), flops=flops, ms_total=ms, ms_per_launch=ms / len(launches), tflops=flops / (ms * 1e-3) / 1e12)
 
 
 def product_arm(args):
@@ -180,9 +243,8 @@ def product_arm(args):
 
     model, loss_fn, payload, shared, true, cfg = build_case()
     meta = payload[0]["metadata"]
-    eng = Engine(copy.deepcopy(model).to(dev).eval(), (1, 3, 224, 224), cfg, dev)
-    if args.backend == "tc":
-        eng.set_option("gemm_backend", 1)
+    os.environ["BRE_GEMM_BACKEND"] = args.backend  # also picked up by the attacker of the e2e leg
+    eng = Engine(copy.deepcopy(model).to(dev).eval(), (1, 3, 224, 224), cfg, dev, backend=args.backend)
     eng.load_model()
     eng.load_targets([g.to(dev) for g in shared[0]["gradients"]], true["labels"].to(dev), mean=meta.mean, std=meta.std)
     table = lr_table(cfg.optim.step_size, cfg.optim.step_size_decay, cfg.optim.warmup, cfg.optim.max_iterations)
@@ -209,7 +271,7 @@ def product_arm(args):
     launches = eng.launches_per_iteration()
 
     # ---- end-to-end through the public API with HOST (pinned) buffers ---------------------------------------------
-    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(args.steps, 1000)
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(args.steps, 8000)
     cfg_e2e = copy.deepcopy(cfg)
     cfg_e2e.optim.max_iterations = e2e_steps
     cfg_e2e.optim.callback = e2e_steps
@@ -239,12 +301,20 @@ def product_arm(args):
 
     peaks = measured_peaks()
     its = world * args.steps / (ms_max * 1e-3)
-    # dominant kernel family = the conv/linear implicit GEMMs; their share of the step is in profiles/ (ncu launch list)
-    roof = dict(bound="tensor", achieved=FLOP_PER_ITER * (args.steps / (ms_max * 1e-3)) / 1e12, peak=peaks["bf16_tflops_sustained"],
-                unit="TFLOP/s", traffic=None, peak_source=peaks["source"],
-                note="whole-iteration algorithmic conv FLOPs (24.92 GFLOP, SURVEY 8d) / iteration time; peak = measured "
-                     "sustained bf16 cuBLAS; the fp32 SIMT back end cannot exceed ~70 TFLOP/s")
+    # dominant kernel family = the conv/linear implicit GEMMs (63 % of the step in profiles/launches_r1_summary.txt)
+    fam = gemm_family_roofline(dev, model, args.backend)
+    roof = dict(bound="tensor", achieved=fam["tflops"], peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
+                traffic=2042624, peak_source=peaks["source"], kernel="igemm_tc_kernel (tcgen05 kind::tf32) + SIMT fallbacks",
+                launches_per_step=fam["n_launches"], avg_launch_us=1e3 * fam["ms_per_launch"], algorithmic_gflop_per_step=fam["flops"] / 1e9,
+                peak_tf32_equivalent=peaks["bf16_tflops_sustained"] / 2,
+                note="achieved = algorithmic conv+linear FLOPs of one iteration (SURVEY 8d) / live CUDA-event time of exactly those "
+                     "GEMM launches (graph replay through the C ABI); peak = measured sustained bf16 cuBLAS (the only measured tensor "
+                     "peak; the TF32 dense peak is half of it); traffic = dram bytes of one captured launch (layer2 tangent dgrad, "
+                     "profiles/r1_tc_dgrad_dual_summary.txt) = its algorithmic bytes; batch-1 GEMMs of 0.03-0.46 GFLOP are "
+                     "latency bound (tensor pipe 4-13 % active), see DESIGN.md section 5")
     roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["frac_of_tf32_peak"] = roof["achieved"] / roof["peak_tf32_equivalent"]
+    roof["whole_step_tflops"] = FLOP_PER_ITER * (args.steps / (ms_max * 1e-3)) / 1e12
     match = kernel_rooflines(dev)
     cpu_threads = torch.get_num_threads()
     cpu_its, cpu_dt = oracle_iters_per_sec(model, loss_fn, payload, shared, true, cfg, "cpu", 2, args.cpu_steps)
@@ -316,7 +386,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--backend", default="simt", choices=["simt", "tc"])
+    ap.add_argument("--backend", default="tc", choices=["simt", "tc"])
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--eager-steps", type=int, default=60)

@@ -883,7 +883,7 @@ int bre_engine_set_option(bre_engine* e, const char* name, int64_t value) {
 // ---- stand-alone kernels --------------------------------------------------------------------------
 int bre_match_reduce(const float* G, const float* g, const float* chunk_weights, int64_t n, float mask_value,
                      double* sums5_host, void* stream) {
-  if (!G || !g || !sums5_host || n <= 0) { set_error("bre_match_reduce: bad arguments"); return BRE_ERR_INVALID; }
+  if (!G || !g || n <= 0) { set_error("bre_match_reduce: bad arguments"); return BRE_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   static thread_local Scalars* sc = nullptr;
   static thread_local double* partials = nullptr;
@@ -894,6 +894,7 @@ int bre_match_reduce(const float* G, const float* g, const float* chunk_weights,
     BRE_TRY(dev_alloc(&counter, 1));
   }
   BRE_TRY(launch_match_reduce(G, g, chunk_weights, n, mask_value, BRE_OBJ_COSINE, 1.f, 0.f, 0.f, false, sc, partials, counter, s));
+  if (sums5_host == nullptr) return BRE_OK;  // launch only (lets callers time / graph-capture the bare kernel)
   Scalars h;
   BRE_CUDA_CHECK(cudaMemcpyAsync(&h, sc, sizeof(h), cudaMemcpyDeviceToHost, s));
   BRE_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -942,6 +943,7 @@ int bre_conv_gemm(int32_t mode, int32_t backend, const float* a, const float* w,
     if (!igemm_tc_supported(g)) { set_error("tcgen05 back end does not cover this shape"); return BRE_ERR_UNSUPPORTED; }
     return launch_igemm_tc(g, s);
   }
+  if (backend == 2 && igemm_tc_supported(g)) return launch_igemm_tc(g, s);  // the engine's own dispatch rule
   return launch_igemm_simt(g, s);
 }
 

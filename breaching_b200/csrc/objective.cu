@@ -95,10 +95,20 @@ __global__ void __launch_bounds__(256) match_reduce_kernel(const float* __restri
       acc[0] += s0; acc[1] += s1; acc[2] += s2; acc[3] += s3; acc[4] += (double)w * s4;
     }
   }
+  // block reduction of the five sums with one barrier: warp shuffles, then [5][8] doubles through shared memory
+  __shared__ double wsum[5][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    const double t = block_sum(acc[k], scratch);
-    if (threadIdx.x == 0) partials[(long long)blockIdx.x * 5 + k] = t;
+    const double t = warp_sum(acc[k]);
+    if (lane == 0) wsum[k][warp] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += wsum[threadIdx.x][w];
+    partials[(long long)blockIdx.x * 5 + threadIdx.x] = t;
   }
   __threadfence();
   __syncthreads();
@@ -110,9 +120,20 @@ __global__ void __launch_bounds__(256) match_reduce_kernel(const float* __restri
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // last block: thread t sums the partials of blocks t, t + 256, ... (fixed assignment), then the same block reduction:
+  // launch-invariant summation order, three dependent memory round trips instead of gridDim.x
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    double t = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) t += __ldcg(partials + (long long)b * 5 + k);
+    t = warp_sum(t);
+    if (lane == 0) wsum[k][warp] = t;
+  }
+  __syncthreads();
   if (threadIdx.x < 5) {
     double t = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(partials + (long long)b * 5 + threadIdx.x);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += wsum[threadIdx.x][w];
     (&sc->dot)[threadIdx.x] = t;
   }
   __syncthreads();

@@ -201,7 +201,10 @@ def make_cfg(cfg_attack, noise_seed=0):
 class Engine:
     """One engine = one model replica + one trial state on one GPU."""
 
-    def __init__(self, model, input_shape, cfg_attack, device, noise_seed=0):
+    def __init__(self, model, input_shape, cfg_attack, device, noise_seed=0, backend=None):
+        """``backend``: "tc" (tcgen05 TF32 tensor-core GEMMs, default; shapes it does not cover run on the fp32 SIMT
+        kernels) or "simt" (fp32 CUDA-core GEMMs everywhere: bit-faithful fp32 products).  Default from
+        ``BRE_GEMM_BACKEND``."""
         self.lib = load_library()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -237,6 +240,11 @@ class Engine:
                                         prog.logits, ctypes.byref(self.ccfg), dev_index, ctypes.byref(handle))
         _check(self.lib, rc, "bre_engine_create")
         self.h = handle
+        backend = backend or os.environ.get("BRE_GEMM_BACKEND", "tc")
+        if backend not in ("tc", "simt"):
+            raise ValueError(f"unknown GEMM backend {backend}")
+        self.backend = backend
+        self.set_option("gemm_backend", 1 if backend == "tc" else 0)
         self.numel = 1
         for s in self.input_shape:
             self.numel *= s
@@ -386,16 +394,16 @@ class Engine:
 
 
 # ---- stand-alone kernels ---------------------------------------------------------------------------
-def match_reduce(G, g, chunk_weights=None, mask_value=-1.0):
+def match_reduce(G, g, chunk_weights=None, mask_value=-1.0, readback=True):
     lib = load_library()
     assert G.is_cuda and g.is_cuda and G.dtype == torch.float32 and G.is_contiguous() and g.is_contiguous()
     out = (ctypes.c_double * 5)()
     stream = torch.cuda.current_stream(G.device).cuda_stream
     with torch.cuda.device(G.device):
-        rc = lib.bre_match_reduce(_ptr(G), _ptr(g), _ptr(chunk_weights), G.numel(), float(mask_value), out,
-                                  ctypes.c_void_p(stream))
+        rc = lib.bre_match_reduce(_ptr(G), _ptr(g), _ptr(chunk_weights), G.numel(), float(mask_value),
+                                  out if readback else None, ctypes.c_void_p(stream))
     _check(lib, rc, "bre_match_reduce")
-    return list(out)
+    return list(out) if readback else None
 
 
 def total_variation(x, scale=0.1, inner_exp=1.0, outer_exp=1.0, eps=1e-8, double_opponents=False, grad=None):

@@ -155,7 +155,7 @@ int bre_engine_set_option(bre_engine* e, const char* name, int64_t value);
 /* ---- stand-alone kernels (each is also a stage of the engine; exposed for parity tests + rooflines) */
 /* Multi-tensor gradient-matching reduction (objectives.py:91-95,135-141,160-164,185-196).
  * G, g: device fp32 [n]; chunk_weights: device fp32 [ceil(n/1024)] or NULL.  sums5 (host, double):
- * <G,g>, |G|^2, |g|^2, sum (G-g)^2, sum w |G-g|.  */
+ * <G,g>, |G|^2, |g|^2, sum (G-g)^2, sum w |G-g|; NULL = launch only, no read-back (for timing the bare kernel).  */
 int bre_match_reduce(const float* G, const float* g, const float* chunk_weights, int64_t n, float mask_value,
                      double* sums5_host, void* stream);
 /* TotalVariation value + gradient (regularizers.py:130-147) for x [N,3,H,W] device fp32;
@@ -167,7 +167,8 @@ int bre_total_variation(const float* x, float* grad, int32_t N, int32_t H, int32
  * mode 0 fprop  : out[N,Ho,Wo,Co]  = conv(in[N,H,W,Ci], w[Co,R,S,Ci]) (+ conv(in2, w2) when in2 != NULL)
  * mode 1 dgrad  : din[N,H,W,Ci]    = conv^T(dout[N,Ho,Wo,Co], w) (+ conv^T(dout2, w2))
  * mode 2 wgrad  : dw[Co,R,S,Ci]    = sum_pixels dout (x) in
- * backend 0 = SIMT fp32, 1 = tcgen05 TF32 (where available, else BRE_ERR_UNSUPPORTED). */
+ * backend 0 = SIMT fp32, 1 = tcgen05 TF32 (where available, else BRE_ERR_UNSUPPORTED), 2 = the engine's dispatch
+ * (tcgen05 where the shape is covered, SIMT otherwise). */
 int bre_conv_gemm(int32_t mode, int32_t backend, const float* a, const float* w, const float* a2, const float* w2,
                   float* out, int32_t N, int32_t H, int32_t W, int32_t Ci, int32_t Co, int32_t R, int32_t S,
                   int32_t stride, int32_t pad, void* stream);

@@ -17,17 +17,15 @@ from breaching_b200.schedule import lr_table  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=3)
-ap.add_argument("--backend", default="simt")
+ap.add_argument("--backend", default="tc")
 ap.add_argument("--graph", type=int, default=0)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 model, loss_fn, payload, shared, true = synthetic.make_case("resnet18", "imagenet", batch=1, seed=233)
 cfg = get_attack_config("invertinggradients")
 meta = payload[0]["metadata"]
-eng = Engine(copy.deepcopy(model).to(dev).eval(), (1, 3, 224, 224), cfg, dev)
+eng = Engine(copy.deepcopy(model).to(dev).eval(), (1, 3, 224, 224), cfg, dev, backend=args.backend)
 eng.set_option("use_graph", args.graph)
-if args.backend == "tc":
-    eng.set_option("gemm_backend", 1)
 eng.load_model()
 eng.load_targets([g.to(dev) for g in shared[0]["gradients"]], true["labels"].to(dev), mean=meta.mean, std=meta.std)
 eng.begin_trial(torch.randn(1, 3, 224, 224, device=dev), lr_table(0.1, "step-lr", 0, 24000, 64))

@@ -21,9 +21,11 @@ def _relerr(a, b):
     return ((a.double().cpu() - b.double().cpu()).norm() / (b.double().cpu().norm() + 1e-30)).item()
 
 
-def _engine_for(model, cfg, shared, labels, meta, shape, features=None):
+def _engine_for(model, cfg, shared, labels, meta, shape, features=None, backend="simt"):
+    """fp32 SIMT back end unless a test asks for the tensor-core one: the tight fp32 tolerances below are about the
+    algorithm, the TF32 back end has its own tests with TF32 tolerances."""
     m = copy.deepcopy(model).to(DEV).eval()
-    eng = Engine(m, shape, cfg, DEV)
+    eng = Engine(m, shape, cfg, DEV, backend=backend)
     eng.load_model()
     tw = None
     if cfg.objective.type == "tag-euclidean":
@@ -225,8 +227,7 @@ def test_tcgen05_backend_closure_and_trajectory():
     orc = restate.TrialOracle(model.eval(), loss_fn, cfg, shared[0]["gradients"], true["labels"], dm, ds)
     x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(4))
     phi, _, raw, terms = orc.closure_gradient(x, 0, 0.1)
-    eng = _engine_for(model, cfg, shared, true["labels"], meta, (2, 3, 64, 64))
-    eng.set_option("gemm_backend", 1)
+    eng = _engine_for(model, cfg, shared, true["labels"], meta, (2, 3, 64, 64), backend="tc")
     val, grad = eng.objective_and_gradient(x.to(DEV))
     rel = _relerr(grad, raw)
     agree = (torch.sign(grad.cpu()) == torch.sign(raw)).float().mean().item()
