@@ -238,6 +238,7 @@ def product_arm(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     bbuild.build()
 
