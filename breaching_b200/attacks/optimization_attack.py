@@ -107,11 +107,11 @@ class OptimizationBasedAttacker:
     def _get_engine(self, rec_models, shared_data, labels):
         if len(rec_models) != 1:
             raise NotImplementedError("multiple model queries per attack are not implemented by the B200 engine")
-        if shared_data[0]["metadata"]["local_hyperparams"] is not None:
-            raise NotImplementedError("FedAvg multi-step updates (local_hyperparams) are not implemented by the B200 engine yet")
+        local = shared_data[0]["metadata"]["local_hyperparams"]
         model = rec_models[0]
         n = shared_data[0]["metadata"]["num_data_points"]
-        shape = (n, *self.data_shape)
+        # FedAvg (objectives.py:48-72): the layer program is compiled for one local step's batch
+        shape = (n if local is None else int(local["data_per_step"]), *self.data_shape)
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if cfg_get(self.cfg.optim, "langevin_noise", 0.0) else 0
         if self._engine is not None:
             self._engine.close()
@@ -130,7 +130,10 @@ class OptimizationBasedAttacker:
                 tw = torch.ones(L)
         mean = self.dm.flatten() if self.dm.numel() > 1 else self.dm.flatten().expand(self.data_shape[0])
         std = self.ds.flatten() if self.ds.numel() > 1 else self.ds.flatten().expand(self.data_shape[0])
-        eng.load_targets(shared_data[0]["gradients"], labels, mean=mean, std=std, tensor_weights=tw)
+        step_labels = labels if local is None else local["labels"][0]
+        eng.load_targets(shared_data[0]["gradients"], step_labels, mean=mean, std=std, tensor_weights=tw)
+        if local is not None:
+            eng.set_local_steps(n, int(local["steps"]), float(local["lr"]), [l for l in local["labels"][: int(local["steps"])]])
         if any(k == "features" for k, _ in self.regularizers):
             eng.load_feature_targets(host.measured_features(shared_data, labels)[0])
         self._engine = eng

@@ -119,6 +119,26 @@ struct bre_engine {
   int* gemm_counters2 = nullptr;
   float* red_partials2 = nullptr;
   int* red_counters2 = nullptr;
+  // FedAvg / multi-step local updates (objectives.py:48-72): K forward+backward passes at W_0 .. W_{K-1}, the matched
+  // quantity is W_K - W_0; the adjoint is carried back over the steps with Hessian-vector products (tangent wgrads).
+  struct StepBufs {
+    std::vector<float*> val, d;
+    std::vector<int*> idx;
+    std::vector<float*> bn_scale, bn_shift;
+    float* p = nullptr; float* loss_n = nullptr; long long* labels = nullptr;
+  };
+  int ms_steps = 0;                 // 0 = single gradient (objectives.py:40-46)
+  float ms_lr = 0.f;
+  std::vector<float*> ms_W;         // K + 1 parameter arenas, ms_W[0] = W
+  std::vector<StepBufs> ms_bufs;    // per-step saved state (step 0 = the default buffers)
+  std::vector<long long> ms_offset; // element offset of each step's candidate slice
+  float* ms_D = nullptr;            // W_K - W_0
+  float* gradx_step = nullptr;      // tangent input gradient of one step (program batch)
+  float* W0 = nullptr;
+  struct BnPrep { int gamma_off, beta_off, C; const float* inv; const float* nrm; float* scale; float* shift; };
+  std::vector<BnPrep*> ms_bnprep_dev;  // per step (k >= 1): device table for the batched BN-constant refresh
+  int n_bn_layers = 0;
+  bool want_tangent_G = false;
   // execution
   bool use_graph = true;
   int gemm_backend = 0;  // 0 = SIMT fp32, 1 = tcgen05 TF32 where supported
@@ -344,6 +364,7 @@ struct bre_engine {
   }
 
   int sweep_tangent_backward() {
+    bool forked = false;
     const bre_tensor_desc& lt = td(logits);
     BRE_LAUNCH(launch_ce_tan_bwd(p, t[logits].tval, lt.N, lt.C, t[logits].td, stream));
     const bool di = cfg.di_scale > 0.f && n_di > 0;
@@ -359,9 +380,29 @@ struct bre_engine {
           a.nsrc = 2;
           a.act[0] = t[op.tout].td; a.wgt[0] = Wp(op.w);
           a.act[1] = t[op.tout].d; a.wgt[1] = Vp(op.w);
-          a.out = op.tin == 0 ? gradx : t[op.tin].td;
+          a.out = op.tin == 0 ? t[0].td : t[op.tin].td;
           a.accumulate = op.tin == 0 ? 0 : op.acc_in;
           BRE_LAUNCH(gemm(a));
+          if (want_tangent_G) {
+            // tangent of the weight gradient: wgrad(a, delta_dot) + wgrad(a_dot, delta)   (a_dot = 0 for the candidate)
+            GemmArgs w = conv_geom(op);
+            w.mode = GEMM_WGRAD;
+            w.act[0] = t[op.tin].val; w.wgt[0] = t[op.tout].td;
+            if (op.tin != 0) { w.nsrc = 2; w.act[1] = t[op.tin].tval; w.wgt[1] = t[op.tout].d; }
+            w.out = Gp(op.w);
+            cudaStream_t wst = stream;
+            if (overlap_wgrad && side != nullptr) {
+              BRE_CUDA_CHECK(cudaEventRecord(ev_fork[i], stream));
+              BRE_CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork[i], 0));
+              w.ws = ws2; w.counters = gemm_counters2;
+              wst = side;
+              forked = true;
+            }
+            BRE_LAUNCH(gemm_on(w, wst));
+            if (op.b >= 0)
+              BRE_LAUNCH(launch_channel_sum(t[op.tout].td, Pout, to.C, Gp(op.b), wst == side ? red_partials2 : red_partials,
+                                            wst == side ? red_counters2 : red_counters, wst));
+          }
           if ((int)i == feat_op && cfg.feat_scale > 0.f && feat_measured != nullptr)
             BRE_LAUNCH(launch_feature_reg(t[op.tin].val, feat_measured, t[op.tin].td, feat_numel, cfg.feat_scale, sc, stream));
           break;
@@ -375,6 +416,8 @@ struct bre_engine {
           if (di && op.has_bn) { const BnBuf& b = bn[op.bn_buffer]; a.di_cm = b.di_cm; a.di_cv = b.di_cv; a.di_mean = b.di_mean; }
           a.tdin = t[op.tin].td; a.acc_in = op.acc_in != 0;
           a.tdres = op.res >= 0 ? t[op.res].td : nullptr; a.acc_res = op.acc_res != 0;
+          a.tin = nullptr; a.tg_gamma = a.tg_beta = nullptr; a.partials = red_partials; a.counters = red_counters;
+          if (want_tangent_G && op.has_bn) { a.tin = t[op.tin].tval; a.tg_gamma = Gp(op.gamma); a.tg_beta = Gp(op.beta); }
           BRE_LAUNCH(launch_bnact_tan_bwd(a, stream));
           break;
         }
@@ -389,6 +432,62 @@ struct bre_engine {
         default: break;
       }
     }
+    if (forked) {
+      BRE_CUDA_CHECK(cudaEventRecord(ev_join, side));
+      BRE_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));
+    }
+    return 0;
+  }
+
+  // ---- multi-step (FedAvg) ------------------------------------------------------------------------------------
+  void bind_step(int k) {
+    const StepBufs& b = ms_bufs[k];
+    for (size_t i = 1; i < t.size(); ++i) { t[i].val = b.val[i]; t[i].d = b.d[i]; }
+    pool_idx = b.idx;
+    p = b.p; loss_n = b.loss_n; labels = b.labels;
+    W = ms_W[k];
+    for (int j = 0; j < n_bn_layers; ++j) { bn[j].scale = b.bn_scale[j]; bn[j].shift = b.bn_shift[j]; }
+    t[0].val = x + ms_offset[k];
+    t[0].td = gradx_step;
+  }
+  int refresh_bn_constants(int k);   // defined below (needs a kernel)
+
+  int multistep_forward() {
+    for (int k = 0; k < ms_steps; ++k) {
+      bind_step(k);
+      if (k > 0) BRE_TRY(refresh_bn_constants(k));
+      BRE_TRY(sweep_forward());
+      BRE_TRY(sweep_backward());
+      // W_{k+1} = W_k - lr * grad (:63-66).  The matched "gradient" W_K - W_0 (:69) is accumulated directly,
+      // D_{k+1} = D_k - lr * grad, instead of being formed as a difference of two nearly equal parameter vectors.
+      BRE_LAUNCH(launch_axpby(ms_W[k], G, -ms_lr, ms_W[k + 1], P_pad, stream));
+      if (k == 0) BRE_CUDA_CHECK(cudaMemsetAsync(ms_D, 0, P_pad * sizeof(float), stream));
+      BRE_LAUNCH(launch_axpby(ms_D, G, -ms_lr, ms_D, P_pad, stream));
+    }
+    return 0;
+  }
+
+  int evaluate_multistep() {
+    BRE_CUDA_CHECK(cudaMemsetAsync(gradx, 0, nx * sizeof(float), stream));
+    BRE_TRY(multistep_forward());
+    const float mv = cfg.objective == BRE_OBJ_MASKED_COSINE ? cfg.mask_value : -1.f;
+    BRE_LAUNCH(launch_match_reduce(ms_D, g, chunk_w, P_pad, mv, cfg.objective, cfg.obj_scale, cfg.tag_scale, cfg.angular_fudge, true, sc,
+                                   dpartials, dcounter, stream));
+    BRE_LAUNCH(launch_make_v(ms_D, g, chunk_w, V, P_pad, mv, sc, stream));          // adjoint of W_K
+    const long long nstep = t[0].numel;
+    for (int k = ms_steps - 1; k >= 0; --k) {
+      bind_step(k);
+      want_tangent_G = k > 0;
+      BRE_TRY(sweep_tangent_forward());
+      const int rc = sweep_tangent_backward();
+      want_tangent_G = false;
+      if (rc != 0) return rc;
+      // d Phi / d x_k = -lr * d/d eps grad_x L(x_k, W_{k-1} + eps u_k)
+      BRE_LAUNCH(launch_axpy(gradx_step, gradx + ms_offset[k], -ms_lr, nstep, stream));
+      if (k > 0) BRE_LAUNCH(launch_axpby(V, G, -ms_lr, V, P_pad, stream));           // u_{k-1} = u_k - lr * H_k u_k
+    }
+    bind_step(0);
+    BRE_TRY(priors());
     return 0;
   }
 
@@ -404,6 +503,7 @@ struct bre_engine {
 
   // objective + its gradient w.r.t. the candidate (closure body, optimization_based_attack.py:146-165)
   int evaluate() {
+    if (ms_steps > 0) return evaluate_multistep();
     BRE_TRY(sweep_forward());
     BRE_TRY(sweep_backward());
     BRE_TRY(reduce_objective(cfg.objective, cfg.obj_scale, cfg.mask_value, true));
@@ -431,6 +531,25 @@ struct bre_engine {
     return 0;
   }
 };
+
+namespace {
+__global__ void bn_refresh_kernel(const bre_engine::BnPrep* table, const float* W) {
+  pdl_prologue();
+  const bre_engine::BnPrep e = table[blockIdx.x];
+  for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+    const float gmm = W[e.gamma_off + c];
+    e.scale[c] = gmm * e.inv[c];
+    e.shift[c] = fmaf(gmm, e.nrm[c], W[e.beta_off + c]);
+  }
+}
+}  // namespace
+
+int bre_engine::refresh_bn_constants(int k) {
+  if (n_bn_layers == 0) return 0;
+  BRE_KLAUNCH(bn_refresh_kernel, n_bn_layers, 128, 0, stream, (const BnPrep*)ms_bnprep_dev[k], (const float*)ms_W[k]);
+  ++launch_count;
+  return 0;
+}
 
 // ======================================================================================================
 // C ABI
@@ -666,6 +785,77 @@ int bre_engine_load_feature_targets(bre_engine* e, const float* measured, int64_
   return BRE_OK;
 }
 
+int bre_engine_set_local_steps(bre_engine* e, int32_t total_images, int32_t steps, float lr, const int64_t* labels) {
+  if (!e || steps < 1 || total_images < 1 || !labels) { set_error("bre_engine_set_local_steps: bad arguments"); return BRE_ERR_INVALID; }
+  if (!e->model_loaded) { set_error("load the model first"); return BRE_ERR_STATE; }
+  if (e->ms_steps > 0) { set_error("local steps already configured"); return BRE_ERR_STATE; }
+  if (e->cfg.task_regularization != 0.f || e->cfg.di_scale > 0.f || e->cfg.feat_scale > 0.f) {
+    set_error("task regularisation / DeepInversion / feature priors are not implemented for multi-step updates "
+              "(the reference crashes on the latter two, SURVEY.md section 0 fact 9)");
+    return BRE_ERR_UNSUPPORTED;
+  }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  const int dps = e->t[0].desc.N;
+  const long long per_image = (long long)e->xC * e->xH * e->xW;
+  e->ms_offset.resize(steps);
+  int seen = 0;
+  for (int k = 0; k < steps; ++k) {               // objectives.py:56-58
+    if (seen + dps > total_images) { set_error("a local step would read a ragged candidate slice (unsupported)"); return BRE_ERR_UNSUPPORTED; }
+    e->ms_offset[k] = seen * per_image;
+    seen = (seen + dps) % total_images;
+  }
+  // candidate-sized state for all images
+  e->xN = total_images;
+  e->nx = total_images * per_image;
+  int rc = 0;
+  rc |= e->alloc(&e->x, e->nx); rc |= e->alloc(&e->gradx, e->nx); rc |= e->alloc(&e->gradx_task, e->nx);
+  rc |= e->alloc(&e->m, e->nx); rc |= e->alloc(&e->v, e->nx); rc |= e->alloc(&e->best, e->nx);
+  rc |= e->alloc(&e->gradx_step, e->t[0].numel);
+  rc |= e->alloc(&e->ms_D, e->P_pad);
+  e->ms_W.assign(steps + 1, nullptr);
+  e->ms_W[0] = e->W;
+  e->W0 = e->W;
+  for (int k = 1; k <= steps; ++k) rc |= e->alloc(&e->ms_W[k], e->P_pad);
+  e->ms_bufs.resize(steps);
+  e->n_bn_layers = (int)e->bn.size();
+  e->ms_bnprep_dev.assign(steps, nullptr);
+  const int nlab = e->n_labels;
+  for (int k = 0; k < steps; ++k) {
+    bre_engine::StepBufs& b = e->ms_bufs[k];
+    b.val.assign(e->t.size(), nullptr); b.d.assign(e->t.size(), nullptr); b.idx.assign(e->ops.size(), nullptr);
+    b.bn_scale.assign(e->bn.size(), nullptr); b.bn_shift.assign(e->bn.size(), nullptr);
+    if (k == 0) {
+      for (size_t i = 1; i < e->t.size(); ++i) { b.val[i] = e->t[i].val; b.d[i] = e->t[i].d; }
+      b.idx = e->pool_idx; b.p = e->p; b.loss_n = e->loss_n; b.labels = e->labels;
+      for (size_t j = 0; j < e->bn.size(); ++j) { b.bn_scale[j] = e->bn[j].scale; b.bn_shift[j] = e->bn[j].shift; }
+    } else {
+      for (size_t i = 1; i < e->t.size(); ++i) { rc |= e->alloc(&b.val[i], e->t[i].numel); rc |= e->alloc(&b.d[i], e->t[i].numel); }
+      for (size_t i = 0; i < e->ops.size(); ++i)
+        if (e->ops[i].kind == BRE_OP_MAXPOOL) rc |= e->alloc(&b.idx[i], e->t[e->ops[i].tout].numel);
+      const bre_tensor_desc& lt = e->t[e->logits].desc;
+      rc |= e->alloc(&b.p, (long long)lt.N * lt.C); rc |= e->alloc(&b.loss_n, lt.N); rc |= e->alloc(&b.labels, lt.N);
+      for (size_t j = 0; j < e->bn.size(); ++j) { rc |= e->alloc(&b.bn_scale[j], e->bn[j].C); rc |= e->alloc(&b.bn_shift[j], e->bn[j].C); }
+      std::vector<bre_engine::BnPrep> table;
+      for (const bre_op_desc& op : e->ops) {
+        if (op.kind != BRE_OP_BNACT || !op.has_bn) continue;
+        const BnBuf& bb = e->bn[op.bn_buffer];
+        table.push_back({(int)e->params[op.gamma].off, (int)e->params[op.beta].off, bb.C, bb.inv, bb.nrm, b.bn_scale[op.bn_buffer],
+                         b.bn_shift[op.bn_buffer]});
+      }
+      rc |= e->alloc(&e->ms_bnprep_dev[k], (long long)table.size());
+      if (rc == 0 && !table.empty())
+        BRE_CUDA_CHECK(cudaMemcpy(e->ms_bnprep_dev[k], table.data(), table.size() * sizeof(bre_engine::BnPrep), cudaMemcpyHostToDevice));
+    }
+    if (rc != 0) return BRE_ERR_CUDA;
+    BRE_CUDA_CHECK(cudaMemcpy(b.labels, labels + (long long)k * nlab, nlab * sizeof(int64_t), cudaMemcpyDefault));
+  }
+  e->ms_steps = steps;
+  e->ms_lr = lr;
+  e->bind_step(0);
+  e->graph_ready = false;
+  return BRE_OK;
+}
+
 static int reset_trial_state(bre_engine* e) {
   Scalars h;
   memset(&h, 0, sizeof(h));
@@ -792,9 +982,16 @@ int bre_engine_score(bre_engine* e, const float* candidate, int32_t scoring, dou
   if (!e->model_loaded || !e->targets_loaded) { set_error("load model and targets first"); return BRE_ERR_STATE; }
   BRE_CUDA_CHECK(cudaSetDevice(e->device));
   BRE_CUDA_CHECK(cudaMemcpyAsync(e->x, candidate, e->nx * sizeof(float), cudaMemcpyDefault, e->stream));
-  BRE_TRY(e->sweep_forward());
-  BRE_TRY(e->sweep_backward());
-  BRE_TRY(e->reduce_objective(scoring, 1.0f, -1.f, true));
+  if (e->ms_steps > 0) {
+    BRE_TRY(e->multistep_forward());
+    BRE_TRY(launch_match_reduce(e->ms_D, e->g, e->chunk_w, e->P_pad, -1.f, scoring, 1.0f, e->cfg.tag_scale, e->cfg.angular_fudge, true,
+                                e->sc, e->dpartials, e->dcounter, e->stream));
+    e->bind_step(0);
+  } else {
+    BRE_TRY(e->sweep_forward());
+    BRE_TRY(e->sweep_backward());
+    BRE_TRY(e->reduce_objective(scoring, 1.0f, -1.f, true));
+  }
   Scalars h;
   BRE_TRY(read_scalars(e, &h));
   const double s = (double)(float)h.match;

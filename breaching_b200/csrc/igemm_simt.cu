@@ -527,7 +527,7 @@ int launch_igemm_simt(const GemmArgs& a, cudaStream_t stream) {
   gemm_dims(a, d.M, d.Nc, d.K);
   const ConvGeom& g = a.g;
   if (d.M <= 0 || d.Nc <= 0 || d.K <= 0) { set_error("igemm: empty problem"); return -1; }
-  if (a.nsrc < 1 || a.nsrc > 2 || (a.nsrc == 2 && a.mode == GEMM_WGRAD)) { set_error("igemm: bad nsrc"); return -1; }
+  if (a.nsrc < 1 || a.nsrc > 2) { set_error("igemm: bad nsrc"); return -1; }
   if (a.mode == GEMM_DGRAD && g.Ci <= 4 && g.Co <= 16 * SC_KCH && g.H <= 65535 && g.N <= 65535 &&
       (size_t)a.nsrc * ((g.R + g.stride - 1) / g.stride) * g.S * g.Co * g.Ci * 4 <= 200 * 1024)
     return launch_dgrad_small_ci(a, stream);

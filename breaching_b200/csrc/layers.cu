@@ -164,6 +164,45 @@ __global__ void bnact_tan_bwd_kernel(BnActTanBwdArgs a, long long total) {
   }
 }
 
+// slab-mapped variant of the tangent backward that also reduces the tangents of the BN parameter gradients
+__global__ void bnact_tan_bwd_g_kernel(BnActTanBwdArgs a, long long pps, int Cpad) {
+  pdl_prologue();
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cv = c < a.C;
+  const long long p0 = blockIdx.y * pps;
+  const long long p1 = (p0 + pps < a.P) ? p0 + pps : a.P;
+  float v[2] = {0.f, 0.f};
+  float inv = 0.f, nrm = 0.f, scale = 1.f, vg = 0.f;
+  if (cv) { inv = __ldg(a.bn.inv + c); nrm = __ldg(a.bn.nrm + c); scale = __ldg(a.bn.scale + c); vg = __ldg(a.v_gamma + c); }
+  if (cv) {
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      const long long o = p * a.C + c;
+      float tdu = a.tdout[o], du = a.dout[o];
+      if (a.relu && !(a.out[o] > 0.f)) { tdu = 0.f; du = 0.f; }
+      const float xhat = fmaf(a.in[o], inv, nrm);
+      const float tz = a.tin != nullptr ? a.tin[o] : 0.f;
+      v[0] += fmaf(tdu, xhat, du * tz * inv);
+      v[1] += tdu;
+      const float tdi = fmaf(scale, tdu, vg * inv * du);
+      if (a.tdin != nullptr) a.tdin[o] = a.acc_in ? a.tdin[o] + tdi : tdi;
+      if (a.tdres != nullptr) a.tdres[o] = a.acc_res ? a.tdres[o] + tdu : tdu;
+    }
+  }
+  float tot[2];
+  if (slab_reduce<2>(v, a.partials, a.counters, Cpad, tot) && cv) {
+    a.tg_gamma[c] = tot[0];
+    a.tg_beta[c] = tot[1];
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float alpha, float* __restrict__ out, long long n4) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i), b = __ldg(reinterpret_cast<const float4*>(y) + i);
+    reinterpret_cast<float4*>(out)[i] = make_float4(fmaf(alpha, b.x, a.x), fmaf(alpha, b.y, a.y), fmaf(alpha, b.z, a.z), fmaf(alpha, b.w, a.w));
+  }
+}
+
 __global__ void channel_sum_kernel(const float* __restrict__ x, long long P, int C, float* out, float* partials,
                                    int* counters, long long pps, int Cpad) {
   pdl_prologue();
@@ -389,7 +428,20 @@ int launch_bnact_tan_fwd(const BnActTanFwdArgs& a, cudaStream_t s) {
   return 0;
 }
 
+int launch_axpby(const float* x, const float* y, float alpha, float* out, long long n, cudaStream_t s) {
+  if (n % 4 != 0) { set_error("axpby: length must be a multiple of 4"); return -1; }
+  BRE_KLAUNCH(axpby_kernel, ew_grid(n / 4), kEwThreads, 0, s, x, y, alpha, out, n / 4);
+  return 0;
+}
+
 int launch_bnact_tan_bwd(const BnActTanBwdArgs& a, cudaStream_t s) {
+  if (a.has_bn && a.tg_gamma != nullptr) {
+    dim3 grid, block;
+    long long pps;
+    slab_grid(a.P, a.C, grid, block, pps);
+    BRE_KLAUNCH(bnact_tan_bwd_g_kernel, grid, block, 0, s, a, pps, (int)(grid.x * 32));
+    return 0;
+  }
   const long long total = a.P * a.C;
   BRE_KLAUNCH(bnact_tan_bwd_kernel, ew_grid(total), kEwThreads, 0, s, a, total);
   BRE_CHECK_LAUNCH();

@@ -53,8 +53,13 @@ struct BnActTanBwdArgs {
   const float* di_cm; const float* di_cv; const float* di_mean;  // DeepInversion adjoint (may be null)
   float* tdin; bool acc_in;
   float* tdres; bool acc_res;
+  // FedAvg (multi-step) only: tangent of the BN parameter gradients, needed for the Hessian-vector product that carries
+  // the adjoint across local steps: tg_gamma = sum(tdu * xhat + du * tin * inv), tg_beta = sum(tdu)   (null = not needed)
+  const float* tin; float* tg_gamma; float* tg_beta; float* partials; int* counters;
 };
 int launch_bnact_tan_bwd(const BnActTanBwdArgs& a, cudaStream_t s);
+// out[i] = x[i] + alpha * y[i]   (parameter-arena updates of the local-step recursion)
+int launch_axpby(const float* x, const float* y, float alpha, float* out, long long n, cudaStream_t s);
 
 // per-channel column sum: out[c] = sum_p x[p][c]   (conv / linear bias gradient)
 int launch_channel_sum(const float* x, long long P, int C, float* out, float* partials, int* counters, cudaStream_t s);

@@ -67,7 +67,7 @@ OPTIMIZERS = {  # reference common.py:6-17 -> (kind, beta1, beta2, eps, weight_d
 
 EXPORTS = [
     "bre_engine_create", "bre_engine_destroy", "bre_engine_load_model", "bre_engine_load_targets",
-    "bre_engine_load_feature_targets", "bre_engine_begin_trial", "bre_engine_run", "bre_engine_run_timed", "bre_engine_sync",
+    "bre_engine_load_feature_targets", "bre_engine_set_local_steps", "bre_engine_begin_trial", "bre_engine_run", "bre_engine_run_timed", "bre_engine_sync",
     "bre_engine_status", "bre_engine_read_history", "bre_engine_get_best", "bre_engine_get_candidate",
     "bre_engine_score", "bre_engine_objective_and_gradient", "bre_engine_last_terms", "bre_engine_debug_param",
     "bre_engine_debug_tensor", "bre_engine_launches_per_iteration", "bre_engine_set_option", "bre_match_reduce",
@@ -96,6 +96,7 @@ def load_library(path=None):
     lib.bre_engine_load_model.argtypes = [vp, P(vp), i32, P(vp), P(vp), i32]
     lib.bre_engine_load_targets.argtypes = [vp, P(vp), i32, vp, vp, i32, vp, vp, i32]
     lib.bre_engine_load_feature_targets.argtypes = [vp, vp, i64]
+    lib.bre_engine_set_local_steps.argtypes = [vp, i32, i32, f32, vp]
     lib.bre_engine_begin_trial.argtypes = [vp, vp, vp, i32]
     lib.bre_engine_run.argtypes = [vp, i32]
     lib.bre_engine_sync.argtypes = [vp]
@@ -299,6 +300,18 @@ class Engine:
         if m.is_cuda:
             torch.cuda.synchronize(self.device)
         _check(self.lib, self.lib.bre_engine_load_feature_targets(self.h, _ptr(m), m.numel()), "bre_engine_load_feature_targets")
+
+    def set_local_steps(self, total_images, steps, lr, labels_per_step):
+        """FedAvg: ``labels_per_step`` = list of ``steps`` LongTensors of length ``data_per_step`` (the program batch)."""
+        labels = torch.cat([l.detach().to(torch.int64).flatten().cpu() for l in labels_per_step]).contiguous()
+        if labels.numel() != steps * self.input_shape[0]:
+            raise EngineError("labels_per_step must hold data_per_step labels for every local step")
+        _check(self.lib, self.lib.bre_engine_set_local_steps(self.h, int(total_images), int(steps), float(lr), _ptr(labels)),
+               "bre_engine_set_local_steps")
+        self.input_shape = (int(total_images), *self.input_shape[1:])
+        self.numel = 1
+        for s_ in self.input_shape:
+            self.numel *= s_
 
     def begin_trial(self, candidate, lr_table):
         cand = _f32c(candidate)

@@ -148,3 +148,43 @@ def make_case(model_name="resnet18", data="imagenet", batch=1, seed=233, provide
     ]
     true_user_data = dict(data=x, labels=y)
     return model, loss_fn, server_payload, shared_data, true_user_data
+
+
+def make_fedavg_case(model_name="resnet18", data="imagenet", num_data_points=4, steps=4, data_per_step=1, lr=1e-3, seed=233,
+                     bn_random=False, image_size=None, classes=None):
+    """Multi-step user (cases/users.py:336-413 ``UserMultiStep`` with ``local_updates.yaml``): ``steps`` SGD steps of size
+    ``lr`` on consecutive slices of ``data_per_step`` images, eval-mode BN with the server's public buffers; the shared
+    "gradient" is ``W_local - W_server`` and the local hyper-parameters (incl. the per-step labels) are shared."""
+    import copy
+
+    base = dict(IMAGENET if data == "imagenet" else CIFAR10)
+    if image_size is not None:
+        base["shape"] = (3, image_size, image_size)
+    if classes is not None:
+        base["classes"] = classes
+    meta = DataConfig(**base)
+    model = build_model(model_name, meta.classes, seed=seed)
+    if bn_random:
+        randomize_bn(model, seed + 1)
+    model.eval()
+    loss_fn = torch.nn.CrossEntropyLoss()
+    gen = torch.Generator().manual_seed(seed + 7)
+    x = torch.randn((num_data_points, *meta.shape), generator=gen)
+    y = torch.randperm(meta.classes, generator=gen)[:num_data_points]
+    server_params = [p.detach().clone() for p in model.parameters()]
+    local = copy.deepcopy(model).eval()
+    optimizer = torch.optim.SGD(local.parameters(), lr=lr)
+    seen, label_list = 0, []
+    for _ in range(steps):
+        xs, ys = x[seen: seen + data_per_step], y[seen: seen + data_per_step]
+        seen = (seen + data_per_step) % num_data_points
+        label_list.append(ys.sort()[0])
+        optimizer.zero_grad()
+        loss_fn(local(xs), ys).backward()
+        optimizer.step()
+    shared_grads = [(pl - ps).clone().detach() for pl, ps in zip(local.parameters(), server_params)]
+    server_payload = [dict(parameters=[p for p in model.parameters()], buffers=[b for b in model.buffers()], metadata=meta)]
+    shared_data = [dict(gradients=shared_grads, buffers=None,
+                        metadata=dict(num_data_points=num_data_points, labels=None,
+                                      local_hyperparams=dict(lr=lr, steps=steps, data_per_step=data_per_step, labels=label_list)))]
+    return model, loss_fn, server_payload, shared_data, dict(data=x, labels=y)

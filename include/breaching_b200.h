@@ -110,6 +110,12 @@ int bre_engine_load_targets(bre_engine* e, const float* const* grads, int32_t n_
                             const float* tensor_weights, const int64_t* labels, int32_t n_labels,
                             const float* mean, const float* std, int32_t n_channels);
 
+/* FedAvg / multi-step local updates (objectives.py:48-72, users.py:336-413): the user ran `steps` SGD steps of size `lr`,
+ * step k on the candidate slice [k*B mod total_images, ... + B) (B = batch of the layer program) with labels
+ * labels[k*B .. (k+1)*B); the matched quantity becomes W_K - W_0.  Re-sizes the candidate state to `total_images`.
+ * Call after bre_engine_load_model / load_targets and before bre_engine_begin_trial.  labels: device or host. */
+int bre_engine_set_local_steps(bre_engine* e, int32_t total_images, int32_t steps, float lr, const int64_t* labels);
+
 /* Measured features for the `features` regulariser (regularizers.py:31-43): [N, F] fp32, device or host. */
 int bre_engine_load_feature_targets(bre_engine* e, const float* measured, int64_t numel);
 

@@ -326,8 +326,9 @@ class TrialOracle:
     (``base_attack.py:169-212``: parameters and buffers loaded, ``.eval()`` when buffers are known).
     """
 
-    def __init__(self, model, loss_fn, cfg, gradients, labels, dm, ds, dtype=torch.float32):
+    def __init__(self, model, loss_fn, cfg, gradients, labels, dm, ds, dtype=torch.float32, local_hyperparams=None):
         self.model, self.loss_fn, self.cfg = model, loss_fn, cfg
+        self.local = local_hyperparams
         self.g = [t.detach().to(dtype) for t in gradients]
         self.labels = labels
         self.dm, self.ds = dm, ds
@@ -356,10 +357,30 @@ class TrialOracle:
 
     # objectives.py:26-46
     def param_gradient(self, x, create_graph):
+        if self.local is not None:
+            return self._multi_step_difference(x, create_graph)
         self.model.zero_grad()
         task_loss = self.loss_fn(self.model(x), self.labels)
         G = torch.autograd.grad(task_loss, list(self.model.parameters()), create_graph=create_graph)
         return G, task_loss
+
+    # objectives.py:48-72 (FedAvg): K local SGD steps kept in the graph; the "gradient" is W_K - W_0.  The reference
+    # deep-copies the module through its vendored make_functional_with_buffers; torch.func.functional_call evaluates
+    # the same module with substituted parameters.
+    def _multi_step_difference(self, x, create_graph):
+        names = [n for n, _ in self.model.named_parameters()]
+        params = [p.detach().clone().requires_grad_(True) for p in self.model.parameters()]
+        initial = [p.clone() for p in params]
+        buffers = dict(self.model.named_buffers())
+        seen, task_loss = 0, None
+        for i in range(self.local["steps"]):
+            data = x[seen: seen + self.local["data_per_step"]]
+            seen = (seen + self.local["data_per_step"]) % x.shape[0]
+            out = torch.func.functional_call(self.model, ({n: p for n, p in zip(names, params)}, buffers), (data,))
+            task_loss = self.loss_fn(out, self.local["labels"][i])
+            grads = torch.autograd.grad(task_loss, params, create_graph=create_graph)
+            params = [p - self.local["lr"] * g for p, g in zip(params, grads)]
+        return [pl - p0 for pl, p0 in zip(params, initial)], task_loss
 
     def objective_terms(self, x):
         o = self.cfg["objective"]

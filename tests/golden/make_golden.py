@@ -50,8 +50,22 @@ CASES = {
 }
 
 
+FEDAVG_CASES = {
+    # FedAvg multi-step updates (objectives.py:48-72).  `features` / `deep_inversion` crash in the reference together with
+    # FedAvg, so the fixture uses the `modern` preset with the features prior switched off.
+    "fedavg_convnet": (dict(model_name="convnet-tiny", data="cifar", num_data_points=4, steps=3, data_per_step=2, lr=0.05, seed=4,
+                            bn_random=True), "modern", {"regularization.features.scale": 0.0}, 6),
+    "fedavg_resnet18": (dict(model_name="resnet18", data="imagenet", num_data_points=4, steps=4, data_per_step=1, lr=0.01, seed=6,
+                             bn_random=True, image_size=64, classes=10), "modern", {"regularization.features.scale": 0.0}, 4),
+}
+
+
 def run_reference(ref, case_kwargs, attack, overrides, iters):
-    model, loss_fn, payload, shared, true = synthetic.make_case(**case_kwargs)
+    if "steps" in case_kwargs:
+        model, loss_fn, payload, shared, true = synthetic.make_fedavg_case(**case_kwargs)
+    else:
+        model, loss_fn, payload, shared, true = synthetic.make_case(**case_kwargs)
+    local_hyperparams = shared[0]["metadata"]["local_hyperparams"]
     cfg = refshim.load_reference_attack_cfg(attack, overrides)
     setup = dict(device=torch.device("cpu"), dtype=torch.float)
     attacker = ref.attacks.prepare_attack(model, loss_fn, cfg, setup)
@@ -59,7 +73,7 @@ def run_reference(ref, case_kwargs, attack, overrides, iters):
     rec_models, labels, stats = attacker.prepare_attack(payload, shared_ref)
     for r in attacker.regularizers:
         r.initialize(rec_models, shared_ref, labels)
-    attacker.objective.initialize(attacker.loss_fn, attacker.cfg.impl, None)
+    attacker.objective.initialize(attacker.loss_fn, attacker.cfg.impl, local_hyperparams)
     n = shared[0]["metadata"]["num_data_points"]
     gen = torch.Generator().manual_seed(case_kwargs["seed"] + 1000)
     x0 = torch.randn([n, *attacker.data_shape], generator=gen)
@@ -73,7 +87,7 @@ def run_reference(ref, case_kwargs, attack, overrides, iters):
     att_raw.dm, att_raw.ds, att_raw.data_shape = attacker.dm, attacker.ds, attacker.data_shape
     for r in att_raw.regularizers:
         r.initialize(rec_models, shared_ref, labels)
-    att_raw.objective.initialize(att_raw.loss_fn, att_raw.cfg.impl, None)
+    att_raw.objective.initialize(att_raw.loss_fn, att_raw.cfg.impl, local_hyperparams)
     cand = att_raw._initialize_data([n, *attacker.data_shape])
     cand.data = x0.clone()
     opt_raw, _ = att_raw._init_optimizer([cand])
@@ -170,7 +184,7 @@ def config_fixtures():
 def main():
     ref = refshim.import_reference()
     torch.manual_seed(0)
-    for name, (case_kwargs, attack, overrides, iters) in CASES.items():
+    for name, (case_kwargs, attack, overrides, iters) in {**CASES, **FEDAVG_CASES}.items():
         fx = run_reference(ref, case_kwargs, attack, overrides, iters)
         torch.save(fx, os.path.join(HERE, f"trial_{name}.pt"))
         print(name, "history", [round(h, 5) for h in fx["history"]], "score", fx["score"])

@@ -24,7 +24,10 @@ def cfg_from_fixture(fx):
 
 
 def case_from_fixture(fx):
-    model, loss_fn, payload, shared, true = synthetic.make_case(**fx["case"])
+    if "steps" in fx["case"]:
+        model, loss_fn, payload, shared, true = synthetic.make_fedavg_case(**fx["case"])
+    else:
+        model, loss_fn, payload, shared, true = synthetic.make_case(**fx["case"])
     checksum = float(sum(p.double().sum() for p in model.parameters()))
     assert abs(checksum - fx["weight_checksum"]) <= 1e-6 * max(1.0, abs(fx["weight_checksum"])), \
         "synthetic case differs from the one the fixture was generated with"
@@ -47,7 +50,9 @@ def oracle_for_fixture(fx):
     dm = torch.tensor(meta.mean)[None, :, None, None]
     ds = torch.tensor(meta.std)[None, :, None, None]
     labels = restate.recover_labels(cfg.label_strategy, shared, shared[0]["metadata"]["num_data_points"])
-    return restate.TrialOracle(m, loss_fn, cfg, shared[0]["gradients"], labels, dm, ds), cfg, labels
+    return restate.TrialOracle(m, loss_fn, cfg, shared[0]["gradients"], labels, dm, ds,
+                               local_hyperparams=shared[0]["metadata"]["local_hyperparams"]), cfg, labels
 
 
 TRIAL_FIXTURES = ["ig_convnet", "ig_resnet18", "stg_resnet18", "modern_convnet", "tag_clip_convnet", "l1_sgd_convnet"]
+FEDAVG_FIXTURES = ["fedavg_convnet", "fedavg_resnet18"]

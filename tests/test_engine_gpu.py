@@ -274,7 +274,7 @@ def test_config3_resnet50_batch8_full_size_closure():
                               dtype=torch.double)
     phi64, _, raw64, _ = o64.closure_gradient(x.double(), 0, 0.0)
     ref_err = _relerr(raw, raw64)
-    for backend, tol_val, factor in (("simt", 1e-3, 1.5), ("tc", 3e-3, 4.0)):
+    for backend, tol_val, factor in (("simt", 1e-3, 1.5), ("tc", 1.5e-2, 4.0)):
         eng = engines[backend]
         val, grad = eng.objective_and_gradient(x.to(DEV))
         t = eng.last_terms()

@@ -4,10 +4,10 @@ import math
 import pytest
 import torch
 
-from helpers import TRIAL_FIXTURES, load_golden, oracle_for_fixture
+from helpers import FEDAVG_FIXTURES, TRIAL_FIXTURES, load_golden, oracle_for_fixture
 
 
-@pytest.mark.parametrize("name", TRIAL_FIXTURES)
+@pytest.mark.parametrize("name", TRIAL_FIXTURES + FEDAVG_FIXTURES)
 def test_oracle_reproduces_reference_trajectory(name):
     fx = load_golden(f"trial_{name}.pt")
     orc, cfg, labels = oracle_for_fixture(fx)
