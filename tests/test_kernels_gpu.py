@@ -80,6 +80,10 @@ def test_conv_fprop_dgrad_wgrad_simt(shape):
     E.conv_gemm(2, _nhwc(x), _nhwc(dy), dw, N, H, W, Ci, Co, R, R, st, pd)
     refw = torch.nn.grad.conv2d_weight(xd, (Co, Ci, R, R), dyd, stride=st, padding=pd)
     assert _relerr(dw.permute(0, 3, 1, 2), refw) < tol, "wgrad"
+    # dual-source wgrad (tangent weight gradients of the FedAvg adjoint): dout^T a + dout2^T a2
+    E.conv_gemm(2, _nhwc(x), _nhwc(dy), dw, N, H, W, Ci, Co, R, R, st, pd, a2=_nhwc(x2), w2=_nhwc(dy2))
+    refw2 = refw + torch.nn.grad.conv2d_weight(x2.double(), (Co, Ci, R, R), dy2.double(), stride=st, padding=pd)
+    assert _relerr(dw.permute(0, 3, 1, 2), refw2) < tol, "wgrad dual"
 
 
 def test_conv_is_deterministic_across_launches():
@@ -128,7 +132,12 @@ def test_total_variation_value_and_gradient(p, q, dbl, shape):
     assert _relerr(acc.cpu(), 2 * gref) < 5e-5
 
 
-TC_SHAPES = [s for s in CONV_SHAPES if s[3] % 32 == 0 and s[4] % 64 == 0] + [(1, 56, 56, 64, 64, 3, 1, 1), (8, 14, 14, 128, 256, 3, 2, 1)]
+TC_SHAPES = [s for s in CONV_SHAPES if s[3] % 32 == 0 and s[4] % 64 == 0] + [
+    (1, 56, 56, 64, 64, 3, 1, 1), (8, 14, 14, 128, 256, 3, 2, 1),
+    (1, 2, 2, 512, 512, 3, 1, 1), (1, 4, 4, 256, 256, 3, 1, 1), (4, 8, 8, 128, 128, 3, 1, 1),   # tiny spatial extents (64x64 inputs)
+    (3, 9, 11, 64, 64, 3, 1, 1), (2, 15, 13, 64, 128, 3, 2, 1), (1, 5, 5, 96, 64, 3, 1, 1),    # ragged tiles, odd sizes, Ci = 96
+    (8, 56, 56, 64, 256, 1, 1, 0), (8, 28, 28, 128, 128, 3, 1, 1), (2, 28, 28, 256, 64, 1, 2, 0),  # ResNet-50 batch-8 shapes
+]
 
 
 @pytest.mark.parametrize("shape", TC_SHAPES)
@@ -156,8 +165,11 @@ def test_conv_tcgen05_tf32_backend(shape):
         refd = torch.nn.grad.conv2d_input((N, Ci, H, W), w.double(), dy.double(), stride=st, padding=pd) + \
             torch.nn.grad.conv2d_input((N, Ci, H, W), w2.double(), dy2.double(), stride=st, padding=pd)
         assert _relerr(din.permute(0, 3, 1, 2), refd) < tol, "dgrad dual"
-    if Co % 128 == 0 and (R * R * Ci) % 64 == 0:
+    if (R * R * Ci) % 64 == 0:
         dw = torch.empty(Co, R, R, Ci, device=DEV)
         E.conv_gemm(2, _nhwc(x), _nhwc(dy), dw, N, H, W, Ci, Co, R, R, st, pd, backend=1)
         refw = torch.nn.grad.conv2d_weight(x.double(), (Co, Ci, R, R), dy.double(), stride=st, padding=pd)
         assert _relerr(dw.permute(0, 3, 1, 2), refw) < tol, "wgrad"
+        E.conv_gemm(2, _nhwc(x), _nhwc(dy), dw, N, H, W, Ci, Co, R, R, st, pd, a2=_nhwc(x2), w2=_nhwc(dy2), backend=1)
+        refw2 = refw + torch.nn.grad.conv2d_weight(x2.double(), (Co, Ci, R, R), dy2.double(), stride=st, padding=pd)
+        assert _relerr(dw.permute(0, 3, 1, 2), refw2) < tol, "wgrad dual"
