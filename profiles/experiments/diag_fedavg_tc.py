@@ -48,3 +48,50 @@ for opts in [dict(), dict(overlap_wgrad=0), dict(pdl=0), dict(overlap_wgrad=0, p
             worst = sorted(((rel(eng.debug_param(which, i), ref.debug_param(which, i)), i) for i in range(nparams)), reverse=True)[:8]
             print("  arena", which, "worst params (rel, index, shape):", [(round(r, 4), i, tuple(ref.prog.params[i].shape)) for r, i in worst])
     eng.close()
+
+# ---- what does the reference's own GPU path (cuDNN TF32 convolutions, torch default) do on this case? -------------------
+from oracle import restate  # noqa: E402
+from breaching_b200 import synthetic  # noqa: E402
+from breaching_b200 import get_attack_config  # noqa: E402
+
+
+def torch_oracle(tf32, fixture=fx):
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    model, loss_fn, payload, shared, true = case_from_fixture(fixture)
+    cfg = cfg_from_fixture(fixture)
+    meta = payload[0]["metadata"]
+    dm = torch.tensor(meta.mean, device=DEV)[None, :, None, None]
+    ds = torch.tensor(meta.std, device=DEV)[None, :, None, None]
+    local = copy.deepcopy(shared[0]["metadata"]["local_hyperparams"])
+    local["labels"] = [l.to(DEV) for l in local["labels"]]
+    orc = restate.TrialOracle(copy.deepcopy(model).to(DEV).eval(), loss_fn, cfg, [g.to(DEV) for g in shared[0]["gradients"]],
+                              torch.cat(local["labels"]), dm, ds, local_hyperparams=local)
+    phi, _, raw, terms = orc.closure_gradient(fixture["x0"].to(DEV), 0, 0.0)
+    orc.close()
+    return float(phi), raw
+
+
+for tf32 in (False, True):
+    phi, raw = torch_oracle(tf32)
+    print(f"torch eager on the GPU, allow_tf32={tf32}: val {phi} grad rel vs fp32 CPU fixture {rel(raw, fx['raw_grad0'])}",
+          "per step", [round(rel(raw[k], fx['raw_grad0'][k]), 4) for k in range(raw.shape[0])])
+
+# ---- growth with the number of local steps / step size (engine simt vs tc) ---------------------------------------------
+for steps, lr in [(1, 0.01), (2, 0.01), (4, 0.01), (4, 0.001), (4, 0.1)]:
+    model, loss_fn, payload, shared, true = synthetic.make_fedavg_case("resnet18", "imagenet", num_data_points=steps, steps=steps,
+                                                                       data_per_step=1, lr=lr, seed=6, bn_random=True, image_size=64, classes=10)
+    cfg = get_attack_config("modern", {"regularization.features.scale": 0.0})
+    local = shared[0]["metadata"]["local_hyperparams"]
+    meta = payload[0]["metadata"]
+    x0 = torch.randn(steps, 3, 64, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    res = {}
+    for backend in ("simt", "tc"):
+        eng = Engine(copy.deepcopy(model).to(DEV).eval(), (1, 3, 64, 64), cfg, DEV, backend=backend)
+        eng.load_model()
+        eng.load_targets([g.to(DEV) for g in shared[0]["gradients"]], local["labels"][0], mean=meta.mean, std=meta.std)
+        eng.set_local_steps(steps, local["steps"], local["lr"], local["labels"])
+        res[backend] = eng.objective_and_gradient(x0)
+        eng.close()
+    print(f"steps={steps} lr={lr}: val simt {res['simt'][0]:.6f} tc {res['tc'][0]:.6f}; grad rel tc vs simt {rel(res['tc'][1], res['simt'][1]):.4f}",
+          "per step", [round(rel(res['tc'][1][k], res['simt'][1][k]), 4) for k in range(steps)])

@@ -34,6 +34,30 @@ def _engine(fx, backend):
     return eng, cfg
 
 
+def _reference_tf32_deviation(fx):
+    """rel. l2 distance between the reference algorithm run in eager PyTorch on the GPU with TF32 convolutions (the
+    reference's default GPU numerics) and the fp32 fixture."""
+    from oracle import restate
+
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    meta = payload[0]["metadata"]
+    dm = torch.tensor(meta.mean, device=DEV)[None, :, None, None]
+    ds = torch.tensor(meta.std, device=DEV)[None, :, None, None]
+    local = copy.deepcopy(shared[0]["metadata"]["local_hyperparams"])
+    local["labels"] = [lab.to(DEV) for lab in local["labels"]]
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        orc = restate.TrialOracle(copy.deepcopy(model).to(DEV).eval(), loss_fn, cfg, [g.to(DEV) for g in shared[0]["gradients"]],
+                                  torch.cat(local["labels"]), dm, ds, local_hyperparams=local)
+        _, _, raw, _ = orc.closure_gradient(fx["x0"].to(DEV), 0, 0.0)
+        orc.close()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return _relerr(raw, fx["raw_grad0"])
+
+
 @pytest.mark.parametrize("backend", ["simt", "tc"])
 @pytest.mark.parametrize("name", FEDAVG_FIXTURES)
 def test_fedavg_closure_matches_reference_fixture(name, backend):
@@ -47,6 +71,12 @@ def test_fedavg_closure_matches_reference_fixture(name, backend):
     # loss of the last local step (evaluated at W_{K-1}, i.e. after K-1 TF32 / fp32 updates)
     assert math.isclose(eng.last_terms()["task_loss"], fx["task_loss0"], rel_tol=1e-3 if backend == "simt" else 1e-2)
     rel = _relerr(grad, fx["raw_grad0"])
+    if backend == "tc":
+        # Hessian-vector products through K local steps are badly conditioned under TF32: the reference's own GPU path
+        # (eager PyTorch, cuDNN TF32 convolutions = torch's default) is 27 % away from its fp32 CPU result on the
+        # ResNet-18 fixture, step by step in the same pattern as the TF32 engine (profiles/experiments/diag_fedavg_tc.py).
+        # The TF32 back end is therefore held to the reference's TF32 deviation, the fp32 back end to the fp32 fixture.
+        tol_g = max(tol_g, 1.5 * _reference_tf32_deviation(fx))
     assert rel < tol_g, rel
     score = eng.score(fx["best"].to(DEV), fx["scoring"])
     assert math.isclose(score, fx["score"], rel_tol=2e-2 if backend == "simt" else 5e-2, abs_tol=1e-5), (score, fx["score"])
