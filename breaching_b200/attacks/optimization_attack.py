@@ -38,6 +38,7 @@ class OptimizationBasedAttacker:
     def __init__(self, model, loss_fn, cfg_attack, setup=dict(dtype=torch.float, device=torch.device("cpu"))):
         self.cfg = cfg_attack
         self.setup = dict(device=torch.device(setup["device"]), dtype=getattr(torch, cfg_attack.impl.dtype))
+        self.backend = setup.get("backend")  # optional extension: "tc" (default, TF32 tensor cores) or "simt" (fp32)
         self.model_template = copy.deepcopy(model)
         self.loss_fn = copy.deepcopy(loss_fn)
 
@@ -115,7 +116,8 @@ class OptimizationBasedAttacker:
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if cfg_get(self.cfg.optim, "langevin_noise", 0.0) else 0
         if self._engine is not None:
             self._engine.close()
-        eng = Engine(model, shape, self.cfg, self.setup["device"], noise_seed=seed)
+        # setup["backend"]: "tc" (tcgen05 TF32, default = torch's cuDNN-TF32 numerics) or "simt" (fp32, = allow_tf32 False)
+        eng = Engine(model, shape, self.cfg, self.setup["device"], noise_seed=seed, backend=self.backend)
         eng.load_model()
         tw = None
         if self.cfg.objective.type == "tag-euclidean":  # objectives.py:115-124
@@ -173,6 +175,13 @@ class OptimizationBasedAttacker:
         opt = self.cfg.optim
         T = int(opt.max_iterations)
         table = lr_table(opt.step_size, cfg_get(opt, "step_size_decay"), cfg_get(opt, "warmup", 0), T)
+        if str(opt.optimizer).lower() == "l-bfgs":  # common.py:18 -- host-driven direction update, closure on the engine
+            from . import lbfgs
+
+            dm, ds = self.dm.to(candidate.device), self.ds.to(candidate.device)
+            best, history = lbfgs.run_trial(engine, candidate, self.cfg, table, -dm / ds, (1 - dm) / ds, dryrun)
+            stats[f"Trial_{trial}_Val"].extend(history)
+            return best.detach()
         engine.begin_trial(candidate, table)
         callback = int(cfg_get(opt, "callback", 0) or 0)
         chunk = callback if callback > 0 else T

@@ -81,6 +81,15 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Round-to-nearest onto the TF32 grid (10-bit mantissa, low 13 bits cleared).  tcgen05 kind::tf32 reads fp32 operands and
+// simply ignores the low mantissa bits (truncation, biased towards zero); tensors that feed the tensor-core GEMMs are
+// therefore rounded by the kernel that produces them, so that the products are those of cuDNN's TF32 path (cvt.rna).
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

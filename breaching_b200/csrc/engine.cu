@@ -86,6 +86,12 @@ struct bre_engine {
 
   long long P_pad = 0, max_param = 0, max_tensor = 0;
   float *W = nullptr, *g = nullptr, *G = nullptr, *V = nullptr, *stage = nullptr, *chunk_w = nullptr;
+  // TF32-rounded shadows of the parameter and direction arenas: what the tcgen05 GEMMs read (the masters stay fp32: a local
+  // SGD step or an adjoint update is far below one TF32 ulp of the weights).  See tf32_rna in common.cuh.
+  float *Wt = nullptr, *Vt = nullptr;
+  std::vector<float*> ms_Wt;
+  bool tc_round_env = [] { const char* e = getenv("BRE_TC_ROUND"); return e ? atoi(e) != 0 : true; }();
+  bool tc_round() const { return gemm_backend == 1 && tc_round_env; }
   float *p = nullptr, *loss_n = nullptr;
   long long* labels = nullptr;
   int n_labels = 0;
@@ -115,6 +121,10 @@ struct bre_engine {
   std::vector<cudaEvent_t> ev_fork;
   cudaEvent_t ev_join = nullptr;
   bool overlap_wgrad = true;
+  // BN + residual + ReLU (and its tangent) in the epilogue of the producing tcgen05 fprop.  Off by default: measured on the
+  // B200 it removes 32 of 201 launches per config-2 iteration and is still 1.5 % slower (the split-K epilogue's extra global
+  // loads cost more than the PDL-overlapped element-wise kernels they replace).  BRE_FUSE_BNACT=1 / option "fuse_bnact".
+  bool fuse_bnact = [] { const char* e = getenv("BRE_FUSE_BNACT"); return e ? atoi(e) != 0 : false; }();
   float* ws2 = nullptr;
   int* gemm_counters2 = nullptr;
   float* red_partials2 = nullptr;
@@ -158,6 +168,27 @@ struct bre_engine {
   float* Wp(int idx) const { return W + params[idx].off; }
   float* Gp(int idx) const { return G + params[idx].off; }
   float* Vp(int idx) const { return V + params[idx].off; }
+  const float* Wg(int idx) const { return (tc_round() ? Wt : W) + params[idx].off; }   // conv / linear weights as GEMM operands
+  const float* Vg(int idx) const { return (tc_round() ? Vt : V) + params[idx].off; }
+  int refresh_Vt() { return tc_round() ? launch_round_tf32(V, Vt, P_pad, stream) : 0; }
+  // Which activation tensors are operands of a tensor-core GEMM: inputs (value / tangent) and output deltas of the
+  // convolutions the tcgen05 back end covers.  Only those are stored TF32-rounded; layers that run on the fp32 SIMT kernels
+  // (3-channel stem, narrow test networks, the classifier head) keep full fp32 operands.
+  std::vector<char> rnd_val, rnd_d;
+  void compute_round_flags() {
+    rnd_val.assign(t.size(), 0);
+    rnd_d.assign(t.size(), 0);
+    for (const bre_op_desc& op : ops) {
+      if (op.kind != BRE_OP_CONV && op.kind != BRE_OP_LINEAR) continue;
+      GemmArgs a = conv_geom(op);
+      a.act[0] = t[op.tin].val; a.wgt[0] = Wp(op.w); a.out = t[op.tout].val;
+      bool any = false;
+      for (int mode = 0; mode < 3; ++mode) { a.mode = mode; any = any || igemm_tc_supported(a); }
+      if (any) { rnd_val[op.tin] = 1; rnd_d[op.tout] = 1; }
+    }
+  }
+  bool round_val(int tensor) { if (rnd_val.size() != t.size()) compute_round_flags(); return tc_round() && rnd_val[tensor]; }
+  bool round_d(int tensor) { if (rnd_d.size() != t.size()) compute_round_flags(); return tc_round() && rnd_d[tensor]; }
 
   // ---- GEMM argument assembly -----------------------------------------------------------------
   GemmArgs conv_geom(const bre_op_desc& op) const {
@@ -181,8 +212,22 @@ struct bre_engine {
   }
   int gemm(const GemmArgs& a) { return gemm_on(a, stream); }
   int gemm_on(const GemmArgs& a, cudaStream_t st) {
-    if (gemm_backend == 1 && igemm_tc_supported(a)) return launch_igemm_tc(a, st);
+    if (gemm_backend == 1 && igemm_tc_supported(a)) {
+      return launch_igemm_tc(a, st);
+    }
     return launch_igemm_simt(a, st);
+  }
+
+  // The BN/residual/ReLU op that directly follows conv `i` and reads its output can run in the GEMM epilogue (tcgen05 back end).
+  bool fuses_with_next(size_t i, const GemmArgs& a) const {
+    if (!fuse_bnact || gemm_backend != 1 || i + 1 >= ops.size()) return false;
+    const bre_op_desc& nx = ops[i + 1];
+    return nx.kind == BRE_OP_BNACT && nx.tin == ops[i].tout && igemm_tc_supported(a);
+  }
+  int consumers_of(int tensor) const {
+    int n = 0;
+    for (const bre_op_desc& o : ops) n += (o.tin == tensor) + (o.res == tensor);
+    return n;
   }
 
   BnConsts bn_consts(const bre_op_desc& op) const {
@@ -207,15 +252,23 @@ struct bre_engine {
         case BRE_OP_LINEAR: {
           GemmArgs a = conv_geom(op);
           a.mode = GEMM_FPROP;
-          a.act[0] = t[op.tin].val; a.wgt[0] = Wp(op.w);
+          a.act[0] = t[op.tin].val; a.wgt[0] = Wg(op.w);
           a.bias = op.b >= 0 ? Wp(op.b) : nullptr;
           a.out = t[op.tout].val;
+          if (fuses_with_next(i, a)) {
+            const bre_op_desc& nx = ops[i + 1];
+            const BnConsts c = bn_consts(nx);
+            a.epi.kind = 1; a.epi.has_bn = nx.has_bn != 0; a.epi.relu = nx.relu != 0;
+            a.epi.out2 = t[nx.tout].val; a.epi.res = nx.res >= 0 ? t[nx.res].val : nullptr;
+            a.epi.scale = c.scale; a.epi.shift = c.shift;
+            ++i;   // the BNACT op ran in the epilogue
+          }
           BRE_LAUNCH(gemm(a));
           break;
         }
         case BRE_OP_BNACT:
           BRE_LAUNCH(launch_bnact_fwd(t[op.tin].val, op.res >= 0 ? t[op.res].val : nullptr, t[op.tout].val, Pout, to.C,
-                                      op.has_bn != 0, op.relu != 0, bn_consts(op), stream));
+                                      op.has_bn != 0, op.relu != 0, bn_consts(op), round_val(op.tout), stream));
           break;
         case BRE_OP_MAXPOOL:
           BRE_LAUNCH(launch_maxpool_fwd(t[op.tin].val, t[op.tout].val, pool_idx[i], pool_geom(op), stream));
@@ -260,7 +313,7 @@ struct bre_engine {
           if (op.tin != 0 || need_task_grad()) {
             GemmArgs b = conv_geom(op);
             b.mode = GEMM_DGRAD;
-            b.act[0] = t[op.tout].d; b.wgt[0] = Wp(op.w);
+            b.act[0] = t[op.tout].d; b.wgt[0] = Wg(op.w);
             b.out = op.tin == 0 ? gradx_task : t[op.tin].d;
             b.accumulate = op.tin == 0 ? 0 : op.acc_in;
             BRE_LAUNCH(gemm(b));
@@ -271,7 +324,7 @@ struct bre_engine {
           BnActBwdArgs a;
           a.P = Pout; a.C = to.C; a.has_bn = op.has_bn != 0; a.relu = op.relu != 0; a.bn = bn_consts(op);
           a.in = t[op.tin].val; a.out = t[op.tout].val; a.dout = t[op.tout].d;
-          a.din = t[op.tin].d; a.acc_in = op.acc_in != 0;
+          a.din = t[op.tin].d; a.acc_in = op.acc_in != 0; a.round_din = round_d(op.tin);
           a.dres = op.res >= 0 ? t[op.res].d : nullptr; a.acc_res = op.acc_res != 0;
           a.g_gamma = op.has_bn ? Gp(op.gamma) : nullptr; a.g_beta = op.has_bn ? Gp(op.beta) : nullptr;
           a.partials = red_partials; a.counters = red_counters;
@@ -314,14 +367,25 @@ struct bre_engine {
           GemmArgs a = conv_geom(op);
           a.mode = GEMM_FPROP;
           if (op.tin == 0) {  // tangent of the candidate is zero: only the v-term
-            a.act[0] = t[op.tin].val; a.wgt[0] = Vp(op.w);
+            a.act[0] = t[op.tin].val; a.wgt[0] = Vg(op.w);
           } else {
             a.nsrc = 2;
-            a.act[0] = t[op.tin].tval; a.wgt[0] = Wp(op.w);
-            a.act[1] = t[op.tin].val; a.wgt[1] = Vp(op.w);
+            a.act[0] = t[op.tin].tval; a.wgt[0] = Wg(op.w);
+            a.act[1] = t[op.tin].val; a.wgt[1] = Vg(op.w);
           }
           a.bias = op.b >= 0 ? Vp(op.b) : nullptr;
           a.out = t[op.tout].tval;
+          if (fuses_with_next(i, a)) {
+            const bre_op_desc& nx = ops[i + 1];
+            const BnConsts c = bn_consts(nx);
+            a.epi.kind = 2; a.epi.has_bn = nx.has_bn != 0; a.epi.relu = nx.relu != 0;
+            a.epi.out2 = t[nx.tout].tval; a.epi.res = nx.res >= 0 ? t[nx.res].tval : nullptr;
+            a.epi.scale = c.scale; a.epi.inv = c.inv; a.epi.nrm = c.nrm;
+            a.epi.v_gamma = nx.has_bn ? Vp(nx.gamma) : nullptr; a.epi.v_beta = nx.has_bn ? Vp(nx.beta) : nullptr;
+            a.epi.pre = t[nx.tin].val; a.epi.post = t[nx.tout].val;
+            if (consumers_of(op.tout) == 1) a.out = nullptr;   // nobody else reads the pre-BN tangent
+            ++i;
+          }
           BRE_LAUNCH(gemm(a));
           break;
         }
@@ -331,7 +395,7 @@ struct bre_engine {
           a.in = t[op.tin].val; a.out = t[op.tout].val;
           a.tin = t[op.tin].tval; a.tres = op.res >= 0 ? t[op.res].tval : nullptr;
           a.v_gamma = op.has_bn ? Vp(op.gamma) : nullptr; a.v_beta = op.has_bn ? Vp(op.beta) : nullptr;
-          a.tout = t[op.tout].tval;
+          a.tout = t[op.tout].tval; a.round_out = round_val(op.tout);
           BRE_LAUNCH(launch_bnact_tan_fwd(a, stream));
           break;
         }
@@ -378,8 +442,8 @@ struct bre_engine {
           GemmArgs a = conv_geom(op);
           a.mode = GEMM_DGRAD;
           a.nsrc = 2;
-          a.act[0] = t[op.tout].td; a.wgt[0] = Wp(op.w);
-          a.act[1] = t[op.tout].d; a.wgt[1] = Vp(op.w);
+          a.act[0] = t[op.tout].td; a.wgt[0] = Wg(op.w);
+          a.act[1] = t[op.tout].d; a.wgt[1] = Vg(op.w);
           a.out = op.tin == 0 ? t[0].td : t[op.tin].td;
           a.accumulate = op.tin == 0 ? 0 : op.acc_in;
           BRE_LAUNCH(gemm(a));
@@ -414,7 +478,7 @@ struct bre_engine {
           a.v_gamma = op.has_bn ? Vp(op.gamma) : nullptr;
           a.di_cm = a.di_cv = a.di_mean = nullptr;
           if (di && op.has_bn) { const BnBuf& b = bn[op.bn_buffer]; a.di_cm = b.di_cm; a.di_cv = b.di_cv; a.di_mean = b.di_mean; }
-          a.tdin = t[op.tin].td; a.acc_in = op.acc_in != 0;
+          a.tdin = t[op.tin].td; a.acc_in = op.acc_in != 0; a.round_din = round_d(op.tin);
           a.tdres = op.res >= 0 ? t[op.res].td : nullptr; a.acc_res = op.acc_res != 0;
           a.tin = nullptr; a.tg_gamma = a.tg_beta = nullptr; a.partials = red_partials; a.counters = red_counters;
           if (want_tangent_G && op.has_bn) { a.tin = t[op.tin].tval; a.tg_gamma = Gp(op.gamma); a.tg_beta = Gp(op.beta); }
@@ -445,7 +509,7 @@ struct bre_engine {
     for (size_t i = 1; i < t.size(); ++i) { t[i].val = b.val[i]; t[i].d = b.d[i]; }
     pool_idx = b.idx;
     p = b.p; loss_n = b.loss_n; labels = b.labels;
-    W = ms_W[k];
+    W = ms_W[k]; Wt = ms_Wt[k];
     for (int j = 0; j < n_bn_layers; ++j) { bn[j].scale = b.bn_scale[j]; bn[j].shift = b.bn_shift[j]; }
     t[0].val = x + ms_offset[k];
     t[0].td = gradx_step;
@@ -461,6 +525,7 @@ struct bre_engine {
       // W_{k+1} = W_k - lr * grad (:63-66).  The matched "gradient" W_K - W_0 (:69) is accumulated directly,
       // D_{k+1} = D_k - lr * grad, instead of being formed as a difference of two nearly equal parameter vectors.
       BRE_LAUNCH(launch_axpby(ms_W[k], G, -ms_lr, ms_W[k + 1], P_pad, stream));
+      if (tc_round()) BRE_LAUNCH(launch_round_tf32(ms_W[k + 1], ms_Wt[k + 1], P_pad, stream));
       if (k == 0) BRE_CUDA_CHECK(cudaMemsetAsync(ms_D, 0, P_pad * sizeof(float), stream));
       BRE_LAUNCH(launch_axpby(ms_D, G, -ms_lr, ms_D, P_pad, stream));
     }
@@ -474,6 +539,7 @@ struct bre_engine {
     BRE_LAUNCH(launch_match_reduce(ms_D, g, chunk_w, P_pad, mv, cfg.objective, cfg.obj_scale, cfg.tag_scale, cfg.angular_fudge, true, sc,
                                    dpartials, dcounter, stream));
     BRE_LAUNCH(launch_make_v(ms_D, g, chunk_w, V, P_pad, mv, sc, stream));          // adjoint of W_K
+    BRE_TRY(refresh_Vt());
     const long long nstep = t[0].numel;
     for (int k = ms_steps - 1; k >= 0; --k) {
       bind_step(k);
@@ -484,7 +550,10 @@ struct bre_engine {
       if (rc != 0) return rc;
       // d Phi / d x_k = -lr * d/d eps grad_x L(x_k, W_{k-1} + eps u_k)
       BRE_LAUNCH(launch_axpy(gradx_step, gradx + ms_offset[k], -ms_lr, nstep, stream));
-      if (k > 0) BRE_LAUNCH(launch_axpby(V, G, -ms_lr, V, P_pad, stream));           // u_{k-1} = u_k - lr * H_k u_k
+      if (k > 0) {
+        BRE_LAUNCH(launch_axpby(V, G, -ms_lr, V, P_pad, stream));                     // u_{k-1} = u_k - lr * H_k u_k
+        BRE_TRY(refresh_Vt());
+      }
     }
     bind_step(0);
     BRE_TRY(priors());
@@ -508,6 +577,7 @@ struct bre_engine {
     BRE_TRY(sweep_backward());
     BRE_TRY(reduce_objective(cfg.objective, cfg.obj_scale, cfg.mask_value, true));
     BRE_LAUNCH(launch_make_v(G, g, chunk_w, V, P_pad, cfg.objective == BRE_OBJ_MASKED_COSINE ? cfg.mask_value : -1.f, sc, stream));
+    BRE_TRY(refresh_Vt());
     BRE_TRY(sweep_tangent_forward());
     BRE_TRY(deep_inversion_stats());
     BRE_TRY(sweep_tangent_backward());
@@ -601,6 +671,7 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
   e->P_pad = off;
   int rc = 0;
   rc |= e->alloc(&e->W, off); rc |= e->alloc(&e->g, off); rc |= e->alloc(&e->G, off); rc |= e->alloc(&e->V, off);
+  rc |= e->alloc(&e->Wt, off); rc |= e->alloc(&e->Vt, off);
   rc |= e->alloc(&e->chunk_w, off / kChunk);
   // ---- activations ---------------------------------------------------------------------------------
   e->t.resize(n_tensors);
@@ -735,6 +806,7 @@ int bre_engine_load_model(bre_engine* e, const float* const* params, int32_t n_p
     BRE_TRY(launch_bn_prepare(e->Wp(op.gamma), e->Wp(op.beta), b.rm, b.rv, op.eps, b.C, b.scale, b.shift, b.inv, b.nrm, e->stream));
   }
   BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  BRE_TRY(launch_round_tf32(e->W, e->Wt, e->P_pad, e->stream));   // GEMM-operand shadow (used by the tcgen05 back end)
   e->model_loaded = true;
   return BRE_OK;
 }
@@ -814,8 +886,10 @@ int bre_engine_set_local_steps(bre_engine* e, int32_t total_images, int32_t step
   rc |= e->alloc(&e->ms_D, e->P_pad);
   e->ms_W.assign(steps + 1, nullptr);
   e->ms_W[0] = e->W;
+  e->ms_Wt.assign(steps + 1, nullptr);
+  e->ms_Wt[0] = e->Wt;
   e->W0 = e->W;
-  for (int k = 1; k <= steps; ++k) rc |= e->alloc(&e->ms_W[k], e->P_pad);
+  for (int k = 1; k <= steps; ++k) { rc |= e->alloc(&e->ms_W[k], e->P_pad); rc |= e->alloc(&e->ms_Wt[k], e->P_pad); }
   e->ms_bufs.resize(steps);
   e->n_bn_layers = (int)e->bn.size();
   e->ms_bnprep_dev.assign(steps, nullptr);
@@ -1069,6 +1143,7 @@ int bre_engine_set_option(bre_engine* e, const char* name, int64_t value) {
   if (n == "use_graph") { e->use_graph = value != 0; e->graph_ready = false; return BRE_OK; }
   if (n == "pdl") { bre::set_pdl(value != 0); e->graph_ready = false; return BRE_OK; }
   if (n == "overlap_wgrad") { e->overlap_wgrad = value != 0; e->graph_ready = false; return BRE_OK; }
+  if (n == "fuse_bnact") { e->fuse_bnact = value != 0; e->graph_ready = false; return BRE_OK; }
   if (n == "gemm_backend") {
     if (value != 0 && value != 1) { set_error("gemm_backend must be 0 (simt) or 1 (tcgen05)"); return BRE_ERR_INVALID; }
     e->gemm_backend = (int)value; e->graph_ready = false; return BRE_OK;

@@ -16,8 +16,27 @@ struct ConvGeom {
   int R, S, stride, pad;
 };
 
+// Optional consumer fused into the FPROP epilogue of the tcgen05 back end: the BN + residual + ReLU op that follows a
+// convolution (layers.cu bnact_fwd_kernel, kind 1) or its tangent (bnact_tan_fwd_kernel, kind 2).  The GEMM result is still
+// written to `out` when `out` is non-null (the backward sweeps need the pre-BN value; nobody reads the pre-BN tangent).
+struct GemmEpilogue {
+  int kind;                 // 0 = none, 1 = value, 2 = tangent
+  int has_bn, relu;
+  float* out2;              // [M][Nc] output of the fused op
+  const float* res;         // residual branch (value / tangent), may be null
+  const float* scale;       // alpha = gamma * invstd
+  const float* shift;       // kind 1: beta - mean * alpha
+  const float* inv;         // kind 2: invstd, -mean * invstd  (xhat = pre * inv + nrm)
+  const float* nrm;
+  const float* v_gamma;     // kind 2: direction components of gamma / beta
+  const float* v_beta;
+  const float* pre;         // kind 2: forward pre-BN value and post-activation value (ReLU mask)
+  const float* post;
+};
+
 struct GemmArgs {
   int mode;
+  GemmEpilogue epi;
   ConvGeom g;
   int nsrc;               // 1 or 2 (dual source: K-concatenation, fprop / dgrad only)
   const float* act[2];    // fprop: in ; dgrad: dout ; wgrad: in

@@ -20,6 +20,7 @@
 #include <array>
 #include <map>
 #include <mutex>
+#include <type_traits>
 
 #include <cuda.h>
 
@@ -31,7 +32,7 @@ namespace {
 
 constexpr int TC_BM = 128;      // UMMA M
 constexpr int TC_BK = 32;       // k-block per pipeline stage (4 MMAs of K = 8)
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 4;       // ring depth (power of two: stage / phase of k-block i are i & 3, (i >> 2) & 1)
 constexpr int TC_THREADS = 128;       // loader / epilogue threads (warps 0-3 <-> TMEM lane quadrants)
 constexpr int TC_BLOCK = TC_THREADS + 32;  // + one MMA-issuer warp
 
@@ -151,9 +152,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 // 16-byte load from the shared memory of CTA `rank` of this cluster at the same offset as local address `saddr`
 __device__ __forceinline__ float4 ld_dsmem4(uint32_t saddr, uint32_t rank) {
   uint32_t raddr;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(saddr), "r"(rank));
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(saddr), "r"(rank));
   float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raddr) : "memory");
+  // volatile (not reordered across the cluster barriers, themselves volatile) but no memory clobber: a batch of these is issued
+  // back to back instead of one round trip at a time (1.5 us -> of the split-K tail, profiles/experiments/tc_trace.py)
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raddr));
   return v;
 }
 
@@ -182,17 +185,51 @@ __device__ __forceinline__ void tma_tile3d(uint32_t dst, const CUtensorMap* tm, 
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// Fused consumer of an FPROP result (GemmEpilogue): NV consecutive channels n..n+NV-1 of GEMM row `row` (element offset
+// row = m * Nc).  Mirrors layers.cu bnact_fwd_kernel (kind 1) / bnact_tan_fwd_kernel (kind 2) expression by expression.
+template <int NV>
+__device__ __forceinline__ void fused_bnact(const GemmEpilogue& e, long long row, int n, float (&v)[NV]) {
+  const long long o = row + n;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float u = v[j];
+    if (e.kind == 1) {
+      if (e.has_bn) u = fmaf(u, __ldg(e.scale + n + j), __ldg(e.shift + n + j));
+      if (e.res != nullptr) u += e.res[o + j];
+      v[j] = e.relu ? fmaxf(u, 0.f) : u;
+    } else {
+      if (e.has_bn) {
+        const float xhat = fmaf(e.pre[o + j], __ldg(e.inv + n + j), __ldg(e.nrm + n + j));
+        u = fmaf(__ldg(e.scale + n + j), u, fmaf(__ldg(e.v_gamma + n + j), xhat, __ldg(e.v_beta + n + j)));
+      }
+      if (e.res != nullptr) u += e.res[o + j];
+      if (e.relu && !(e.post[o + j] > 0.f)) u = 0.f;
+      v[j] = u;
+    }
+  }
+}
+
+// Phase timestamps of CTA (0,0,0) (SM clock), compiled in with -DBRE_TC_TRACE for profiles/experiments/tc_trace.py only.
+#ifdef BRE_TC_TRACE
+__device__ long long g_tc_trace[16];
+#define TC_MARK(i, cond) do { if ((cond) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tc_trace[i] = clock64(); } while (0)
+#else
+#define TC_MARK(i, cond) do { } while (0)
+#endif
+
 template <int MODE, int BN, bool TMA>
 __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d, int proxy_fence, const __grid_constant__ TcMaps maps) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;                                  // [STAGES][A_BYTES]
-  uint8_t* sB = smem + TC_STAGES * A_BYTES;            // [STAGES][B_BYTES]
+  constexpr int nst = TC_STAGES;
+  uint8_t* sB = smem + nst * A_BYTES;                  // [stages][B_BYTES]
   __shared__ __align__(8) uint64_t bar_full[TC_STAGES];   // loaders -> MMA issuer (cp.async completion, 128 arrivals)
   __shared__ __align__(8) uint64_t bar_empty[TC_STAGES];  // MMA issuer -> loaders (tcgen05.commit)
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ uint32_t s_tmem;
 
+  TC_MARK(0, threadIdx.x == 0);
   pdl_launch_dependents();   // the successor may start its own prologue; it blocks in its griddepcontrol.wait
   const ConvGeom g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -212,6 +249,7 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = s_tmem;
+  TC_MARK(1, threadIdx.x == 0);
 
   // instruction descriptor (UMMA::InstrDescriptor): D = F32, A = B = TF32, majors, N >> 3, M >> 4
   constexpr uint32_t a_mn = (MODE == GEMM_WGRAD) ? 1u : 0u;
@@ -274,7 +312,14 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
 
   // Everything above touched only kernel parameters, shared memory and TMEM; from here on global memory written by the
   // predecessor kernel is read.
+  if (TMA && tid == 0 && (proxy_fence & 2)) {
+    for (int sidx = 0; sidx < a.nsrc; ++sidx) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.act[sidx])) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.wgt[sidx])) : "memory");
+    }
+  }
   pdl_wait();
+  TC_MARK(2, threadIdx.x == 0);
 
   // Stage one k-block: cp.async (LDGSTS, 16 B, zero-fill for padding / out-of-range taps) straight from global memory
   // into the UMMA operand layouts -- no register staging, so up to TC_STAGES k-blocks of loads stay in flight.
@@ -385,41 +430,67 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
     if (MODE == GEMM_FPROP) { base_h = p0 * g.stride - g.pad; base_w = q0 * g.stride - g.pad; }
     else { base_h = p0 + g.pad - (g.R - 1); base_w = q0 + g.pad - (g.S - 1); }   // stride-1 dgrad: flipped taps
   }
-  auto issue_block_tma = [&](int stage) {
-    const int src = it_src;
+  // Running decode of the producer's k-block sequence.  The producer lane is a single thread on the critical path of the
+  // whole CTA: no divisions inside the loop (an integer division costs it ~100 cycles), everything advances incrementally.
+  struct KbState { int src, rs, r, s, c0, img, p, q; };
+  auto kb_init = [&](int kb) {
+    KbState st;
+    const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
+    st.src = kb / d.kblocks_per_src;
+    const int kbase = (kb - st.src * d.kblocks_per_src) * TC_BK;
+    if (MODE == GEMM_WGRAD) {
+      st.rs = st.r = st.s = 0; st.c0 = kbase;
+      st.img = kbase / HoWo;
+      const int rem = kbase - st.img * HoWo;
+      st.p = rem / g.Wo; st.q = rem - st.p * g.Wo;
+    } else {
+      st.rs = kbase / kch; st.c0 = kbase - st.rs * kch;
+      st.r = st.rs / g.S; st.s = st.rs - st.r * g.S;
+      st.img = st.p = st.q = 0;
+    }
+    return st;
+  };
+  auto kb_advance = [&](KbState& st) {
+    const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
+    st.c0 += TC_BK;
+    if (MODE == GEMM_WGRAD) {
+      if (st.c0 >= d.kblocks_per_src * TC_BK) { st.c0 = 0; ++st.src; st.img = st.p = st.q = 0; }
+      else {
+        st.q += TC_BK;
+        while (st.q >= g.Wo) { st.q -= g.Wo; if (++st.p == g.Ho) { st.p = 0; ++st.img; } }
+      }
+    } else if (st.c0 >= kch) {
+      st.c0 = 0; ++st.rs;
+      if (++st.s == g.S) { st.s = 0; if (++st.r == g.R) { st.r = 0; st.rs = 0; ++st.src; } }
+    }
+  };
+  // WGRAD: the filter tap / channel of the CTA's B columns are fixed
+  int wg_c[BN / 32], wg_r[BN / 32], wg_s[BN / 32];
+  if (TMA && MODE == GEMM_WGRAD) {
+#pragma unroll
+    for (int h = 0; h < BN / 32; ++h) {
+      const int n = n0 + 32 * h;
+      const int rs = n / g.Ci;
+      wg_c[h] = n - rs * g.Ci; wg_r[h] = rs / g.S; wg_s[h] = rs - wg_r[h] * g.S;
+    }
+  }
+  auto issue_block_tma = [&](int stage, const KbState& st) {
     uint64_t* bar = &bar_full[stage];
-    const uint32_t pa = smem_u32(sA + stage * A_BYTES), pb = smem_u32(sB + stage * B_BYTES);
+    const uint32_t pa = smem_u32(sA) + stage * A_BYTES, pb = smem_u32(sB) + stage * B_BYTES;
     mbar_expect_tx(bar, A_BYTES + B_BYTES);
     if (MODE == GEMM_FPROP) {
-      const int r = it_rs / g.S, s = it_rs - r * g.S;
-      tma_im2col(pa, &maps.act[src], bar, it_c0, base_w, base_h, base_n, s, r);
-      tma_tile2d(pb, &maps.wgt[src], bar, it_rs * g.Ci + it_c0, n0);
+      tma_im2col(pa, &maps.act[st.src], bar, st.c0, base_w, base_h, base_n, st.s, st.r);
+      tma_tile2d(pb, &maps.wgt[st.src], bar, st.rs * g.Ci + st.c0, n0);
     } else if (MODE == GEMM_DGRAD) {
-      const int r = it_rs / g.S, s = it_rs - r * g.S;
-      tma_im2col(pa, &maps.act[src], bar, it_c0, base_w, base_h, base_n, g.S - 1 - s, g.R - 1 - r);
+      tma_im2col(pa, &maps.act[st.src], bar, st.c0, base_w, base_h, base_n, g.S - 1 - st.s, g.R - 1 - st.r);
 #pragma unroll
-      for (int h = 0; h < BN / 32; ++h) tma_tile3d(pb + h * 4096, &maps.wgt[src], bar, n0 + 32 * h, it_rs, it_c0);
+      for (int h = 0; h < BN / 32; ++h) tma_tile3d(pb + h * 4096, &maps.wgt[st.src], bar, n0 + 32 * h, st.rs, st.c0);
     } else {
-      const int pix0 = it_c0;   // WGRAD: k = pixel
 #pragma unroll
-      for (int h = 0; h < TC_BM / 32; ++h) tma_tile2d(pa + h * 4096, &maps.wgt[src], bar, m0 + 32 * h, pix0);
-      const int img = pix0 / HoWo, rem = pix0 - img * HoWo;
-      const int p = rem / g.Wo, q = rem - p * g.Wo;
+      for (int h = 0; h < TC_BM / 32; ++h) tma_tile2d(pa + h * 4096, &maps.wgt[st.src], bar, m0 + 32 * h, st.c0);   // k = pixel
 #pragma unroll
-      for (int h = 0; h < BN / 32; ++h) {
-        const int n = n0 + 32 * h;
-        const int rs = n / g.Ci, c = n - rs * g.Ci;
-        const int r = rs / g.S, s = rs - r * g.S;
-        tma_im2col(pb + h * 4096, &maps.act[src], bar, c, q * g.stride - g.pad, p * g.stride - g.pad, img, s, r);
-      }
-    }
-    const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
-    it_c0 += TC_BK;
-    if (MODE == GEMM_WGRAD) {
-      if (it_c0 >= d.kblocks_per_src * TC_BK) { it_c0 = 0; ++it_src; }
-    } else if (it_c0 >= kch) {
-      it_c0 = 0;
-      if (++it_rs == g.R * g.S) { it_rs = 0; ++it_src; }
+      for (int h = 0; h < BN / 32; ++h)
+        tma_im2col(pb + h * 4096, &maps.act[st.src], bar, wg_c[h], st.q * g.stride - g.pad, st.p * g.stride - g.pad, st.img, wg_s[h], wg_r[h]);
     }
   };
 
@@ -430,45 +501,58 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   const int nkb = kb_end > kb_begin ? kb_end - kb_begin : 0;  // a trailing split may be empty: it contributes zeros
   if (warp == TC_THREADS / 32) {
     if (tid == TC_THREADS) {
+      // descriptors of stage 0 / MMA slice 0; the 14-bit address field counts 16-byte units, so stage and slice offsets are
+      // plain additions on the low word (shared memory is < 256 KB: no carry out of the field)
+      const uint64_t adesc0 = a_mn ? make_desc(smem_u32(sA), 4096, 512, 1) : make_desc(smem_u32(sA), 16, 1024, 2);
+      const uint64_t bdesc0 = b_mn ? make_desc(smem_u32(sB), 4096, 512, 1) : make_desc(smem_u32(sB), 16, 1024, 2);
+      constexpr uint32_t a_step = (a_mn ? 1024u : 32u) >> 4, b_step = (b_mn ? 1024u : 32u) >> 4;
       for (int i = 0; i < nkb; ++i) {
-        const int stage = i % TC_STAGES;
-        mbar_wait(&bar_full[stage], (uint32_t)((i / TC_STAGES) & 1));
+        const int stage = i & (TC_STAGES - 1);
+        mbar_wait(&bar_full[stage], (uint32_t)((i >> 2) & 1));
+        TC_MARK(4, i == 0);
+        TC_MARK(11, i == nkb - 1);
         // The mbarrier phase completes only after every cp.async of this stage has been performed, so the data is in
         // shared memory when the wait returns; like CUTLASS' sm100 cp.async mainloop no fence.proxy.async is issued
         // here (measured: it costs ~0.5 us per k-block on the single-thread critical path).  BRE_TC_PROXY_FENCE=1 re-enables it.
-        if (proxy_fence) fence_proxy_async();
+        if (proxy_fence & 1) fence_proxy_async();
         tc_fence_after();
-        const uint32_t sa = smem_u32(sA + stage * A_BYTES), sb = smem_u32(sB + stage * B_BYTES);
+        const uint64_t adesc_s = adesc0 + (uint64_t)((uint32_t)stage * (A_BYTES >> 4));
+        const uint64_t bdesc_s = bdesc0 + (uint64_t)((uint32_t)stage * (B_BYTES >> 4));
 #pragma unroll
-        for (int j = 0; j < TC_BK / 8; ++j) {
-          const uint64_t adesc = a_mn ? make_desc(sa + j * 1024, 4096, 512, 1) : make_desc(sa + j * 32, 16, 1024, 2);
-          const uint64_t bdesc = b_mn ? make_desc(sb + j * 1024, 4096, 512, 1) : make_desc(sb + j * 32, 16, 1024, 2);
-          umma_tf32(tmem_d, adesc, bdesc, idesc, (i > 0 || j > 0) ? 1u : 0u);
-        }
+        for (int j = 0; j < TC_BK / 8; ++j)
+          umma_tf32(tmem_d, adesc_s + (uint64_t)(j * a_step), bdesc_s + (uint64_t)(j * b_step), idesc, (i > 0 || j > 0) ? 1u : 0u);
         umma_commit(&bar_empty[stage]);
       }
       umma_commit(&bar_done);
+      TC_MARK(5, true);
     }
     __syncwarp();
   } else {
     if (TMA) {
-      if (tid == 0) {
-        for (int i = 0; i < nkb; ++i) {
-          const int stage = i % TC_STAGES;
-          if (i >= TC_STAGES) mbar_wait(&bar_empty[stage], (uint32_t)((i / TC_STAGES - 1) & 1));
-          issue_block_tma(stage);
+      // one producer lane per loader warp, k-blocks dealt round-robin: a cp.async.bulk.tensor costs its issuing thread ~140
+      // cycles (profiles/experiments/tc_trace.py), so four issuers keep the ring full where one could not
+      const int nprod = (proxy_fence >> 2) & 7;
+      if ((tid & 31) == 0 && warp < nprod && warp < nkb) {
+        KbState st = kb_init(kb_begin + warp);
+        for (int i = warp; i < nkb; i += nprod) {
+          const int stage = i & (TC_STAGES - 1);
+          if (i >= nst) mbar_wait(&bar_empty[stage], (uint32_t)(((i >> 2) - 1) & 1));
+          issue_block_tma(stage, st);
+          TC_MARK(3, i == (nkb < nst ? nkb : nst) - 1);
+          for (int u = 0; u < nprod; ++u) kb_advance(st);
         }
       }
       __syncwarp();
     } else {
       for (int i = 0; i < nkb; ++i) {
-        const int stage = i % TC_STAGES;
-        if (i >= TC_STAGES) mbar_wait(&bar_empty[stage], (uint32_t)((i / TC_STAGES - 1) & 1));
+        const int stage = i & (TC_STAGES - 1);
+        if (i >= nst) mbar_wait(&bar_empty[stage], (uint32_t)(((i >> 2) - 1) & 1));
         issue_block(stage);
         cp_async_arrive(&bar_full[stage]);
       }
     }
     mbar_wait(&bar_done, 0);
+    TC_MARK(6, tid == 0);
     tc_fence_after();
   }
 
@@ -506,7 +590,16 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
         for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + n + j);
       }
       float* op = a.out + row + (long long)n * cs;
-      if (cs == 1) {
+      if (MODE == GEMM_FPROP && a.epi.kind != 0) {
+        if (a.out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        fused_bnact<32>(a.epi, row, n, v);
+        float* op2 = a.epi.out2 + row + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op2 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else if (cs == 1) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -545,50 +638,78 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
     }
   }
   if (splits > 1) {
+    TC_MARK(7, tid == 0);
     cluster_sync_all();   // every thread of every CTA in the cluster (partials visible cluster-wide)
+    TC_MARK(8, tid == 0);
     if (is_loader) {
-      const int rows_per = TC_BM / splits;
-      constexpr int C4 = BN / 4;
-      const uint32_t part_s = smem_u32(sA);
-      const int nslots = rows_per * C4;
-      for (int slot = tid; slot < nslots; slot += TC_THREADS) {
-        const int r = z * rows_per + slot / C4, c4 = slot % C4;
-        if (m0 + r >= d.M) continue;
-        const uint32_t local = part_s + (uint32_t)(r * BN + ((c4 ^ (r & 15)) << 2)) * 4u;
-        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < splits; ++q) {
-          const float4 t = ld_dsmem4(local, (uint32_t)q);
-          acc4.x += t.x; acc4.y += t.y; acc4.z += t.z; acc4.w += t.w;
-        }
-        const int n = n0 + c4 * 4;
-        if (MODE == GEMM_FPROP && a.bias != nullptr) {
-          acc4.x += __ldg(a.bias + n); acc4.y += __ldg(a.bias + n + 1); acc4.z += __ldg(a.bias + n + 2); acc4.w += __ldg(a.bias + n + 3);
-        }
-        long long row;
-        int cs;
-        out_row(m0 + r, row, cs);
-        float* op = a.out + row + (long long)n * cs;
-        if (cs == 1) {
-          if (a.accumulate) {
-            const float4 o = *reinterpret_cast<const float4*>(op);
-            acc4.x += o.x; acc4.y += o.y; acc4.z += o.z; acc4.w += o.w;
-          }
-          *reinterpret_cast<float4*>(op) = acc4;
-        } else {
-          const float vv[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+      // Every thread owns BN/(4 S) float4 slots of this CTA's row slice and needs the S peers' copies of each: BN/4 = 16
+      // remote 16-byte loads per thread whatever S is.  All of them are issued before the first is consumed (a DSMEM round
+      // trip is ~0.5 us; one slot at a time made this phase 2.2 us), then summed in fixed rank order.
+      auto reduce_rows = [&](auto s_tag) {
+        constexpr int S = decltype(s_tag)::value;
+        constexpr int C4 = BN / 4, SLOTS = (TC_BM / S) * C4 / TC_THREADS;
+        const uint32_t part_s = smem_u32(sA);
+        float4 t[SLOTS][S];
+        int rr[SLOTS], cc[SLOTS];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float* qq = op + (long long)j * cs;
-            *qq = a.accumulate ? *qq + vv[j] : vv[j];
+        for (int sl = 0; sl < SLOTS; ++sl) {
+          const int slot = tid + sl * TC_THREADS;
+          rr[sl] = z * (TC_BM / S) + slot / C4;
+          cc[sl] = slot % C4;
+          const uint32_t local = part_s + (uint32_t)(rr[sl] * BN + ((cc[sl] ^ (rr[sl] & 15)) << 2)) * 4u;
+#pragma unroll
+          for (int q = 0; q < S; ++q) t[sl][q] = ld_dsmem4(local, (uint32_t)q);
+        }
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) {
+          const int r = rr[sl], c4 = cc[sl];
+          if (m0 + r >= d.M) continue;
+          float4 acc4 = t[sl][0];
+#pragma unroll
+          for (int q = 1; q < S; ++q) { acc4.x += t[sl][q].x; acc4.y += t[sl][q].y; acc4.z += t[sl][q].z; acc4.w += t[sl][q].w; }
+          const int n = n0 + c4 * 4;
+          if (MODE == GEMM_FPROP && a.bias != nullptr) {
+            acc4.x += __ldg(a.bias + n); acc4.y += __ldg(a.bias + n + 1); acc4.z += __ldg(a.bias + n + 2); acc4.w += __ldg(a.bias + n + 3);
+          }
+          long long row;
+          int cs;
+          out_row(m0 + r, row, cs);
+          float* op = a.out + row + (long long)n * cs;
+          if (MODE == GEMM_FPROP && a.epi.kind != 0) {
+            if (a.out != nullptr) *reinterpret_cast<float4*>(op) = acc4;
+            float vv[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+            fused_bnact<4>(a.epi, row, n, vv);
+            *reinterpret_cast<float4*>(a.epi.out2 + row + n) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+          } else if (cs == 1) {
+            if (a.accumulate) {
+              const float4 o = *reinterpret_cast<const float4*>(op);
+              acc4.x += o.x; acc4.y += o.y; acc4.z += o.z; acc4.w += o.w;
+            }
+            *reinterpret_cast<float4*>(op) = acc4;
+          } else {
+            const float vv[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float* qq = op + (long long)j * cs;
+              *qq = a.accumulate ? *qq + vv[j] : vv[j];
+            }
           }
         }
+      };
+      switch (splits) {
+        case 2: reduce_rows(std::integral_constant<int, 2>{}); break;
+        case 4: reduce_rows(std::integral_constant<int, 4>{}); break;
+        case 8: reduce_rows(std::integral_constant<int, 8>{}); break;
+        default: reduce_rows(std::integral_constant<int, 16>{}); break;
       }
     }
+    TC_MARK(9, tid == 0);
     cluster_sync_all();   // nobody leaves (and frees its shared memory) while a peer may still be reading it
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, BN);
+  TC_MARK(10, tid == 0);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -738,7 +859,7 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, cudaStream_t stream) {
   // split-K factor = cluster size along z: a power of two <= 8 (portable cluster limit) that brings the grid to ~100 CTAs
   static const int max_splits_env = [] { const char* e = getenv("BRE_TC_MAX_SPLITS"); return e ? atoi(e) : 0; }();
   static const int target_ctas_env = [] { const char* e = getenv("BRE_TC_TARGET_CTAS"); return e ? atoi(e) : 0; }();
-  const int target = target_ctas_env > 0 ? target_ctas_env : 96;
+  const int target = target_ctas_env > 0 ? target_ctas_env : 144;   // re-tuned with the TMA producer: 96 -> 144 is +2 % on config 2, 288 is -4 %
   constexpr int kMaxCluster = 16;  // non-portable cluster size (8 is the portable limit); opted in below
   int splits = a.splits;
   if (splits <= 0) {
@@ -752,6 +873,8 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, cudaStream_t stream) {
   while (splits > 1 && splits > d.total_kblocks) splits /= 2;
   d.kblocks_per_split = ceil_div(d.total_kblocks, splits);
   if (tn > 65535) { set_error("igemm_tc: grid too large"); return -1; }
+  // (an 8-deep ring for single-wave launches was tried: 192 KB of shared memory per CTA stops the next kernel's CTAs from
+  // becoming resident during this one's tail -- programmatic dependent launch loses its overlap -- and layer4 got 2x slower)
   const size_t smem = (size_t)TC_STAGES * (TC_BM + BN) * TC_BK * 4;
   static bool attr_done = false;
   if (!attr_done) {
@@ -759,7 +882,14 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, cudaStream_t stream) {
     BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN, TMA>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_done = true;
   }
-  static const int proxy_fence_env = [] { const char* e = getenv("BRE_TC_PROXY_FENCE"); return e ? atoi(e) : 0; }();
+  static const int proxy_fence_env = [] {
+    const char* e = getenv("BRE_TC_PROXY_FENCE");
+    const char* pf = getenv("BRE_TC_PREFETCH");
+    const char* np = getenv("BRE_TC_PRODUCERS");
+    int nprod = np ? atoi(np) : 2;
+    if (nprod < 1 || nprod > 4) nprod = 2;
+    return (e && atoi(e) ? 1 : 0) | ((pf ? atoi(pf) : 1) ? 2 : 0) | (nprod << 2);
+  }();
   {
     cudaError_t lerr = launch_kernel(igemm_tc_kernel<MODE, BN, TMA>, dim3(tm, tn, splits), dim3(TC_BLOCK), smem, stream, splits, a, d,
                                      proxy_fence_env, maps);
@@ -802,3 +932,9 @@ int launch_igemm_tc(const GemmArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace bre
+
+#ifdef BRE_TC_TRACE
+extern "C" int bre_debug_tc_trace(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, bre::g_tc_trace, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#endif

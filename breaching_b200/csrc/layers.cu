@@ -32,7 +32,7 @@ __global__ void bn_prepare_kernel(const float* __restrict__ gamma, const float* 
 
 // ---- fused BN + residual + ReLU forward ------------------------------------------------------------
 __global__ void bnact_fwd_kernel(const float* __restrict__ in, const float* __restrict__ res, float* __restrict__ out,
-                                 long long total, int C, bool has_bn, bool relu, BnConsts bn) {
+                                 long long total, int C, bool has_bn, bool relu, BnConsts bn, bool round_out) {
   pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -40,7 +40,8 @@ __global__ void bnact_fwd_kernel(const float* __restrict__ in, const float* __re
     // eval-mode BN as ATen applies it: x * alpha + beta', alpha = gamma * invstd, beta' = beta - mean * alpha
     if (has_bn) u = fmaf(u, __ldg(bn.scale + c), __ldg(bn.shift + c));
     if (res != nullptr) u += res[i];
-    out[i] = relu ? fmaxf(u, 0.f) : u;
+    u = relu ? fmaxf(u, 0.f) : u;
+    out[i] = round_out ? tf32_rna(u) : u;
   }
 }
 
@@ -120,7 +121,10 @@ __global__ void bnact_bwd_kernel(BnActBwdArgs a, long long pps, int Cpad) {
         v[1] += du;
         di = scale * du;
       }
-      if (a.din != nullptr) a.din[o] = a.acc_in ? a.din[o] + di : di;
+      if (a.din != nullptr) {
+        if (a.acc_in) di += a.din[o];
+        a.din[o] = a.round_din ? tf32_rna(di) : di;
+      }
       if (a.dres != nullptr) a.dres[o] = a.acc_res ? a.dres[o] + du : du;
     }
   }
@@ -143,7 +147,7 @@ __global__ void bnact_tan_fwd_kernel(BnActTanFwdArgs a, long long total) {
     }
     if (a.tres != nullptr) u += a.tres[i];
     if (a.relu && !(a.out[i] > 0.f)) u = 0.f;
-    a.tout[i] = u;
+    a.tout[i] = a.round_out ? tf32_rna(u) : u;
   }
 }
 
@@ -159,7 +163,10 @@ __global__ void bnact_tan_bwd_kernel(BnActTanBwdArgs a, long long total) {
       tdi = fmaf(__ldg(a.bn.scale + c), tdu, __ldg(a.v_gamma + c) * __ldg(a.bn.inv + c) * du);
       if (a.di_cm != nullptr) tdi += fmaf(__ldg(a.di_cv + c), a.in[i] - __ldg(a.di_mean + c), __ldg(a.di_cm + c));
     }
-    if (a.tdin != nullptr) a.tdin[i] = a.acc_in ? a.tdin[i] + tdi : tdi;
+    if (a.tdin != nullptr) {
+      if (a.acc_in) tdi += a.tdin[i];
+      a.tdin[i] = a.round_din ? tf32_rna(tdi) : tdi;
+    }
     if (a.tdres != nullptr) a.tdres[i] = a.acc_res ? a.tdres[i] + tdu : tdu;
   }
 }
@@ -183,8 +190,11 @@ __global__ void bnact_tan_bwd_g_kernel(BnActTanBwdArgs a, long long pps, int Cpa
       const float tz = a.tin != nullptr ? a.tin[o] : 0.f;
       v[0] += fmaf(tdu, xhat, du * tz * inv);
       v[1] += tdu;
-      const float tdi = fmaf(scale, tdu, vg * inv * du);
-      if (a.tdin != nullptr) a.tdin[o] = a.acc_in ? a.tdin[o] + tdi : tdi;
+      float tdi = fmaf(scale, tdu, vg * inv * du);
+      if (a.tdin != nullptr) {
+        if (a.acc_in) tdi += a.tdin[o];
+        a.tdin[o] = a.round_din ? tf32_rna(tdi) : tdi;
+      }
       if (a.tdres != nullptr) a.tdres[o] = a.acc_res ? a.tdres[o] + tdu : tdu;
     }
   }
@@ -200,6 +210,16 @@ __global__ void axpby_kernel(const float* __restrict__ x, const float* __restric
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i), b = __ldg(reinterpret_cast<const float4*>(y) + i);
     reinterpret_cast<float4*>(out)[i] = make_float4(fmaf(alpha, b.x, a.x), fmaf(alpha, b.y, a.y), fmaf(alpha, b.z, a.z), fmaf(alpha, b.w, a.w));
+  }
+}
+
+// round-to-nearest (ties away) of fp32 values to the TF32 grid, in place: the tensor core drops the 13 low mantissa bits of
+// kind::tf32 operands (truncation), so operands rounded beforehand are multiplied as if converted with cvt.rna.tf32
+__global__ void round_tf32_kernel(const float* src, float* dst, long long n4) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<float4*>(dst)[i] = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
   }
 }
 
@@ -405,9 +425,9 @@ int launch_bn_prepare(const float* gamma, const float* beta, const float* rm, co
 }
 
 int launch_bnact_fwd(const float* in, const float* res, float* out, long long P, int C, bool has_bn, bool relu,
-                     BnConsts bn, cudaStream_t s) {
+                     BnConsts bn, bool round_out, cudaStream_t s) {
   const long long total = P * C;
-  BRE_KLAUNCH(bnact_fwd_kernel, ew_grid(total), kEwThreads, 0, s, in, res, out, total, C, has_bn, relu, bn);
+  BRE_KLAUNCH(bnact_fwd_kernel, ew_grid(total), kEwThreads, 0, s, in, res, out, total, C, has_bn, relu, bn, round_out);
   BRE_CHECK_LAUNCH();
   return 0;
 }
@@ -431,6 +451,12 @@ int launch_bnact_tan_fwd(const BnActTanFwdArgs& a, cudaStream_t s) {
 int launch_axpby(const float* x, const float* y, float alpha, float* out, long long n, cudaStream_t s) {
   if (n % 4 != 0) { set_error("axpby: length must be a multiple of 4"); return -1; }
   BRE_KLAUNCH(axpby_kernel, ew_grid(n / 4), kEwThreads, 0, s, x, y, alpha, out, n / 4);
+  return 0;
+}
+
+int launch_round_tf32(const float* src, float* dst, long long n, cudaStream_t s) {
+  if (n % 4 != 0) { set_error("round_tf32: length must be a multiple of 4"); return -1; }
+  BRE_KLAUNCH(round_tf32_kernel, ew_grid(n / 4), kEwThreads, 0, s, src, dst, n / 4);
   return 0;
 }
 

@@ -17,8 +17,9 @@ int launch_bn_prepare(const float* gamma, const float* beta, const float* rm, co
                       float* scale, float* shift, float* inv, float* nrm, cudaStream_t s);
 
 // out = relu?( bn?(in) + res? )
+// round_out: store `out` rounded onto the TF32 grid (it is an operand of tcgen05 GEMMs, see tf32_rna in common.cuh)
 int launch_bnact_fwd(const float* in, const float* res, float* out, long long P, int C, bool has_bn, bool relu,
-                     BnConsts bn, cudaStream_t s);
+                     BnConsts bn, bool round_out, cudaStream_t s);
 
 struct BnActBwdArgs {
   long long P; int C; bool has_bn, relu;
@@ -28,6 +29,7 @@ struct BnActBwdArgs {
   const float* dout;    // delta of out
   float* din; bool acc_in;     // may be null
   float* dres; bool acc_res;   // may be null
+  bool round_din;              // store din on the TF32 grid (GEMM operand of dgrad / wgrad)
   float* g_gamma; float* g_beta;  // parameter-gradient outputs (may be null)
   float* partials; int* counters; // scratch: >= slabs*Cpad*2 floats, >= Cgroups ints (zeroed, self-resetting)
 };
@@ -40,6 +42,7 @@ struct BnActTanFwdArgs {
   const float* tin; const float* tres; // tangents (may be null = zero)
   const float* v_gamma; const float* v_beta;
   float* tout;
+  bool round_out;                      // store tout on the TF32 grid
 };
 int launch_bnact_tan_fwd(const BnActTanFwdArgs& a, cudaStream_t s);
 
@@ -53,6 +56,7 @@ struct BnActTanBwdArgs {
   const float* di_cm; const float* di_cv; const float* di_mean;  // DeepInversion adjoint (may be null)
   float* tdin; bool acc_in;
   float* tdres; bool acc_res;
+  bool round_din;                      // store tdin on the TF32 grid
   // FedAvg (multi-step) only: tangent of the BN parameter gradients, needed for the Hessian-vector product that carries
   // the adjoint across local steps: tg_gamma = sum(tdu * xhat + du * tin * inv), tg_beta = sum(tdu)   (null = not needed)
   const float* tin; float* tg_gamma; float* tg_beta; float* partials; int* counters;
@@ -60,6 +64,7 @@ struct BnActTanBwdArgs {
 int launch_bnact_tan_bwd(const BnActTanBwdArgs& a, cudaStream_t s);
 // out[i] = x[i] + alpha * y[i]   (parameter-arena updates of the local-step recursion)
 int launch_axpby(const float* x, const float* y, float alpha, float* out, long long n, cudaStream_t s);
+int launch_round_tf32(const float* src, float* dst, long long n, cudaStream_t s);   // dst = src rounded onto the TF32 grid (may alias)
 
 // per-channel column sum: out[c] = sum_p x[p][c]   (conv / linear bias gradient)
 int launch_channel_sum(const float* x, long long P, int C, float* out, float* partials, int* counters, cudaStream_t s);

@@ -158,11 +158,10 @@ def make_cfg(cfg_attack, noise_seed=0):
     c.angular_fudge = 1e-7  # objectives.py:208
     opt = cfg_attack["optim"]
     name = str(opt["optimizer"]).lower()
-    if name not in OPTIMIZERS:
-        if name == "l-bfgs":
-            raise EngineError("L-BFGS is not implemented by the engine")
+    if name not in OPTIMIZERS and name != "l-bfgs":
         raise ValueError(f"Invalid optimizer {opt['optimizer']} given.")
-    c.optimizer, c.beta1, c.beta2, c.adam_eps, c.weight_decay, c.momentum, c.nesterov = OPTIMIZERS[name]
+    # L-BFGS trials are driven by attacks/lbfgs.py through objective_and_gradient(); the fused on-device step is unused then
+    c.optimizer, c.beta1, c.beta2, c.adam_eps, c.weight_decay, c.momentum, c.nesterov = OPTIMIZERS["gd" if name == "l-bfgs" else name]
     signed = cfg_get(opt, "signed")
     c.signed_mode = {"hard": 1, "soft": 2}.get(signed, 0) if isinstance(signed, str) else 0
     c.boxed = int(bool(cfg_get(opt, "boxed", False)))

@@ -440,6 +440,8 @@ class TrialOracle:
         T = opt["max_iterations"]
         n = T if iterations is None else min(T, iterations)
         lrs = lr_table(opt["step_size"], cfg_get(opt, "step_size_decay"), cfg_get(opt, "warmup", 0) or 0, T, n)
+        if opt["optimizer"].lower() == "l-bfgs":
+            return self._run_lbfgs(x0, n, lrs, dryrun, record)
         kind, b1, b2, eps, wd, mom, nesterov = _OPTIMS[opt["optimizer"].lower()]
         x = x0.detach().clone().to(self.dtype)
         m = torch.zeros_like(x)
@@ -476,6 +478,38 @@ class TrialOracle:
             if record:
                 trace.append(dict(objective=phi_f, raw_grad=raw, grad=g, candidate=x.clone(), lr=lr, terms=terms))
             if not math.isfinite(phi_f):  # :131-133
+                break
+            hist.append(phi_f)
+            if dryrun:
+                break
+        return best, hist, trace
+
+    def _run_lbfgs(self, x0, n, lrs, dryrun, record):
+        """L-BFGS trials (common.py:18: ``torch.optim.LBFGS(params, lr=step_size)``, torch defaults).  The update rule lives in
+        the third-party optimiser the reference calls; the oracle calls the same class with the reference's closure
+        (optimization_based_attack.py:146-189) -- the device restatement under test is breaching_b200/attacks/lbfgs.py."""
+        opt = self.cfg["optim"]
+        x = torch.nn.Parameter(x0.detach().clone().to(self.dtype))
+        optimizer = torch.optim.LBFGS([x], lr=opt["step_size"])
+        best, fmin, hist, trace = x.detach().clone(), float("inf"), [], []
+        lo, hi = -self.dm / self.ds, (1 - self.dm) / self.ds
+        for it in range(n):
+            optimizer.param_groups[0]["lr"] = lrs[it]
+
+            def closure():
+                phi, g, _, _ = self.closure_gradient(x.detach(), it, lrs[it], None)
+                x.grad = g.to(x.dtype)
+                return phi
+
+            phi_f = float(optimizer.step(closure))
+            with torch.no_grad():
+                if cfg_get(opt, "boxed", False):
+                    x.data = torch.max(torch.min(x, hi), lo)
+                if phi_f < fmin:
+                    fmin, best = phi_f, x.detach().clone()
+            if record:
+                trace.append(dict(objective=phi_f, candidate=x.detach().clone(), lr=lrs[it]))
+            if not math.isfinite(phi_f):
                 break
             hist.append(phi_f)
             if dryrun:

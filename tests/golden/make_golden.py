@@ -50,6 +50,17 @@ CASES = {
 }
 
 
+LBFGS_CASES = {
+    # L-BFGS presets (common.py:18; `beyondinfering.yaml`, `wei.yaml`): 20 inner iterations per optimizer.step, hard-signed
+    # gradients (the default `optim.signed`) resp. task-loss regularisation + euclidean matching
+    "lbfgs_convnet": (dict(model_name="convnet-tiny", data="cifar", batch=1, seed=15, bn_random=True), "beyondinfering", {}, 3),
+    "lbfgs_wei_convnet": (dict(model_name="convnet-tiny", data="cifar", batch=2, seed=16, bn_random=True), "wei",
+                          {"optim.signed": None}, 3),
+    "lbfgs_cosine_convnet": (dict(model_name="convnet-tiny", data="cifar", batch=2, seed=17, bn_random=True), "invertinggradients",
+                             {"optim.optimizer": "L-BFGS", "optim.signed": None, "optim.step_size": 0.5,
+                              "optim.step_size_decay": "cosine-decay"}, 4),
+}
+
 FEDAVG_CASES = {
     # FedAvg multi-step updates (objectives.py:48-72).  `features` / `deep_inversion` crash in the reference together with
     # FedAvg, so the fixture uses the `modern` preset with the features prior switched off.
@@ -184,10 +195,15 @@ def config_fixtures():
 def main():
     ref = refshim.import_reference()
     torch.manual_seed(0)
-    for name, (case_kwargs, attack, overrides, iters) in {**CASES, **FEDAVG_CASES}.items():
+    only = sys.argv[1:]   # optional: regenerate just the named fixtures
+    for name, (case_kwargs, attack, overrides, iters) in {**CASES, **FEDAVG_CASES, **LBFGS_CASES}.items():
+        if only and name not in only:
+            continue
         fx = run_reference(ref, case_kwargs, attack, overrides, iters)
         torch.save(fx, os.path.join(HERE, f"trial_{name}.pt"))
         print(name, "history", [round(h, 5) for h in fx["history"]], "score", fx["score"])
+    if only:
+        return
     torch.save(label_fixtures(ref), os.path.join(HERE, "labels.pt"))
     torch.save(lr_fixtures(ref), os.path.join(HERE, "lr_tables.pt"))
     torch.save(config_fixtures(), os.path.join(HERE, "attack_configs.pt"))

@@ -56,3 +56,4 @@ def oracle_for_fixture(fx):
 
 TRIAL_FIXTURES = ["ig_convnet", "ig_resnet18", "stg_resnet18", "modern_convnet", "tag_clip_convnet", "l1_sgd_convnet"]
 FEDAVG_FIXTURES = ["fedavg_convnet", "fedavg_resnet18"]
+LBFGS_FIXTURES = ["lbfgs_convnet", "lbfgs_wei_convnet", "lbfgs_cosine_convnet"]

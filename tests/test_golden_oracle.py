@@ -4,10 +4,10 @@ import math
 import pytest
 import torch
 
-from helpers import FEDAVG_FIXTURES, TRIAL_FIXTURES, load_golden, oracle_for_fixture
+from helpers import FEDAVG_FIXTURES, LBFGS_FIXTURES, TRIAL_FIXTURES, load_golden, oracle_for_fixture
 
 
-@pytest.mark.parametrize("name", TRIAL_FIXTURES + FEDAVG_FIXTURES)
+@pytest.mark.parametrize("name", TRIAL_FIXTURES + FEDAVG_FIXTURES + LBFGS_FIXTURES)
 def test_oracle_reproduces_reference_trajectory(name):
     fx = load_golden(f"trial_{name}.pt")
     orc, cfg, labels = oracle_for_fixture(fx)
@@ -18,13 +18,16 @@ def test_oracle_reproduces_reference_trajectory(name):
     assert rel < 1e-4, rel
     best, hist, trace = orc.run(fx["x0"], iterations=fx["iters"], record=True)
     assert len(hist) == len(fx["history"])
+    # L-BFGS takes 20 inner iterations per recorded value: float32 summation-order differences (and, with the default hard
+    # sign, flipped entries of near-zero gradients) are amplified by the curvature estimate
+    tol = 3e-2 if name in LBFGS_FIXTURES else 2e-4
     for a, b in zip(hist, fx["history"]):
-        assert math.isclose(a, b, rel_tol=2e-4, abs_tol=1e-6), (hist, fx["history"])
+        assert math.isclose(a, b, rel_tol=tol, abs_tol=1e-6), (hist, fx["history"])
     for t, lr in zip(trace, fx["lrs"]):
         assert math.isclose(t["lr"], lr, rel_tol=1e-9, abs_tol=1e-12)
-    assert (trace[0]["candidate"] - fx["candidate_after_1"]).abs().max().item() < 1e-4
+    assert (trace[0]["candidate"] - fx["candidate_after_1"]).abs().max().item() < (5e-2 if name in LBFGS_FIXTURES else 1e-4)
     # later iterates may differ where a hard sign flips on a near-zero gradient entry: compare in the mean
-    assert (trace[-1]["candidate"] - fx["candidate_final"]).abs().mean().item() < 2e-3
+    assert (trace[-1]["candidate"] - fx["candidate_final"]).abs().mean().item() < (2e-2 if name in LBFGS_FIXTURES else 2e-3)
     score = orc.score(best, fx["scoring"])
     assert math.isclose(score, fx["score"], rel_tol=5e-2, abs_tol=1e-5)
     orc.close()

@@ -1,5 +1,6 @@
 """Host-side pieces that need no GPU: compiler, C-ABI library symbols, multi-rank selection over gloo."""
 import ctypes
+import math
 import os
 import re
 import subprocess
@@ -149,3 +150,45 @@ def test_trial_selection_over_two_gloo_ranks(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_device_lbfgs_restates_torch_lbfgs():
+    """breaching_b200/attacks/lbfgs.py against the optimiser the reference constructs (common.py:18:
+    ``torch.optim.LBFGS(params, lr)``, torch defaults) on a smooth non-quadratic test function: same loss sequence,
+    same iterate, across several ``step`` calls (the optimiser state persists between them) and a changing lr."""
+    from breaching_b200.attacks.lbfgs import DeviceLBFGS
+
+    gen = torch.Generator().manual_seed(0)
+    A = torch.randn(40, 24, generator=gen)
+    b = torch.randn(40, generator=gen)
+
+    def f(z):
+        r = A @ z - b
+        return 0.5 * (r * r).sum() / 40 + 0.1 * torch.log1p(z * z).sum()
+
+    x_ref = torch.nn.Parameter(torch.randn(24, generator=gen))
+    x_dev = x_ref.detach().clone()
+    ref_opt = torch.optim.LBFGS([x_ref], lr=1.0)
+    dev_opt = DeviceLBFGS(x_dev)
+
+    def ref_closure():
+        ref_opt.zero_grad()
+        loss = f(x_ref)
+        loss.backward()
+        return loss
+
+    def dev_closure():
+        z = x_dev.detach().clone().requires_grad_(True)
+        loss = f(z)
+        (g,) = torch.autograd.grad(loss, z)
+        return float(loss), g
+
+    for lr in (0.05, 0.3, 1.0, 1.0, 0.5):
+        ref_opt.param_groups[0]["lr"] = lr
+        a = float(ref_opt.step(ref_closure))
+        c = dev_opt.step(dev_closure, lr)
+        assert math.isclose(a, c, rel_tol=1e-4, abs_tol=1e-6), (a, c)
+        assert (x_ref.detach() - x_dev).abs().max().item() < 1e-3 * (1 + x_ref.detach().abs().max().item())
+    # at convergence the `directional derivative > -1e-9` exit is taken on a float32 rounding difference: one evaluation apart
+    assert abs(dev_opt.func_evals - ref_opt.state[x_ref]["func_evals"]) <= 1
+    assert dev_opt.total_iters == ref_opt.state[x_ref]["n_iter"]
