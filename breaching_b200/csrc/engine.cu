@@ -170,7 +170,10 @@ struct bre_engine {
   float* Vp(int idx) const { return V + params[idx].off; }
   const float* Wg(int idx) const { return (tc_round() ? Wt : W) + params[idx].off; }   // conv / linear weights as GEMM operands
   const float* Vg(int idx) const { return (tc_round() ? Vt : V) + params[idx].off; }
-  int refresh_Vt() { return tc_round() ? launch_round_tf32(V, Vt, P_pad, stream) : 0; }
+  int refresh_Vt() {
+    if (tc_round()) BRE_LAUNCH(launch_round_tf32(V, Vt, P_pad, stream));
+    return 0;
+  }
   // Which activation tensors are operands of a tensor-core GEMM: inputs (value / tangent) and output deltas of the
   // convolutions the tcgen05 back end covers.  Only those are stored TF32-rounded; layers that run on the fp32 SIMT kernels
   // (3-channel stem, narrow test networks, the classifier head) keep full fp32 operands.
@@ -328,6 +331,8 @@ struct bre_engine {
           a.dres = op.res >= 0 ? t[op.res].d : nullptr; a.acc_res = op.acc_res != 0;
           a.g_gamma = op.has_bn ? Gp(op.gamma) : nullptr; a.g_beta = op.has_bn ? Gp(op.beta) : nullptr;
           a.partials = red_partials; a.counters = red_counters;
+          // (splitting this op into an element-wise kernel on the main stream and the gamma / beta reductions on the side
+          // stream was measured: config 2 unchanged, configs 1 and 3 3-5 % slower -- the side stream is already full)
           BRE_LAUNCH(launch_bnact_bwd(a, stream));
           break;
         }
