@@ -1,7 +1,8 @@
 """Drop-in for ``breaching.attacks`` (reference ``attacks/__init__.py:12-37``)."""
 import torch
 
-from .optimization_attack import OptimizationBasedAttacker
+from .joint_attack import OptimizationJointAttacker
+from .optimization_attack import OptimizationBasedAttacker, _loss_name
 
 _OTHER_ATTACKS = (
     "multiscale", "analytic", "april-analytic", "imprint-readout", "decepticon-readout", "recursive",
@@ -18,6 +19,9 @@ def prepare_attack(model, loss, cfg_attack, setup=dict(dtype=torch.float, device
     """
     if cfg_attack.attack_type == "optimization":
         return OptimizationBasedAttacker(model, loss, cfg_attack, setup)
+    if cfg_attack.attack_type == "joint-optimization" and _loss_name(loss) == "CrossEntropyLoss":
+        # classification models (deepleakage.yaml); token models with CausalLoss (tag.yaml) fall through to the delegation below
+        return OptimizationJointAttacker(model, loss, cfg_attack, setup)
     if cfg_attack.attack_type in _OTHER_ATTACKS:
         from ..install import reference_prepare_attack
 
@@ -31,4 +35,4 @@ def prepare_attack(model, loss, cfg_attack, setup=dict(dtype=torch.float, device
     raise ValueError(f"Invalid type of attack {cfg_attack.attack_type} given.")
 
 
-__all__ = ["prepare_attack", "OptimizationBasedAttacker"]
+__all__ = ["prepare_attack", "OptimizationBasedAttacker", "OptimizationJointAttacker"]

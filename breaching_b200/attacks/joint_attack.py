@@ -1,0 +1,191 @@
+"""``OptimizationJointAttacker`` on the sm_100a engine: data and labels are optimised together ("deep leakage from
+gradients"-style attacks; reference ``attacks/optimization_with_label_attack.py:38-230``, presets ``deepleakage.yaml``).
+
+The label candidate is a second leaf ``[N, classes]``; the closure hands ``labels.softmax(-1)`` to the task loss as class
+probabilities (:154), back-propagates the objective onto both leaves (:162), post-processes both gradients separately
+(:164-186) and one optimiser steps both (:108).  On the engine one closure evaluation is one pass of the four sweeps with
+soft targets in the cross-entropy (``bre_engine_load_soft_labels``); the gradient w.r.t. the probabilities falls out of the
+tangent logits of that same pass (``bre_engine_label_gradient``: the matching term sees the probabilities only through
+``dL/dq = -log_softmax(z)/N``) and is chained through the softmax here.  The loop is host-driven (two small leaves, any
+torch-style optimiser incl. L-BFGS); the fused on-device step of the single-leaf attacker is not used.
+
+Vision classification models only: the text / transformer variant (``tag.yaml``) needs
+attention / LayerNorm sweeps the engine does not have yet and raises.
+"""
+import logging
+import math
+
+import torch
+
+from .. import dist as bdist
+from ..config import cfg_get
+from ..schedule import lr_table
+from . import host, lbfgs
+from .optimization_attack import OptimizationBasedAttacker
+
+log = logging.getLogger(__name__)
+
+# common.py:6-17 -> (kind, beta1, beta2, eps, weight_decay, momentum, nesterov)
+_OPTIMIZERS = {
+    "adam": ("adam", 0.9, 0.999, 1e-8, 0.0, 0.0, False),
+    "adam-safe": ("adam", 0.5, 0.99, 1e-4, 0.0, 0.0, False),
+    "bert-adam": ("adamw", 0.9, 0.999, 1e-6, 0.01, 0.0, False),
+    "momgd": ("sgd", 0.0, 0.0, 0.0, 0.0, 0.9, True),
+    "gd": ("sgd", 0.0, 0.0, 0.0, 0.0, 0.0, False),
+}
+
+
+class _LeafOptimizer:
+    """torch.optim.Adam / AdamW / SGD update rules (the classes ``optimizer_lookup`` builds) for a list of device leaves."""
+
+    def __init__(self, leaves, name):
+        self.kind, self.b1, self.b2, self.eps, self.wd, self.mom, self.nesterov = _OPTIMIZERS[name]
+        self.leaves = leaves
+        self.m = [torch.zeros_like(p) for p in leaves]
+        self.v = [torch.zeros_like(p) for p in leaves]
+        self.t = 0
+
+    def step(self, grads, lr):
+        self.t += 1
+        for p, g, m, v in zip(self.leaves, grads, self.m, self.v):
+            if self.kind in ("adam", "adamw"):
+                if self.kind == "adamw":
+                    p.mul_(1 - lr * self.wd)
+                m.mul_(self.b1).add_(g, alpha=1 - self.b1)
+                v.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+                bc1, bc2 = 1 - self.b1 ** self.t, 1 - self.b2 ** self.t
+                denom = v.sqrt().div_(math.sqrt(bc2)).add_(self.eps)
+                p.addcdiv_(m, denom, value=-lr / bc1)
+            else:
+                d = g
+                if self.mom != 0:
+                    if self.t == 1:
+                        m.copy_(g)
+                    else:
+                        m.mul_(self.mom).add_(g)
+                    d = g.add(m, alpha=self.mom) if self.nesterov else m
+                p.add_(d, alpha=-lr)
+
+
+class OptimizationJointAttacker(OptimizationBasedAttacker):
+    """Optimises jointly for candidate data and labels on the B200 engine."""
+
+    # optimization_with_label_attack.py:43-51 -- the "recovered labels" are a template of label logits
+    def _label_template(self, shared_data, metadata):
+        n = shared_data[0]["metadata"]["num_data_points"]
+        if metadata["task"] != "classification":
+            raise NotImplementedError("joint optimisation of token labels (text models) is not implemented by the B200 engine")
+        return host.initialize_data(self.cfg.init, [n, metadata.classes], self.dm, self.ds, self.setup)
+
+    def prepare_attack(self, server_payload, shared_data):
+        if shared_data[0]["metadata"]["labels"] is not None:  # :56-60
+            raise ValueError(
+                "Joint optimization only makes sense if no labels are provided. Switch to attack.attack_type=optimization instead"
+            )
+        metadata = server_payload[0]["metadata"]
+        # the base class would run a label-recovery strategy; the joint attacker replaces it by the template (:43-51)
+        placeholder = shared_data[0]["metadata"]["num_data_points"]
+        shared = [dict(d) for d in shared_data]
+        shared[0] = dict(shared[0], metadata=dict(shared[0]["metadata"], labels=torch.zeros(placeholder, dtype=torch.long)))
+        rec_models, _, stats, shared = super().prepare_attack(server_payload, shared)
+        shared[0]["metadata"]["labels"] = None
+        template = self._label_template(shared, metadata)
+        return rec_models, template, stats, shared
+
+    def reconstruct(self, server_payload, shared_data, server_secrets=None, initial_data=None, dryrun=False):
+        rec_models, labels, stats, shared_data = self.prepare_attack(server_payload, shared_data)
+        if any(True for _ in self.regularizers) and any(k in ("deep_inversion", "features") for k, _ in self.regularizers):
+            raise NotImplementedError("feature / DeepInversion priors are not implemented for the joint attacker")
+        engine = self._get_engine(rec_models, shared_data, torch.zeros(labels.shape[0], dtype=torch.long))
+        num_trials = self.cfg.restarts.num_trials
+        rank, world = bdist.rank_and_world()
+        scores = torch.full((num_trials,), float("inf"))
+        candidate_solutions = [None] * num_trials
+        shape = [shared_data[0]["metadata"]["num_data_points"], *self.data_shape]
+        hard_labels = labels.argmax(dim=-1)  # :67 -- of the template, not of the optimised labels (reference behaviour)
+        try:
+            for trial in range(num_trials):
+                candidate = host.initialize_data(self.cfg.init, shape, self.dm, self.ds, self.setup)
+                candidate_labels = host.initialize_data(self.cfg.init, list(labels.shape), self.dm, self.ds, self.setup)
+                if initial_data is not None:
+                    candidate = initial_data.detach().clone().to(**self.setup)
+                if trial % world != rank:
+                    continue
+                data, _ = self._run_joint_trial(engine, candidate, candidate_labels, stats, trial, dryrun)
+                candidate_solutions[trial] = data
+                scores[trial] = self._score_joint(engine, data, hard_labels)
+        except KeyboardInterrupt:
+            print("Trial procedure manually interruped.")
+        optimal_solution = self._select_optimal_reconstruction(candidate_solutions, scores, stats, shape)
+        reconstructed_data = dict(data=optimal_solution, labels=hard_labels)
+        if server_secrets is not None and "ClassAttack" in server_secrets:
+            true_num_data = server_secrets["ClassAttack"]["true_num_data"]
+            reconstructed_data["data"] = torch.zeros([true_num_data, *self.data_shape], **self.setup)
+            reconstructed_data["data"][server_secrets["ClassAttack"]["target_indx"]] = optimal_solution
+            reconstructed_data["labels"] = server_secrets["ClassAttack"]["all_labels"]
+        return reconstructed_data, stats
+
+    # ------------------------------------------------------------------------------------------------
+    def _closure(self, engine, x, ell, iteration, lr):
+        """optimization_with_label_attack.py:145-189 -> (objective, processed d/dx, processed d/dlabels, raw pair)."""
+        q = ell.softmax(dim=-1)
+        engine.load_soft_labels(q)
+        value, gx = engine.objective_and_gradient(x)
+        gq = engine.label_gradient(tuple(ell.shape))
+        gl = q * (gq - (q * gq).sum(dim=-1, keepdim=True))   # chain through the softmax (autograd does this at :162)
+        raw = (gx, gl)
+        opt = self.cfg.optim
+        gx = lbfgs.postprocess_gradient(gx, opt, iteration, lr)
+        gl = lbfgs.postprocess_gradient(gl, opt, iteration, lr)
+        return float(value), gx, gl, raw
+
+    def _run_joint_trial(self, engine, candidate, candidate_labels, stats, trial, dryrun=False, iterations=None):
+        opt = self.cfg.optim
+        T = int(opt.max_iterations)
+        table = lr_table(opt.step_size, cfg_get(opt, "step_size_decay"), cfg_get(opt, "warmup", 0), T)
+        x = candidate.detach().clone().contiguous()
+        ell = candidate_labels.detach().clone().contiguous()
+        best, best_l, fmin = x.clone(), ell.clone(), float("inf")
+        dm, ds = self.dm.to(x.device), self.ds.to(x.device)
+        lo, hi = -dm / ds, (1 - dm) / ds
+        name = str(opt.optimizer).lower()
+        if name == "l-bfgs":
+            flat = torch.cat([x.view(-1), ell.view(-1)])   # torch's L-BFGS treats all leaves as one flat vector
+            x, ell = flat[: x.numel()].view_as(x), flat[x.numel():].view_as(ell)
+            optimizer = lbfgs.DeviceLBFGS(flat)
+        elif name in _OPTIMIZERS:
+            optimizer = _LeafOptimizer([x, ell], name)
+        else:
+            raise ValueError(f"Invalid optimizer {opt.optimizer} given.")
+        total = 1 if dryrun else (T if iterations is None else iterations)
+        history = []
+        for it in range(total):
+            lr = float(table[it])
+            if name == "l-bfgs":
+                def closure():
+                    val, gx, gl, _ = self._closure(engine, x, ell, it, lr)
+                    return val, torch.cat([gx.reshape(-1), gl.reshape(-1)])
+
+                value = optimizer.step(closure, lr)
+            else:
+                value, gx, gl, _ = self._closure(engine, x, ell, it, lr)
+                optimizer.step([gx, gl], lr)
+            if cfg_get(opt, "boxed", False):
+                torch.max(torch.min(x, hi, out=x), lo, out=x)
+            if value < fmin:
+                fmin = value
+                best.copy_(x)
+                best_l.copy_(ell)
+            if not math.isfinite(value):
+                log.info(f"Recovery loss is non-finite in iteration {it}. Cancelling reconstruction!")
+                break
+            history.append(value)
+        stats[f"Trial_{trial}_Val"].extend(history)
+        self._last_joint_state = (x.detach().clone(), ell.detach().clone())
+        return best.detach(), best_l.detach()
+
+    def _score_joint(self, engine, candidate, hard_labels):
+        """optimization_with_label_attack.py:207-221: a fresh objective with the template's arg-max labels."""
+        engine.load_soft_labels(None)
+        engine.set_labels(hard_labels)
+        return self._score_trial(engine, candidate)

@@ -94,6 +94,9 @@ struct bre_engine {
   bool tc_round() const { return gemm_backend == 1 && tc_round_env; }
   float *p = nullptr, *loss_n = nullptr;
   long long* labels = nullptr;
+  float* soft_q = nullptr;        // class-probability targets [N, C] (joint-optimisation attacks), null = index labels
+  float* soft_q_buf = nullptr;    // owned storage behind soft_q
+  float* label_grad = nullptr;    // d(objective)/d(soft_q) of the last evaluation
   int n_labels = 0;
   // candidate state
   long long nx = 0;
@@ -285,7 +288,7 @@ struct bre_engine {
       }
     }
     const bre_tensor_desc& lt = td(logits);
-    BRE_LAUNCH(launch_ce_fwd(t[logits].val, labels, lt.N, lt.C, p, loss_n, t[logits].d, stream));
+    BRE_LAUNCH(launch_ce_fwd(t[logits].val, labels, soft_q, lt.N, lt.C, p, loss_n, t[logits].d, stream));
     BRE_LAUNCH(launch_loss_mean(loss_n, lt.N, sc, stream));
     return 0;
   }
@@ -859,6 +862,40 @@ int bre_engine_load_feature_targets(bre_engine* e, const float* measured, int64_
   e->feat_numel = numel;
   BRE_CUDA_CHECK(cudaMemcpy(e->feat_measured, measured, numel * sizeof(float), cudaMemcpyDefault));
   e->graph_ready = false;
+  return BRE_OK;
+}
+
+int bre_engine_load_soft_labels(bre_engine* e, const float* probabilities, int64_t numel) {
+  if (!e) return BRE_ERR_INVALID;
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  e->graph_ready = false;
+  if (probabilities == nullptr) { e->soft_q = nullptr; return BRE_OK; }   // back to index labels
+  const bre_tensor_desc& lt = e->td(e->logits);
+  if (numel != (int64_t)lt.N * lt.C) { set_error("bre_engine_load_soft_labels: expected N x classes probabilities"); return BRE_ERR_INVALID; }
+  if (e->ms_steps > 0) { set_error("soft labels are not supported together with local steps"); return BRE_ERR_UNSUPPORTED; }
+  if (!e->soft_q_buf) { BRE_TRY(e->alloc(&e->soft_q_buf, numel)); BRE_TRY(e->alloc(&e->label_grad, numel)); }
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->soft_q_buf, probabilities, numel * sizeof(float), cudaMemcpyDefault, e->stream));
+  e->soft_q = e->soft_q_buf;
+  return BRE_OK;
+}
+
+int bre_engine_set_labels(bre_engine* e, const int64_t* labels, int32_t n_labels) {
+  if (!e || !labels) return BRE_ERR_INVALID;
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  if (n_labels != e->td(e->logits).N) { set_error("bre_engine_set_labels: one label per row of the logits expected"); return BRE_ERR_INVALID; }
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->labels, labels, n_labels * sizeof(int64_t), cudaMemcpyDefault, e->stream));
+  return BRE_OK;
+}
+
+int bre_engine_label_gradient(bre_engine* e, float* grad_out) {
+  if (!e || !grad_out) return BRE_ERR_INVALID;
+  if (!e->soft_q) { set_error("bre_engine_label_gradient: no soft labels loaded"); return BRE_ERR_STATE; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  const bre_tensor_desc& lt = e->td(e->logits);
+  BRE_TRY(launch_ce_label_grad(e->t[e->logits].val, e->p, e->t[e->logits].tval, lt.N, lt.C, e->cfg.task_regularization, e->label_grad,
+                               e->stream));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(grad_out, e->label_grad, (size_t)lt.N * lt.C * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   return BRE_OK;
 }
 

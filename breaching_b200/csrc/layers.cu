@@ -342,8 +342,10 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dout, float* __rest
 }
 
 // ---- softmax cross-entropy -------------------------------------------------------------------------
-__global__ void ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int N, int C, float* p,
-                              float* loss_n, float* dlogits) {
+// Softmax cross-entropy, mean over N.  Targets: class indices, or -- joint data / label optimisation
+// (optimization_with_label_attack.py:154: `labels.softmax(dim=-1)` handed to the loss) -- class probabilities q [N, C].
+__global__ void ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, const float* __restrict__ q, int N,
+                              int C, float* p, float* loss_n, float* dlogits) {
   pdl_prologue();
   __shared__ double scratch[32];
   __shared__ float s_max, s_sum;
@@ -368,14 +370,66 @@ __global__ void ce_fwd_kernel(const float* __restrict__ logits, const long long*
   if (threadIdx.x == 0) s_sum = (float)tot;
   __syncthreads();
   const float sum = s_sum;
-  const int y = (int)labels[n];
   const float invN = 1.0f / (float)N;
+  if (q != nullptr) {
+    const float lse = mx + logf(sum);
+    double lpart = 0.0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float pc = expf(z[c] - mx) / sum, qc = q[(long long)n * C + c];
+      p[(long long)n * C + c] = pc;
+      dlogits[(long long)n * C + c] = (pc - qc) * invN;
+      lpart -= (double)qc * (double)(z[c] - lse);
+    }
+    const double ltot = block_sum(lpart, scratch);
+    if (threadIdx.x == 0) loss_n[n] = (float)ltot;
+    return;
+  }
+  const int y = (int)labels[n];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float pc = expf(z[c] - mx) / sum;
     p[(long long)n * C + c] = pc;
     dlogits[(long long)n * C + c] = (pc - (c == y ? 1.f : 0.f)) * invN;
   }
   if (threadIdx.x == 0) loss_n[n] = -(z[y] - mx - logf(sum));
+}
+
+// d(objective)/d(target probabilities): the matching term sees q only through dL/dq = -log_softmax(z) / N, whose tangent in
+// the weight direction v is -(zdot - <p, zdot>) / N; the task-loss regulariser adds task_reg * dL/dq itself.
+__global__ void ce_label_grad_kernel(const float* __restrict__ logits, const float* __restrict__ p, const float* __restrict__ zdot, int N,
+                                     int C, float task_reg, float* __restrict__ out) {
+  pdl_prologue();
+  __shared__ double scratch[32];
+  __shared__ float s_dot, s_lse;
+  const int n = blockIdx.x;
+  const float* z = logits + (long long)n * C;
+  const float* pp = p + (long long)n * C;
+  const float* zz = zdot + (long long)n * C;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) part += (double)pp[c] * (double)zz[c];
+  const double tot = block_sum(part, scratch);
+  if (threadIdx.x == 0) s_dot = (float)tot;
+  __syncthreads();
+  if (task_reg != 0.f) {   // log-sum-exp of the row (uniform branch)
+    float mx = -FLT_MAX;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, z[c]);
+    __shared__ float wmax[32];
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = wmax[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, wmax[w]);
+    double spart = 0.0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) spart += (double)expf(z[c] - mx);
+    const double stot = block_sum(spart, scratch);
+    if (threadIdx.x == 0) s_lse = mx + logf((float)stot);
+    __syncthreads();
+  }
+  const float dot = s_dot, invN = 1.0f / (float)N;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = -(zz[c] - dot) * invN;
+    if (task_reg != 0.f) v -= task_reg * (z[c] - s_lse) * invN;
+    out[(long long)n * C + c] = v;
+  }
 }
 
 __global__ void ce_tan_bwd_kernel(const float* __restrict__ p, const float* __restrict__ zdot, int N, int C, float* tdl) {
@@ -523,9 +577,14 @@ int launch_avgpool_bwd(const float* dout, float* din, bool acc, int N, int HW, i
   return 0;
 }
 
-int launch_ce_fwd(const float* logits, const long long* labels, int N, int C, float* p, float* loss_n, float* dlogits,
-                  cudaStream_t s) {
-  BRE_KLAUNCH(ce_fwd_kernel, N, 256, 0, s, logits, labels, N, C, p, loss_n, dlogits);
+int launch_ce_fwd(const float* logits, const long long* labels, const float* q, int N, int C, float* p, float* loss_n,
+                  float* dlogits, cudaStream_t s) {
+  BRE_KLAUNCH(ce_fwd_kernel, N, 256, 0, s, logits, labels, q, N, C, p, loss_n, dlogits);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+int launch_ce_label_grad(const float* logits, const float* p, const float* zdot, int N, int C, float task_reg, float* out, cudaStream_t s) {
+  BRE_KLAUNCH(ce_label_grad_kernel, N, 256, 0, s, logits, p, zdot, N, C, task_reg, out);
   BRE_CHECK_LAUNCH();
   return 0;
 }

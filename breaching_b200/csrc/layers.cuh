@@ -80,8 +80,12 @@ int launch_avgpool_fwd(const float* in, float* out, int N, int HW, int C, cudaSt
 int launch_avgpool_bwd(const float* dout, float* din, bool acc, int N, int HW, int C, cudaStream_t s);
 
 // softmax cross-entropy (mean over N): p, per-sample loss and dlogits = (p - onehot)/N
-int launch_ce_fwd(const float* logits, const long long* labels, int N, int C, float* p, float* loss_n, float* dlogits,
-                  cudaStream_t s);
+// q (may be null): class-probability targets [N, C] instead of the index labels (joint data / label optimisation)
+int launch_ce_fwd(const float* logits, const long long* labels, const float* q, int N, int C, float* p, float* loss_n,
+                  float* dlogits, cudaStream_t s);
+// d(objective)/dq from the tangent logits of the last tangent-forward sweep (+ task_reg * dL/dq)
+int launch_ce_label_grad(const float* logits, const float* p, const float* zdot, int N, int C, float task_reg, float* out,
+                         cudaStream_t s);
 // tangent of dlogits: (p*zdot - p * sum(p*zdot)) / N
 int launch_ce_tan_bwd(const float* p, const float* zdot, int N, int C, float* tdlogits, cudaStream_t s);
 

@@ -51,6 +51,7 @@ __device__ void finalize_objective(Scalars* sc, int objective, float scale, floa
   sc->c1 = (float)c1; sc->c2 = (float)c2; sc->c3 = (float)c3;
 }
 
+template <int U>
 __global__ void __launch_bounds__(256) match_reduce_kernel(const float* __restrict__ G, const float* __restrict__ g,
                                                           const float* __restrict__ chunk_w, long long n, long long nchunks,
                                                           float mask_value, int objective, float scale, float tag_scale,
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(256) match_reduce_kernel(const float* __restri
   __shared__ int s_last;
   double acc[5] = {0, 0, 0, 0, 0};
   const bool masked = mask_value >= 0.f;
-  constexpr int U = 4;  // chunks in flight per block iteration: 8 independent 128-bit loads per thread
+  // U chunks in flight per block iteration: 2 U independent 128-bit loads per thread
   for (long long base = (long long)blockIdx.x * U; base < nchunks; base += (long long)gridDim.x * U) {
     float a[U][4], b[U][4];
 #pragma unroll
@@ -493,14 +494,24 @@ __global__ void __launch_bounds__(256) feature_reg_kernel(const float* __restric
 
 }  // namespace
 
+// launch shape of the matching reduction (tuned on the B200 with profiles/experiments/tune_match_reduce.py)
+static int g_match_blocks_per_sm = 4, g_match_unroll = 4;
+
 int launch_match_reduce(const float* G, const float* g, const float* chunk_w, long long n, float mask_value,
                         int objective, float scale, float tag_scale, float fudge, bool finalize, Scalars* sc,
                         double* partials, int* counter, cudaStream_t s) {
   const long long nchunks = (n + kChunk - 1) / kChunk;
-  const long long groups = (nchunks + 3) / 4;
-  const int grid = (int)(groups < kMatchMaxBlocks ? (groups > 0 ? groups : 1) : kMatchMaxBlocks);
-  BRE_KLAUNCH(match_reduce_kernel, grid, 256, 0, s, G, g, chunk_w, n, nchunks, mask_value, objective, scale, tag_scale, fudge,
-                                           finalize, sc, partials, counter);
+  const int unroll = g_match_unroll == 8 ? 8 : 4;
+  const long long groups = (nchunks + unroll - 1) / unroll;
+  int cap = kNumSMs * g_match_blocks_per_sm;
+  if (cap > kMatchMaxBlocks) cap = kMatchMaxBlocks;
+  const int grid = (int)(groups < cap ? (groups > 0 ? groups : 1) : cap);
+  if (unroll == 8)
+    BRE_KLAUNCH(match_reduce_kernel<8>, grid, 256, 0, s, G, g, chunk_w, n, nchunks, mask_value, objective, scale, tag_scale, fudge,
+                finalize, sc, partials, counter);
+  else
+    BRE_KLAUNCH(match_reduce_kernel<4>, grid, 256, 0, s, G, g, chunk_w, n, nchunks, mask_value, objective, scale, tag_scale, fudge,
+                finalize, sc, partials, counter);
   BRE_CHECK_LAUNCH();
   return 0;
 }
@@ -561,3 +572,9 @@ int launch_feature_reg(const float* feat, const float* measured, float* tdelta, 
 }
 
 }  // namespace bre
+
+// tuning hook for profiles/experiments/tune_match_reduce.py (not part of the reference-facing ABI)
+extern "C" void bre_debug_match_config(int blocks_per_sm, int unroll) {
+  if (blocks_per_sm >= 1 && blocks_per_sm <= 8) bre::g_match_blocks_per_sm = blocks_per_sm;
+  if (unroll == 4 || unroll == 8) bre::g_match_unroll = unroll;
+}

@@ -14,7 +14,7 @@ constexpr int kChunk = 1024;  // arena granularity of the matching reduction (pe
 int launch_match_reduce(const float* G, const float* g, const float* chunk_w, long long n, float mask_value,
                         int objective, float scale, float tag_scale, float fudge, bool finalize, Scalars* sc,
                         double* partials, int* counter, cudaStream_t s);
-constexpr int kMatchMaxBlocks = kNumSMs * 4;
+constexpr int kMatchMaxBlocks = kNumSMs * 8;   // capacity of the partials buffers; the launch uses g_match_blocks_per_sm (default 4)
 
 // v = c1*g + c2*G + c3*w_chunk*sign(G-g)  (coefficients read from sc)
 int launch_make_v(const float* G, const float* g, const float* chunk_w, float* v, long long n, float mask_value,

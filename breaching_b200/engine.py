@@ -72,6 +72,7 @@ EXPORTS = [
     "bre_engine_score", "bre_engine_objective_and_gradient", "bre_engine_last_terms", "bre_engine_debug_param",
     "bre_engine_debug_tensor", "bre_engine_launches_per_iteration", "bre_engine_set_option", "bre_match_reduce",
     "bre_total_variation", "bre_conv_gemm", "bre_last_error", "bre_version",
+    "bre_engine_load_soft_labels", "bre_engine_label_gradient", "bre_engine_set_labels",
 ]
 
 
@@ -97,6 +98,9 @@ def load_library(path=None):
     lib.bre_engine_load_targets.argtypes = [vp, P(vp), i32, vp, vp, i32, vp, vp, i32]
     lib.bre_engine_load_feature_targets.argtypes = [vp, vp, i64]
     lib.bre_engine_set_local_steps.argtypes = [vp, i32, i32, f32, vp]
+    lib.bre_engine_load_soft_labels.argtypes = [vp, vp, i64]
+    lib.bre_engine_label_gradient.argtypes = [vp, vp]
+    lib.bre_engine_set_labels.argtypes = [vp, vp, i32]
     lib.bre_engine_begin_trial.argtypes = [vp, vp, vp, i32]
     lib.bre_engine_run.argtypes = [vp, i32]
     lib.bre_engine_sync.argtypes = [vp]
@@ -381,6 +385,25 @@ class Engine:
         arr = (ctypes.c_double * 6)()
         _check(self.lib, self.lib.bre_engine_last_terms(self.h, arr), "bre_engine_last_terms")
         return dict(zip(("match", "task_loss", "total_variation", "norm", "deep_inversion", "features"), list(arr)))
+
+    # ---- joint data / label optimisation (optimization_with_label_attack.py) --------------------------------
+    def load_soft_labels(self, probabilities):
+        """Class probabilities [N, classes] as the targets of the task loss (``None`` -> back to index labels)."""
+        if probabilities is None:
+            _check(self.lib, self.lib.bre_engine_load_soft_labels(self.h, None, 0), "bre_engine_load_soft_labels")
+            return
+        q = _f32c(probabilities, self.device)
+        _check(self.lib, self.lib.bre_engine_load_soft_labels(self.h, _ptr(q), q.numel()), "bre_engine_load_soft_labels")
+
+    def label_gradient(self, shape):
+        """d(objective)/d(probabilities) of the last ``objective_and_gradient`` call."""
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        _check(self.lib, self.lib.bre_engine_label_gradient(self.h, _ptr(out)), "bre_engine_label_gradient")
+        return out
+
+    def set_labels(self, labels):
+        lab = labels.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        _check(self.lib, self.lib.bre_engine_set_labels(self.h, _ptr(lab), lab.numel()), "bre_engine_set_labels")
 
     def debug_param(self, which, index):
         p = self.prog.params[index]

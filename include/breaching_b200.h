@@ -116,6 +116,16 @@ int bre_engine_load_targets(bre_engine* e, const float* const* grads, int32_t n_
  * Call after bre_engine_load_model / load_targets and before bre_engine_begin_trial.  labels: device or host. */
 int bre_engine_set_local_steps(bre_engine* e, int32_t total_images, int32_t steps, float lr, const int64_t* labels);
 
+/* Joint data / label optimisation (OptimizationJointAttacker, optimization_with_label_attack.py:145-189): the closure hands
+ * `labels.softmax(dim=-1)` to the loss as class probabilities (:154).  `probabilities` [N, classes] fp32 (device or host)
+ * replaces the index labels in the task loss until cleared with NULL.  After bre_engine_objective_and_gradient,
+ * bre_engine_label_gradient writes d(objective)/d(probabilities) [N, classes] (the caller chains it through its softmax,
+ * as autograd does for the reference at :162).  bre_engine_set_labels replaces the index labels (scoring with
+ * `labels.argmax`, :67-70). */
+int bre_engine_load_soft_labels(bre_engine* e, const float* probabilities, int64_t numel);
+int bre_engine_label_gradient(bre_engine* e, float* grad_out);
+int bre_engine_set_labels(bre_engine* e, const int64_t* labels, int32_t n_labels);
+
 /* Measured features for the `features` regulariser (regularizers.py:31-43): [N, F] fp32, device or host. */
 int bre_engine_load_feature_targets(bre_engine* e, const float* measured, int64_t numel);
 

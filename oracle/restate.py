@@ -526,6 +526,80 @@ class TrialOracle:
         raise ValueError(f"Scoring mechanism {scoring} not implemented.")
 
 
+class JointTrialOracle(TrialOracle):
+    """``OptimizationJointAttacker`` (optimization_with_label_attack.py:89-205): data and soft labels are optimised together.
+    The closure feeds ``labels.softmax(-1)`` to the loss as class probabilities (:154), back-propagates onto both leaves
+    (:162), post-processes both gradients (noise, per-tensor clipping, sign; :164-186) and one torch optimiser steps both
+    (:108, common.py:5-18)."""
+
+    def closure_gradients(self, x, ell, iteration, lr):
+        opt = self.cfg["optim"]
+        x = x.detach().clone().requires_grad_(True)
+        ell = ell.detach().clone().requires_grad_(True)
+        self.labels = ell.softmax(dim=-1)
+        total, terms = self.objective_terms(x)
+        gx, gl = torch.autograd.grad(total, [x, ell])
+        raw = (gx.clone(), gl.clone())
+        out = []
+        for grad in (gx, gl):
+            if (cfg_get(opt, "langevin_noise", 0.0) or 0.0) > 0:
+                grad = grad + opt["langevin_noise"] * lr * torch.randn_like(grad)
+            clip = cfg_get(opt, "grad_clip")
+            if clip is not None:
+                norm = grad.norm()
+                if norm > clip:
+                    grad = grad * (clip / (norm + 1e-6))
+            signed = cfg_get(opt, "signed")
+            if signed == "soft":
+                s = 1 - iteration / opt["max_iterations"]
+                grad = (grad * s).tanh() / s
+            elif signed == "hard":
+                grad = grad.sign()
+            out.append(grad)
+        return total.detach(), out[0], out[1], raw, terms
+
+    def run_joint(self, x0, ell0, iterations=None, dryrun=False):
+        """optimization_with_label_attack.py:89-143; the optimiser is the torch class the reference constructs."""
+        opt = self.cfg["optim"]
+        T = opt["max_iterations"]
+        n = T if iterations is None else min(T, iterations)
+        lrs = lr_table(opt["step_size"], cfg_get(opt, "step_size_decay"), cfg_get(opt, "warmup", 0) or 0, T, n)
+        x = torch.nn.Parameter(x0.detach().clone().to(self.dtype))
+        ell = torch.nn.Parameter(ell0.detach().clone().to(self.dtype))
+        name = opt["optimizer"].lower()
+        if name == "l-bfgs":
+            optimizer = torch.optim.LBFGS([x, ell], lr=opt["step_size"])
+        elif name in ("adam", "adam-safe"):
+            kw = {} if name == "adam" else dict(betas=(0.5, 0.99), eps=1e-4)
+            optimizer = torch.optim.Adam([x, ell], lr=opt["step_size"], **kw)
+        elif name == "bert-adam":
+            optimizer = torch.optim.AdamW([x, ell], lr=opt["step_size"], betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01)
+        else:
+            optimizer = torch.optim.SGD([x, ell], lr=opt["step_size"], momentum=0.9 if name == "momgd" else 0.0, nesterov=name == "momgd")
+        best, best_l, fmin, hist = x.detach().clone(), ell.detach().clone(), float("inf"), []
+        lo, hi = -self.dm / self.ds, (1 - self.dm) / self.ds
+        for it in range(n):
+            optimizer.param_groups[0]["lr"] = lrs[it]
+
+            def closure():
+                phi, gx, gl, _, _ = self.closure_gradients(x.detach(), ell.detach(), it, lrs[it])
+                x.grad, ell.grad = gx.to(x.dtype), gl.to(ell.dtype)
+                return phi
+
+            phi_f = float(optimizer.step(closure))
+            with torch.no_grad():
+                if cfg_get(opt, "boxed", False):
+                    x.data = torch.max(torch.min(x, hi), lo)
+                if phi_f < fmin:
+                    fmin, best, best_l = phi_f, x.detach().clone(), ell.detach().clone()
+            if not math.isfinite(phi_f):
+                break
+            hist.append(phi_f)
+            if dryrun:
+                break
+        return best, best_l, hist, x.detach().clone(), ell.detach().clone()
+
+
 def select_optimal(candidates, scores):
     """optimization_based_attack.py:206-218: first minimum wins; all non-finite -> zeros."""
     scores_t = torch.as_tensor(scores, dtype=torch.float32)

@@ -61,6 +61,14 @@ LBFGS_CASES = {
                               "optim.step_size_decay": "cosine-decay"}, 4),
 }
 
+JOINT_CASES = {
+    # attack_type joint-optimization (optimization_with_label_attack.py): data and soft labels optimised together
+    "joint_dlg_convnet": (dict(model_name="convnet-tiny", data="cifar", batch=1, seed=21, bn_random=True), "deepleakage", {}, 3),
+    "joint_adam_convnet": (dict(model_name="convnet-tiny", data="cifar", batch=2, seed=22, bn_random=True), "invertinggradients",
+                           {"attack_type": "joint-optimization", "label_strategy": None, "optim.signed": "soft",
+                            "optim.step_size": 0.05, "optim.grad_clip": 0.5}, 6),
+}
+
 FEDAVG_CASES = {
     # FedAvg multi-step updates (objectives.py:48-72).  `features` / `deep_inversion` crash in the reference together with
     # FedAvg, so the fixture uses the `modern` preset with the features prior switched off.
@@ -137,6 +145,58 @@ def run_reference(ref, case_kwargs, attack, overrides, iters):
     )
 
 
+def run_reference_joint(ref, case_kwargs, attack, overrides, iters):
+    """Drive the reference's OptimizationJointAttacker loop body (optimization_with_label_attack.py:100-128) iteration by
+    iteration from seeded initial data / label logits."""
+    model, loss_fn, payload, shared, true = synthetic.make_case(**case_kwargs)
+    cfg = refshim.load_reference_attack_cfg(attack, overrides)
+    setup = dict(device=torch.device("cpu"), dtype=torch.float)
+    attacker = ref.attacks.prepare_attack(model, loss_fn, cfg, setup)
+    shared_ref = copy.deepcopy(shared)
+    rec_models, label_template, stats = attacker.prepare_attack(payload, shared_ref)
+    attacker.objective.initialize(attacker.loss_fn, attacker.cfg.impl, None)
+    n = shared[0]["metadata"]["num_data_points"]
+    gen = torch.Generator().manual_seed(case_kwargs["seed"] + 1000)
+    x0 = torch.randn([n, *attacker.data_shape], generator=gen)
+    l0 = torch.randn(list(label_template.shape), generator=gen)
+    cand = attacker._initialize_data([n, *attacker.data_shape])
+    cand.data = x0.clone()
+    labels = attacker._initialize_data(label_template.shape)
+    labels.data = l0.clone()
+    optimizer, scheduler = attacker._init_optimizer([cand, labels])
+    best, best_l, fmin = cand.detach().clone(), labels.detach().clone(), torch.as_tensor(float("inf"))
+    history, lrs = [], []
+    raw = None
+    for it in range(iters):
+        lrs.append(optimizer.param_groups[0]["lr"])
+        closure = attacker._compute_objective(cand, labels, rec_models, optimizer, shared_ref, it)
+        val = optimizer.step(closure)
+        scheduler.step()
+        with torch.no_grad():
+            if attacker.cfg.optim.boxed:
+                cand.data = torch.max(torch.min(cand, (1 - attacker.dm) / attacker.ds), -attacker.dm / attacker.ds)
+            if val < fmin:
+                fmin, best, best_l = val.detach(), cand.detach().clone(), labels.detach().clone()
+        history.append(val.item())
+    # raw objective and gradients at the initial point (post-processing disabled)
+    cfg_raw = copy.deepcopy(cfg)
+    cfg_raw.optim.signed, cfg_raw.optim.grad_clip, cfg_raw.optim.langevin_noise = None, None, 0.0
+    att_raw = ref.attacks.prepare_attack(model, loss_fn, cfg_raw, setup)
+    att_raw.dm, att_raw.ds, att_raw.data_shape = attacker.dm, attacker.ds, attacker.data_shape
+    att_raw.objective.initialize(att_raw.loss_fn, att_raw.cfg.impl, None)
+    c0 = att_raw._initialize_data([n, *attacker.data_shape]); c0.data = x0.clone()
+    lab0 = att_raw._initialize_data(label_template.shape); lab0.data = l0.clone()
+    opt_raw, _ = att_raw._init_optimizer([c0, lab0])
+    obj0 = att_raw._compute_objective(c0, lab0, rec_models, opt_raw, shared_ref, 0)()
+    score = float(attacker._score_trial(best, label_template.argmax(dim=-1), rec_models, shared_ref))
+    checksum = float(sum(p.double().sum() for p in model.parameters()))
+    return dict(case=case_kwargs, attack=attack, overrides=overrides, iters=iters, x0=x0, l0=l0, label_template=label_template.detach().clone(),
+                objective0=float(obj0), raw_grad_x0=c0.grad.detach().clone(), raw_grad_l0=lab0.grad.detach().clone(),
+                task_loss0=float(att_raw.current_task_loss), history=history, lrs=lrs, candidate_final=cand.detach().clone(),
+                labels_final=labels.detach().clone(), best=best, best_labels=best_l, score=score, scoring=cfg.restarts.scoring,
+                true_labels=true["labels"], weight_checksum=checksum, torch_version=torch.__version__)
+
+
 def label_fixtures(ref):
     from breaching.attacks.base_attack import _BaseAttacker
 
@@ -200,6 +260,13 @@ def main():
         if only and name not in only:
             continue
         fx = run_reference(ref, case_kwargs, attack, overrides, iters)
+        torch.save(fx, os.path.join(HERE, f"trial_{name}.pt"))
+        print(name, "history", [round(h, 5) for h in fx["history"]], "score", fx["score"])
+    for name, (case_kwargs, attack, overrides, iters) in JOINT_CASES.items():
+        if only and name not in only:
+            continue
+        torch.manual_seed(0)
+        fx = run_reference_joint(ref, case_kwargs, attack, overrides, iters)
         torch.save(fx, os.path.join(HERE, f"trial_{name}.pt"))
         print(name, "history", [round(h, 5) for h in fx["history"]], "score", fx["score"])
     if only:

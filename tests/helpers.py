@@ -57,3 +57,17 @@ def oracle_for_fixture(fx):
 TRIAL_FIXTURES = ["ig_convnet", "ig_resnet18", "stg_resnet18", "modern_convnet", "tag_clip_convnet", "l1_sgd_convnet"]
 FEDAVG_FIXTURES = ["fedavg_convnet", "fedavg_resnet18"]
 LBFGS_FIXTURES = ["lbfgs_convnet", "lbfgs_wei_convnet", "lbfgs_cosine_convnet"]
+JOINT_FIXTURES = ["joint_dlg_convnet", "joint_adam_convnet"]
+
+
+def joint_oracle_for_fixture(fx):
+    """JointTrialOracle (CPU restatement of OptimizationJointAttacker) for a joint-optimisation fixture."""
+    from oracle import restate
+
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    m = copy.deepcopy(model).eval()
+    meta = payload[0]["metadata"]
+    dm = torch.tensor(meta.mean)[None, :, None, None]
+    ds = torch.tensor(meta.std)[None, :, None, None]
+    return restate.JointTrialOracle(m, loss_fn, cfg, shared[0]["gradients"], None, dm, ds), cfg

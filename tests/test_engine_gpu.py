@@ -344,3 +344,40 @@ def test_lbfgs_trials_match_reference_fixture(name):
         rec, stats2 = attacker2.reconstruct(payload, copy.deepcopy(shared), {})
         assert rec["data"].shape == fx["x0"].shape and len(stats2["Trial_0_Val"]) == 2
         assert math.isclose(stats2["Trial_0_Val"][0] > 0, True) and torch.isfinite(rec["data"]).all()
+
+
+@pytest.mark.parametrize("name", ["joint_dlg_convnet", "joint_adam_convnet"])
+def test_joint_optimization_matches_reference_fixture(name):
+    """attack_type joint-optimization (OptimizationJointAttacker, optimization_with_label_attack.py; `deepleakage.yaml`): soft
+    labels in the task loss, gradient w.r.t. data *and* label logits from one engine pass, both leaves stepped together --
+    against the unmodified reference (closure at the initial point, then the recorded trajectory)."""
+    from helpers import case_from_fixture, cfg_from_fixture
+
+    fx = load_golden(f"trial_{name}.pt")
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    attacker = prepare_attack(model, loss_fn, cfg, dict(device=DEV, dtype=torch.float, backend="simt"))
+    assert type(attacker).__name__ == "OptimizationJointAttacker"
+    rec_models, template, stats, shared2 = attacker.prepare_attack(payload, copy.deepcopy(shared))
+    assert tuple(template.shape) == tuple(fx["label_template"].shape)
+    engine = attacker._get_engine(rec_models, shared2, torch.zeros(template.shape[0], dtype=torch.long))
+    x0, l0 = fx["x0"].to(DEV), fx["l0"].to(DEV)
+    val, gx, gl, raw = attacker._closure(engine, x0, l0, 0, 0.0)
+    assert math.isclose(val, fx["objective0"], rel_tol=1e-4, abs_tol=1e-6), (val, fx["objective0"])
+    assert _relerr(raw[0], fx["raw_grad_x0"]) < 2e-3
+    assert _relerr(raw[1], fx["raw_grad_l0"]) < 2e-3
+    best, best_l = attacker._run_joint_trial(engine, x0, l0, stats, 0, iterations=fx["iters"])
+    hist = stats["Trial_0_Val"]
+    tol = 5e-2 if str(cfg.optim.optimizer).lower() == "l-bfgs" else 2e-3
+    assert len(hist) == len(fx["history"])
+    for a, b in zip(hist, fx["history"]):
+        assert math.isclose(a, b, rel_tol=tol, abs_tol=1e-5), (hist, fx["history"])
+    x_final, l_final = attacker._last_joint_state
+    assert (x_final.cpu() - fx["candidate_final"]).abs().mean().item() < (3e-2 if tol > 1e-2 else 3e-3)
+    assert (l_final.cpu() - fx["labels_final"]).abs().mean().item() < (3e-2 if tol > 1e-2 else 3e-3)
+    score = attacker._score_joint(engine, best, fx["label_template"].argmax(dim=-1))
+    assert math.isclose(score, fx["score"], rel_tol=5e-2, abs_tol=1e-5), (score, fx["score"])
+    if name == "joint_dlg_convnet":  # the whole call with the preset
+        cfg2 = get_attack_config("deepleakage", {"optim.max_iterations": 2})
+        rec, st = prepare_attack(model, loss_fn, cfg2, dict(device=DEV, dtype=torch.float)).reconstruct(payload, copy.deepcopy(shared), {})
+        assert rec["data"].shape == fx["x0"].shape and rec["labels"].shape == (fx["x0"].shape[0],) and len(st["Trial_0_Val"]) == 2

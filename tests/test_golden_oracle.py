@@ -4,7 +4,8 @@ import math
 import pytest
 import torch
 
-from helpers import FEDAVG_FIXTURES, LBFGS_FIXTURES, TRIAL_FIXTURES, load_golden, oracle_for_fixture
+from helpers import (FEDAVG_FIXTURES, JOINT_FIXTURES, LBFGS_FIXTURES, TRIAL_FIXTURES, joint_oracle_for_fixture, load_golden,
+                     oracle_for_fixture)
 
 
 @pytest.mark.parametrize("name", TRIAL_FIXTURES + FEDAVG_FIXTURES + LBFGS_FIXTURES)
@@ -30,6 +31,26 @@ def test_oracle_reproduces_reference_trajectory(name):
     assert (trace[-1]["candidate"] - fx["candidate_final"]).abs().mean().item() < (2e-2 if name in LBFGS_FIXTURES else 2e-3)
     score = orc.score(best, fx["scoring"])
     assert math.isclose(score, fx["score"], rel_tol=5e-2, abs_tol=1e-5)
+    orc.close()
+
+
+@pytest.mark.parametrize("name", JOINT_FIXTURES)
+def test_joint_oracle_reproduces_reference_trajectory(name):
+    """attack_type joint-optimization (optimization_with_label_attack.py): soft labels optimised with the data."""
+    fx = load_golden(f"trial_{name}.pt")
+    orc, cfg = joint_oracle_for_fixture(fx)
+    cfg_raw = dict(cfg["optim"])
+    phi0, _, _, raw, terms = orc.closure_gradients(fx["x0"], fx["l0"], 0, 0.0)
+    assert math.isclose(float(phi0), fx["objective0"], rel_tol=1e-5, abs_tol=1e-7)
+    assert ((raw[0] - fx["raw_grad_x0"]).norm() / fx["raw_grad_x0"].norm()).item() < 1e-4
+    assert ((raw[1] - fx["raw_grad_l0"]).norm() / fx["raw_grad_l0"].norm()).item() < 1e-4
+    best, best_l, hist, x_final, l_final = orc.run_joint(fx["x0"], fx["l0"], iterations=fx["iters"])
+    tol = 3e-2 if cfg_raw["optimizer"].lower() == "l-bfgs" else 2e-4
+    assert len(hist) == len(fx["history"])
+    for a, b in zip(hist, fx["history"]):
+        assert math.isclose(a, b, rel_tol=tol, abs_tol=1e-5), (hist, fx["history"])
+    assert (x_final - fx["candidate_final"]).abs().mean().item() < (2e-2 if tol > 1e-3 else 2e-3)
+    assert (l_final - fx["labels_final"]).abs().mean().item() < (2e-2 if tol > 1e-3 else 2e-3)
     orc.close()
 
 
