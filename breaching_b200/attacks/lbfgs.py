@@ -143,7 +143,13 @@ def run_trial(engine, candidate, cfg, lr_of_iteration, lo, hi, dryrun=False, log
     opt = cfg.optim
     x = candidate.detach().clone().contiguous()
     flat = x.view(-1)
-    optimizer = DeviceLBFGS(flat)
+    name = str(opt.optimizer).lower()
+    if name == "l-bfgs":
+        optimizer = DeviceLBFGS(flat)
+    else:  # multi-query attacks with the first-order optimisers: same host-driven loop, torch.optim update rules
+        from .host_optim import LeafOptimizer
+
+        optimizer = LeafOptimizer([flat], name)
     best = x.clone()
     fmin = float("inf")
     history = []
@@ -155,7 +161,11 @@ def run_trial(engine, candidate, cfg, lr_of_iteration, lo, hi, dryrun=False, log
             val, grad = engine.objective_and_gradient(x)
             return float(val), postprocess_gradient(grad, opt, it, lr).reshape(-1)
 
-        value = optimizer.step(closure, lr)
+        if name == "l-bfgs":
+            value = optimizer.step(closure, lr)
+        else:
+            value, grad = closure()
+            optimizer.step([grad], lr)
         if cfg_get(opt, "boxed", False):
             torch.max(torch.min(x, hi, out=x), lo, out=x)   # :117-118
         if value < fmin:                                     # :119-121 (objective before the step, candidate after it)

@@ -32,6 +32,25 @@ def _loss_name(loss_fn):
     return getattr(loss_fn, "original_name", None) or type(loss_fn).__name__
 
 
+class _EngineSum:
+    """Several engines behind the two calls the host-driven loops use: objective and candidate gradient are summed over the
+    (model, update) pairs (optimization_based_attack.py:157-160); only the first engine carries the image priors."""
+
+    def __init__(self, engines):
+        self.engines = engines
+
+    def objective_and_gradient(self, x):
+        total, grad = 0.0, None
+        for eng in self.engines:
+            val, g = eng.objective_and_gradient(x)
+            total += float(val)
+            grad = g if grad is None else grad.add_(g)
+        return total, grad
+
+    def score(self, candidate, scoring):
+        return sum(eng.score(candidate, scoring) for eng in self.engines)
+
+
 class OptimizationBasedAttacker:
     """Implements the optimisation-based attacks of the reference on the B200 engine."""
 
@@ -105,23 +124,25 @@ class OptimizationBasedAttacker:
             shared_data = host.normalize_gradients(shared_data)
         return rec_models, labels, stats, shared_data
 
-    def _get_engine(self, rec_models, shared_data, labels):
-        if len(rec_models) != 1:
-            raise NotImplementedError("multiple model queries per attack are not implemented by the B200 engine")
-        local = shared_data[0]["metadata"]["local_hyperparams"]
-        model = rec_models[0]
-        n = shared_data[0]["metadata"]["num_data_points"]
+    def _get_engine(self, rec_models, shared_data, labels, index=0, cfg=None):
+        """Engine for model / payload ``index`` (``cfg`` overrides the attack config, used for the extra queries)."""
+        if len(rec_models) != 1 and cfg is None:
+            raise NotImplementedError("use _get_engines for several model queries")
+        cfg = self.cfg if cfg is None else cfg
+        local = shared_data[index]["metadata"]["local_hyperparams"]
+        model = rec_models[index]
+        n = shared_data[index]["metadata"]["num_data_points"]
         # FedAvg (objectives.py:48-72): the layer program is compiled for one local step's batch
         shape = (n if local is None else int(local["data_per_step"]), *self.data_shape)
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if cfg_get(self.cfg.optim, "langevin_noise", 0.0) else 0
-        if self._engine is not None:
+        if self._engine is not None and index == 0:
             self._engine.close()
         # setup["backend"]: "tc" (tcgen05 TF32, default = torch's cuDNN-TF32 numerics) or "simt" (fp32, = allow_tf32 False)
-        eng = Engine(model, shape, self.cfg, self.setup["device"], noise_seed=seed, backend=self.backend)
+        eng = Engine(model, shape, cfg, self.setup["device"], noise_seed=seed, backend=self.backend)
         eng.load_model()
         tw = None
         if self.cfg.objective.type == "tag-euclidean":  # objectives.py:115-124
-            L = len(shared_data[0]["gradients"])
+            L = len(shared_data[index]["gradients"])
             scheme = cfg_get(self.cfg.objective, "scale_scheme", "linear")
             if scheme == "linear":
                 tw = torch.arange(L, 0, -1, dtype=torch.float32) / L
@@ -133,17 +154,37 @@ class OptimizationBasedAttacker:
         mean = self.dm.flatten() if self.dm.numel() > 1 else self.dm.flatten().expand(self.data_shape[0])
         std = self.ds.flatten() if self.ds.numel() > 1 else self.ds.flatten().expand(self.data_shape[0])
         step_labels = labels if local is None else local["labels"][0]
-        eng.load_targets(shared_data[0]["gradients"], step_labels, mean=mean, std=std, tensor_weights=tw)
+        eng.load_targets(shared_data[index]["gradients"], step_labels, mean=mean, std=std, tensor_weights=tw)
         if local is not None:
             eng.set_local_steps(n, int(local["steps"]), float(local["lr"]), [l for l in local["labels"][: int(local["steps"])]])
         if any(k == "features" for k, _ in self.regularizers):
             eng.load_feature_targets(host.measured_features(shared_data, labels)[0])
-        self._engine = eng
+        if index == 0:
+            self._engine = eng
         return eng
+
+    def _get_engines(self, rec_models, shared_data, labels):
+        """One engine per (model, update) pair of a multi-query attack (optimization_based_attack.py:157-160: the objective
+        is summed over ``zip(rec_model, shared_data)``, the regularisers are added once)."""
+        if any(d["metadata"]["local_hyperparams"] is not None for d in shared_data):
+            raise NotImplementedError("multi-step local updates with several model queries are not implemented by the B200 engine")
+        if any(k in ("deep_inversion", "features") for k, _ in self.regularizers):
+            raise NotImplementedError("DeepInversion / feature priors with several model queries are not implemented by the B200 engine")
+        no_priors = copy.deepcopy(self.cfg)
+        reg = cfg_get(no_priors, "regularization")
+        if reg is not None:
+            for key in reg.keys():
+                reg[key].scale = 0.0
+        for eng in getattr(self, "_extra_engines", []):
+            eng.close()
+        first = self._get_engine(rec_models, shared_data, labels, 0, self.cfg)
+        self._extra_engines = [self._get_engine(rec_models, shared_data, labels, i, no_priors) for i in range(1, len(rec_models))]
+        return [first] + self._extra_engines
 
     def reconstruct(self, server_payload, shared_data, server_secrets=None, initial_data=None, dryrun=False):
         rec_models, labels, stats, shared_data = self.prepare_attack(server_payload, shared_data)
-        engine = self._get_engine(rec_models, shared_data, labels)
+        multi = len(rec_models) > 1
+        engine = _EngineSum(self._get_engines(rec_models, shared_data, labels)) if multi else self._get_engine(rec_models, shared_data, labels)
         num_trials = self.cfg.restarts.num_trials
         rank, world = bdist.rank_and_world()
         scores = torch.full((num_trials,), float("inf"))
@@ -175,7 +216,10 @@ class OptimizationBasedAttacker:
         opt = self.cfg.optim
         T = int(opt.max_iterations)
         table = lr_table(opt.step_size, cfg_get(opt, "step_size_decay"), cfg_get(opt, "warmup", 0), T)
-        if str(opt.optimizer).lower() == "l-bfgs":  # common.py:18 -- host-driven direction update, closure on the engine
+        name = str(opt.optimizer).lower()
+        if name == "l-bfgs" or isinstance(engine, _EngineSum):
+            # host-driven loops, every closure evaluation on the engine(s): L-BFGS (common.py:18), and multi-query attacks,
+            # whose candidate gradient is a sum over engines and cannot use one engine's fused on-device step
             from . import lbfgs
 
             dm, ds = self.dm.to(candidate.device), self.ds.to(candidate.device)

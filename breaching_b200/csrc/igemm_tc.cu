@@ -847,13 +847,8 @@ bool build_maps(const GemmArgs& a, int BN, TcMaps* maps) {
 }
 
 template <int MODE, int BN, bool TMA>
-int launch_tc(const GemmArgs& a, const TcDims& d0, cudaStream_t stream) {
+int launch_tc(const GemmArgs& a, const TcDims& d0, const TcMaps& maps, cudaStream_t stream) {
   TcDims d = d0;
-  TcMaps maps;
-  memset(&maps, 0, sizeof(maps));
-  if (TMA) {
-    if (!build_maps(a, BN, &maps)) { set_error("igemm_tc: cuTensorMapEncode failed"); return -5; }
-  }
   const int tm = ceil_div(d.M, TC_BM), tn = d.Nc / BN;
   const long long tiles = (long long)tm * tn;
   // split-K factor = cluster size along z: a power of two <= 8 (portable cluster limit) that brings the grid to ~100 CTAs
@@ -925,10 +920,14 @@ int launch_igemm_tc(const GemmArgs& a, cudaStream_t stream) {
   d.kblocks_per_src = ceil_div(d.K, TC_BK);
   d.total_kblocks = d.kblocks_per_src * a.nsrc;
   d.kblocks_per_split = d.total_kblocks;
-  const bool tma = tma_eligible(a);
-  if (a.mode == GEMM_FPROP) return tma ? launch_tc<GEMM_FPROP, 64, true>(a, d, stream) : launch_tc<GEMM_FPROP, 64, false>(a, d, stream);
-  if (a.mode == GEMM_DGRAD) return tma ? launch_tc<GEMM_DGRAD, 64, true>(a, d, stream) : launch_tc<GEMM_DGRAD, 64, false>(a, d, stream);
-  return tma ? launch_tc<GEMM_WGRAD, 64, true>(a, d, stream) : launch_tc<GEMM_WGRAD, 64, false>(a, d, stream);
+  // TMA producer where the geometry allows it and the driver encodes the maps; otherwise the cp.async producer of the same
+  // kernel (still tcgen05, still on the GPU: a different loader, not a fallback to another implementation)
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const bool tma = tma_eligible(a) && build_maps(a, 64, &maps);
+  if (a.mode == GEMM_FPROP) return tma ? launch_tc<GEMM_FPROP, 64, true>(a, d, maps, stream) : launch_tc<GEMM_FPROP, 64, false>(a, d, maps, stream);
+  if (a.mode == GEMM_DGRAD) return tma ? launch_tc<GEMM_DGRAD, 64, true>(a, d, maps, stream) : launch_tc<GEMM_DGRAD, 64, false>(a, d, maps, stream);
+  return tma ? launch_tc<GEMM_WGRAD, 64, true>(a, d, maps, stream) : launch_tc<GEMM_WGRAD, 64, false>(a, d, maps, stream);
 }
 
 }  // namespace bre

@@ -188,3 +188,25 @@ def make_fedavg_case(model_name="resnet18", data="imagenet", num_data_points=4, 
                         metadata=dict(num_data_points=num_data_points, labels=None,
                                       local_hyperparams=dict(lr=lr, steps=steps, data_per_step=data_per_step, labels=label_list)))]
     return model, loss_fn, server_payload, shared_data, dict(data=x, labels=y)
+
+
+def make_multi_query_case(model_name="convnet-tiny", data="cifar", batch=1, seed=233, queries=2, bn_random=True, image_size=None,
+                          classes=None):
+    """Several model queries on the same user data (cases/servers.py ``num_queries``; the attack sums its objective over
+    ``zip(rec_models, shared_data)``, optimization_based_attack.py:157-160): query 0 is ``make_case(seed)``, query k a
+    model of the same architecture initialised with ``seed + 100 k``; the user answers each with the gradient on the same
+    batch.  Returns ``(model_template, loss_fn, server_payload[list], shared_data[list], true_user_data)``."""
+    model, loss_fn, payload, shared, true = make_case(model_name, data, batch=batch, seed=seed, bn_random=bn_random,
+                                                      image_size=image_size, classes=classes)
+    meta = payload[0]["metadata"]
+    for k in range(1, queries):
+        other = build_model(model_name, meta.classes, seed=seed + 100 * k)
+        if bn_random:
+            randomize_bn(other, seed + 100 * k + 1)
+        other.eval()
+        params = [p for p in other.parameters()]
+        grads = torch.autograd.grad(loss_fn(other(true["data"]), true["labels"]), params)
+        payload.append(dict(parameters=params, buffers=[b for b in other.buffers()], metadata=meta))
+        shared.append(dict(gradients=[g.detach().clone() for g in grads], buffers=None,
+                           metadata=dict(num_data_points=batch, labels=None, local_hyperparams=None)))
+    return model, loss_fn, payload, shared, true

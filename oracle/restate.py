@@ -526,6 +526,33 @@ class TrialOracle:
         raise ValueError(f"Scoring mechanism {scoring} not implemented.")
 
 
+class MultiQueryOracle(TrialOracle):
+    """Several (model, update) pairs attacked with one candidate: the closure sums the matching objective over
+    ``zip(rec_model, shared_data)`` and adds the regularisers once (optimization_based_attack.py:157-162).  ``oracles[0]`` is
+    built with the full attack config, the others with all regulariser scales set to zero."""
+
+    def __init__(self, oracles):
+        self.oracles = oracles
+        first = oracles[0]
+        self.cfg, self.dm, self.ds, self.dtype = first.cfg, first.dm, first.ds, first.dtype
+
+    def objective_terms(self, x):
+        total, terms = 0.0, {}
+        for orc in self.oracles:
+            val, t = orc.objective_terms(x)
+            total = total + val
+            for key, v in t.items():
+                terms[key] = terms.get(key, 0.0) + v
+        return total, terms
+
+    def score(self, x, scoring):
+        return sum(orc.score(x, scoring) for orc in self.oracles)
+
+    def close(self):
+        for orc in self.oracles:
+            orc.close()
+
+
 class JointTrialOracle(TrialOracle):
     """``OptimizationJointAttacker`` (optimization_with_label_attack.py:89-205): data and soft labels are optimised together.
     The closure feeds ``labels.softmax(-1)`` to the loss as class probabilities (:154), back-propagates onto both leaves

@@ -69,6 +69,12 @@ JOINT_CASES = {
                             "optim.step_size": 0.05, "optim.grad_clip": 0.5}, 6),
 }
 
+MULTI_QUERY_CASES = {
+    # two model queries answered on the same user batch; the objective sums over them (optimization_based_attack.py:157-160)
+    "multiquery_convnet": (dict(model_name="convnet-tiny", data="cifar", batch=2, seed=31, queries=2, bn_random=True),
+                           "invertinggradients", {"optim.signed": "soft"}, 6),
+}
+
 FEDAVG_CASES = {
     # FedAvg multi-step updates (objectives.py:48-72).  `features` / `deep_inversion` crash in the reference together with
     # FedAvg, so the fixture uses the `modern` preset with the features prior switched off.
@@ -82,6 +88,8 @@ FEDAVG_CASES = {
 def run_reference(ref, case_kwargs, attack, overrides, iters):
     if "steps" in case_kwargs:
         model, loss_fn, payload, shared, true = synthetic.make_fedavg_case(**case_kwargs)
+    elif "queries" in case_kwargs:
+        model, loss_fn, payload, shared, true = synthetic.make_multi_query_case(**case_kwargs)
     else:
         model, loss_fn, payload, shared, true = synthetic.make_case(**case_kwargs)
     local_hyperparams = shared[0]["metadata"]["local_hyperparams"]
@@ -256,7 +264,7 @@ def main():
     ref = refshim.import_reference()
     torch.manual_seed(0)
     only = sys.argv[1:]   # optional: regenerate just the named fixtures
-    for name, (case_kwargs, attack, overrides, iters) in {**CASES, **FEDAVG_CASES, **LBFGS_CASES}.items():
+    for name, (case_kwargs, attack, overrides, iters) in {**CASES, **FEDAVG_CASES, **LBFGS_CASES, **MULTI_QUERY_CASES}.items():
         if only and name not in only:
             continue
         fx = run_reference(ref, case_kwargs, attack, overrides, iters)

@@ -26,6 +26,8 @@ def cfg_from_fixture(fx):
 def case_from_fixture(fx):
     if "steps" in fx["case"]:
         model, loss_fn, payload, shared, true = synthetic.make_fedavg_case(**fx["case"])
+    elif "queries" in fx["case"]:
+        model, loss_fn, payload, shared, true = synthetic.make_multi_query_case(**fx["case"])
     else:
         model, loss_fn, payload, shared, true = synthetic.make_case(**fx["case"])
     checksum = float(sum(p.double().sum() for p in model.parameters()))
@@ -58,6 +60,7 @@ TRIAL_FIXTURES = ["ig_convnet", "ig_resnet18", "stg_resnet18", "modern_convnet",
 FEDAVG_FIXTURES = ["fedavg_convnet", "fedavg_resnet18"]
 LBFGS_FIXTURES = ["lbfgs_convnet", "lbfgs_wei_convnet", "lbfgs_cosine_convnet"]
 JOINT_FIXTURES = ["joint_dlg_convnet", "joint_adam_convnet"]
+MULTI_QUERY_FIXTURES = ["multiquery_convnet"]
 
 
 def joint_oracle_for_fixture(fx):
@@ -71,3 +74,30 @@ def joint_oracle_for_fixture(fx):
     dm = torch.tensor(meta.mean)[None, :, None, None]
     ds = torch.tensor(meta.std)[None, :, None, None]
     return restate.JointTrialOracle(m, loss_fn, cfg, shared[0]["gradients"], None, dm, ds), cfg
+
+
+def multi_query_oracle_for_fixture(fx):
+    """MultiQueryOracle: one TrialOracle per (model, update) pair, regularisers only on the first."""
+    from oracle import restate
+
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    no_priors = copy.deepcopy(cfg)
+    if no_priors.get("regularization") is not None:
+        for key in no_priors["regularization"].keys():
+            no_priors["regularization"][key]["scale"] = 0.0
+    meta = payload[0]["metadata"]
+    dm = torch.tensor(meta.mean)[None, :, None, None]
+    ds = torch.tensor(meta.std)[None, :, None, None]
+    labels = restate.recover_labels(cfg.label_strategy, copy.deepcopy(shared), shared[0]["metadata"]["num_data_points"])
+    oracles = []
+    for i, (pl, sh) in enumerate(zip(payload, shared)):
+        m = copy.deepcopy(model)
+        with torch.no_grad():
+            for p, src in zip(m.parameters(), pl["parameters"]):
+                p.copy_(src)
+            for b, src in zip(m.buffers(), pl["buffers"]):
+                b.copy_(src)
+        m.eval()
+        oracles.append(restate.TrialOracle(m, loss_fn, cfg if i == 0 else no_priors, sh["gradients"], labels, dm, ds))
+    return restate.MultiQueryOracle(oracles), cfg, labels

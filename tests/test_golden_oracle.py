@@ -4,8 +4,8 @@ import math
 import pytest
 import torch
 
-from helpers import (FEDAVG_FIXTURES, JOINT_FIXTURES, LBFGS_FIXTURES, TRIAL_FIXTURES, joint_oracle_for_fixture, load_golden,
-                     oracle_for_fixture)
+from helpers import (FEDAVG_FIXTURES, JOINT_FIXTURES, LBFGS_FIXTURES, MULTI_QUERY_FIXTURES, TRIAL_FIXTURES, joint_oracle_for_fixture,
+                     load_golden, multi_query_oracle_for_fixture, oracle_for_fixture)
 
 
 @pytest.mark.parametrize("name", TRIAL_FIXTURES + FEDAVG_FIXTURES + LBFGS_FIXTURES)
@@ -51,6 +51,22 @@ def test_joint_oracle_reproduces_reference_trajectory(name):
         assert math.isclose(a, b, rel_tol=tol, abs_tol=1e-5), (hist, fx["history"])
     assert (x_final - fx["candidate_final"]).abs().mean().item() < (2e-2 if tol > 1e-3 else 2e-3)
     assert (l_final - fx["labels_final"]).abs().mean().item() < (2e-2 if tol > 1e-3 else 2e-3)
+    orc.close()
+
+
+@pytest.mark.parametrize("name", MULTI_QUERY_FIXTURES)
+def test_multi_query_oracle_reproduces_reference_trajectory(name):
+    """Two model queries on the same user batch (optimization_based_attack.py:157-160)."""
+    fx = load_golden(f"trial_{name}.pt")
+    orc, cfg, labels = multi_query_oracle_for_fixture(fx)
+    assert labels.tolist() == fx["labels"].tolist()
+    phi0, _, raw, _ = orc.closure_gradient(fx["x0"], 0, 0.0)
+    assert math.isclose(float(phi0), fx["objective0"], rel_tol=1e-5, abs_tol=1e-7)
+    assert ((raw - fx["raw_grad0"]).norm() / fx["raw_grad0"].norm()).item() < 1e-4
+    best, hist, _ = orc.run(fx["x0"], iterations=fx["iters"])
+    for a, b in zip(hist, fx["history"]):
+        assert math.isclose(a, b, rel_tol=2e-4, abs_tol=1e-6), (hist, fx["history"])
+    assert math.isclose(orc.score(best, fx["scoring"]), fx["score"], rel_tol=5e-2, abs_tol=1e-5)
     orc.close()
 
 
