@@ -569,12 +569,19 @@ struct bre_engine {
   }
 
   int priors() {
-    if (cfg.tv_scale == 0.f && cfg.norm_scale == 0.f) return 0;
+    const bool image_terms = cfg.tv_scale != 0.f || cfg.norm_scale != 0.f;
+    if (!image_terms) {
+      if (cfg.orthogonality != 0)
+        BRE_LAUNCH(launch_orthogonality(x, gradx, xN, (long long)xC * xH * xW, true, sc, dpartials, dcounter, stream));
+      return 0;
+    }
     PriorArgs a;
     a.x = x; a.grad = gradx; a.N = xN; a.H = xH; a.W = xW; a.accumulate = 1;
     a.tv_scale = cfg.tv_scale; a.p = cfg.tv_inner_exp; a.q = cfg.tv_outer_exp; a.eps = cfg.tv_eps;
     a.double_opponents = cfg.tv_double_opponents; a.norm_scale = cfg.norm_scale; a.norm_p = cfg.norm_p;
     BRE_LAUNCH(launch_image_priors(a, sc, dpartials, dcounter, stream));
+    if (cfg.orthogonality != 0)
+      BRE_LAUNCH(launch_orthogonality(x, gradx, xN, (long long)xC * xH * xW, false, sc, dpartials, dcounter, stream));
     return 0;
   }
 

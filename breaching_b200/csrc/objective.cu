@@ -494,6 +494,56 @@ __global__ void __launch_bounds__(256) feature_reg_kernel(const float* __restric
 
 }  // namespace
 
+// ---- OrthogonalityRegularization ---------------------------------------------------------------------------------
+// R = sum_{i != j} (1/D) sum_k x_ik^2 x_jk^2 = (1/D) sum_k [S_k^2 - Q_k],  S_k = sum_j x_jk^2, Q_k = sum_j x_jk^4
+// dR/dx_ik = (4/D) x_ik (S_k - x_ik^2).  One thread per position k, the batch (small) in a register loop.
+__global__ void orthogonality_kernel(const float* __restrict__ x, float* __restrict__ grad, int N, long long D, bool overwrite,
+                                     Scalars* sc, double* partials, int* counter) {
+  pdl_prologue();
+  __shared__ double scratch[32];
+  __shared__ int s_last;
+  double part = 0.0;
+  const float scale = 4.0f / (float)D;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < D; k += (long long)gridDim.x * blockDim.x) {
+    float S = 0.f, Q = 0.f;
+    for (int j = 0; j < N; ++j) { const float v = x[(long long)j * D + k]; const float v2 = v * v; S += v2; Q = fmaf(v2, v2, Q); }
+    part += (double)S * (double)S - (double)Q;
+    for (int j = 0; j < N; ++j) {
+      const float v = x[(long long)j * D + k];
+      grad[(long long)j * D + k] += scale * v * (S - v * v);
+    }
+  }
+  const double tot = block_sum(part, scratch);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = tot;
+    __threadfence();
+    const int prev = atomicAdd(counter, 1);
+    s_last = (prev == (int)gridDim.x - 1);
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) acc += partials[b];
+  const double all = block_sum(acc, scratch);
+  if (threadIdx.x == 0) {
+    const double r = all / (double)D;
+    sc->norm = overwrite ? r : sc->norm + r;
+  }
+}
+
+int launch_orthogonality(const float* x, float* grad, int N, long long D, bool overwrite, Scalars* sc, double* partials, int* counter,
+                         cudaStream_t s) {
+  if (N < 2) return 0;   // regularizers.py:170-171: a single image contributes 0
+  long long blocks = (D + 255) / 256;
+  const long long cap = (long long)kNumSMs * 4;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  BRE_KLAUNCH(orthogonality_kernel, grid, 256, 0, s, x, grad, N, D, overwrite, sc, partials, counter);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
 // launch shape of the matching reduction (tuned on the B200 with profiles/experiments/tune_match_reduce.py)
 static int g_match_blocks_per_sm = 4, g_match_unroll = 4;
 

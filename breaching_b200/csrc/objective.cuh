@@ -26,6 +26,10 @@ struct PriorArgs {   // TotalVariation (regularizers.py:130-147) + NormRegulariz
   float norm_scale, norm_p;
 };
 int launch_image_priors(const PriorArgs& a, Scalars* sc, double* partials, int* counter, cudaStream_t s);
+// OrthogonalityRegularization (regularizers.py:169-178): sum_{i != j} mean_k (x_ik x_jk)^2 over the batch; value added to (or,
+// with overwrite, stored in) the `norm` slot of the scalar block, gradient accumulated into grad.  x, grad: [N, D].
+int launch_orthogonality(const float* x, float* grad, int N, long long D, bool overwrite, Scalars* sc, double* partials, int* counter,
+                         cudaStream_t s);
 
 struct StepArgs {   // closure tail + optimiser + projection + best-so-far (optimization_based_attack.py:112-121,166-184)
   float* x; float* m; float* v; float* best;

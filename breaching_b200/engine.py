@@ -50,6 +50,7 @@ class AttackCfg(ctypes.Structure):
         ("norm_scale", ctypes.c_float), ("norm_p", ctypes.c_float),
         ("di_scale", ctypes.c_float), ("di_first_bn_multiplier", ctypes.c_float),
         ("feat_scale", ctypes.c_float),
+        ("orthogonality", ctypes.c_int32),
     ]
 
 
@@ -196,7 +197,7 @@ def make_cfg(cfg_attack, noise_seed=0):
             elif key == "features":
                 c.feat_scale = float(r["scale"])
             elif key == "orthogonality":
-                raise EngineError("orthogonality regularisation is not implemented by the engine")
+                c.orthogonality = 1  # regularizers.py:169-178 never multiplies by its scale
             else:
                 raise KeyError(key)
     return c

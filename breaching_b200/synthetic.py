@@ -210,3 +210,81 @@ def make_multi_query_case(model_name="convnet-tiny", data="cifar", batch=1, seed
         shared.append(dict(gradients=[g.detach().clone() for g in grads], buffers=None,
                            metadata=dict(num_data_points=batch, labels=None, local_hyperparams=None)))
     return model, loss_fn, payload, shared, true
+
+
+class TransformerLM(torch.nn.Module):
+    """Architecture of the reference's ``TransformerModel`` (cases/models/language_models.py:150-205, BASELINE config 5:
+    ntokens 50257, ninp 96, nhead 8, nhid 1536, nlayers 3, dropout 0, learnable positional embedding): token embedding
+    (scaled by sqrt(ninp) at init), positional embedding added, ``nn.TransformerEncoder`` of post-norm ReLU layers
+    (batch first, no mask), linear decoder.  Module names follow the reference so that ``parameters()`` has its order."""
+
+    def __init__(self, ntokens=50257, ninp=96, nhead=8, nhid=1536, nlayers=3, max_positions=1024):
+        super().__init__()
+        import math
+
+        self.pos_encoder = torch.nn.Module()
+        self.pos_encoder.embedding = torch.nn.Embedding(max_positions, ninp)
+        layer = torch.nn.TransformerEncoderLayer(ninp, nhead, nhid, 0.0, batch_first=True)
+        self.transformer_encoder = torch.nn.TransformerEncoder(layer, nlayers, enable_nested_tensor=False)
+        self.encoder = torch.nn.Embedding(ntokens, ninp)
+        self.encoder.weight.data *= math.sqrt(ninp)
+        self.decoder = torch.nn.Linear(ninp, ntokens)
+        torch.nn.init.uniform_(self.encoder.weight, -0.1, 0.1)   # init_weights(), :177-181
+        torch.nn.init.uniform_(self.decoder.weight, -0.1, 0.1)
+
+    @property
+    def pos_embedding(self):
+        return self.pos_encoder.embedding
+
+    @property
+    def layers(self):
+        return self.transformer_encoder.layers
+
+    def attack_parameters(self):
+        """Parameters in the order of the shared gradient after the attack has removed the token-embedding entry
+        (base_attack.py:88-95)."""
+        return [p for n, p in self.named_parameters() if n != "encoder.weight"]
+
+    def forward(self, input_ids=None, inputs_embeds=None):
+        inputs = self.encoder(input_ids) if inputs_embeds is None else inputs_embeds
+        positions = torch.arange(inputs.shape[1], device=inputs.device)
+        inputs = inputs + self.pos_encoder.embedding(positions[None, :])
+        return self.decoder(self.transformer_encoder(inputs))
+
+
+def causal_loss(outputs, labels):
+    """``CausalLoss`` (cases/models/losses.py:7-26): next-token cross-entropy; ``labels`` are token ids [N, T] or class
+    probabilities [N, T, vocab] (what the joint attacker passes)."""
+    shift_logits = outputs[:, :-1, :].reshape(-1, outputs.shape[-1])
+    if labels.dtype == torch.long:
+        return torch.nn.functional.cross_entropy(shift_logits, labels[:, 1:].reshape(-1))
+    return torch.nn.functional.cross_entropy(shift_logits, labels[:, 1:, :].reshape(-1, labels.shape[-1]))
+
+
+class CausalLoss(torch.nn.Module):
+    """Module form of :func:`causal_loss` (reference cases/models/losses.py:7-26)."""
+
+    def forward(self, outputs, labels):
+        return causal_loss(outputs, labels)
+
+
+def make_text_case(batch=1, seq_len=8, seed=233, ntokens=50, ninp=16, nhead=4, nhid=24, nlayers=2):
+    """BASELINE config 5 in miniature: a causal language model user (cases/data/datasets_text.py token batches, users.py
+    single step) on ``TransformerLM``.  Returns ``(model, loss_fn, server_payload, shared_data, true_user_data)``; the shared
+    gradient list includes the token-embedding entry (the attack removes it, base_attack.py:88-95)."""
+    torch.manual_seed(seed)
+    model = TransformerLM(ntokens, ninp, nhead, nhid, nlayers, max_positions=max(64, seq_len)).eval()
+    gen = torch.Generator().manual_seed(seed + 7)
+    with torch.no_grad():  # non-trivial LayerNorm parameters / biases
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    tokens = torch.randint(0, ntokens, (batch, seq_len), generator=gen)
+    loss_fn = CausalLoss()
+    params = [p for p in model.parameters()]
+    grads = torch.autograd.grad(loss_fn(model(tokens), tokens), params)
+    meta = DataConfig(name="synthetic-text", modality="text", task="causal-lm", vocab_size=ntokens, shape=(seq_len,), classes=ntokens)
+    server_payload = [dict(parameters=params, buffers=[], metadata=meta)]
+    shared_data = [dict(gradients=[g.detach().clone() for g in grads], buffers=None,
+                        metadata=dict(num_data_points=batch, labels=None, local_hyperparams=None))]
+    return model, loss_fn, server_payload, shared_data, dict(data=tokens, labels=tokens)

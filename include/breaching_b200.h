@@ -84,6 +84,7 @@ typedef struct bre_attack_cfg {
   float norm_scale, norm_p;
   float di_scale, di_first_bn_multiplier;
   float feat_scale;
+  int32_t orthogonality;          /* regularizers.py:156-181 (the reference ignores its `scale`; != 0 enables the term) */
 } bre_attack_cfg;
 
 /* ---- engine life cycle -------------------------------------------------------------------------- */

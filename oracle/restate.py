@@ -560,12 +560,15 @@ class JointTrialOracle(TrialOracle):
     (:108, common.py:5-18)."""
 
     def closure_gradients(self, x, ell, iteration, lr):
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+
         opt = self.cfg["optim"]
         x = x.detach().clone().requires_grad_(True)
         ell = ell.detach().clone().requires_grad_(True)
         self.labels = ell.softmax(dim=-1)
-        total, terms = self.objective_terms(x)
-        gx, gl = torch.autograd.grad(total, [x, ell])
+        with sdpa_kernel(SDPBackend.MATH):  # attention models: the fused CPU kernel has no double backward (SURVEY 8c, shim 3)
+            total, terms = self.objective_terms(x)
+            gx, gl = torch.autograd.grad(total, [x, ell])
         raw = (gx.clone(), gl.clone())
         out = []
         for grad in (gx, gl):

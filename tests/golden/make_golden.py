@@ -67,6 +67,9 @@ JOINT_CASES = {
     "joint_adam_convnet": (dict(model_name="convnet-tiny", data="cifar", batch=2, seed=22, bn_random=True), "invertinggradients",
                            {"attack_type": "joint-optimization", "label_strategy": None, "optim.signed": "soft",
                             "optim.step_size": 0.05, "optim.grad_clip": 0.5}, 6),
+    # BASELINE config 5 in miniature: TAG (tag.yaml) on a 2-layer transformer, candidate in embedding space, token-level soft labels
+    "joint_tag_transformer": (dict(batch=1, seq_len=8, seed=51, ntokens=50, ninp=16, nhead=4, nhid=24, nlayers=2), "tag",
+                              {"optim.warmup": 2}, 6),
 }
 
 MULTI_QUERY_CASES = {
@@ -156,7 +159,10 @@ def run_reference(ref, case_kwargs, attack, overrides, iters):
 def run_reference_joint(ref, case_kwargs, attack, overrides, iters):
     """Drive the reference's OptimizationJointAttacker loop body (optimization_with_label_attack.py:100-128) iteration by
     iteration from seeded initial data / label logits."""
-    model, loss_fn, payload, shared, true = synthetic.make_case(**case_kwargs)
+    if "seq_len" in case_kwargs:
+        model, loss_fn, payload, shared, true = synthetic.make_text_case(**case_kwargs)
+    else:
+        model, loss_fn, payload, shared, true = synthetic.make_case(**case_kwargs)
     cfg = refshim.load_reference_attack_cfg(attack, overrides)
     setup = dict(device=torch.device("cpu"), dtype=torch.float)
     attacker = ref.attacks.prepare_attack(model, loss_fn, cfg, setup)
@@ -274,7 +280,10 @@ def main():
         if only and name not in only:
             continue
         torch.manual_seed(0)
-        fx = run_reference_joint(ref, case_kwargs, attack, overrides, iters)
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+
+        with sdpa_kernel(SDPBackend.MATH):  # torch >= 2 fused CPU attention has no double backward (SURVEY section 8c shim 3)
+            fx = run_reference_joint(ref, case_kwargs, attack, overrides, iters)
         torch.save(fx, os.path.join(HERE, f"trial_{name}.pt"))
         print(name, "history", [round(h, 5) for h in fx["history"]], "score", fx["score"])
     if only:

@@ -24,7 +24,9 @@ def cfg_from_fixture(fx):
 
 
 def case_from_fixture(fx):
-    if "steps" in fx["case"]:
+    if "seq_len" in fx["case"]:
+        model, loss_fn, payload, shared, true = synthetic.make_text_case(**fx["case"])
+    elif "steps" in fx["case"]:
         model, loss_fn, payload, shared, true = synthetic.make_fedavg_case(**fx["case"])
     elif "queries" in fx["case"]:
         model, loss_fn, payload, shared, true = synthetic.make_multi_query_case(**fx["case"])
@@ -59,7 +61,7 @@ def oracle_for_fixture(fx):
 TRIAL_FIXTURES = ["ig_convnet", "ig_resnet18", "stg_resnet18", "modern_convnet", "tag_clip_convnet", "l1_sgd_convnet"]
 FEDAVG_FIXTURES = ["fedavg_convnet", "fedavg_resnet18"]
 LBFGS_FIXTURES = ["lbfgs_convnet", "lbfgs_wei_convnet", "lbfgs_cosine_convnet"]
-JOINT_FIXTURES = ["joint_dlg_convnet", "joint_adam_convnet"]
+JOINT_FIXTURES = ["joint_dlg_convnet", "joint_adam_convnet", "joint_tag_transformer"]
 MULTI_QUERY_FIXTURES = ["multiquery_convnet"]
 
 
@@ -71,9 +73,18 @@ def joint_oracle_for_fixture(fx):
     cfg = cfg_from_fixture(fx)
     m = copy.deepcopy(model).eval()
     meta = payload[0]["metadata"]
-    dm = torch.tensor(meta.mean)[None, :, None, None]
-    ds = torch.tensor(meta.std)[None, :, None, None]
-    return restate.JointTrialOracle(m, loss_fn, cfg, shared[0]["gradients"], None, dm, ds), cfg
+    grads = list(shared[0]["gradients"])
+    if getattr(meta, "modality", "vision") == "text":
+        # base_attack.py:76-128 ("run-embedding"): optimise in embedding space -- drop the token-embedding gradient and bypass
+        # the embedding layer; no input normalisation
+        names = [n for n, _ in m.named_parameters()]
+        grads.pop(names.index("encoder.weight"))
+        m.encoder = torch.nn.Identity()
+        dm, ds = torch.tensor(0.0), torch.tensor(1.0)
+    else:
+        dm = torch.tensor(meta.mean)[None, :, None, None]
+        ds = torch.tensor(meta.std)[None, :, None, None]
+    return restate.JointTrialOracle(m, loss_fn, cfg, grads, None, dm, ds), cfg
 
 
 def multi_query_oracle_for_fixture(fx):

@@ -418,3 +418,30 @@ def test_multi_query_attack_matches_reference_fixture():
     # and through the public call (dryrun: one iteration)
     rec, st = attacker.reconstruct(payload, copy.deepcopy(shared), {}, dryrun=True)
     assert rec["data"].shape == fx["x0"].shape and len(st["Trial_0_Val"]) == 1
+
+
+@pytest.mark.parametrize("with_image_priors", [True, False])
+def test_orthogonality_regulariser_vs_oracle(with_image_priors):
+    """OrthogonalityRegularization (regularizers.py:156-181; its `scale` is ignored by the reference): value and candidate
+    gradient on a batch of 3, alone and on top of TV + norm (which share the scalar slot it is accumulated into)."""
+    from oracle import restate
+
+    model, loss_fn, payload, shared, true = synthetic.make_case("convnet-tiny", "cifar", batch=3, seed=41, bn_random=True)
+    over = {"regularization.orthogonality.scale": 0.1}
+    if with_image_priors:
+        over["regularization.norm.scale"] = 1e-3
+    else:
+        over["regularization.total_variation.scale"] = 0.0
+    cfg = get_attack_config("invertinggradients", over)
+    meta = payload[0]["metadata"]
+    dm, ds = torch.tensor(meta.mean)[None, :, None, None], torch.tensor(meta.std)[None, :, None, None]
+    orc = restate.TrialOracle(model.eval(), loss_fn, cfg, shared[0]["gradients"], true["labels"], dm, ds)
+    x = torch.randn(3, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    phi, _, raw, terms = orc.closure_gradient(x, 0, 0.1)
+    assert terms["orthogonality"] > 0
+    eng = _engine_for(model, cfg, shared, true["labels"], meta, (3, 3, 32, 32))
+    for _ in range(2):  # twice: the shared scalar slot must not accumulate across evaluations
+        val, grad = eng.objective_and_gradient(x.to(DEV))
+        assert math.isclose(val, float(phi), rel_tol=2e-4, abs_tol=1e-6), (val, float(phi), terms, eng.last_terms())
+        assert _relerr(grad, raw) < 2e-3, _relerr(grad, raw)
+    eng.close()

@@ -1,0 +1,77 @@
+"""The four-sweep formulation for the transformer / TAG path (oracle/transformer_interp.py: attention, LayerNorm, token-level
+soft-label cross-entropy, label-leaf gradient) against autograd's double backward through the real ``nn.TransformerEncoder``
+modules, in float64.  This is the CPU specification of the kernels SURVEY section 8 rows a15 / a16 still need."""
+import pytest
+import torch
+from torch.nn.attention import SDPBackend, sdpa_kernel
+
+from breaching_b200 import synthetic
+from oracle.transformer_interp import TransformerFourSweep
+
+
+def _relerr(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-300)).item()
+
+
+@pytest.mark.parametrize("nlayers,T", [(1, 5), (3, 8)])
+def test_transformer_four_sweeps_match_double_backward(nlayers, T):
+    torch.manual_seed(3)
+    N, vocab, d, heads, dff = 2, 37, 16, 4, 24
+    model = synthetic.TransformerLM(vocab, d, heads, dff, nlayers, max_positions=16).double().eval()
+    with torch.no_grad():  # non-trivial LayerNorm affine parameters and biases
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    params = model.attack_parameters()
+    g = [0.3 * torch.randn_like(p) for p in params]                        # the "shared gradient" to be matched
+    x = torch.randn(N, T, d, dtype=torch.double, requires_grad=True)      # candidate in embedding space
+    q = torch.softmax(torch.randn(N, T, vocab, dtype=torch.double), dim=-1).requires_grad_(True)   # labels.softmax(-1)
+
+    with sdpa_kernel(SDPBackend.MATH):   # the fused CPU attention kernel has no double backward
+        loss = synthetic.causal_loss(model(inputs_embeds=x), q)
+        G = torch.autograd.grad(loss, params, create_graph=True)
+        phi = 0.5 * sum((a - b).pow(2).sum() for a, b in zip(G, g))
+        dx_ref, dq_ref = torch.autograd.grad(phi, [x, q])
+
+    fs = TransformerFourSweep(model)
+    assert abs(float(fs.forward(x.detach(), q.detach())) - float(loss)) < 1e-12
+    G_fs = fs.backward()
+    assert len(G_fs) == len(G)
+    for a, b in zip(G_fs, G):
+        assert a.shape == b.shape and _relerr(a, b.detach()) < 1e-10
+    V = [a - b for a, b in zip(G_fs, g)]                                    # d phi / d G for the euclidean objective
+    fs.tangent_forward(V)
+    dx, dq = fs.tangent_backward()
+    assert _relerr(dx, dx_ref) < 1e-9, _relerr(dx, dx_ref)
+    assert _relerr(dq[:, 1:], dq_ref[:, 1:]) < 1e-9, _relerr(dq[:, 1:], dq_ref[:, 1:])
+    assert dq[:, 0].abs().max().item() == 0.0 and dq_ref[:, 0].abs().max().item() == 0.0   # position 0 is never a target
+
+
+def test_transformer_four_sweeps_reproduce_the_reference_tag_closure():
+    """Same formulation against the unmodified reference: the TAG joint attacker's closure (tag.yaml: tag-euclidean objective,
+    candidate in embedding space, token-level soft labels) on the miniature config-5 fixture -- objective value, gradient
+    w.r.t. the candidate embeddings and w.r.t. the label logits (chained through the softmax)."""
+    import sys, os
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import case_from_fixture, cfg_from_fixture, load_golden
+    from oracle.program_interp import objective_direction
+
+    fx = load_golden("trial_joint_tag_transformer.pt")
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    names = [n for n, _ in model.named_parameters()]
+    g = [t.double() for t in shared[0]["gradients"]]
+    g.pop(names.index("encoder.weight"))
+    fs = TransformerFourSweep(model.double())
+    q = fx["l0"].double().softmax(dim=-1)
+    fs.forward(fx["x0"].double(), q)
+    G = fs.backward()
+    o = cfg.objective
+    val, V = objective_direction(o.type, G, g, scale=o.scale, tag_scale=o.tag_scale, scale_scheme=o.scale_scheme)
+    assert abs(float(val) - fx["objective0"]) < 1e-5 * abs(fx["objective0"])
+    fs.tangent_forward(V)
+    dx, dq = fs.tangent_backward()
+    dl = q * (dq - (q * dq).sum(dim=-1, keepdim=True))
+    assert _relerr(dx.float(), fx["raw_grad_x0"]) < 1e-4, _relerr(dx.float(), fx["raw_grad_x0"])
+    assert _relerr(dl.float(), fx["raw_grad_l0"]) < 1e-4, _relerr(dl.float(), fx["raw_grad_l0"])
