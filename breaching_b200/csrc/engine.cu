@@ -264,7 +264,7 @@ struct bre_engine {
           if (fuses_with_next(i, a)) {
             const bre_op_desc& nx = ops[i + 1];
             const BnConsts c = bn_consts(nx);
-            a.epi.kind = 1; a.epi.has_bn = nx.has_bn != 0; a.epi.relu = nx.relu != 0;
+            a.epi.kind = 1; a.epi.has_bn = nx.has_bn != 0; a.epi.relu = nx.relu != 0; a.epi.round_out = round_val(nx.tout);
             a.epi.out2 = t[nx.tout].val; a.epi.res = nx.res >= 0 ? t[nx.res].val : nullptr;
             a.epi.scale = c.scale; a.epi.shift = c.shift;
             ++i;   // the BNACT op ran in the epilogue
@@ -386,7 +386,7 @@ struct bre_engine {
           if (fuses_with_next(i, a)) {
             const bre_op_desc& nx = ops[i + 1];
             const BnConsts c = bn_consts(nx);
-            a.epi.kind = 2; a.epi.has_bn = nx.has_bn != 0; a.epi.relu = nx.relu != 0;
+            a.epi.kind = 2; a.epi.has_bn = nx.has_bn != 0; a.epi.relu = nx.relu != 0; a.epi.round_out = round_val(nx.tout);
             a.epi.out2 = t[nx.tout].tval; a.epi.res = nx.res >= 0 ? t[nx.res].tval : nullptr;
             a.epi.scale = c.scale; a.epi.inv = c.inv; a.epi.nrm = c.nrm;
             a.epi.v_gamma = nx.has_bn ? Vp(nx.gamma) : nullptr; a.epi.v_beta = nx.has_bn ? Vp(nx.beta) : nullptr;

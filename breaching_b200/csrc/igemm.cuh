@@ -22,6 +22,7 @@ struct ConvGeom {
 struct GemmEpilogue {
   int kind;                 // 0 = none, 1 = value, 2 = tangent
   int has_bn, relu;
+  int round_out;            // store out2 on the TF32 grid (it feeds tensor-core GEMMs, see tf32_rna)
   float* out2;              // [M][Nc] output of the fused op
   const float* res;         // residual branch (value / tangent), may be null
   const float* scale;       // alpha = gamma * invstd

@@ -196,7 +196,8 @@ __device__ __forceinline__ void fused_bnact(const GemmEpilogue& e, long long row
     if (e.kind == 1) {
       if (e.has_bn) u = fmaf(u, __ldg(e.scale + n + j), __ldg(e.shift + n + j));
       if (e.res != nullptr) u += e.res[o + j];
-      v[j] = e.relu ? fmaxf(u, 0.f) : u;
+      u = e.relu ? fmaxf(u, 0.f) : u;
+      v[j] = e.round_out ? tf32_rna(u) : u;
     } else {
       if (e.has_bn) {
         const float xhat = fmaf(e.pre[o + j], __ldg(e.inv + n + j), __ldg(e.nrm + n + j));
@@ -204,7 +205,7 @@ __device__ __forceinline__ void fused_bnact(const GemmEpilogue& e, long long row
       }
       if (e.res != nullptr) u += e.res[o + j];
       if (e.relu && !(e.post[o + j] > 0.f)) u = 0.f;
-      v[j] = u;
+      v[j] = e.round_out ? tf32_rna(u) : u;
     }
   }
 }
@@ -529,8 +530,9 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
     __syncwarp();
   } else {
     if (TMA) {
-      // one producer lane per loader warp, k-blocks dealt round-robin: a cp.async.bulk.tensor costs its issuing thread ~140
-      // cycles (profiles/experiments/tc_trace.py), so four issuers keep the ring full where one could not
+      // `nprod` producer lanes (lane 0 of loader warps 0..nprod-1, default 2), k-blocks dealt round-robin: a cp.async.bulk.tensor
+      // costs its issuing thread ~140 cycles (profiles/experiments/tc_trace.py); two issuers keep up with the six loads per
+      // k-block of the wgrad form, more make no difference
       const int nprod = (proxy_fence >> 2) & 7;
       if ((tid & 31) == 0 && warp < nprod && warp < nkb) {
         KbState st = kb_init(kb_begin + warp);

@@ -192,3 +192,32 @@ def test_device_lbfgs_restates_torch_lbfgs():
     # at convergence the `directional derivative > -1e-9` exit is taken on a float32 rounding difference: one evaluation apart
     assert abs(dev_opt.func_evals - ref_opt.state[x_ref]["func_evals"]) <= 1
     assert dev_opt.total_iters == ref_opt.state[x_ref]["n_iter"]
+
+
+@pytest.mark.parametrize("name", ["adam", "adam-safe", "bert-adam", "momgd", "gd"])
+def test_leaf_optimizer_restates_torch_optimisers(name):
+    """breaching_b200/attacks/host_optim.py (host-driven loops of the joint and multi-query attackers) against the torch
+    optimisers the reference's ``optimizer_lookup`` constructs (common.py:5-18), two leaves, changing step size."""
+    from breaching_b200.attacks.host_optim import LeafOptimizer
+
+    gen = torch.Generator().manual_seed(1)
+    a0, b0 = torch.randn(5, 7, generator=gen), torch.randn(3, generator=gen)
+    ra, rb = torch.nn.Parameter(a0.clone()), torch.nn.Parameter(b0.clone())
+    if name == "adam":
+        ref = torch.optim.Adam([ra, rb], lr=0.1)
+    elif name == "adam-safe":
+        ref = torch.optim.Adam([ra, rb], lr=0.1, betas=(0.5, 0.99), eps=1e-4)
+    elif name == "bert-adam":
+        ref = torch.optim.AdamW([ra, rb], lr=0.1, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01)
+    else:
+        ref = torch.optim.SGD([ra, rb], lr=0.1, momentum=0.9 if name == "momgd" else 0.0, nesterov=name == "momgd")
+    da, db = a0.clone(), b0.clone()
+    dev = LeafOptimizer([da, db], name)
+    for step, lr in enumerate([0.0, 0.05, 0.1, 0.1, 0.02, 0.3]):
+        ga, gb = torch.randn(5, 7, generator=gen), torch.randn(3, generator=gen)
+        ref.param_groups[0]["lr"] = lr
+        ra.grad, rb.grad = ga.clone(), gb.clone()
+        ref.step()
+        dev.step([ga, gb], lr)
+        assert (ra.detach() - da).abs().max().item() < 1e-6, (name, step)
+        assert (rb.detach() - db).abs().max().item() < 1e-6, (name, step)
