@@ -75,6 +75,7 @@ class Op:
     b: int = -1
     # bnact
     has_bn: bool = False
+    bn_train: bool = False      # BN normalises with the batch statistics of its input (train mode without buffers)
     relu: bool = False
     res: int = -1  # residual tensor id
     gamma: int = -1
@@ -199,15 +200,13 @@ def compile_model(model, input_shape):
                 prog.params[pidx(mod.weight)].perm = PERM_OIHW_TO_OHWI
                 env[node] = tout
             elif isinstance(mod, torch.nn.BatchNorm2d):
-                if mod.training or mod.running_mean is None:
-                    raise UnsupportedModelError(
-                        "train-mode BatchNorm (no server/user buffers, base_attack.py:192-197) is not supported yet"
-                    )
                 if mod.weight is None:
                     raise UnsupportedModelError("BatchNorm without affine parameters unsupported")
                 tout = new_tensor(ti.N, ti.C, ti.H, ti.W)
+                # train mode (no server / user buffers: base_attack.py:192-197 puts the model in .train() with
+                # track_running_stats = False): normalisation by the statistics of the candidate batch itself
                 prim.append(dict(kind="bn", tin=tin, tout=tout, gamma=pidx(mod.weight), beta=pidx(mod.bias),
-                                 eps=float(mod.eps), module=node.target))
+                                 eps=float(mod.eps), module=node.target, train=bool(mod.training or mod.running_mean is None)))
                 env[node] = tout
             elif isinstance(mod, torch.nn.ReLU):
                 tout = new_tensor(ti.N, ti.C, ti.H, ti.W)
@@ -310,6 +309,7 @@ def compile_model(model, input_shape):
             cur = p
             if cur["kind"] == "bn":
                 op.has_bn, op.gamma, op.beta, op.eps, op.bn_module = True, cur["gamma"], cur["beta"], cur["eps"], cur["module"]
+                op.bn_train = cur.get("train", False)
                 nxt = single_next(cur["tout"], "add")
                 if nxt is not None:
                     used.add(id(nxt))

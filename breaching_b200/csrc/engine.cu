@@ -48,6 +48,9 @@ struct BnBuf {
   int C = 0;
   float *rm = nullptr, *rv = nullptr, *scale = nullptr, *shift = nullptr, *inv = nullptr, *nrm = nullptr;
   float *di_mean = nullptr, *di_var = nullptr, *di_cm = nullptr, *di_cv = nullptr;
+  // train-mode BN reuses di_mean / di_var for the batch statistics and di_cm / di_cv for the tangent-forward means; the
+  // tangent-backward means live here
+  float *tb1 = nullptr, *tb2 = nullptr;
 };
 
 #define BRE_TRY(call)            \
@@ -228,12 +231,28 @@ struct bre_engine {
   bool fuses_with_next(size_t i, const GemmArgs& a) const {
     if (!fuse_bnact || gemm_backend != 1 || i + 1 >= ops.size()) return false;
     const bre_op_desc& nx = ops[i + 1];
-    return nx.kind == BRE_OP_BNACT && nx.tin == ops[i].tout && igemm_tc_supported(a);
+    return nx.kind == BRE_OP_BNACT && nx.tin == ops[i].tout && !nx.bn_train && igemm_tc_supported(a);
   }
   int consumers_of(int tensor) const {
     int n = 0;
     for (const bre_op_desc& o : ops) n += (o.tin == tensor) + (o.res == tensor);
     return n;
+  }
+
+  // common part of the train-mode BN argument block of op (rules in layers.cuh)
+  BnTrainArgs bn_train_args(const bre_op_desc& op) {
+    const bre_tensor_desc& to = td(op.tout);
+    const BnBuf& b = bn[op.bn_buffer];
+    BnTrainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = (long long)to.N * to.H * to.W; a.C = to.C; a.relu = op.relu != 0;
+    a.in = t[op.tin].val; a.out = t[op.tout].val;
+    a.inv = b.inv; a.nrm = b.nrm; a.scale = b.scale;
+    a.v_gamma = Vp(op.gamma); a.v_beta = Vp(op.beta);
+    a.sum_du = Gp(op.beta); a.sum_duxh = Gp(op.gamma);
+    a.m1 = b.di_cm; a.m2 = b.di_cv; a.b1 = b.tb1; a.b2 = b.tb2;
+    a.dout = t[op.tout].d; a.tdout = t[op.tout].td; a.xd = t[op.tin].tval;
+    return a;
   }
 
   BnConsts bn_consts(const bre_op_desc& op) const {
@@ -273,6 +292,12 @@ struct bre_engine {
           break;
         }
         case BRE_OP_BNACT:
+          if (op.has_bn && op.bn_train) {   // batch statistics of this forward -> the per-channel constants the kernels read
+            BnBuf& b = bn[op.bn_buffer];
+            BRE_LAUNCH(launch_channel_stats(t[op.tin].val, Pout, to.C, b.di_mean, b.di_var, red_partials, red_counters, stream));
+            BRE_LAUNCH(launch_bn_train_prepare(b.di_mean, b.di_var, Wp(op.gamma), Wp(op.beta), op.eps, to.C, b.scale, b.shift, b.inv,
+                                               b.nrm, stream));
+          }
           BRE_LAUNCH(launch_bnact_fwd(t[op.tin].val, op.res >= 0 ? t[op.res].val : nullptr, t[op.tout].val, Pout, to.C,
                                       op.has_bn != 0, op.relu != 0, bn_consts(op), round_val(op.tout), stream));
           break;
@@ -336,6 +361,16 @@ struct bre_engine {
           a.partials = red_partials; a.counters = red_counters;
           // (splitting this op into an element-wise kernel on the main stream and the gamma / beta reductions on the side
           // stream was measured: config 2 unchanged, configs 1 and 3 3-5 % slower -- the side stream is already full)
+          if (op.has_bn && op.bn_train) {
+            // pass 1: sum(du), sum(du xh) (= the gamma / beta gradients) and the residual delta; pass 2: dx needs those sums
+            BnActBwdArgs r = a;
+            r.din = nullptr;
+            BRE_LAUNCH(launch_bnact_bwd(r, stream));
+            BnTrainArgs ta = bn_train_args(op);
+            ta.dst = t[op.tin].d; ta.acc = op.acc_in != 0; ta.round_out = round_d(op.tin);
+            BRE_LAUNCH(launch_bn_train_bwd(ta, stream));
+            break;
+          }
           BRE_LAUNCH(launch_bnact_bwd(a, stream));
           break;
         }
@@ -398,6 +433,15 @@ struct bre_engine {
           break;
         }
         case BRE_OP_BNACT: {
+          if (op.has_bn && op.bn_train) {
+            BnBuf& b = bn[op.bn_buffer];
+            BnTrainArgs ta = bn_train_args(op);
+            BRE_LAUNCH(launch_bn_train_tan_stats(ta, b.di_cm, b.di_cv, red_partials, red_counters, stream));
+            ta.tres = op.res >= 0 ? t[op.res].tval : nullptr;
+            ta.dst = t[op.tout].tval; ta.round_out = round_val(op.tout);
+            BRE_LAUNCH(launch_bn_train_tan_fwd(ta, stream));
+            break;
+          }
           BnActTanFwdArgs a;
           a.P = Pout; a.C = to.C; a.has_bn = op.has_bn != 0; a.relu = op.relu != 0; a.bn = bn_consts(op);
           a.in = t[op.tin].val; a.out = t[op.tout].val;
@@ -480,6 +524,15 @@ struct bre_engine {
           break;
         }
         case BRE_OP_BNACT: {
+          if (op.has_bn && op.bn_train) {
+            BnBuf& b = bn[op.bn_buffer];
+            BnTrainArgs ta = bn_train_args(op);
+            BRE_LAUNCH(launch_bn_train_tanbwd_stats(ta, b.tb1, b.tb2, red_partials, red_counters, stream));
+            ta.dst = t[op.tin].td; ta.acc = op.acc_in != 0; ta.round_out = round_d(op.tin);
+            ta.dres = op.res >= 0 ? t[op.res].td : nullptr; ta.acc_res = op.acc_res != 0;
+            BRE_LAUNCH(launch_bn_train_tan_bwd(ta, stream));
+            break;
+          }
           BnActTanBwdArgs a;
           a.P = Pout; a.C = to.C; a.has_bn = op.has_bn != 0; a.relu = op.relu != 0; a.bn = bn_consts(op);
           a.in = t[op.tin].val; a.out = t[op.tout].val; a.tdout = t[op.tout].td; a.dout = t[op.tout].d;
@@ -720,7 +773,7 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
     if (op.kind == BRE_OP_BNACT && op.has_bn) {
       BnBuf& b = e->bn[op.bn_buffer];
       b.C = tensors[op.tout].C;
-      float** ptrs[] = {&b.rm, &b.rv, &b.scale, &b.shift, &b.inv, &b.nrm, &b.di_mean, &b.di_var, &b.di_cm, &b.di_cv};
+      float** ptrs[] = {&b.rm, &b.rv, &b.scale, &b.shift, &b.inv, &b.nrm, &b.di_mean, &b.di_var, &b.di_cm, &b.di_cv, &b.tb1, &b.tb2};
       for (float** pp : ptrs) rc |= e->alloc(pp, b.C);
     }
   }
@@ -749,6 +802,12 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
   rc |= e->alloc(&e->dcounter, 4);
   if (rc != 0) return fail(BRE_ERR_CUDA);
   // DeepInversion layer table
+  bool any_bn_train = false;
+  for (int i = 0; i < n_ops; ++i) any_bn_train = any_bn_train || (ops[i].kind == BRE_OP_BNACT && ops[i].has_bn && ops[i].bn_train);
+  if (any_bn_train && (cfg->di_scale > 0.f || cfg->feat_scale > 0.f)) {
+    set_error("DeepInversion / feature priors need running statistics: not available with train-mode BatchNorm");
+    return fail(BRE_ERR_UNSUPPORTED);
+  }
   if (cfg->di_scale > 0.f && n_bn > 0) {
     std::vector<DiLayer> layers;
     bool first = true;
@@ -910,6 +969,8 @@ int bre_engine_set_local_steps(bre_engine* e, int32_t total_images, int32_t step
   if (!e || steps < 1 || total_images < 1 || !labels) { set_error("bre_engine_set_local_steps: bad arguments"); return BRE_ERR_INVALID; }
   if (!e->model_loaded) { set_error("load the model first"); return BRE_ERR_STATE; }
   if (e->ms_steps > 0) { set_error("local steps already configured"); return BRE_ERR_STATE; }
+  for (const bre_op_desc& o : e->ops)
+    if (o.kind == BRE_OP_BNACT && o.has_bn && o.bn_train) { set_error("multi-step updates with train-mode BatchNorm are not implemented"); return BRE_ERR_UNSUPPORTED; }
   if (e->cfg.task_regularization != 0.f || e->cfg.di_scale > 0.f || e->cfg.feat_scale > 0.f) {
     set_error("task regularisation / DeepInversion / feature priors are not implemented for multi-step updates "
               "(the reference crashes on the latter two, SURVEY.md section 0 fact 9)");

@@ -259,6 +259,117 @@ __global__ void channel_stats_kernel(const float* __restrict__ x, long long P, i
   }
 }
 
+// ---- train-mode BatchNorm (rules in layers.cuh) -------------------------------------------------------------
+__global__ void bn_train_prepare_kernel(const float* mean, const float* var, const float* gamma, const float* beta, float eps, int C,
+                                        float* scale, float* shift, float* inv, float* nrm) {
+  pdl_prologue();
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    const float iv = 1.0f / sqrtf(var[c] + eps);
+    const float nr = -mean[c] * iv;
+    inv[c] = iv; nrm[c] = nr;
+    scale[c] = gamma[c] * iv;
+    shift[c] = fmaf(gamma[c], nr, beta[c]);
+  }
+}
+
+__global__ void bn_train_bwd_kernel(BnTrainArgs a, long long total) {
+  pdl_prologue();
+  const float invP = 1.0f / (float)a.P;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % a.C);
+    float du = a.dout[i];
+    if (a.relu && !(a.out[i] > 0.f)) du = 0.f;
+    const float xh = fmaf(a.in[i], __ldg(a.inv + c), __ldg(a.nrm + c));
+    float di = __ldg(a.scale + c) * (du - __ldg(a.sum_du + c) * invP - xh * __ldg(a.sum_duxh + c) * invP);
+    if (a.acc) di += a.dst[i];
+    a.dst[i] = a.round_out ? tf32_rna(di) : di;
+  }
+}
+
+__global__ void bn_train_tan_stats_kernel(BnTrainArgs a, float* m1, float* m2, float* partials, int* counters, long long pps, int Cpad) {
+  pdl_prologue();
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cv = c < a.C;
+  const long long p0 = blockIdx.y * pps;
+  const long long p1 = (p0 + pps < a.P) ? p0 + pps : a.P;
+  float v[2] = {0.f, 0.f};
+  if (cv) {
+    const float inv = __ldg(a.inv + c), nrm = __ldg(a.nrm + c);
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      const long long o = p * a.C + c;
+      const float xd = a.xd[o];
+      v[0] += xd;
+      v[1] = fmaf(fmaf(a.in[o], inv, nrm), xd, v[1]);
+    }
+  }
+  float tot[2];
+  if (slab_reduce<2>(v, partials, counters, Cpad, tot) && cv) {
+    m1[c] = tot[0] / (float)a.P;
+    m2[c] = tot[1] / (float)a.P;
+  }
+}
+
+__global__ void bn_train_tan_fwd_kernel(BnTrainArgs a, long long total) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % a.C);
+    const float xh = fmaf(a.in[i], __ldg(a.inv + c), __ldg(a.nrm + c));
+    float u = fmaf(__ldg(a.v_gamma + c), xh, __ldg(a.v_beta + c)) +
+              __ldg(a.scale + c) * (a.xd[i] - __ldg(a.m1 + c) - xh * __ldg(a.m2 + c));
+    if (a.tres != nullptr) u += a.tres[i];
+    if (a.relu && !(a.out[i] > 0.f)) u = 0.f;
+    a.dst[i] = a.round_out ? tf32_rna(u) : u;
+  }
+}
+
+__global__ void bn_train_tanbwd_stats_kernel(BnTrainArgs a, float* b1, float* b2, float* partials, int* counters, long long pps, int Cpad) {
+  pdl_prologue();
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cv = c < a.C;
+  const long long p0 = blockIdx.y * pps;
+  const long long p1 = (p0 + pps < a.P) ? p0 + pps : a.P;
+  float v[2] = {0.f, 0.f};
+  if (cv) {
+    const float inv = __ldg(a.inv + c), nrm = __ldg(a.nrm + c), m1 = __ldg(a.m1 + c), m2 = __ldg(a.m2 + c);
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      const long long o = p * a.C + c;
+      float du = a.dout[o], tdu = a.tdout[o];
+      if (a.relu && !(a.out[o] > 0.f)) { du = 0.f; tdu = 0.f; }
+      const float xh = fmaf(a.in[o], inv, nrm);
+      const float xhd = inv * (a.xd[o] - m1 - xh * m2);
+      v[0] += tdu;
+      v[1] += fmaf(tdu, xh, du * xhd);
+    }
+  }
+  float tot[2];
+  if (slab_reduce<2>(v, partials, counters, Cpad, tot) && cv) {
+    b1[c] = tot[0] / (float)a.P;
+    b2[c] = tot[1] / (float)a.P;
+  }
+}
+
+__global__ void bn_train_tan_bwd_kernel(BnTrainArgs a, long long total) {
+  pdl_prologue();
+  const float invP = 1.0f / (float)a.P;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % a.C);
+    float du = a.dout[i], tdu = a.tdout[i];
+    if (a.relu && !(a.out[i] > 0.f)) { du = 0.f; tdu = 0.f; }
+    const float inv = __ldg(a.inv + c), scale = __ldg(a.scale + c), m2 = __ldg(a.m2 + c);
+    const float xh = fmaf(a.in[i], inv, __ldg(a.nrm + c));
+    const float xhd = inv * (a.xd[i] - __ldg(a.m1 + c) - xh * m2);
+    const float a1 = __ldg(a.sum_du + c) * invP, a2 = __ldg(a.sum_duxh + c) * invP;
+    const float w = du - a1 - xh * a2;
+    const float wd = tdu - __ldg(a.b1 + c) - xhd * a2 - xh * __ldg(a.b2 + c);
+    float tdi = (__ldg(a.v_gamma + c) * inv - scale * inv * m2) * w + scale * wd;
+    if (a.dst != nullptr) {
+      if (a.acc) tdi += a.dst[i];
+      a.dst[i] = a.round_out ? tf32_rna(tdi) : tdi;
+    }
+    if (a.dres != nullptr) a.dres[i] = a.acc_res ? a.dres[i] + tdu : tdu;
+  }
+}
+
 // ---- pooling ---------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int* __restrict__ idx, PoolGeom g,
                                    long long total) {
@@ -525,6 +636,41 @@ int launch_bnact_tan_bwd(const BnActTanBwdArgs& a, cudaStream_t s) {
   const long long total = a.P * a.C;
   BRE_KLAUNCH(bnact_tan_bwd_kernel, ew_grid(total), kEwThreads, 0, s, a, total);
   BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_bn_train_prepare(const float* mean, const float* var, const float* gamma, const float* beta, float eps, int C, float* scale,
+                            float* shift, float* inv, float* nrm, cudaStream_t s) {
+  BRE_KLAUNCH(bn_train_prepare_kernel, ceil_div(C, 128), 128, 0, s, mean, var, gamma, beta, eps, C, scale, shift, inv, nrm);
+  return 0;
+}
+int launch_bn_train_bwd(const BnTrainArgs& a, cudaStream_t s) {
+  const long long total = a.P * a.C;
+  BRE_KLAUNCH(bn_train_bwd_kernel, ew_grid(total), kEwThreads, 0, s, a, total);
+  return 0;
+}
+int launch_bn_train_tan_stats(const BnTrainArgs& a, float* m1, float* m2, float* partials, int* counters, cudaStream_t s) {
+  dim3 grid, block;
+  long long pps;
+  slab_grid(a.P, a.C, grid, block, pps);
+  BRE_KLAUNCH(bn_train_tan_stats_kernel, grid, block, 0, s, a, m1, m2, partials, counters, pps, (int)(grid.x * 32));
+  return 0;
+}
+int launch_bn_train_tan_fwd(const BnTrainArgs& a, cudaStream_t s) {
+  const long long total = a.P * a.C;
+  BRE_KLAUNCH(bn_train_tan_fwd_kernel, ew_grid(total), kEwThreads, 0, s, a, total);
+  return 0;
+}
+int launch_bn_train_tanbwd_stats(const BnTrainArgs& a, float* b1, float* b2, float* partials, int* counters, cudaStream_t s) {
+  dim3 grid, block;
+  long long pps;
+  slab_grid(a.P, a.C, grid, block, pps);
+  BRE_KLAUNCH(bn_train_tanbwd_stats_kernel, grid, block, 0, s, a, b1, b2, partials, counters, pps, (int)(grid.x * 32));
+  return 0;
+}
+int launch_bn_train_tan_bwd(const BnTrainArgs& a, cudaStream_t s) {
+  const long long total = a.P * a.C;
+  BRE_KLAUNCH(bn_train_tan_bwd_kernel, ew_grid(total), kEwThreads, 0, s, a, total);
   return 0;
 }
 

@@ -67,6 +67,36 @@ int launch_axpby(const float* x, const float* y, float alpha, float* out, long l
 int launch_round_tf32(const float* src, float* dst, long long n, cudaStream_t s);   // dst = src rounded onto the TF32 grid (may alias)
 
 // per-channel column sum: out[c] = sum_p x[p][c]   (conv / linear bias gradient)
+// ---- train-mode BatchNorm (no server / user buffers, base_attack.py:192-197: batch statistics of the candidate) ----------
+// Rules (oracle/program_interp.py, verified against autograd's double backward): with xh the normalised input, m(.) the
+// per-channel mean over (N, H, W), inv = 1/sigma, du the ReLU-masked delta of the op's output
+//   F :  statistics -> (inv, nrm, scale, shift), then the eval-mode kernel
+//   B :  dx  = gamma inv (du - m(du) - xh m(du xh))                    [m(du), m(du xh) = G_beta / P, G_gamma / P]
+//   TF:  xh' = inv (x' - m(x') - xh m(xh x'));  y' = v_gamma xh + gamma xh' + v_beta
+//   TB:  dx' = (v_gamma inv - scale inv m(xh x')) w + scale (du' - m(du') - xh' m(du xh) - xh m(du' xh + du xh')),
+//        w = du - m(du) - xh m(du xh)
+struct BnTrainArgs {
+  long long P; int C; bool relu;
+  const float* in;  const float* out;                 // BN input value, post-activation value (ReLU mask)
+  const float *inv, *nrm, *scale;                     // per-channel constants of this forward
+  const float *v_gamma, *v_beta;                      // direction components (tangent sweeps)
+  const float *sum_du, *sum_duxh;                     // G_beta, G_gamma of sweep B (sums over P)
+  const float *m1, *m2;                               // TF means  m(x'), m(xh x')
+  const float *b1, *b2;                               // TB means  m(du'), m(du' xh + du xh')
+  const float *dout, *tdout;                          // delta / tangent delta of the op's output
+  const float* xd;                                    // tangent of the BN input
+  const float* tres;                                  // tangent of the residual branch (may be null)
+  float* dst; bool acc; bool round_out;               // result of the pass (din / tout / tdin)
+  float* dres; bool acc_res;                          // TB: tangent delta of the residual branch (may be null)
+};
+int launch_bn_train_prepare(const float* mean, const float* var, const float* gamma, const float* beta, float eps, int C, float* scale,
+                            float* shift, float* inv, float* nrm, cudaStream_t s);
+int launch_bn_train_bwd(const BnTrainArgs& a, cudaStream_t s);                                  // B, second pass
+int launch_bn_train_tan_stats(const BnTrainArgs& a, float* m1, float* m2, float* partials, int* counters, cudaStream_t s);
+int launch_bn_train_tan_fwd(const BnTrainArgs& a, cudaStream_t s);                              // TF, second pass
+int launch_bn_train_tanbwd_stats(const BnTrainArgs& a, float* b1, float* b2, float* partials, int* counters, cudaStream_t s);
+int launch_bn_train_tan_bwd(const BnTrainArgs& a, cudaStream_t s);                              // TB, second pass
+
 int launch_channel_sum(const float* x, long long P, int C, float* out, float* partials, int* counters, cudaStream_t s);
 // per-channel mean / biased variance over pixels (DeepInversion statistics, deepinversion.py:96-98)
 int launch_channel_stats(const float* x, long long P, int C, float* mean, float* var, float* partials, int* counters,

@@ -30,7 +30,8 @@ class ParamDesc(ctypes.Structure):
 class OpDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("kind", "tin", "tout", "res", "R", "S", "stride", "pad", "w", "b", "has_bn", "relu", "gamma", "beta",
-                 "bn_buffer")] + [("eps", ctypes.c_float), ("acc_in", ctypes.c_int32), ("acc_res", ctypes.c_int32)]
+                 "bn_buffer")] + [("eps", ctypes.c_float), ("acc_in", ctypes.c_int32), ("acc_res", ctypes.c_int32),
+                                  ("bn_train", ctypes.c_int32)]
 
 
 class AttackCfg(ctypes.Structure):
@@ -237,7 +238,8 @@ class Engine:
                 bn_idx = len(self._bn_modules)
                 self._bn_modules.append(mod)
             ops.append(OpDesc(op.kind, op.tin, op.tout, op.res, op.R, op.S, op.stride, op.pad, op.w, op.b, int(op.has_bn),
-                              int(op.relu), op.gamma, op.beta, bn_idx, float(op.eps), int(op.acc_in), int(op.acc_res)))
+                              int(op.relu), op.gamma, op.beta, bn_idx, float(op.eps), int(op.acc_in), int(op.acc_res),
+                              int(getattr(op, "bn_train", False))))
         self._keep = (tens, (OpDesc * len(ops))(*ops), (ParamDesc * len(pds))(*pds))
         handle = ctypes.c_void_p()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()

@@ -94,7 +94,7 @@ def randomize_bn(model, seed=1):
 
 
 def make_case(model_name="resnet18", data="imagenet", batch=1, seed=233, provide_labels=False,
-              user_buffers=False, bn_random=False, image_size=None, classes=None, unique_labels=True):
+              user_buffers=False, bn_random=False, image_size=None, classes=None, unique_labels=True, no_buffers=False):
     """Return ``(model, loss_fn, server_payload, shared_data, true_user_data)`` with CPU tensors.
 
     Single local step (``local_hyperparams=None``); honest server with public buffers (eval-mode BN) or,
@@ -120,7 +120,14 @@ def make_case(model_name="resnet18", data="imagenet", batch=1, seed=233, provide
         y = torch.randint(0, meta.classes, (batch,), generator=gen).sort()[0]
 
     params = [p for p in model.parameters()]
-    if user_buffers:
+    if no_buffers:
+        # neither the server nor the user publishes BN buffers: the user computes its update in train mode (batch statistics)
+        # and the attacker has to do the same (base_attack.py:192-197)
+        model.train()
+        loss = loss_fn(model(x), y)
+        grads = torch.autograd.grad(loss, params)
+        shared_buffers, payload_buffers = None, None
+    elif user_buffers:
         model.train()
         for m in model.modules():
             if isinstance(m, torch.nn.BatchNorm2d):

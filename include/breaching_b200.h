@@ -57,6 +57,8 @@ typedef struct bre_op_desc {
   int32_t bn_buffer;              /* index into the running-stat arrays passed to bre_engine_load_model */
   float eps;
   int32_t acc_in, acc_res;        /* reverse sweeps: accumulate into (1) or overwrite (0) the input delta */
+  int32_t bn_train;               /* BNACT: BN uses the batch statistics of its input (model in train mode without buffers,
+                                     base_attack.py:192-197) instead of running statistics */
 } bre_op_desc;
 
 /* ---- attack configuration (cfg_attack of the reference, flattened) ------------------------------- */

@@ -78,7 +78,8 @@ class ProgramInterpreter:
         self.dtype = dtype
         self.P = [p.detach().to(dtype) for p in model.parameters()]
         mods = C.bn_modules(model, prog)
-        self.bn = [None if m is None else (m.running_mean.detach().to(dtype), m.running_var.detach().to(dtype)) for m in mods]
+        self.bn = [None if (m is None or m.running_mean is None) else (m.running_mean.detach().to(dtype), m.running_var.detach().to(dtype))
+                   for m in mods]
 
     # ------------------------------------------------------------------ helpers
     def _flat_in(self, op, t):
@@ -103,7 +104,12 @@ class ProgramInterpreter:
             elif op.kind == C.OP_BNACT:
                 u = xin
                 if op.has_bn:
-                    rm, inv = self._bn_consts(i, op)
+                    if getattr(op, "bn_train", False):   # batch statistics of this very input (biased variance, F.batch_norm)
+                        rm = xin.mean(dim=(0, 2, 3), keepdim=True)
+                        inv = 1.0 / torch.sqrt(xin.var(dim=(0, 2, 3), unbiased=False, keepdim=True) + op.eps)
+                        aux[("inv", i)] = inv
+                    else:
+                        rm, inv = self._bn_consts(i, op)
                     xhat = (xin - rm) * inv
                     u = self.P[op.gamma].view(1, -1, 1, 1) * xhat + self.P[op.beta].view(1, -1, 1, 1)
                     aux[i] = xhat
@@ -168,7 +174,29 @@ class ProgramInterpreter:
                 du_saved[i] = du
                 if op.res >= 0:
                     add(op.res, du)
-                if op.has_bn:
+                if op.has_bn and getattr(op, "bn_train", False):
+                    # train-mode BN: the statistics depend on the input.  With xh the normalised input, m(.) the mean over
+                    # (N, H, W) per channel and inv = 1/sigma:
+                    #   B :  dx  = gamma inv (du - m(du) - xh m(du xh))
+                    #   TB:  dx' = (v_gamma inv + gamma inv') w + gamma inv (du' - m(du') - xh' m(du xh) - xh m(du' xh + du xh')),
+                    #        w = du - m(du) - xh m(du xh),  inv' = -inv^2 m(xh x'),  xh' from the tangent-forward sweep
+                    xh, inv = self.aux[i], self.aux[("inv", i)]
+                    gam = self.P[op.gamma].view(1, -1, 1, 1)
+                    m = lambda t: t.mean(dim=(0, 2, 3), keepdim=True)  # noqa: E731
+                    if V is None:
+                        if want_G:
+                            G[op.gamma] = (du * xh).sum(dim=(0, 2, 3))
+                            G[op.beta] = du.sum(dim=(0, 2, 3))
+                        add(op.tin, gam * inv * (du - m(du) - xh * m(du * xh)))
+                    else:
+                        duB = self.du_B[i]
+                        xhd, xd = self.taux[i], self.ta[op.tin]
+                        vg = V[op.gamma].view(1, -1, 1, 1)
+                        invd = -inv * inv * m(xh * xd)
+                        w = duB - m(duB) - xh * m(duB * xh)
+                        wd = du - m(du) - xhd * m(duB * xh) - xh * m(du * xh + duB * xhd)
+                        add(op.tin, (vg * inv + gam * invd) * w + gam * inv * wd)
+                elif op.has_bn:
                     rm, inv = self._bn_consts(i, op)
                     s = self.P[op.gamma].view(1, -1, 1, 1) * inv
                     if V is None:
@@ -208,6 +236,7 @@ class ProgramInterpreter:
     def tangent_forward(self, V):
         prog = self.prog
         ta = {0: None}  # tangent of the candidate is zero
+        self.taux = {}
         for i, op in enumerate(prog.ops):
             tin, xin = ta[op.tin], self.a[op.tin]
             if op.kind == C.OP_CONV:
@@ -217,7 +246,15 @@ class ProgramInterpreter:
                 ta[op.tout] = out
             elif op.kind == C.OP_BNACT:
                 u = tin if tin is not None else torch.zeros_like(xin)
-                if op.has_bn:
+                if op.has_bn and getattr(op, "bn_train", False):
+                    #   TF:  xh' = inv (x' - m(x') - xh m(xh x'));   y' = v_gamma xh + gamma xh' + v_beta
+                    xh, inv = self.aux[i], self.aux[("inv", i)]
+                    m = lambda t: t.mean(dim=(0, 2, 3), keepdim=True)  # noqa: E731
+                    xhd = inv * (u - m(u) - xh * m(xh * u))
+                    self.taux[i] = xhd
+                    ta[op.tin] = u
+                    u = V[op.gamma].view(1, -1, 1, 1) * xh + self.P[op.gamma].view(1, -1, 1, 1) * xhd + V[op.beta].view(1, -1, 1, 1)
+                elif op.has_bn:
                     rm, inv = self._bn_consts(i, op)
                     u = self.P[op.gamma].view(1, -1, 1, 1) * inv * u + V[op.gamma].view(1, -1, 1, 1) * self.aux[i] \
                         + V[op.beta].view(1, -1, 1, 1)

@@ -50,6 +50,14 @@ CASES = {
 }
 
 
+TRAIN_BN_CASES = {
+    # no BN buffers anywhere: the reference puts the attacked model in train mode (base_attack.py:192-197)
+    "trainbn_convnet": (dict(model_name="convnet-tiny", data="cifar", batch=3, seed=61, bn_random=True, no_buffers=True),
+                        "invertinggradients", {"optim.signed": "soft"}, 6),
+    "trainbn_resnet18": (dict(model_name="resnet18", data="imagenet", batch=2, seed=62, bn_random=True, no_buffers=True, image_size=64,
+                              classes=10), "invertinggradients", {"optim.signed": "soft"}, 4),
+}
+
 LBFGS_CASES = {
     # L-BFGS presets (common.py:18; `beyondinfering.yaml`, `wei.yaml`): 20 inner iterations per optimizer.step, hard-signed
     # gradients (the default `optim.signed`) resp. task-loss regularisation + euclidean matching
@@ -270,7 +278,7 @@ def main():
     ref = refshim.import_reference()
     torch.manual_seed(0)
     only = sys.argv[1:]   # optional: regenerate just the named fixtures
-    for name, (case_kwargs, attack, overrides, iters) in {**CASES, **FEDAVG_CASES, **LBFGS_CASES, **MULTI_QUERY_CASES}.items():
+    for name, (case_kwargs, attack, overrides, iters) in {**CASES, **FEDAVG_CASES, **LBFGS_CASES, **MULTI_QUERY_CASES, **TRAIN_BN_CASES}.items():
         if only and name not in only:
             continue
         fx = run_reference(ref, case_kwargs, attack, overrides, iters)

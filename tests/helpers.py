@@ -50,6 +50,11 @@ def oracle_for_fixture(fx):
         for buf, src in zip(m.buffers(), shared[0]["buffers"]):
             buf.data.copy_(src)
     m.eval()
+    if shared[0]["buffers"] is None and payload[0]["buffers"] is None:  # base_attack.py:192-197: no buffers anywhere -> train mode
+        m.train()
+        for mod in m.modules():
+            if hasattr(mod, "track_running_stats"):
+                mod.track_running_stats = False
     meta = payload[0]["metadata"]
     dm = torch.tensor(meta.mean)[None, :, None, None]
     ds = torch.tensor(meta.std)[None, :, None, None]
@@ -63,6 +68,7 @@ FEDAVG_FIXTURES = ["fedavg_convnet", "fedavg_resnet18"]
 LBFGS_FIXTURES = ["lbfgs_convnet", "lbfgs_wei_convnet", "lbfgs_cosine_convnet"]
 JOINT_FIXTURES = ["joint_dlg_convnet", "joint_adam_convnet", "joint_tag_transformer"]
 MULTI_QUERY_FIXTURES = ["multiquery_convnet"]
+TRAIN_BN_FIXTURES = ["trainbn_convnet", "trainbn_resnet18"]
 
 
 def joint_oracle_for_fixture(fx):

@@ -445,3 +445,36 @@ def test_orthogonality_regulariser_vs_oracle(with_image_priors):
         assert math.isclose(val, float(phi), rel_tol=2e-4, abs_tol=1e-6), (val, float(phi), terms, eng.last_terms())
         assert _relerr(grad, raw) < 2e-3, _relerr(grad, raw)
     eng.close()
+
+
+@pytest.mark.parametrize("backend", ["simt", "tc"])
+@pytest.mark.parametrize("name", ["trainbn_convnet", "trainbn_resnet18"])
+def test_train_mode_batchnorm_matches_reference_fixture(name, backend):
+    """No BN buffers from server or user: the reference attacks the model in train mode (base_attack.py:192-197) and so does
+    the engine -- batch statistics recomputed every forward, two-pass BN kernels in all four sweeps.  Closure and a short
+    trajectory through the attacker API against the unmodified reference."""
+    from helpers import case_from_fixture, cfg_from_fixture
+
+    fx = load_golden(f"trial_{name}.pt")
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    assert payload[0]["buffers"] is None and shared[0]["buffers"] is None
+    cfg = cfg_from_fixture(fx)
+    attacker = prepare_attack(model, loss_fn, cfg, dict(device=DEV, dtype=torch.float, backend=backend))
+    rec_models, labels, stats, shared2 = attacker.prepare_attack(payload, copy.deepcopy(shared))
+    assert rec_models[0].training and labels.tolist() == fx["labels"].tolist()
+    engine = attacker._get_engine(rec_models, shared2, labels)
+    assert any(getattr(op, "bn_train", False) for op in engine.prog.ops)
+    val, grad = engine.objective_and_gradient(fx["x0"].to(DEV))
+    tol_v, tol_g = (2e-4, 2e-3) if backend == "simt" else (1e-2, 5e-2)
+    assert math.isclose(val, fx["objective0"], rel_tol=tol_v, abs_tol=1e-6), (val, fx["objective0"], engine.last_terms())
+    assert _relerr(grad, fx["raw_grad0"]) < tol_g, _relerr(grad, fx["raw_grad0"])
+    if backend == "simt":
+        from breaching_b200.schedule import lr_table
+
+        opt = cfg.optim
+        engine.begin_trial(fx["x0"].to(DEV), lr_table(opt.step_size, opt.step_size_decay, opt.warmup, opt.max_iterations))
+        engine.run(fx["iters"])
+        engine.sync()
+        for a, b in zip(engine.history().tolist(), fx["history"]):
+            assert math.isclose(a, b, rel_tol=2e-3, abs_tol=1e-5), (engine.history().tolist(), fx["history"])
+        assert (engine.candidate().cpu() - fx["candidate_final"]).abs().mean().item() < 5e-3

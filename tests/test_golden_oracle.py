@@ -4,11 +4,12 @@ import math
 import pytest
 import torch
 
-from helpers import (FEDAVG_FIXTURES, JOINT_FIXTURES, LBFGS_FIXTURES, MULTI_QUERY_FIXTURES, TRIAL_FIXTURES, joint_oracle_for_fixture,
+from helpers import (FEDAVG_FIXTURES, JOINT_FIXTURES, LBFGS_FIXTURES, MULTI_QUERY_FIXTURES, TRAIN_BN_FIXTURES, TRIAL_FIXTURES,
+                     joint_oracle_for_fixture,
                      load_golden, multi_query_oracle_for_fixture, oracle_for_fixture)
 
 
-@pytest.mark.parametrize("name", TRIAL_FIXTURES + FEDAVG_FIXTURES + LBFGS_FIXTURES)
+@pytest.mark.parametrize("name", TRIAL_FIXTURES + FEDAVG_FIXTURES + LBFGS_FIXTURES + TRAIN_BN_FIXTURES)
 def test_oracle_reproduces_reference_trajectory(name):
     fx = load_golden(f"trial_{name}.pt")
     orc, cfg, labels = oracle_for_fixture(fx)

@@ -68,3 +68,26 @@ def test_regulariser_adjoints_are_injected_into_the_tangent_backward_stream():
     assert abs(vals["di"] - terms["deep_inversion"]) < 1e-9 * max(1.0, abs(terms["deep_inversion"]))
     assert abs(vals["feat"] - terms["features"]) < 1e-9 * max(1.0, abs(terms["features"]))
     assert ((dx - raw).norm() / raw.norm()).item() < 1e-9
+
+
+@pytest.mark.parametrize("mname,data,size,batch", [("convnet-tiny", "cifar", 32, 3), ("resnet18", "imagenet", 32, 2)])
+def test_train_mode_batchnorm_rules_match_double_backward(mname, data, size, batch):
+    """No server / user buffers (base_attack.py:192-197): the attacked model runs BatchNorm in train mode with
+    ``track_running_stats = False`` -- batch statistics of the candidate itself, so every BN couples the whole batch in the
+    forward, the backward and both tangent sweeps."""
+    model, g, x, labels, cfg, orc = _setup(mname, data, size, batch, "cosine-similarity", treg=0.2)
+    model.train()
+    for mod in model.modules():
+        if hasattr(mod, "track_running_stats"):
+            mod.track_running_stats = False
+    phi, _, raw, _ = orc.closure_gradient(x, 0, 0.1)
+    prog = compiler.compile_model(model, x.shape)
+    assert any(getattr(op, "bn_train", False) for op in prog.ops)
+    it = PI.ProgramInterpreter(model, prog)
+    val, dx, loss, G = it.matching_gradient(x, labels, g, "cosine-similarity", scale=1.0, task_regularization=0.2)
+    assert abs(float(val) - float(phi)) < 1e-9 * max(1.0, abs(float(phi)))
+    assert ((dx - raw).norm() / raw.norm()).item() < 1e-8
+    Gref, _ = orc.param_gradient(x, False)
+    scale = max(b.abs().max().item() for b in Gref)   # conv biases in front of a train-mode BN have an exactly-zero gradient
+    for a, b in zip(G, Gref):
+        assert (a - b).abs().max().item() <= 1e-9 * b.abs().max().item() + 1e-12 * scale
