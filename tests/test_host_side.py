@@ -38,9 +38,11 @@ def test_compile_rejects_unsupported_graphs():
 
     with pytest.raises(compiler.UnsupportedModelError):
         compiler.compile_model(Odd().eval(), (1, 3, 8, 8))
+    # train-mode BatchNorm (no buffers, base_attack.py:192-197) is lowered to batch-statistics BN ops
     train_bn = synthetic.build_model("convnet-tiny", 10).train()
-    with pytest.raises(compiler.UnsupportedModelError):
-        compiler.compile_model(train_bn, (1, 3, 32, 32))
+    prog = compiler.compile_model(train_bn, (2, 3, 32, 32))
+    assert all(op.bn_train for op in prog.ops if op.kind == compiler.OP_BNACT and op.has_bn)
+    assert not any(op.bn_train for op in compiler.compile_model(train_bn.eval(), (2, 3, 32, 32)).ops)
 
 
 def test_reference_style_container_and_scripted_loss_are_accepted():
