@@ -174,8 +174,11 @@ struct bre_engine {
   float* Wp(int idx) const { return W + params[idx].off; }
   float* Gp(int idx) const { return G + params[idx].off; }
   float* Vp(int idx) const { return V + params[idx].off; }
-  const float* Wg(int idx) const { return (tc_round() ? Wt : W) + params[idx].off; }   // conv / linear weights as GEMM operands
-  const float* Vg(int idx) const { return (tc_round() ? Vt : V) + params[idx].off; }
+  // conv / linear weights as GEMM operands: the TF32-rounded shadow for the layers the tcgen05 back end covers, the fp32
+  // master for the layers that run on the SIMT kernels (so that a network with no eligible layer is bit-identical on both
+  // back ends)
+  const float* Wg(const bre_op_desc& op) { return (round_val(op.tin) ? Wt : W) + params[op.w].off; }
+  const float* Vg(const bre_op_desc& op) { return (round_val(op.tin) ? Vt : V) + params[op.w].off; }
   int refresh_Vt() {
     if (tc_round()) BRE_LAUNCH(launch_round_tf32(V, Vt, P_pad, stream));
     return 0;
@@ -277,7 +280,7 @@ struct bre_engine {
         case BRE_OP_LINEAR: {
           GemmArgs a = conv_geom(op);
           a.mode = GEMM_FPROP;
-          a.act[0] = t[op.tin].val; a.wgt[0] = Wg(op.w);
+          a.act[0] = t[op.tin].val; a.wgt[0] = Wg(op);
           a.bias = op.b >= 0 ? Wp(op.b) : nullptr;
           a.out = t[op.tout].val;
           if (fuses_with_next(i, a)) {
@@ -344,7 +347,7 @@ struct bre_engine {
           if (op.tin != 0 || need_task_grad()) {
             GemmArgs b = conv_geom(op);
             b.mode = GEMM_DGRAD;
-            b.act[0] = t[op.tout].d; b.wgt[0] = Wg(op.w);
+            b.act[0] = t[op.tout].d; b.wgt[0] = Wg(op);
             b.out = op.tin == 0 ? gradx_task : t[op.tin].d;
             b.accumulate = op.tin == 0 ? 0 : op.acc_in;
             BRE_LAUNCH(gemm(b));
@@ -410,11 +413,11 @@ struct bre_engine {
           GemmArgs a = conv_geom(op);
           a.mode = GEMM_FPROP;
           if (op.tin == 0) {  // tangent of the candidate is zero: only the v-term
-            a.act[0] = t[op.tin].val; a.wgt[0] = Vg(op.w);
+            a.act[0] = t[op.tin].val; a.wgt[0] = Vg(op);
           } else {
             a.nsrc = 2;
-            a.act[0] = t[op.tin].tval; a.wgt[0] = Wg(op.w);
-            a.act[1] = t[op.tin].val; a.wgt[1] = Vg(op.w);
+            a.act[0] = t[op.tin].tval; a.wgt[0] = Wg(op);
+            a.act[1] = t[op.tin].val; a.wgt[1] = Vg(op);
           }
           a.bias = op.b >= 0 ? Vp(op.b) : nullptr;
           a.out = t[op.tout].tval;
@@ -494,8 +497,8 @@ struct bre_engine {
           GemmArgs a = conv_geom(op);
           a.mode = GEMM_DGRAD;
           a.nsrc = 2;
-          a.act[0] = t[op.tout].td; a.wgt[0] = Wg(op.w);
-          a.act[1] = t[op.tout].d; a.wgt[1] = Vg(op.w);
+          a.act[0] = t[op.tout].td; a.wgt[0] = Wg(op);
+          a.act[1] = t[op.tout].d; a.wgt[1] = Vg(op);
           a.out = op.tin == 0 ? t[0].td : t[op.tin].td;
           a.accumulate = op.tin == 0 ? 0 : op.acc_in;
           BRE_LAUNCH(gemm(a));
