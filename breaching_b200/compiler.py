@@ -22,7 +22,10 @@ import torch
 import torch.fx
 
 OP_CONV, OP_BNACT, OP_MAXPOOL, OP_AVGPOOL, OP_LINEAR = 1, 2, 3, 4, 5
-OP_NAMES = {OP_CONV: "conv", OP_BNACT: "bnact", OP_MAXPOOL: "maxpool", OP_AVGPOOL: "avgpool", OP_LINEAR: "linear"}
+# token-sequence models (the TAG / transformer path): tensors are [rows = batch x seq_len, C, 1, 1]
+OP_POSADD, OP_LAYERNORM, OP_ATTENTION = 6, 7, 8
+OP_NAMES = {OP_CONV: "conv", OP_BNACT: "bnact", OP_MAXPOOL: "maxpool", OP_AVGPOOL: "avgpool", OP_LINEAR: "linear",
+            OP_POSADD: "posadd", OP_LAYERNORM: "layernorm", OP_ATTENTION: "attention"}
 
 # how a parameter tensor is laid out in the engine arena relative to torch's layout
 PERM_NONE, PERM_OIHW_TO_OHWI, PERM_LINEAR_CHW_TO_HWC = 0, 1, 2
@@ -94,6 +97,7 @@ class Program:
     params: List[ParamDesc] = field(default_factory=list)
     logits: int = -1  # tensor id of the network output
     num_classes: int = 0
+    seq_len: int = 0  # > 0: token-sequence program (rows = batch * seq_len), causal next-token loss over rows
 
     def describe(self):
         lines = []
@@ -380,3 +384,68 @@ def bn_modules(model, prog):
     """Map each BNACT op with BN to its module (for running statistics)."""
     modules = dict(model.named_modules())
     return [modules[op.bn_module] if (op.kind == OP_BNACT and op.has_bn) else None for op in prog.ops]
+
+
+def compile_transformer(model, batch, seq_len):
+    """Lower the reference's ``TransformerModel`` (cases/models/language_models.py:150-205) *as the attack runs it* -- token
+    embedding bypassed, the candidate is the embedding sequence [batch, seq_len, d] (base_attack.py:76-128) -- to the layer
+    program: learnable positional embedding added, post-norm encoder layers (self-attention without mask, ReLU FFN), linear
+    decoder.  ``model`` needs ``pos_encoder.embedding``, ``transformer_encoder.layers`` and ``decoder`` (``synthetic.TransformerLM``
+    has the reference's attribute names).  Parameter indices follow ``model.parameters()`` with the token embedding removed,
+    i.e. the order of the shared gradient list after base_attack.py:88-95.
+
+    The program is the contract between this lowering and the sweeps; today it is executed by ``oracle/program_interp.py``
+    (CPU, float64-verified against autograd and the reference's TAG closure) -- the CUDA engine does not implement the three
+    token ops yet and rejects it.
+    """
+    names = [n for n, _ in model.named_parameters() if n != "encoder.weight"]
+    shapes = {n: tuple(p.shape) for n, p in model.named_parameters()}
+    prog = Program(seq_len=int(seq_len))
+    prog.params = [ParamDesc(i, shapes[n]) for i, n in enumerate(names)]
+    pidx = {n: i for i, n in enumerate(names)}
+    rows = int(batch) * int(seq_len)
+    d = model.decoder.in_features
+
+    def new_tensor(C):
+        prog.tensors.append(TensorDesc(len(prog.tensors), rows, C, 1, 1))
+        return len(prog.tensors) - 1
+
+    x = new_tensor(d)   # tensor 0: the candidate embeddings
+    cur = new_tensor(d)
+    prog.ops.append(Op(OP_POSADD, x, cur, w=pidx["pos_encoder.embedding.weight"]))
+    for li, layer in enumerate(model.transformer_encoder.layers):
+        if getattr(layer, "norm_first", False) or not getattr(layer.self_attn, "batch_first", True):
+            raise UnsupportedModelError("only post-norm, batch-first encoder layers (the reference's configuration) are lowered")
+        pre = f"transformer_encoder.layers.{li}."
+        heads = layer.self_attn.num_heads
+        qkv = new_tensor(3 * d)
+        prog.ops.append(Op(OP_LINEAR, cur, qkv, w=pidx[pre + "self_attn.in_proj_weight"], b=pidx[pre + "self_attn.in_proj_bias"]))
+        att = new_tensor(d)
+        prog.ops.append(Op(OP_ATTENTION, qkv, att, R=heads, S=int(seq_len)))
+        proj = new_tensor(d)
+        prog.ops.append(Op(OP_LINEAR, att, proj, w=pidx[pre + "self_attn.out_proj.weight"], b=pidx[pre + "self_attn.out_proj.bias"]))
+        r1 = new_tensor(d)
+        prog.ops.append(Op(OP_BNACT, proj, r1, res=cur))                       # residual add
+        n1 = new_tensor(d)
+        prog.ops.append(Op(OP_LAYERNORM, r1, n1, gamma=pidx[pre + "norm1.weight"], beta=pidx[pre + "norm1.bias"], eps=float(layer.norm1.eps)))
+        f1 = new_tensor(layer.linear1.out_features)
+        prog.ops.append(Op(OP_LINEAR, n1, f1, w=pidx[pre + "linear1.weight"], b=pidx[pre + "linear1.bias"]))
+        hid = new_tensor(layer.linear1.out_features)
+        prog.ops.append(Op(OP_BNACT, f1, hid, relu=True))
+        f2 = new_tensor(d)
+        prog.ops.append(Op(OP_LINEAR, hid, f2, w=pidx[pre + "linear2.weight"], b=pidx[pre + "linear2.bias"]))
+        r2 = new_tensor(d)
+        prog.ops.append(Op(OP_BNACT, f2, r2, res=n1))
+        cur = new_tensor(d)
+        prog.ops.append(Op(OP_LAYERNORM, r2, cur, gamma=pidx[pre + "norm2.weight"], beta=pidx[pre + "norm2.bias"], eps=float(layer.norm2.eps)))
+    logits = new_tensor(model.decoder.out_features)
+    prog.ops.append(Op(OP_LINEAR, cur, logits, w=pidx["decoder.weight"], b=pidx["decoder.bias"]))
+    prog.logits, prog.num_classes = logits, model.decoder.out_features
+    written = set()
+    for op in reversed(prog.ops):
+        op.acc_in = op.tin in written
+        written.add(op.tin)
+        if op.res >= 0:
+            op.acc_res = op.res in written
+            written.add(op.res)
+    return prog

@@ -22,6 +22,7 @@ import torch
 import torch.nn.functional as F
 
 from breaching_b200 import compiler as C
+from oracle import transformer_interp as TI
 
 
 def objective_direction(kind, G, g, scale=1.0, tag_scale=0.1, scale_scheme="linear", fudge=1e-7, mask_value=1e-6):
@@ -91,9 +92,50 @@ class ProgramInterpreter:
         inv = 1.0 / torch.sqrt(rv + op.eps)
         return rm.view(1, -1, 1, 1), inv.view(1, -1, 1, 1)
 
+    # ---- token-sequence helpers (rows = batch * seq_len; formulas verified in oracle/transformer_interp.py)
+    @staticmethod
+    def _pos_rows(pos, rows, T):
+        return pos[:T].repeat(rows // T, 1).view(rows, -1, 1, 1)
+
+    @staticmethod
+    def _split_heads(t, heads, T):
+        rows, three_d = t.shape[0], t.shape[1]
+        d = three_d // 3
+        q, k, v = t.view(rows // T, T, three_d).split(d, dim=-1)
+        f = lambda u: u.reshape(rows // T, T, heads, d // heads).transpose(1, 2)  # noqa: E731  [B, h, T, dh]
+        return f(q), f(k), f(v)
+
+    @staticmethod
+    def _merge_heads(t):
+        B, h, T, dh = t.shape
+        return t.transpose(1, 2).reshape(B * T, h * dh, 1, 1)
+
+    def _token_loss(self, a, aux, targets, T):
+        """CausalLoss (losses.py:7-26): row (b, t) predicts the target of row (b, t + 1); the last position of each sequence
+        has no target.  ``targets``: token ids [B, T] or class probabilities [B, T, V]."""
+        z = a[self.prog.logits].flatten(1)
+        rows, V = z.shape
+        keep = (torch.arange(rows) % T) != (T - 1)
+        logp = torch.log_softmax(z, dim=1)
+        if targets.dtype == torch.long:
+            q = F.one_hot(targets.reshape(-1), V).to(self.dtype)
+        else:
+            q = targets.reshape(rows, V).to(self.dtype)
+        q_next = torch.zeros_like(q)
+        q_next[:-1] = q[1:]
+        q_next = q_next * keep.view(-1, 1)
+        M = int(keep.sum())
+        loss = -(q_next * logp).sum() / M
+        self.a, self.aux, self.p, self.onehot, self.loss = a, aux, logp.exp(), q_next, loss
+        self.row_keep, self.M = keep.view(-1, 1).to(self.dtype), M
+        return loss
+
     # ------------------------------------------------------------------ sweeps
     def forward(self, x, labels, soft_labels=None):
         prog = self.prog
+        T = getattr(prog, "seq_len", 0)
+        if T:   # token-sequence program: the candidate [B, T, d] becomes rows x features
+            x = x.reshape(-1, x.shape[-1], 1, 1)
         a = {0: x.to(self.dtype)}
         aux = {}
         for i, op in enumerate(prog.ops):
@@ -124,6 +166,17 @@ class ProgramInterpreter:
             elif op.kind == C.OP_LINEAR:
                 b = None if op.b < 0 else self.P[op.b]
                 a[op.tout] = F.linear(self._flat_in(op, xin), self.P[op.w], b).view(xin.shape[0], -1, 1, 1)
+            elif op.kind == C.OP_POSADD:      # + learnable positional embedding of position (row mod T)
+                a[op.tout] = xin + self._pos_rows(self.P[op.w], xin.shape[0], T)
+            elif op.kind == C.OP_LAYERNORM:
+                y, xh, inv = TI._ln_forward(xin.flatten(1), self.P[op.gamma], self.P[op.beta], op.eps)
+                a[op.tout], aux[i] = y.view_as(xin), (xh, inv)
+            elif op.kind == C.OP_ATTENTION:
+                Q, K, Vv = self._split_heads(xin, op.R, T)
+                P_ = torch.softmax(Q @ K.transpose(-1, -2) / (Q.shape[-1] ** 0.5), dim=-1)
+                a[op.tout], aux[i] = self._merge_heads(P_ @ Vv), (Q, K, Vv, P_)
+        if T:
+            return self._token_loss(a, aux, soft_labels if soft_labels is not None else labels, T)
         z = a[prog.logits].view(x.shape[0], -1)
         logp = torch.log_softmax(z, dim=1)
         if soft_labels is None:
@@ -147,6 +200,8 @@ class ProgramInterpreter:
         d = {prog.logits: seed.view(seed.shape[0], -1, 1, 1)}
         G = [None] * len(self.P)
         du_saved = {}
+        if V is None:
+            self.rsave = {}
 
         def add(tid, val):
             d[tid] = val if tid not in d else d[tid] + val
@@ -212,6 +267,49 @@ class ProgramInterpreter:
                 add(op.tin, _maxpool_scatter(dout, self.aux[i], xin.shape))
             elif op.kind == C.OP_AVGPOOL:
                 add(op.tin, (dout / (xin.shape[2] * xin.shape[3])).expand_as(xin))
+            elif op.kind == C.OP_POSADD:
+                if V is None and want_G:
+                    T = self.prog.seq_len
+                    Gp = torch.zeros_like(self.P[op.w])
+                    Gp[:T] = dout.flatten(1).view(-1, T, dout.shape[1]).sum(dim=0)
+                    G[op.w] = Gp
+                add(op.tin, dout)
+            elif op.kind == C.OP_LAYERNORM:
+                xh, inv = self.aux[i]
+                gam = self.P[op.gamma]
+                if V is None:
+                    dx, Gg, Gb, t_, u_ = TI._ln_backward(dout.flatten(1)[None], xh[None], inv[None], gam)
+                    self.rsave[i] = (dout.flatten(1), t_[0], u_[0])
+                    if want_G:
+                        G[op.gamma], G[op.beta] = Gg, Gb
+                    add(op.tin, dx[0].view_as(xin))
+                else:
+                    dyB, t_, u_ = self.rsave[i]
+                    xd, xhd = self.ta[op.tin].flatten(1), self.taux[i]
+                    dxd = TI._ln_tangent_backward(dout.flatten(1), dyB, t_, u_, xd, xh, xhd, inv, gam, V[op.gamma])
+                    add(op.tin, dxd.view_as(xin))
+            elif op.kind == C.OP_ATTENTION:
+                Q, K, Vv, P_ = self.aux[i]
+                T, sc = self.prog.seq_len, 1.0 / (Q.shape[-1] ** 0.5)
+                dO = dout.flatten(1).view(-1, T, op.R, Q.shape[-1]).transpose(1, 2)
+                if V is None:
+                    dV = P_.transpose(-1, -2) @ dO
+                    dP = dO @ Vv.transpose(-1, -2)
+                    r = (dP * P_).sum(dim=-1, keepdim=True)
+                    dS = P_ * (dP - r)
+                    dQ, dK = dS @ K * sc, dS.transpose(-1, -2) @ Q * sc
+                    self.rsave[i] = (dO, dP, r, dS)
+                else:
+                    dOB, dP, r, dS = self.rsave[i]
+                    Qd, Kd, Vd, Pd = self.taux[i]
+                    dV = Pd.transpose(-1, -2) @ dOB + P_.transpose(-1, -2) @ dO
+                    dPd = dO @ Vv.transpose(-1, -2) + dOB @ Vd.transpose(-1, -2)
+                    rd = (dPd * P_ + dP * Pd).sum(dim=-1, keepdim=True)
+                    dSd = Pd * (dP - r) + P_ * (dPd - rd)
+                    dQ = (dSd @ K + dS @ Kd) * sc
+                    dK = (dSd.transpose(-1, -2) @ Q + dS.transpose(-1, -2) @ Qd) * sc
+                m = lambda u: u.transpose(1, 2).reshape(xin.shape[0], -1)  # noqa: E731
+                add(op.tin, torch.cat([m(dQ), m(dK), m(dV)], dim=1).view_as(xin))
             elif op.kind == C.OP_LINEAR:
                 do2 = dout.view(dout.shape[0], -1)
                 xf = self._flat_in(op, xin)
@@ -228,6 +326,11 @@ class ProgramInterpreter:
 
     def backward(self, want_dx=False):
         n = self.p.shape[0]
+        if getattr(self.prog, "seq_len", 0):
+            seed = (self.p - self.onehot) * self.row_keep / self.M
+            d, G, du = self._reverse(seed, want_dx=True)
+            self.d_B, self.du_B, self.G = d, du, G
+            return G
         seed = (self.p - self.onehot) / n
         d, G, du = self._reverse(seed, want_dx=want_dx)
         self.d_B, self.du_B, self.G = d, du, G
@@ -268,8 +371,22 @@ class ProgramInterpreter:
                 ta[op.tout] = tin.mean(dim=(2, 3), keepdim=True)
             elif op.kind == C.OP_LINEAR:
                 out = F.linear(self._flat_in(op, xin), V[op.w], None if op.b < 0 else V[op.b])
-                out = out + F.linear(self._flat_in(op, tin), self.P[op.w])
+                if tin is not None:
+                    out = out + F.linear(self._flat_in(op, tin), self.P[op.w])
                 ta[op.tout] = out.view(xin.shape[0], -1, 1, 1)
+            elif op.kind == C.OP_POSADD:
+                ta[op.tout] = self._pos_rows(V[op.w], xin.shape[0], self.prog.seq_len)
+            elif op.kind == C.OP_LAYERNORM:
+                xh, inv = self.aux[i]
+                yd, xhd = TI._ln_tangent_forward(tin.flatten(1), xh, inv, self.P[op.gamma], V[op.gamma], V[op.beta])
+                ta[op.tout], self.taux[i] = yd.view_as(xin), xhd
+            elif op.kind == C.OP_ATTENTION:
+                Q, K, Vv, P_ = self.aux[i]
+                T, sc = self.prog.seq_len, 1.0 / (Q.shape[-1] ** 0.5)
+                Qd, Kd, Vd = self._split_heads(tin, op.R, T)
+                Sd = (Qd @ K.transpose(-1, -2) + Q @ Kd.transpose(-1, -2)) * sc
+                Pd = P_ * (Sd - (P_ * Sd).sum(dim=-1, keepdim=True))
+                ta[op.tout], self.taux[i] = self._merge_heads(Pd @ Vv + P_ @ Vd), (Qd, Kd, Vd, Pd)
         self.ta = ta
         return ta
 
@@ -277,6 +394,16 @@ class ProgramInterpreter:
         n = self.p.shape[0]
         zdot = self.ta[self.prog.logits].view(n, -1)
         p = self.p
+        if getattr(self.prog, "seq_len", 0):
+            T = self.prog.seq_len
+            centred = (zdot - (p * zdot).sum(dim=1, keepdim=True)) * self.row_keep
+            seed = p * centred / self.M
+            d, _, _ = self._reverse(seed, V=V, d_prev=self.d_B, inject=inject)
+            # d objective / d (target probabilities): row (b, t) receives the term of the logits row (b, t - 1)
+            dq = torch.zeros_like(centred)
+            dq[1:] = -centred[:-1] / self.M
+            self.dq = dq.view(n // T, T, -1)
+            return d[0].flatten(1).view(n // T, T, -1)
         seed = (p * zdot - p * (p * zdot).sum(dim=1, keepdim=True)) / n
         d, _, _ = self._reverse(seed, V=V, d_prev=self.d_B, inject=inject)
         return d[0]

@@ -75,3 +75,48 @@ def test_transformer_four_sweeps_reproduce_the_reference_tag_closure():
     dl = q * (dq - (q * dq).sum(dim=-1, keepdim=True))
     assert _relerr(dx.float(), fx["raw_grad_x0"]) < 1e-4, _relerr(dx.float(), fx["raw_grad_x0"])
     assert _relerr(dl.float(), fx["raw_grad_l0"]) < 1e-4, _relerr(dl.float(), fx["raw_grad_l0"])
+
+
+def test_transformer_layer_program_reproduces_the_reference_tag_closure():
+    """``compiler.compile_transformer`` (posadd / linear / attention / layernorm / residual / ReLU ops over row x feature
+    tensors) executed by the generic four-sweep program interpreter -- the contract the CUDA engine will implement for
+    config 5 -- against the reference's TAG closure on the fixture."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import case_from_fixture, cfg_from_fixture, load_golden
+    from breaching_b200 import compiler
+    from oracle import program_interp as PI
+
+    fx = load_golden("trial_joint_tag_transformer.pt")
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    names = [n for n, _ in model.named_parameters()]
+    g = [t.double() for t in shared[0]["gradients"]]
+    g.pop(names.index("encoder.weight"))
+    B, T, d = fx["x0"].shape
+    prog = compiler.compile_transformer(model, B, T)
+    assert prog.seq_len == T and len(prog.params) == len(g)
+
+    class _Params:  # the interpreter reads parameters in program order (token embedding removed)
+        def parameters(self):
+            return [p for n, p in model.named_parameters() if n != "encoder.weight"]
+
+        def named_modules(self):
+            return model.named_modules()
+
+    it = PI.ProgramInterpreter(_Params(), prog)
+    q = fx["l0"].double().softmax(dim=-1)
+    o = cfg.objective
+    val, dx, loss, G = it.matching_gradient(fx["x0"].double(), q, g, o.type, scale=o.scale, tag_scale=o.tag_scale,
+                                            scale_scheme=o.scale_scheme)
+    assert abs(float(val) - fx["objective0"]) < 1e-5 * abs(fx["objective0"])
+    assert _relerr(dx.float(), fx["raw_grad_x0"]) < 1e-4
+    dl = q * (it.dq - (q * it.dq).sum(dim=-1, keepdim=True))
+    assert _relerr(dl.float(), fx["raw_grad_l0"]) < 1e-4
+    # and the direct restatement agrees to round-off
+    fs = TransformerFourSweep(model.double())
+    fs.forward(fx["x0"].double(), q)
+    for a, b in zip(G, fs.backward()):
+        assert _relerr(a, b) < 1e-10
