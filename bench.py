@@ -240,7 +240,7 @@ def product_arm(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # (its banner goes to stderr either way, see _claim_stdout)
         dist.init_process_group("nccl", device_id=dev)
     bbuild.build()
 
@@ -352,7 +352,7 @@ def product_arm(args):
                                              "the same B200; denominator of the north-star >=10x target"},
         "final_objective": st["min_objective"],
     }
-    print(json.dumps(out))
+    _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -380,10 +380,30 @@ def reference_arm(args):
         "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    _emit(out)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is exactly ONE JSON line on rank 0's stdout.  Libraries write there too (NCCL prints its version banner
+    from C at NCCL_DEBUG >= VERSION, which the launch environment may set): keep a private handle on the real stdout for the
+    result line and point file descriptor 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
