@@ -1,0 +1,310 @@
+// Token-sequence ops of the TAG / transformer path (BASELINE config 5): LayerNorm and
+// multi-head self-attention in the four sweeps of the engine (forward, backward, tangent-forward, tangent-backward).  Rules
+// and a float64-verified CPU statement of every formula: oracle/transformer_interp.py (header) and
+// oracle/program_interp.py (OP_LAYERNORM / OP_ATTENTION of compiler.compile_transformer).  Tensors are [rows, C] fp32
+// row-major with rows = batch * seq_len; attention reads the fused projection [rows, 3 d] = (q | k | v), head h in columns
+// h*dh .. (h+1)*dh of each third.
+//
+// Sizes on this path are tiny (config 5: rows = 32, d = 96, 8 heads of 12): one warp per row for LayerNorm, one block per
+// (sequence, head) for attention with the whole head resident in shared memory; plain fp32, deterministic (no atomics).
+// First correct version -- exposed through a stand-alone C ABI (bre_token_layernorm / bre_token_attention) for kernel-level
+// parity tests; the engine's sweeps do not dispatch to them yet.
+#include "common.cuh"
+
+namespace bre {
+namespace {
+
+// ---- LayerNorm -----------------------------------------------------------------------------------------------------
+// sweep 0 (F):  y = gamma xh + beta, stats[row] = (mean, inv)
+// sweep 1 (B):  dx = inv (t - mean(t) - xh mean(t xh)),  t = dy gamma          [in1 = dy]
+// sweep 2 (TF): y' = v_gamma xh + gamma xh' + v_beta,  xh' = inv (x' - mean(x') - xh mean(xh x'))   [in1 = x']
+// sweep 3 (TB): dx' = inv u' - u mean(xh x') inv^2                              [in1 = dy', in2 = dy, in3 = x']
+//               t' = dy' gamma + dy v_gamma, u = t - mean(t) - xh mean(t xh),
+//               u' = t' - mean(t') - xh' mean(t xh) - xh mean(t' xh + t xh')
+__global__ void layernorm_kernel(int sweep, const float* __restrict__ x, const float* __restrict__ in1, const float* __restrict__ in2,
+                                 const float* __restrict__ in3, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ v_gamma, const float* __restrict__ v_beta, float eps, int rows, int C,
+                                 float* __restrict__ stats, float* __restrict__ out, int accumulate) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * C;
+  const float invC = 1.0f / (float)C;
+  float mean, inv;
+  if (sweep == 0) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    mean = warp_sum(s) * invC;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) { const float dlt = xr[c] - mean; q = fmaf(dlt, dlt, q); }
+    inv = 1.0f / sqrtf(warp_sum(q) * invC + eps);
+    if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = inv; }
+    for (int c = lane; c < C; c += 32) out[(long long)row * C + c] = fmaf(gamma[c], (xr[c] - mean) * inv, beta[c]);
+    return;
+  }
+  mean = stats[2 * row];
+  inv = stats[2 * row + 1];
+  const float* a1 = in1 + (long long)row * C;
+  float* o = out + (long long)row * C;
+  if (sweep == 1) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float t = a1[c] * gamma[c], xh = (xr[c] - mean) * inv;
+      s0 += t; s1 = fmaf(t, xh, s1);
+    }
+    const float m0 = warp_sum(s0) * invC, m1 = warp_sum(s1) * invC;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (xr[c] - mean) * inv;
+      const float v = inv * (a1[c] * gamma[c] - m0 - xh * m1);
+      o[c] = accumulate ? o[c] + v : v;
+    }
+  } else if (sweep == 2) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = lane; c < C; c += 32) { const float xd = a1[c]; s0 += xd; s1 = fmaf((xr[c] - mean) * inv, xd, s1); }
+    const float m0 = warp_sum(s0) * invC, m1 = warp_sum(s1) * invC;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (xr[c] - mean) * inv;
+      const float xhd = inv * (a1[c] - m0 - xh * m1);
+      o[c] = fmaf(v_gamma[c], xh, fmaf(gamma[c], xhd, v_beta[c]));
+    }
+  } else {
+    const float* dyB = in2 + (long long)row * C;
+    const float* xd = in3 + (long long)row * C;
+    // pass 1: the means that xh' needs
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = lane; c < C; c += 32) { s0 += xd[c]; s1 = fmaf((xr[c] - mean) * inv, xd[c], s1); }
+    const float mxd = warp_sum(s0) * invC, mxhxd = warp_sum(s1) * invC;
+    // pass 2: means of t, t xh, t', t' xh + t xh'
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (xr[c] - mean) * inv;
+      const float xhd = inv * (xd[c] - mxd - xh * mxhxd);
+      const float t = dyB[c] * gamma[c];
+      const float td = fmaf(a1[c], gamma[c], dyB[c] * v_gamma[c]);
+      r0 += t; r1 = fmaf(t, xh, r1); r2 += td; r3 += fmaf(td, xh, t * xhd);
+    }
+    const float mt = warp_sum(r0) * invC, mtxh = warp_sum(r1) * invC, mtd = warp_sum(r2) * invC, mmix = warp_sum(r3) * invC;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (xr[c] - mean) * inv;
+      const float xhd = inv * (xd[c] - mxd - xh * mxhxd);
+      const float t = dyB[c] * gamma[c];
+      const float td = fmaf(a1[c], gamma[c], dyB[c] * v_gamma[c]);
+      const float u = t - mt - xh * mtxh;
+      const float ud = td - mtd - xhd * mtxh - xh * mmix;
+      const float v = inv * ud - u * mxhxd * inv * inv;
+      o[c] = accumulate ? o[c] + v : v;
+    }
+  }
+}
+
+// gamma / beta gradients of LayerNorm: G_gamma[c] = sum_rows dy xh, G_beta[c] = sum_rows dy  (one thread per column, rows in order)
+__global__ void layernorm_param_grad_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stats,
+                                            int rows, int C, float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sg = 0.f, sb = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float d = dy[(long long)r * C + c];
+    sg = fmaf(d, (x[(long long)r * C + c] - stats[2 * r]) * stats[2 * r + 1], sg);
+    sb += d;
+  }
+  g_gamma[c] = sg;
+  g_beta[c] = sb;
+}
+
+// ---- multi-head self-attention (no mask) ---------------------------------------------------------------------------
+// One block per (sequence b, head h), T threads (thread i = query / key row i).  Shared memory: Q, K, V [T][dh] (+ their
+// tangents), probabilities P [T][T] and scratch matrices.  P (and the tangent P') are also kept in global memory
+// [B, heads, T, T] between sweeps.
+//   sweep 0 (F):  O = P V                                  writes out [rows, d], P
+//   sweep 1 (B):  d(qkv) from dO (= in1 [rows, d])          writes out [rows, 3 d]
+//   sweep 2 (TF): O' from (qkv)' (= in1 [rows, 3 d])        writes out [rows, d], P'
+//   sweep 3 (TB): d(qkv)' from dO' (= in1), dO (= in2), (qkv)' (= in3), P, P'     writes out [rows, 3 d]
+__global__ void attention_kernel(int sweep, const float* __restrict__ qkv, const float* __restrict__ in1, const float* __restrict__ in2,
+                                 const float* __restrict__ in3, int T, int heads, int dh, float* __restrict__ P, float* __restrict__ Pd,
+                                 float* __restrict__ out, int accumulate) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int i = threadIdx.x, d = heads * dh;
+  const float scale = 1.0f / sqrtf((float)dh);
+  float* sQ = sm;                 // [T][dh]
+  float* sK = sQ + T * dh;
+  float* sV = sK + T * dh;
+  float* sA = sV + T * dh;        // [T][dh]  dO  /  Q'
+  float* sB = sA + T * dh;        // [T][dh]  dO' /  K'
+  float* sC = sB + T * dh;        // [T][dh]         V'
+  float* sP = sC + T * dh;        // [T][T]
+  float* sM = sP + T * T;         // [T][T]  dS  (B, TB)  /  P' (TF, TB)
+  float* sN = sM + T * T;         // [T][T]  dS' (TB)
+  const long long row = (long long)b * T + i;
+  const long long pbase = ((long long)blockIdx.x * T + i) * T;
+  auto load_qkv = [&](const float* src, float* q, float* k, float* v) {
+    for (int c = 0; c < dh; ++c) {
+      q[i * dh + c] = src[row * 3 * d + h * dh + c];
+      k[i * dh + c] = src[row * 3 * d + d + h * dh + c];
+      v[i * dh + c] = src[row * 3 * d + 2 * d + h * dh + c];
+    }
+  };
+  load_qkv(qkv, sQ, sK, sV);
+  if (sweep == 0) {
+    __syncthreads();
+    float mx = -3.0e38f;
+    for (int j = 0; j < T; ++j) {
+      float s = 0.f;
+      for (int c = 0; c < dh; ++c) s = fmaf(sQ[i * dh + c], sK[j * dh + c], s);
+      s *= scale;
+      sP[i * T + j] = s;
+      mx = fmaxf(mx, s);
+    }
+    float den = 0.f;
+    for (int j = 0; j < T; ++j) { const float e = expf(sP[i * T + j] - mx); sP[i * T + j] = e; den += e; }
+    const float rden = 1.0f / den;
+    for (int j = 0; j < T; ++j) { sP[i * T + j] *= rden; P[pbase + j] = sP[i * T + j]; }
+    for (int c = 0; c < dh; ++c) {
+      float o = 0.f;
+      for (int j = 0; j < T; ++j) o = fmaf(sP[i * T + j], sV[j * dh + c], o);
+      out[row * d + h * dh + c] = o;
+    }
+    return;
+  }
+  for (int j = 0; j < T; ++j) sP[i * T + j] = P[pbase + j];
+  if (sweep == 1) {
+    for (int c = 0; c < dh; ++c) sA[i * dh + c] = in1[row * d + h * dh + c];    // dO
+    __syncthreads();
+    float r = 0.f;
+    for (int j = 0; j < T; ++j) {
+      float dp = 0.f;
+      for (int c = 0; c < dh; ++c) dp = fmaf(sA[i * dh + c], sV[j * dh + c], dp);
+      sM[i * T + j] = dp;
+      r = fmaf(dp, sP[i * T + j], r);
+    }
+    for (int j = 0; j < T; ++j) sM[i * T + j] = sP[i * T + j] * (sM[i * T + j] - r);   // dS
+    __syncthreads();
+    for (int c = 0; c < dh; ++c) {
+      float dq = 0.f, dk = 0.f, dv = 0.f;
+      for (int j = 0; j < T; ++j) {
+        dq = fmaf(sM[i * T + j], sK[j * dh + c], dq);
+        dk = fmaf(sM[j * T + i], sQ[j * dh + c], dk);
+        dv = fmaf(sP[j * T + i], sA[j * dh + c], dv);
+      }
+      float* o = out + row * 3 * d + h * dh + c;
+      const float vq = dq * scale, vk = dk * scale;
+      o[0] = accumulate ? o[0] + vq : vq;
+      o[d] = accumulate ? o[d] + vk : vk;
+      o[2 * d] = accumulate ? o[2 * d] + dv : dv;
+    }
+    return;
+  }
+  if (sweep == 2) {
+    load_qkv(in1, sA, sB, sC);   // Q', K', V'
+    __syncthreads();
+    float acc = 0.f;
+    for (int j = 0; j < T; ++j) {
+      float s = 0.f;
+      for (int c = 0; c < dh; ++c) s += sA[i * dh + c] * sK[j * dh + c] + sQ[i * dh + c] * sB[j * dh + c];
+      s *= scale;
+      sM[i * T + j] = s;
+      acc = fmaf(sP[i * T + j], s, acc);
+    }
+    for (int j = 0; j < T; ++j) { sM[i * T + j] = sP[i * T + j] * (sM[i * T + j] - acc); Pd[pbase + j] = sM[i * T + j]; }
+    for (int c = 0; c < dh; ++c) {
+      float o = 0.f;
+      for (int j = 0; j < T; ++j) o += sM[i * T + j] * sV[j * dh + c] + sP[i * T + j] * sC[j * dh + c];
+      out[row * d + h * dh + c] = o;
+    }
+    return;
+  }
+  // sweep 3: tangent backward.  Needs Q', K', V' (in3), dO (in2), dO' (in1), P, P'.
+  float* sQd = sA; float* sKd = sB; float* sVd = sC;
+  load_qkv(in3, sQd, sKd, sVd);
+  float* sPd = sM;                    // P'
+  for (int j = 0; j < T; ++j) sPd[i * T + j] = Pd[pbase + j];
+  __syncthreads();
+  // row-wise pieces: dP_ij = dO_i . V_j ; dP'_ij = dO'_i . V_j + dO_i . V'_j ; r, r'
+  float* sdO = sN + T * T;            // [T][dh]
+  float* sdOd = sdO + T * dh;         // [T][dh]
+  float* sdS = sdOd + T * dh;         // [T][T]
+  for (int c = 0; c < dh; ++c) { sdO[i * dh + c] = in2[row * d + h * dh + c]; sdOd[i * dh + c] = in1[row * d + h * dh + c]; }
+  __syncthreads();
+  float r = 0.f, rd = 0.f;
+  for (int j = 0; j < T; ++j) {
+    float dp = 0.f, dpd = 0.f;
+    for (int c = 0; c < dh; ++c) {
+      dp = fmaf(sdO[i * dh + c], sV[j * dh + c], dp);
+      dpd += sdOd[i * dh + c] * sV[j * dh + c] + sdO[i * dh + c] * sVd[j * dh + c];
+    }
+    sdS[i * T + j] = dp;       // dP for now
+    sN[i * T + j] = dpd;       // dP' for now
+    r = fmaf(dp, sP[i * T + j], r);
+    rd += dpd * sP[i * T + j] + dp * sPd[i * T + j];
+  }
+  for (int j = 0; j < T; ++j) {
+    const float dp = sdS[i * T + j], dpd = sN[i * T + j];
+    sN[i * T + j] = sPd[i * T + j] * (dp - r) + sP[i * T + j] * (dpd - rd);   // dS'
+    sdS[i * T + j] = sP[i * T + j] * (dp - r);                               // dS
+  }
+  __syncthreads();
+  for (int c = 0; c < dh; ++c) {
+    float dq = 0.f, dk = 0.f, dv = 0.f;
+    for (int j = 0; j < T; ++j) {
+      dq += sN[i * T + j] * sK[j * dh + c] + sdS[i * T + j] * sKd[j * dh + c];
+      dk += sN[j * T + i] * sQ[j * dh + c] + sdS[j * T + i] * sQd[j * dh + c];
+      dv += sPd[j * T + i] * sdO[j * dh + c] + sP[j * T + i] * sdOd[j * dh + c];
+    }
+    float* o = out + row * 3 * d + h * dh + c;
+    const float vq = dq * scale, vk = dk * scale;
+    o[0] = accumulate ? o[0] + vq : vq;
+    o[d] = accumulate ? o[d] + vk : vk;
+    o[2 * d] = accumulate ? o[2 * d] + dv : dv;
+  }
+}
+
+}  // namespace
+}  // namespace bre
+
+extern "C" {
+
+// Stand-alone LayerNorm sweeps over [rows, C] fp32 device tensors (see layernorm_kernel for the meaning of in1..in3 per sweep).
+// sweep 1 additionally writes the parameter gradients when g_gamma / g_beta are non-null.
+int bre_token_layernorm(int32_t sweep, const float* x, const float* in1, const float* in2, const float* in3, const float* gamma,
+                        const float* beta, const float* v_gamma, const float* v_beta, float eps, int32_t rows, int32_t C, float* stats,
+                        float* out, float* g_gamma, float* g_beta, void* stream) {
+  using namespace bre;
+  if (!x || !out || !stats || !gamma || rows < 1 || C < 1 || sweep < 0 || sweep > 3) { set_error("bre_token_layernorm: bad arguments"); return -1; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int warps = 4;
+  layernorm_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(sweep, x, in1, in2, in3, gamma, beta, v_gamma, v_beta, eps, rows, C, stats,
+                                                                     out, 0);
+  if (sweep == 1 && g_gamma && g_beta)
+    layernorm_param_grad_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, in1, stats, rows, C, g_gamma, g_beta);
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error(std::string("bre_token_layernorm: ") + cudaGetErrorString(err)); return -2; }
+  return 0;
+}
+
+// Stand-alone attention sweeps: qkv [B*T, 3 d], P / Pd [B, heads, T, T] scratch kept by the caller between sweeps.
+int bre_token_attention(int32_t sweep, const float* qkv, const float* in1, const float* in2, const float* in3, int32_t B, int32_t T,
+                        int32_t heads, int32_t dh, float* P, float* Pd, float* out, void* stream) {
+  using namespace bre;
+  if (!qkv || !out || !P || B < 1 || T < 1 || T > 128 || heads < 1 || dh < 1 || sweep < 0 || sweep > 3) {
+    set_error("bre_token_attention: bad arguments (T <= 128)");
+    return -1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = (size_t)(8 * T * dh + 4 * T * T) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      set_error("bre_token_attention: shared memory opt-in failed");
+      return -2;
+    }
+    attr_done = true;
+  }
+  if (smem > 200 * 1024) { set_error("bre_token_attention: head too large for the resident-head kernel"); return -4; }
+  attention_kernel<<<B * heads, T, smem, s>>>(sweep, qkv, in1, in2, in3, T, heads, dh, P, Pd, out, 0);
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error(std::string("bre_token_attention: ") + cudaGetErrorString(err)); return -2; }
+  return 0;
+}
+
+}  // extern "C"

@@ -75,6 +75,7 @@ EXPORTS = [
     "bre_engine_debug_tensor", "bre_engine_launches_per_iteration", "bre_engine_set_option", "bre_match_reduce",
     "bre_total_variation", "bre_conv_gemm", "bre_last_error", "bre_version",
     "bre_engine_load_soft_labels", "bre_engine_label_gradient", "bre_engine_set_labels",
+    "bre_token_layernorm", "bre_token_attention",
 ]
 
 
@@ -121,6 +122,8 @@ def load_library(path=None):
     lib.bre_match_reduce.argtypes = [vp, vp, vp, i64, f32, P(ctypes.c_double), vp]
     lib.bre_total_variation.argtypes = [vp, vp, i32, i32, i32, f32, f32, f32, f32, i32, i32, P(ctypes.c_double), vp]
     lib.bre_conv_gemm.argtypes = [i32, i32, vp, vp, vp, vp, vp] + [i32] * 9 + [vp]
+    lib.bre_token_layernorm.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp, vp, vp]
+    lib.bre_token_attention.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("bre_last_error", "bre_version", "bre_engine_destroy"):
             getattr(lib, name).restype = ctypes.c_int
@@ -466,4 +469,33 @@ def conv_gemm(mode, a, w, out, N, H, W, Ci, Co, R, S, stride, pad, a2=None, w2=N
         rc = lib.bre_conv_gemm(mode, backend, _ptr(a), _ptr(w), _ptr(a2), _ptr(w2), _ptr(out), N, H, W, Ci, Co, R, S, stride,
                                pad, ctypes.c_void_p(stream))
     _check(lib, rc, "bre_conv_gemm")
+    return out
+
+
+def token_layernorm(sweep, x, gamma, beta, stats, in1=None, in2=None, in3=None, v_gamma=None, v_beta=None, eps=1e-5, want_param_grad=False):
+    """Stand-alone LayerNorm sweep (csrc/tokens.cu) on [rows, C] device tensors; returns ``out`` (and the gamma / beta
+    gradients for sweep 1 with ``want_param_grad``)."""
+    lib = load_library()
+    rows, C = x.shape
+    out = torch.empty_like(x)
+    gg = torch.empty(C, device=x.device) if want_param_grad else None
+    gb = torch.empty(C, device=x.device) if want_param_grad else None
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        rc = lib.bre_token_layernorm(sweep, _ptr(x), _ptr(in1), _ptr(in2), _ptr(in3), _ptr(gamma), _ptr(beta), _ptr(v_gamma), _ptr(v_beta),
+                                     float(eps), rows, C, _ptr(stats), _ptr(out), _ptr(gg), _ptr(gb), ctypes.c_void_p(stream))
+    _check(lib, rc, "bre_token_layernorm")
+    return (out, gg, gb) if want_param_grad else out
+
+
+def token_attention(sweep, qkv, B, T, heads, P, Pd, in1=None, in2=None, in3=None):
+    """Stand-alone multi-head self-attention sweep (csrc/tokens.cu); qkv [B*T, 3 d]."""
+    lib = load_library()
+    d = qkv.shape[1] // 3
+    out = torch.empty(qkv.shape[0], d if sweep in (0, 2) else 3 * d, device=qkv.device)
+    stream = torch.cuda.current_stream(qkv.device).cuda_stream
+    with torch.cuda.device(qkv.device):
+        rc = lib.bre_token_attention(sweep, _ptr(qkv), _ptr(in1), _ptr(in2), _ptr(in3), B, T, heads, d // heads, _ptr(P), _ptr(Pd), _ptr(out),
+                                     ctypes.c_void_p(stream))
+    _check(lib, rc, "bre_token_attention")
     return out

@@ -182,6 +182,20 @@ int bre_match_reduce(const float* G, const float* g, const float* chunk_weights,
 int bre_total_variation(const float* x, float* grad, int32_t N, int32_t H, int32_t W, float scale, float inner_exp,
                         float outer_exp, float eps, int32_t double_opponents, int32_t accumulate,
                         double* value_host, void* stream);
+/* Token-sequence ops of the transformer / TAG path (language_models.py:150-205 as attacked in embedding space; SURVEY
+ * section 8 rows a15 / a16), stand-alone, one call per sweep (0 forward, 1 backward, 2 tangent-forward, 3 tangent-backward;
+ * rules in oracle/transformer_interp.py).  fp32 device pointers, [rows, C] row-major, rows = batch * seq_len.
+ *   layernorm: x = the op's input; in1..in3 per sweep: (1) dy | (2) x' | (3) dy', dy, x'; stats [rows, 2] is written by
+ *              sweep 0 and read by the others; sweep 1 also writes g_gamma / g_beta when non-NULL.
+ *   attention: qkv [rows, 3 d] = (q | k | v) projections, heads x dh = d, no mask; in1..in3 per sweep: (1) dO [rows, d] |
+ *              (2) (qkv)' | (3) dO', dO, (qkv)'; P / Pd [B, heads, T, T] are written by sweeps 0 / 2 and read later.
+ * The engine's sweeps do not dispatch to these kernels yet (the transformer model family is the next row to be built). */
+int bre_token_layernorm(int32_t sweep, const float* x, const float* in1, const float* in2, const float* in3, const float* gamma,
+                        const float* beta, const float* v_gamma, const float* v_beta, float eps, int32_t rows, int32_t C, float* stats,
+                        float* out, float* g_gamma, float* g_beta, void* stream);
+int bre_token_attention(int32_t sweep, const float* qkv, const float* in1, const float* in2, const float* in3, int32_t B, int32_t T,
+                        int32_t heads, int32_t dh, float* P, float* Pd, float* out, void* stream);
+
 /* Implicit-GEMM convolution family, NHWC activations / OHWI weights, fp32:
  * mode 0 fprop  : out[N,Ho,Wo,Co]  = conv(in[N,H,W,Ci], w[Co,R,S,Ci]) (+ conv(in2, w2) when in2 != NULL)
  * mode 1 dgrad  : din[N,H,W,Ci]    = conv^T(dout[N,Ho,Wo,Co], w) (+ conv^T(dout2, w2))

@@ -1,0 +1,84 @@
+"""Token-sequence kernels of the transformer / TAG path (csrc/tokens.cu: LayerNorm and multi-head self-attention in all four
+sweeps) against the float64 formulas of oracle/transformer_interp.py -- which are themselves verified against autograd's
+double backward and the reference's TAG closure (tests/test_transformer_interp.py)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from breaching_b200 import engine as E  # noqa: E402
+from oracle import transformer_interp as TI  # noqa: E402
+
+DEV = torch.device("cuda:0")
+
+
+def _relerr(a, b):
+    return ((a.double().cpu() - b.double().cpu()).norm() / (b.double().cpu().norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("rows,C", [(32, 96), (16, 16), (7, 50), (64, 1536)])
+def test_layernorm_four_sweeps(rows, C):
+    gen = torch.Generator().manual_seed(rows * 1000 + C)
+    r = lambda *s: torch.randn(*s, generator=gen, dtype=torch.double)  # noqa: E731
+    x, dy, xd, dyd = r(rows, C), r(rows, C), r(rows, C), r(rows, C)
+    gamma, beta, vg, vb = 1 + 0.2 * r(C), 0.1 * r(C), r(C), r(C)
+    eps = 1e-5
+    y, xh, inv = TI._ln_forward(x, gamma, beta, eps)
+    dx, Gg, Gb, t, u = TI._ln_backward(dy[None], xh[None], inv[None], gamma)
+    yd, xhd = TI._ln_tangent_forward(xd, xh, inv, gamma, vg, vb)
+    dxd = TI._ln_tangent_backward(dyd, dy, t[0], u[0], xd, xh, xhd, inv, gamma, vg)
+    f = lambda v: v.float().to(DEV).contiguous()  # noqa: E731
+    stats = torch.empty(rows, 2, device=DEV)
+    out0 = E.token_layernorm(0, f(x), f(gamma), f(beta), stats, eps=eps)
+    assert _relerr(out0, y) < 1e-5
+    out1, gg, gb = E.token_layernorm(1, f(x), f(gamma), f(beta), stats, in1=f(dy), eps=eps, want_param_grad=True)
+    assert _relerr(out1, dx[0]) < 2e-5 and _relerr(gg, Gg) < 2e-5 and _relerr(gb, Gb) < 2e-5
+    out2 = E.token_layernorm(2, f(x), f(gamma), f(beta), stats, in1=f(xd), v_gamma=f(vg), v_beta=f(vb), eps=eps)
+    assert _relerr(out2, yd) < 2e-5
+    out3 = E.token_layernorm(3, f(x), f(gamma), f(beta), stats, in1=f(dyd), in2=f(dy), in3=f(xd), v_gamma=f(vg), v_beta=f(vb), eps=eps)
+    assert _relerr(out3, dxd) < 5e-5
+
+
+@pytest.mark.parametrize("B,T,heads,dh", [(1, 32, 8, 12), (2, 8, 4, 4), (3, 5, 2, 7)])
+def test_attention_four_sweeps(B, T, heads, dh):
+    gen = torch.Generator().manual_seed(B * 100 + T)
+    d = heads * dh
+    r = lambda *s: torch.randn(*s, generator=gen, dtype=torch.double)  # noqa: E731
+    qkv, qkvd, dO, dOd = r(B * T, 3 * d), r(B * T, 3 * d), r(B * T, d), r(B * T, d)
+
+    def heads_of(t):   # [B*T, d] -> [B, h, T, dh]
+        return t.view(B, T, heads, dh).transpose(1, 2)
+
+    def merge(t):
+        return t.transpose(1, 2).reshape(B * T, d)
+
+    Q, K, V = (heads_of(t) for t in qkv.split(d, dim=1))
+    Qd, Kd, Vd = (heads_of(t) for t in qkvd.split(d, dim=1))
+    s = 1.0 / dh ** 0.5
+    P = torch.softmax(Q @ K.transpose(-1, -2) * s, dim=-1)
+    O = merge(P @ V)
+    dOh, dOdh = heads_of(dO), heads_of(dOd)
+    dV = P.transpose(-1, -2) @ dOh
+    dP = dOh @ V.transpose(-1, -2)
+    rr = (dP * P).sum(-1, keepdim=True)
+    dS = P * (dP - rr)
+    dqkv = torch.cat([merge(dS @ K * s), merge(dS.transpose(-1, -2) @ Q * s), merge(dV)], dim=1)
+    Sd = (Qd @ K.transpose(-1, -2) + Q @ Kd.transpose(-1, -2)) * s
+    Pd = P * (Sd - (P * Sd).sum(-1, keepdim=True))
+    Od = merge(Pd @ V + P @ Vd)
+    dVd = Pd.transpose(-1, -2) @ dOh + P.transpose(-1, -2) @ dOdh
+    dPd = dOdh @ V.transpose(-1, -2) + dOh @ Vd.transpose(-1, -2)
+    rd = (dPd * P + dP * Pd).sum(-1, keepdim=True)
+    dSd = Pd * (dP - rr) + P * (dPd - rd)
+    dqkvd = torch.cat([merge((dSd @ K + dS @ Kd) * s), merge((dSd.transpose(-1, -2) @ Q + dS.transpose(-1, -2) @ Qd) * s), merge(dVd)],
+                      dim=1)
+    f = lambda v: v.float().to(DEV).contiguous()  # noqa: E731
+    Pg, Pdg = torch.empty(B, heads, T, T, device=DEV), torch.empty(B, heads, T, T, device=DEV)
+    out0 = E.token_attention(0, f(qkv), B, T, heads, Pg, Pdg)
+    assert _relerr(out0, O) < 1e-5 and _relerr(Pg, P) < 1e-5
+    out1 = E.token_attention(1, f(qkv), B, T, heads, Pg, Pdg, in1=f(dO))
+    assert _relerr(out1, dqkv) < 2e-5
+    out2 = E.token_attention(2, f(qkv), B, T, heads, Pg, Pdg, in1=f(qkvd))
+    assert _relerr(out2, Od) < 2e-5 and _relerr(Pdg, Pd) < 2e-5
+    out3 = E.token_attention(3, f(qkv), B, T, heads, Pg, Pdg, in1=f(dOd), in2=f(dO), in3=f(qkvd))
+    assert _relerr(out3, dqkvd) < 5e-5
