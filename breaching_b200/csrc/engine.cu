@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "igemm.cuh"
 #include "layers.cuh"
+#include "tokens.cuh"
 #include "objective.cuh"
 
 namespace bre {
@@ -97,6 +98,9 @@ struct bre_engine {
   bool tc_round() const { return gemm_backend == 1 && tc_round_env; }
   float *p = nullptr, *loss_n = nullptr;
   long long* labels = nullptr;
+  // token-sequence programs (compiler.compile_transformer): rows = batch * seq_len, next-token loss over rows
+  int seq_len = 0;
+  std::vector<float*> tok_a, tok_b;   // per op: LayerNorm (mean, inv) per row | attention probabilities P and their tangent P'
   float* soft_q = nullptr;        // class-probability targets [N, C] (joint-optimisation attacks), null = index labels
   float* soft_q_buf = nullptr;    // owned storage behind soft_q
   float* label_grad = nullptr;    // d(objective)/d(soft_q) of the last evaluation
@@ -312,10 +316,27 @@ struct bre_engine {
           BRE_LAUNCH(launch_avgpool_fwd(t[op.tin].val, t[op.tout].val, ti.N, ti.H * ti.W, ti.C, stream));
           break;
         }
+        case BRE_OP_POSADD:
+          BRE_LAUNCH(launch_token_posadd(t[op.tin].val, Wp(op.w), t[op.tout].val, to.N, to.C, op.S, stream));
+          break;
+        case BRE_OP_LAYERNORM:
+          BRE_LAUNCH(launch_token_layernorm(0, t[op.tin].val, nullptr, nullptr, nullptr, Wp(op.gamma), Wp(op.beta), nullptr, nullptr, op.eps,
+                                            to.N, to.C, tok_a[i], t[op.tout].val, 0, stream));
+          break;
+        case BRE_OP_ATTENTION:
+          BRE_LAUNCH(launch_token_attention(0, t[op.tin].val, nullptr, nullptr, nullptr, to.N / op.S, op.S, op.R, to.C / op.R, tok_a[i], tok_b[i],
+                                            t[op.tout].val, 0, stream));
+          break;
         default: set_error("unknown op kind"); return BRE_ERR_INVALID;
       }
     }
     const bre_tensor_desc& lt = td(logits);
+    if (seq_len > 0) {   // next-token loss over rows with class-probability targets (joint attacker on a causal language model)
+      if (soft_q == nullptr) { set_error("token programs need soft labels (bre_engine_load_soft_labels)"); return BRE_ERR_STATE; }
+      BRE_LAUNCH(launch_token_ce_fwd(t[logits].val, soft_q, lt.N, lt.C, seq_len, p, loss_n, t[logits].d, stream));
+      BRE_LAUNCH(launch_loss_mean(loss_n, lt.N, sc, stream));
+      return 0;
+    }
     BRE_LAUNCH(launch_ce_fwd(t[logits].val, labels, soft_q, lt.N, lt.C, p, loss_n, t[logits].d, stream));
     BRE_LAUNCH(launch_loss_mean(loss_n, lt.N, sc, stream));
     return 0;
@@ -385,6 +406,18 @@ struct bre_engine {
           BRE_LAUNCH(launch_avgpool_bwd(t[op.tout].d, t[op.tin].d, op.acc_in != 0, ti.N, ti.H * ti.W, ti.C, stream));
           break;
         }
+        case BRE_OP_POSADD:      // gradient of the positional table (the candidate's own first-backward delta is not needed)
+          BRE_LAUNCH(launch_token_pos_grad(t[op.tout].d, Gp(op.w), to.N, to.C, op.S, stream));
+          break;
+        case BRE_OP_LAYERNORM:
+          BRE_LAUNCH(launch_token_ln_param_grad(t[op.tin].val, t[op.tout].d, tok_a[i], to.N, to.C, Gp(op.gamma), Gp(op.beta), stream));
+          BRE_LAUNCH(launch_token_layernorm(1, t[op.tin].val, t[op.tout].d, nullptr, nullptr, Wp(op.gamma), Wp(op.beta), nullptr, nullptr, op.eps,
+                                            to.N, to.C, tok_a[i], t[op.tin].d, op.acc_in != 0, stream));
+          break;
+        case BRE_OP_ATTENTION:
+          BRE_LAUNCH(launch_token_attention(1, t[op.tin].val, t[op.tout].d, nullptr, nullptr, to.N / op.S, op.S, op.R, to.C / op.R, tok_a[i],
+                                            tok_b[i], t[op.tin].d, op.acc_in != 0, stream));
+          break;
         default: break;
       }
     }
@@ -462,6 +495,17 @@ struct bre_engine {
           BRE_LAUNCH(launch_avgpool_fwd(t[op.tin].tval, t[op.tout].tval, ti.N, ti.H * ti.W, ti.C, stream));
           break;
         }
+        case BRE_OP_POSADD:      // the candidate's tangent is zero: only the direction component of the positional table
+          BRE_LAUNCH(launch_token_posadd(nullptr, Vp(op.w), t[op.tout].tval, to.N, to.C, op.S, stream));
+          break;
+        case BRE_OP_LAYERNORM:
+          BRE_LAUNCH(launch_token_layernorm(2, t[op.tin].val, t[op.tin].tval, nullptr, nullptr, Wp(op.gamma), Wp(op.beta), Vp(op.gamma),
+                                            Vp(op.beta), op.eps, to.N, to.C, tok_a[i], t[op.tout].tval, 0, stream));
+          break;
+        case BRE_OP_ATTENTION:
+          BRE_LAUNCH(launch_token_attention(2, t[op.tin].val, t[op.tin].tval, nullptr, nullptr, to.N / op.S, op.S, op.R, to.C / op.R, tok_a[i],
+                                            tok_b[i], t[op.tout].tval, 0, stream));
+          break;
         default: break;
       }
     }
@@ -485,7 +529,8 @@ struct bre_engine {
   int sweep_tangent_backward() {
     bool forked = false;
     const bre_tensor_desc& lt = td(logits);
-    BRE_LAUNCH(launch_ce_tan_bwd(p, t[logits].tval, lt.N, lt.C, t[logits].td, stream));
+    if (seq_len > 0) BRE_LAUNCH(launch_token_ce_tan_bwd(p, t[logits].tval, lt.N, lt.C, seq_len, t[logits].td, stream));
+    else BRE_LAUNCH(launch_ce_tan_bwd(p, t[logits].tval, lt.N, lt.C, t[logits].td, stream));
     const bool di = cfg.di_scale > 0.f && n_di > 0;
     for (int i = (int)ops.size() - 1; i >= 0; --i) {
       const bre_op_desc& op = ops[i];
@@ -557,6 +602,17 @@ struct bre_engine {
           BRE_LAUNCH(launch_avgpool_bwd(t[op.tout].td, t[op.tin].td, op.acc_in != 0, ti.N, ti.H * ti.W, ti.C, stream));
           break;
         }
+        case BRE_OP_POSADD:      // d objective / d candidate = tangent delta of the embedded sequence
+          BRE_CUDA_CHECK(cudaMemcpyAsync(t[0].td, t[op.tout].td, (size_t)to.N * to.C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+          break;
+        case BRE_OP_LAYERNORM:
+          BRE_LAUNCH(launch_token_layernorm(3, t[op.tin].val, t[op.tout].td, t[op.tout].d, t[op.tin].tval, Wp(op.gamma), Wp(op.beta),
+                                            Vp(op.gamma), nullptr, op.eps, to.N, to.C, tok_a[i], t[op.tin].td, op.acc_in != 0, stream));
+          break;
+        case BRE_OP_ATTENTION:
+          BRE_LAUNCH(launch_token_attention(3, t[op.tin].val, t[op.tout].td, t[op.tout].d, t[op.tin].tval, to.N / op.S, op.S, op.R, to.C / op.R,
+                                            tok_a[i], tok_b[i], t[op.tin].td, op.acc_in != 0, stream));
+          break;
         default: break;
       }
     }
@@ -721,7 +777,7 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
     if (op.tin < 0 || op.tin >= n_tensors || op.tout <= 0 || op.tout >= n_tensors || op.res >= n_tensors) { set_error("op tensor id out of range"); return fail(BRE_ERR_INVALID); }
     if (op.tin == 0 || op.res == 0) {
       ++consumers0;
-      if (op.res == 0 || (op.kind != BRE_OP_CONV && op.kind != BRE_OP_LINEAR)) { set_error("the candidate must feed exactly one conv/linear layer"); return fail(BRE_ERR_UNSUPPORTED); }
+      if (op.res == 0 || (op.kind != BRE_OP_CONV && op.kind != BRE_OP_LINEAR && op.kind != BRE_OP_POSADD)) { set_error("the candidate must feed exactly one conv/linear/posadd layer"); return fail(BRE_ERR_UNSUPPORTED); }
     }
     if (op.kind == BRE_OP_BNACT && op.has_bn) n_bn = op.bn_buffer + 1 > n_bn ? op.bn_buffer + 1 : n_bn;
     if ((op.kind == BRE_OP_CONV || op.kind == BRE_OP_LINEAR) && (op.w < 0 || op.w >= n_params)) { set_error("conv/linear without weight"); return fail(BRE_ERR_INVALID); }
@@ -769,6 +825,21 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
   rc |= e->alloc(&e->sc, 1);
   // ---- per-op buffers --------------------------------------------------------------------------------
   e->pool_idx.assign(n_ops, nullptr);
+  e->tok_a.assign(n_ops, nullptr);
+  e->tok_b.assign(n_ops, nullptr);
+  for (int i = 0; i < n_ops; ++i) {
+    const bre_op_desc& op = ops[i];
+    if (op.kind == BRE_OP_LAYERNORM) rc |= e->alloc(&e->tok_a[i], 2LL * tensors[op.tin].N);
+    if (op.kind == BRE_OP_ATTENTION || op.kind == BRE_OP_POSADD) {
+      if (op.S < 1 || tensors[op.tin].N % op.S != 0) { set_error("token op: rows must be a multiple of seq_len"); return fail(BRE_ERR_INVALID); }
+      e->seq_len = op.S;
+    }
+    if (op.kind == BRE_OP_ATTENTION) {
+      const long long np = (long long)(tensors[op.tin].N / op.S) * op.R * op.S * op.S;
+      rc |= e->alloc(&e->tok_a[i], np);
+      rc |= e->alloc(&e->tok_b[i], np);
+    }
+  }
   e->bn.resize(n_bn);
   for (int i = 0; i < n_ops; ++i) {
     const bre_op_desc& op = ops[i];
@@ -961,8 +1032,12 @@ int bre_engine_label_gradient(bre_engine* e, float* grad_out) {
   if (!e->soft_q) { set_error("bre_engine_label_gradient: no soft labels loaded"); return BRE_ERR_STATE; }
   BRE_CUDA_CHECK(cudaSetDevice(e->device));
   const bre_tensor_desc& lt = e->td(e->logits);
-  BRE_TRY(launch_ce_label_grad(e->t[e->logits].val, e->p, e->t[e->logits].tval, lt.N, lt.C, e->cfg.task_regularization, e->label_grad,
-                               e->stream));
+  if (e->seq_len > 0)
+    BRE_TRY(launch_token_label_grad(e->t[e->logits].val, e->p, e->t[e->logits].tval, lt.N, lt.C, e->seq_len, e->cfg.task_regularization,
+                                    e->label_grad, e->stream));
+  else
+    BRE_TRY(launch_ce_label_grad(e->t[e->logits].val, e->p, e->t[e->logits].tval, lt.N, lt.C, e->cfg.task_regularization, e->label_grad,
+                                 e->stream));
   BRE_CUDA_CHECK(cudaMemcpyAsync(grad_out, e->label_grad, (size_t)lt.N * lt.C * sizeof(float), cudaMemcpyDefault, e->stream));
   BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   return BRE_OK;

@@ -9,7 +9,9 @@
 // (sequence, head) for attention with the whole head resident in shared memory; plain fp32, deterministic (no atomics).
 // First correct version -- exposed through a stand-alone C ABI (bre_token_layernorm / bre_token_attention) for kernel-level
 // parity tests; the engine's sweeps do not dispatch to them yet.
-#include "common.cuh"
+#include <float.h>
+
+#include "tokens.cuh"
 
 namespace bre {
 namespace {
@@ -259,7 +261,183 @@ __global__ void attention_kernel(int sweep, const float* __restrict__ qkv, const
   }
 }
 
+// ---- positional embedding ------------------------------------------------------------------------------------------
+__global__ void posadd_kernel(const float* __restrict__ x, const float* __restrict__ pos, float* __restrict__ out, long long total, int C, int T) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / C;
+    const int c = (int)(i - row * C);
+    const float v = pos[(row % T) * C + c];
+    out[i] = x != nullptr ? x[i] + v : v;
+  }
+}
+
+__global__ void pos_grad_kernel(const float* __restrict__ d, float* __restrict__ g_pos, int rows, int C, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (t, c)
+  if (i >= T * C) return;
+  const int t = i / C, c = i - t * C;
+  float s = 0.f;
+  for (int b = 0; b < rows / T; ++b) s += d[((long long)b * T + t) * C + c];
+  g_pos[i] = s;
+}
+
+// ---- next-token cross-entropy with probability targets ----------------------------------------------------------------
+__device__ __forceinline__ void row_softmax_stats(const float* z, int V, double* scratch, float& mx_out, float& sum_out) {
+  __shared__ float wmax[32];
+  __shared__ float s_max, s_sum;
+  float mx = -FLT_MAX;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, z[c]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = wmax[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, wmax[w]);
+    s_max = m;
+  }
+  __syncthreads();
+  mx = s_max;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) part += (double)expf(z[c] - mx);
+  const double tot = block_sum(part, scratch);
+  if (threadIdx.x == 0) s_sum = (float)tot;
+  __syncthreads();
+  mx_out = mx;
+  sum_out = s_sum;
+}
+
+__global__ void token_ce_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ q, int rows, int V, int T, float* p,
+                                    float* loss_n, float* dlogits) {
+  __shared__ double scratch[32];
+  const int row = blockIdx.x;
+  const float* z = logits + (long long)row * V;
+  float mx, sum;
+  row_softmax_stats(z, V, scratch, mx, sum);
+  const bool scored = (row % T) != T - 1;
+  const float invM = 1.0f / (float)(rows - rows / T);
+  const float lse = mx + logf(sum);
+  const float* qn = q + (long long)(row + 1) * V;   // target of the next position (never read for the last position)
+  double lpart = 0.0;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    const float pc = expf(z[c] - mx) / sum;
+    p[(long long)row * V + c] = pc;
+    if (scored) {
+      const float qc = qn[c];
+      dlogits[(long long)row * V + c] = (pc - qc) * invM;
+      lpart -= (double)qc * (double)(z[c] - lse);
+    } else {
+      dlogits[(long long)row * V + c] = 0.f;
+    }
+  }
+  const double ltot = block_sum(lpart, scratch);
+  if (threadIdx.x == 0) loss_n[row] = scored ? (float)(ltot * (double)rows * (double)invM) : 0.f;
+}
+
+__global__ void token_ce_tan_bwd_kernel(const float* __restrict__ p, const float* __restrict__ zdot, int rows, int V, int T, float* tdl) {
+  __shared__ double scratch[32];
+  __shared__ float s_dot;
+  const int row = blockIdx.x;
+  const float* pp = p + (long long)row * V;
+  const float* zz = zdot + (long long)row * V;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) part += (double)pp[c] * (double)zz[c];
+  const double tot = block_sum(part, scratch);
+  if (threadIdx.x == 0) s_dot = (float)tot;
+  __syncthreads();
+  const bool scored = (row % T) != T - 1;
+  const float dot = s_dot, invM = 1.0f / (float)(rows - rows / T);
+  for (int c = threadIdx.x; c < V; c += blockDim.x) tdl[(long long)row * V + c] = scored ? pp[c] * (zz[c] - dot) * invM : 0.f;
+}
+
+__global__ void token_label_grad_kernel(const float* __restrict__ logits, const float* __restrict__ p, const float* __restrict__ zdot, int rows,
+                                        int V, int T, float task_reg, float* __restrict__ out) {
+  __shared__ double scratch[32];
+  __shared__ float s_dot;
+  const int row = blockIdx.x;                      // output row = target position (b, t); source = logits row (b, t - 1)
+  float* o = out + (long long)row * V;
+  if (row % T == 0) {                              // position 0 is never a target
+    for (int c = threadIdx.x; c < V; c += blockDim.x) o[c] = 0.f;
+    return;
+  }
+  const long long src = row - 1;
+  const float* z = logits + src * V;
+  const float* pp = p + src * V;
+  const float* zz = zdot + src * V;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) part += (double)pp[c] * (double)zz[c];
+  const double tot = block_sum(part, scratch);
+  if (threadIdx.x == 0) s_dot = (float)tot;
+  __syncthreads();
+  float mx = 0.f, sum = 1.f;
+  if (task_reg != 0.f) row_softmax_stats(z, V, scratch, mx, sum);
+  const float dot = s_dot, invM = 1.0f / (float)(rows - rows / T);
+  const float lse = mx + logf(sum);
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    float v = -(zz[c] - dot) * invM;
+    if (task_reg != 0.f) v -= task_reg * (z[c] - lse) * invM;
+    o[c] = v;
+  }
+}
+
 }  // namespace
+
+static int check_launch(const char* what) {
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(err)); return -2; }
+  return 0;
+}
+
+int launch_token_layernorm(int sweep, const float* x, const float* in1, const float* in2, const float* in3, const float* gamma,
+                           const float* beta, const float* v_gamma, const float* v_beta, float eps, int rows, int C, float* stats, float* out,
+                           int accumulate, cudaStream_t s) {
+  const int warps = 4;
+  layernorm_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(sweep, x, in1, in2, in3, gamma, beta, v_gamma, v_beta, eps, rows, C, stats,
+                                                                     out, accumulate);
+  return check_launch("token layernorm");
+}
+int launch_token_ln_param_grad(const float* x, const float* dy, const float* stats, int rows, int C, float* g_gamma, float* g_beta,
+                               cudaStream_t s) {
+  layernorm_param_grad_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, dy, stats, rows, C, g_gamma, g_beta);
+  return check_launch("token layernorm parameter gradient");
+}
+int launch_token_attention(int sweep, const float* qkv, const float* in1, const float* in2, const float* in3, int B, int T, int heads, int dh,
+                           float* P, float* Pd, float* out, int accumulate, cudaStream_t s) {
+  if (T > 128) { set_error("token attention: seq_len > 128 needs the tiled kernel (not written yet)"); return -4; }
+  const size_t smem = (size_t)(8 * T * dh + 4 * T * T) * sizeof(float);
+  if (smem > 200 * 1024) { set_error("token attention: head too large for the resident-head kernel"); return -4; }
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      set_error("token attention: shared memory opt-in failed");
+      return -2;
+    }
+    attr_done = true;
+  }
+  attention_kernel<<<B * heads, T, smem, s>>>(sweep, qkv, in1, in2, in3, T, heads, dh, P, Pd, out, accumulate);
+  return check_launch("token attention");
+}
+int launch_token_posadd(const float* x, const float* pos, float* out, int rows, int C, int T, cudaStream_t s) {
+  const long long total = (long long)rows * C;
+  posadd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, pos, out, total, C, T);
+  return check_launch("token posadd");
+}
+int launch_token_pos_grad(const float* d, float* g_pos, int rows, int C, int T, cudaStream_t s) {
+  pos_grad_kernel<<<(T * C + 255) / 256, 256, 0, s>>>(d, g_pos, rows, C, T);
+  return check_launch("token positional gradient");
+}
+int launch_token_ce_fwd(const float* logits, const float* q, int rows, int V, int T, float* p, float* loss_n, float* dlogits, cudaStream_t s) {
+  token_ce_fwd_kernel<<<rows, 256, 0, s>>>(logits, q, rows, V, T, p, loss_n, dlogits);
+  return check_launch("token cross-entropy");
+}
+int launch_token_ce_tan_bwd(const float* p, const float* zdot, int rows, int V, int T, float* tdlogits, cudaStream_t s) {
+  token_ce_tan_bwd_kernel<<<rows, 256, 0, s>>>(p, zdot, rows, V, T, tdlogits);
+  return check_launch("token cross-entropy tangent");
+}
+int launch_token_label_grad(const float* logits, const float* p, const float* zdot, int rows, int V, int T, float task_reg, float* out,
+                            cudaStream_t s) {
+  token_label_grad_kernel<<<rows, 256, 0, s>>>(logits, p, zdot, rows, V, T, task_reg, out);
+  return check_launch("token label gradient");
+}
+
 }  // namespace bre
 
 extern "C" {
@@ -272,14 +450,9 @@ int bre_token_layernorm(int32_t sweep, const float* x, const float* in1, const f
   using namespace bre;
   if (!x || !out || !stats || !gamma || rows < 1 || C < 1 || sweep < 0 || sweep > 3) { set_error("bre_token_layernorm: bad arguments"); return -1; }
   cudaStream_t s = (cudaStream_t)stream;
-  const int warps = 4;
-  layernorm_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(sweep, x, in1, in2, in3, gamma, beta, v_gamma, v_beta, eps, rows, C, stats,
-                                                                     out, 0);
-  if (sweep == 1 && g_gamma && g_beta)
-    layernorm_param_grad_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, in1, stats, rows, C, g_gamma, g_beta);
-  const cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) { set_error(std::string("bre_token_layernorm: ") + cudaGetErrorString(err)); return -2; }
-  return 0;
+  int rc = launch_token_layernorm(sweep, x, in1, in2, in3, gamma, beta, v_gamma, v_beta, eps, rows, C, stats, out, 0, s);
+  if (rc == 0 && sweep == 1 && g_gamma && g_beta) rc = launch_token_ln_param_grad(x, in1, stats, rows, C, g_gamma, g_beta, s);
+  return rc;
 }
 
 // Stand-alone attention sweeps: qkv [B*T, 3 d], P / Pd [B, heads, T, T] scratch kept by the caller between sweeps.
@@ -290,21 +463,7 @@ int bre_token_attention(int32_t sweep, const float* qkv, const float* in1, const
     set_error("bre_token_attention: bad arguments (T <= 128)");
     return -1;
   }
-  cudaStream_t s = (cudaStream_t)stream;
-  const size_t smem = (size_t)(8 * T * dh + 4 * T * T) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
-      set_error("bre_token_attention: shared memory opt-in failed");
-      return -2;
-    }
-    attr_done = true;
-  }
-  if (smem > 200 * 1024) { set_error("bre_token_attention: head too large for the resident-head kernel"); return -4; }
-  attention_kernel<<<B * heads, T, smem, s>>>(sweep, qkv, in1, in2, in3, T, heads, dh, P, Pd, out, 0);
-  const cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) { set_error(std::string("bre_token_attention: ") + cudaGetErrorString(err)); return -2; }
-  return 0;
+  return launch_token_attention(sweep, qkv, in1, in2, in3, B, T, heads, dh, P, Pd, out, 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -210,7 +210,7 @@ def make_cfg(cfg_attack, noise_seed=0):
 class Engine:
     """One engine = one model replica + one trial state on one GPU."""
 
-    def __init__(self, model, input_shape, cfg_attack, device, noise_seed=0, backend=None):
+    def __init__(self, model, input_shape, cfg_attack, device, noise_seed=0, backend=None, program=None):
         """``backend``: "tc" (tcgen05 TF32 tensor-core GEMMs, default; shapes it does not cover run on the fp32 SIMT
         kernels) or "simt" (fp32 CUDA-core GEMMs everywhere: bit-faithful fp32 products).  Default from
         ``BRE_GEMM_BACKEND``."""
@@ -219,7 +219,9 @@ class Engine:
         if self.device.type != "cuda":
             raise EngineError("the engine runs on CUDA devices only (no CPU fallback)")
         self.model = model
-        self.prog = C.compile_model(model, input_shape)
+        # ``program``: an already lowered layer program (compiler.compile_transformer for token-sequence models, whose
+        # candidate is the embedding sequence [batch, seq_len, d]); default: lower the vision model with torch.fx
+        self.prog = program if program is not None else C.compile_model(model, input_shape)
         self.input_shape = tuple(int(s) for s in input_shape)
         self.ccfg = make_cfg(cfg_attack, noise_seed)
         prog = self.prog
@@ -234,7 +236,7 @@ class Engine:
                 pds.append(ParamDesc(p.numel, 0, 0, 0, 0))
         self._bn_modules = []
         ops = []
-        mods = C.bn_modules(model, prog)
+        mods = C.bn_modules(model, prog) if program is None else [None] * len(prog.ops)
         for op, mod in zip(prog.ops, mods):
             bn_idx = -1
             if mod is not None:

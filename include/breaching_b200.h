@@ -36,7 +36,11 @@ enum bre_status {
 };
 
 /* ---- layer program (produced by breaching_b200.compiler from the nn.Module) ---------------------- */
-enum bre_op_kind { BRE_OP_CONV = 1, BRE_OP_BNACT = 2, BRE_OP_MAXPOOL = 3, BRE_OP_AVGPOOL = 4, BRE_OP_LINEAR = 5 };
+enum bre_op_kind { BRE_OP_CONV = 1, BRE_OP_BNACT = 2, BRE_OP_MAXPOOL = 3, BRE_OP_AVGPOOL = 4, BRE_OP_LINEAR = 5,
+                   /* token-sequence programs (transformer / TAG path): tensors are [rows = batch * seq_len, C, 1, 1] */
+                   BRE_OP_POSADD = 6,      /* out = candidate + positional embedding `w` of position (row mod seq_len) */
+                   BRE_OP_LAYERNORM = 7,   /* gamma, beta, eps */
+                   BRE_OP_ATTENTION = 8 }; /* tin = fused (q | k | v) projection, R = heads, S = seq_len, no mask */
 enum bre_param_perm { BRE_PERM_NONE = 0, BRE_PERM_OIHW_TO_OHWI = 1, BRE_PERM_LINEAR_CHW_TO_HWC = 2 };
 
 typedef struct bre_tensor_desc { int32_t N, C, H, W; } bre_tensor_desc; /* tensor 0 = candidate (NCHW) */

@@ -82,3 +82,43 @@ def test_attention_four_sweeps(B, T, heads, dh):
     assert _relerr(out2, Od) < 2e-5 and _relerr(Pdg, Pd) < 2e-5
     out3 = E.token_attention(3, f(qkv), B, T, heads, Pg, Pdg, in1=f(dOd), in2=f(dO), in3=f(qkvd))
     assert _relerr(out3, dqkvd) < 5e-5
+
+
+@pytest.mark.parametrize("backend", ["simt", "tc"])
+def test_transformer_closure_on_the_engine_matches_reference_tag_fixture(backend):
+    """BASELINE config 5 in miniature on the CUDA engine: the layer program of ``compiler.compile_transformer`` (positional
+    embedding, QKV / output / feed-forward / decoder GEMMs, multi-head attention, LayerNorm, residuals, next-token
+    cross-entropy with the joint attacker's soft labels) through all four sweeps -- objective value, gradient w.r.t. the
+    candidate embeddings and w.r.t. the label logits against the *reference's* TAG closure (tag.yaml)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import case_from_fixture, cfg_from_fixture, load_golden
+    from breaching_b200 import compiler
+
+    fx = load_golden("trial_joint_tag_transformer.pt")
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    names = [n for n, _ in model.named_parameters()]
+    grads = list(shared[0]["gradients"])
+    grads.pop(names.index("encoder.weight"))                       # base_attack.py:88-95
+    params = [p.detach() for n, p in model.named_parameters() if n != "encoder.weight"]
+    B, T, d = fx["x0"].shape
+    V = fx["l0"].shape[-1]
+    prog = compiler.compile_transformer(model, B, T)
+    eng = E.Engine(None, (B * T, d, 1, 1), cfg, DEV, backend=backend, program=prog)
+    eng.load_model(params=params)
+    L = len(grads)
+    tag_weights = torch.arange(L, 0, -1, dtype=torch.float32) / L  # objectives.py:115-124, scale_scheme linear
+    eng.load_targets([g.to(DEV) for g in grads], torch.zeros(B * T, dtype=torch.long), tensor_weights=tag_weights)
+    q = fx["l0"].to(DEV).softmax(dim=-1)
+    eng.load_soft_labels(q.reshape(B * T, V))
+    val, gx = eng.objective_and_gradient(fx["x0"].to(DEV).reshape(B * T, d, 1, 1))
+    gq = eng.label_gradient((B, T, V))
+    gl = q * (gq - (q * gq).sum(dim=-1, keepdim=True))
+    tol_v, tol_g = (2e-4, 2e-3) if backend == "simt" else (5e-3, 3e-2)
+    assert abs(val - fx["objective0"]) < tol_v * abs(fx["objective0"]), (val, fx["objective0"], eng.last_terms())
+    assert _relerr(gx.reshape(B, T, d), fx["raw_grad_x0"]) < tol_g, _relerr(gx.reshape(B, T, d), fx["raw_grad_x0"])
+    assert _relerr(gl, fx["raw_grad_l0"]) < tol_g, _relerr(gl, fx["raw_grad_l0"])
+    eng.close()
