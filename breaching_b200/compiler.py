@@ -412,7 +412,7 @@ def compile_transformer(model, batch, seq_len):
 
     x = new_tensor(d)   # tensor 0: the candidate embeddings
     cur = new_tensor(d)
-    prog.ops.append(Op(OP_POSADD, x, cur, w=pidx["pos_encoder.embedding.weight"]))
+    prog.ops.append(Op(OP_POSADD, x, cur, w=pidx["pos_encoder.embedding.weight"], S=int(seq_len)))
     for li, layer in enumerate(model.transformer_encoder.layers):
         if getattr(layer, "norm_first", False) or not getattr(layer.self_attn, "batch_first", True):
             raise UnsupportedModelError("only post-norm, batch-first encoder layers (the reference's configuration) are lowered")
