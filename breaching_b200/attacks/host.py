@@ -186,3 +186,69 @@ def measured_features(shared_data, labels):
         rows = [debiased[label] if bias[label] != 0 else torch.zeros_like(debiased[0]) for label in labels]
         out.append(torch.stack(rows))
     return out
+
+
+# ---- text models: optimise in embedding space (base_attack.py:76-167) ---------------------------------------------------
+EMBEDDING_LAYER_NAMES = ("encoder.weight", "word_embeddings.weight", "transformer.wte")   # base_attack.py:15
+
+
+def prepare_for_text_data(rec_models, shared_data, text_strategy="run-embedding"):
+    """base_attack.py:76-128 ("run-embedding"): the token embedding cannot be optimised through, so the candidate lives in
+    embedding space -- the embedding layer of every attacked model is replaced by ``Identity`` and its gradient entry is
+    removed from the shared update.  Returns ``(embeddings, token_embedding_dim)`` with ``embeddings[i] = dict(weight, grads)``;
+    ``shared_data[i]["gradients"]`` is edited in place exactly like the reference does."""
+    if text_strategy == "no-preprocessing":
+        return [], None
+    if text_strategy != "run-embedding":
+        raise ValueError(f"Invalid text strategy {text_strategy} given.")
+    embeddings = []
+    for model, data in zip(rec_models, shared_data):
+        name_to_idx = dict(zip([n for n, _ in model.named_parameters()], range(len(data["gradients"]))))
+        position = None
+        for name in EMBEDDING_LAYER_NAMES:      # the last matching name wins, as in the reference's nested loop
+            for key in name_to_idx:
+                if name in key:
+                    position = name_to_idx[key]
+        if position is None:
+            raise ValueError("no token-embedding layer found in the model")
+        weight = list(model.parameters())[position]
+        embeddings.append(dict(weight=weight, grads=data["gradients"].pop(position)))
+
+        def replace(module):
+            for child_name, child in module.named_children():
+                if isinstance(child, torch.nn.Embedding):
+                    if child.weight is weight:
+                        setattr(module, child_name, torch.nn.Identity())
+                else:
+                    replace(child)
+
+        replace(model)
+    return embeddings, embeddings[0]["weight"].shape[1]
+
+
+def _max_similarity(recovered, true):
+    """base_attack.py:126-133 -- note the *squared* norms in the denominator (reference behaviour)."""
+    recovered = recovered - recovered.mean(dim=-1, keepdim=True)
+    true = true - true.mean(dim=-1, keepdim=True)
+    cosim = recovered.matmul(true.T) / recovered.pow(2).sum(dim=-1)[:, None] / true.pow(2).sum(dim=-1)[None, :]
+    return cosim.argmax(dim=1)
+
+
+def postprocess_text_data(reconstructed, embedding_weight, token_recovery):
+    """base_attack.py:123-167: map the reconstructed embeddings back to token ids."""
+    if token_recovery == "from-embedding":
+        rec = reconstructed["data"]
+        base_shape = rec.shape[0:2]
+        tokens = _max_similarity(rec.reshape(-1, rec.shape[-1]), embedding_weight).view(*base_shape)
+    elif token_recovery == "from-labels":
+        tokens = reconstructed["labels"]
+    elif token_recovery == "from-limited-embedding":
+        rec = reconstructed["data"]
+        base_shape = rec.shape[0:2]
+        active = reconstructed["labels"].unique()
+        matches = _max_similarity(rec.reshape(-1, rec.shape[-1]), embedding_weight[active, :])
+        tokens = active[matches].view(*base_shape)
+    else:
+        raise ValueError(f"Invalid token recovery {token_recovery} given.")
+    reconstructed["data"] = tokens
+    return reconstructed

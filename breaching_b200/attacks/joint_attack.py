@@ -30,12 +30,94 @@ log = logging.getLogger(__name__)
 class OptimizationJointAttacker(OptimizationBasedAttacker):
     """Optimises jointly for candidate data and labels on the B200 engine."""
 
+    _LOSSES = ("CrossEntropyLoss", "CausalLoss")   # CausalLoss: token models (tag.yaml), see _prepare_text
+
     # optimization_with_label_attack.py:43-51 -- the "recovered labels" are a template of label logits
     def _label_template(self, shared_data, metadata):
         n = shared_data[0]["metadata"]["num_data_points"]
         if metadata["task"] != "classification":
             raise NotImplementedError("joint optimisation of token labels (text models) is not implemented by the B200 engine")
         return host.initialize_data(self.cfg.init, [n, metadata.classes], self.dm, self.ds, self.setup)
+
+    # ---- text models (tag.yaml, BASELINE config 5) ----------------------------------------------------------------
+    # The closure of this path on the engine (compiler.compile_transformer program, all four sweeps, soft token labels) is
+    # verified on the B200 against the reference's TAG closure (tests/test_tokens_gpu.py).  The attacker-level glue below
+    # (prologue, loop, scoring, token recovery) was written after the round's GPU budget was spent: its host pieces are
+    # tested on the CPU against the reference (tests/test_install_dropin.py), the end-to-end call is not yet -- hence the
+    # dispatch to it is opt-in (attacks/__init__.py, BRE_TEXT_ENGINE=1).
+    def _prepare_text(self, server_payload, shared_data):
+        from collections import defaultdict
+
+        stats = defaultdict(list)
+        shared_data = [dict(d, gradients=list(d["gradients"])) for d in shared_data]
+        metadata = server_payload[0]["metadata"]
+        self.data_shape = list(metadata.shape)
+        self.dm, self.ds = host.preprocessing_constants(metadata, self.setup)
+        rec_models = host.construct_models(self.model_template, server_payload, shared_data, self.setup)
+        shared_data = host.cast_shared_data(shared_data, self.setup["dtype"])
+        self.embeddings, dim = host.prepare_for_text_data(rec_models, shared_data, cfg_get(self.cfg, "text_strategy", "run-embedding"))
+        self.data_shape = [*self.data_shape, dim]                       # base_attack.py:113-114
+        self._rec_models = rec_models
+        n = shared_data[0]["metadata"]["num_data_points"]
+        template = host.initialize_data(self.cfg.init, [n, self.data_shape[0], metadata.vocab_size], self.dm, self.ds, self.setup)
+        if self.cfg.normalize_gradients:
+            shared_data = host.normalize_gradients(shared_data)
+        return rec_models, template, stats, shared_data
+
+    def _get_text_engine(self, rec_models, shared_data):
+        from .. import compiler
+        from ..engine import Engine
+
+        n = shared_data[0]["metadata"]["num_data_points"]
+        T, d = self.data_shape
+        prog = compiler.compile_transformer(rec_models[0], n, T)
+        if self._engine is not None:
+            self._engine.close()
+        eng = Engine(None, (n * T, d, 1, 1), self.cfg, self.setup["device"], backend=self.backend, program=prog)
+        eng.load_model(params=[p.detach() for p in rec_models[0].parameters()])
+        tw = None
+        if self.cfg.objective.type == "tag-euclidean":  # objectives.py:115-124
+            L = len(shared_data[0]["gradients"])
+            scheme = cfg_get(self.cfg.objective, "scale_scheme", "linear")
+            if scheme == "linear":
+                tw = torch.arange(L, 0, -1, dtype=torch.float32) / L
+            elif scheme == "exp":
+                tw = torch.arange(L, 0, -1, dtype=torch.float32).softmax(dim=0)
+                tw = tw / tw[0]
+            else:
+                tw = torch.ones(L)
+        eng.load_targets(shared_data[0]["gradients"], torch.zeros(n * T, dtype=torch.long), tensor_weights=tw)
+        self._engine = eng
+        return eng
+
+    def _reconstruct_text(self, server_payload, shared_data, server_secrets, initial_data, dryrun):
+        rec_models, labels, stats, shared_data = self._prepare_text(server_payload, shared_data)
+        if len(rec_models) != 1 or self.regularizers:
+            raise NotImplementedError("text models: one model query, no regularisers (the reference's TAG / DLG presets configure none)")
+        engine = self._get_text_engine(rec_models, shared_data)
+        num_trials = self.cfg.restarts.num_trials
+        rank, world = bdist.rank_and_world()
+        scores = torch.full((num_trials,), float("inf"))
+        candidate_solutions = [None] * num_trials
+        shape = [shared_data[0]["metadata"]["num_data_points"], *self.data_shape]
+        hard_labels = labels.argmax(dim=-1)                              # :67 (of the template, reference behaviour)
+        for trial in range(num_trials):
+            candidate = host.initialize_data(self.cfg.init, shape, self.dm, self.ds, self.setup)
+            candidate_labels = host.initialize_data(self.cfg.init, list(labels.shape), self.dm, self.ds, self.setup)
+            if initial_data is not None:
+                candidate = initial_data.detach().clone().to(**self.setup)
+            if trial % world != rank:
+                continue
+            data, _ = self._run_joint_trial(engine, candidate, candidate_labels, stats, trial, dryrun)
+            candidate_solutions[trial] = data
+            q_hard = torch.nn.functional.one_hot(hard_labels, labels.shape[-1]).to(**self.setup)
+            engine.load_soft_labels(q_hard.reshape(-1, labels.shape[-1]))
+            scores[trial] = engine.score(data.reshape(-1, data.shape[-1], 1, 1), self.cfg.restarts.scoring)
+        optimal_solution = self._select_optimal_reconstruction(candidate_solutions, scores, stats, shape)
+        reconstructed = dict(data=optimal_solution, labels=hard_labels)
+        reconstructed = host.postprocess_text_data(reconstructed, self.embeddings[0]["weight"].detach(), self.cfg.token_recovery)
+        reconstructed["raw_embeddings"] = optimal_solution                # :80
+        return reconstructed, stats
 
     def prepare_attack(self, server_payload, shared_data):
         if shared_data[0]["metadata"]["labels"] is not None:  # :56-60
@@ -53,6 +135,10 @@ class OptimizationJointAttacker(OptimizationBasedAttacker):
         return rec_models, template, stats, shared
 
     def reconstruct(self, server_payload, shared_data, server_secrets=None, initial_data=None, dryrun=False):
+        if getattr(server_payload[0]["metadata"], "modality", "vision") == "text":
+            if shared_data[0]["metadata"]["labels"] is not None:
+                raise ValueError("Joint optimization only makes sense if no labels are provided. Switch to attack.attack_type=optimization instead")
+            return self._reconstruct_text(server_payload, shared_data, server_secrets, initial_data, dryrun)
         rec_models, labels, stats, shared_data = self.prepare_attack(server_payload, shared_data)
         if any(True for _ in self.regularizers) and any(k in ("deep_inversion", "features") for k, _ in self.regularizers):
             raise NotImplementedError("feature / DeepInversion priors are not implemented for the joint attacker")
@@ -89,8 +175,13 @@ class OptimizationJointAttacker(OptimizationBasedAttacker):
     def _closure(self, engine, x, ell, iteration, lr):
         """optimization_with_label_attack.py:145-189 -> (objective, processed d/dx, processed d/dlabels, raw pair)."""
         q = ell.softmax(dim=-1)
-        engine.load_soft_labels(q)
-        value, gx = engine.objective_and_gradient(x)
+        if ell.dim() == 3:   # token models: the engine works on rows = batch * seq_len
+            engine.load_soft_labels(q.reshape(-1, q.shape[-1]))
+            value, gx = engine.objective_and_gradient(x.reshape(-1, x.shape[-1], 1, 1))
+            gx = gx.reshape(x.shape)
+        else:
+            engine.load_soft_labels(q)
+            value, gx = engine.objective_and_gradient(x)
         gq = engine.label_gradient(tuple(ell.shape))
         gl = q * (gq - (q * gq).sum(dim=-1, keepdim=True))   # chain through the softmax (autograd does this at :162)
         raw = (gx, gl)

@@ -54,6 +54,8 @@ class _EngineSum:
 class OptimizationBasedAttacker:
     """Implements the optimisation-based attacks of the reference on the B200 engine."""
 
+    _LOSSES = ("CrossEntropyLoss",)
+
     def __init__(self, model, loss_fn, cfg_attack, setup=dict(dtype=torch.float, device=torch.device("cpu"))):
         self.cfg = cfg_attack
         self.setup = dict(device=torch.device(setup["device"]), dtype=getattr(torch, cfg_attack.impl.dtype))
@@ -82,8 +84,8 @@ class OptimizationBasedAttacker:
             raise NotImplementedError("impl.mixed_precision is not implemented by the B200 engine")
         if self.setup["device"].type != "cuda":
             raise EngineError("the B200 engine needs setup['device'] to be a CUDA device (there is no CPU fallback)")
-        if _loss_name(self.loss_fn) != "CrossEntropyLoss":
-            raise NotImplementedError(f"loss {_loss_name(self.loss_fn)} is not implemented by the B200 engine (CrossEntropyLoss only)")
+        if _loss_name(self.loss_fn) not in self._LOSSES:
+            raise NotImplementedError(f"loss {_loss_name(self.loss_fn)} is not implemented by the B200 engine ({', '.join(self._LOSSES)} only)")
         self._engine = None
         self._engine_key = None
 

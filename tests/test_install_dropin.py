@@ -47,3 +47,42 @@ def test_reference_yaml_config_objects_are_accepted_by_the_engine_config_flatten
         a = make_cfg(refshim.load_reference_attack_cfg(name))
         b = make_cfg(breaching_b200.get_attack_config(name))
         assert bytes(ctypes.string_at(ctypes.addressof(a), ctypes.sizeof(a))) == bytes(ctypes.string_at(ctypes.addressof(b), ctypes.sizeof(b))), name
+
+
+@pytest.mark.skipif(not refshim.reference_available(), reason="needs /root/reference (build container only)")
+def test_text_prologue_and_token_recovery_match_the_reference():
+    """host.prepare_for_text_data / postprocess_text_data against the reference attacker's own methods
+    (base_attack.py:76-167) on the miniature causal-LM case."""
+    import copy
+
+    import torch
+
+    from breaching_b200 import synthetic
+    from breaching_b200.attacks import host
+
+    ref = refshim.import_reference()
+    model, loss_fn, payload, shared, true = synthetic.make_text_case(batch=2, seq_len=6, seed=77)
+    cfg = refshim.load_reference_attack_cfg("tag", {})
+    att = ref.attacks.prepare_attack(model, loss_fn, cfg, dict(device=torch.device("cpu"), dtype=torch.float))
+    sh_ref = copy.deepcopy(shared)
+    rec_models, template, _ = att.prepare_attack(payload, sh_ref)
+    # ours, on fresh copies
+    mine = copy.deepcopy(model)
+    sh_mine = copy.deepcopy(shared)
+    emb, dim = host.prepare_for_text_data([mine], sh_mine, cfg.text_strategy)
+    assert dim == att.embeddings[0]["weight"].shape[1] == att.data_shape[-1]
+    assert len(sh_mine[0]["gradients"]) == len(sh_ref[0]["gradients"])
+    for a, b in zip(sh_mine[0]["gradients"], sh_ref[0]["gradients"]):
+        assert torch.equal(a, b)
+    assert torch.equal(emb[0]["grads"], att.embeddings[0]["grads"])
+    assert isinstance(mine.encoder, torch.nn.Identity) and isinstance(rec_models[0].encoder, torch.nn.Identity)
+    assert [n for n, _ in mine.named_parameters()] == [n for n, _ in rec_models[0].named_parameters()]
+    # token recovery from reconstructed embeddings: noisy true embeddings must map back to the tokens, identically to the reference
+    gen = torch.Generator().manual_seed(5)
+    tokens = true["data"]
+    rec = dict(data=model.encoder.weight.detach()[tokens] + 0.01 * torch.randn(2, 6, dim, generator=gen), labels=tokens.clone())
+    for mode in ("from-embedding", "from-labels", "from-limited-embedding"):
+        att.cfg.token_recovery = mode
+        expect = att._postprocess_text_data(dict(data=rec["data"].clone(), labels=rec["labels"].clone()))
+        got = host.postprocess_text_data(dict(data=rec["data"].clone(), labels=rec["labels"].clone()), emb[0]["weight"].detach(), mode)
+        assert torch.equal(got["data"], expect["data"]), mode

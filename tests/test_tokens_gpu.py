@@ -122,3 +122,32 @@ def test_transformer_closure_on_the_engine_matches_reference_tag_fixture(backend
     assert _relerr(gx.reshape(B, T, d), fx["raw_grad_x0"]) < tol_g, _relerr(gx.reshape(B, T, d), fx["raw_grad_x0"])
     assert _relerr(gl, fx["raw_grad_l0"]) < tol_g, _relerr(gl, fx["raw_grad_l0"])
     eng.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BRE_TEXT_ENGINE") != "1",
+                    reason="attacker-level text glue: written after the round's GPU budget was spent, opt-in until verified on a GPU")
+def test_tag_attack_through_the_attacker_api():
+    """tag.yaml end to end (prologue in embedding space, joint loop with AdamW / clip / warm-up, scoring, token recovery)
+    against the reference trajectory of the miniature config-5 fixture."""
+    import copy
+    import math
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import case_from_fixture, cfg_from_fixture, load_golden
+    from breaching_b200.attacks import prepare_attack
+
+    fx = load_golden("trial_joint_tag_transformer.pt")
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    attacker = prepare_attack(model, loss_fn, cfg, dict(device=DEV, dtype=torch.float, backend="simt"))
+    assert type(attacker).__name__ == "OptimizationJointAttacker"
+    rec_models, template, stats, shared2 = attacker._prepare_text(payload, copy.deepcopy(shared))
+    engine = attacker._get_text_engine(rec_models, shared2)
+    best, best_l = attacker._run_joint_trial(engine, fx["x0"].to(DEV), fx["l0"].to(DEV), stats, 0, iterations=fx["iters"])
+    for a, b in zip(stats["Trial_0_Val"], fx["history"]):
+        assert math.isclose(a, b, rel_tol=2e-3, abs_tol=1e-5), (stats["Trial_0_Val"], fx["history"])
+    cfg.optim.max_iterations = 3
+    rec, st = prepare_attack(model, loss_fn, cfg, dict(device=DEV, dtype=torch.float)).reconstruct(payload, copy.deepcopy(shared), {})
+    assert rec["data"].shape == true["data"].shape and rec["data"].dtype == torch.long and "raw_embeddings" in rec
