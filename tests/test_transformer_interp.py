@@ -120,3 +120,19 @@ def test_transformer_layer_program_reproduces_the_reference_tag_closure():
     fs.forward(fx["x0"].double(), q)
     for a, b in zip(G, fs.backward()):
         assert _relerr(a, b) < 1e-10
+
+
+def test_config5_program_has_the_survey_dimensions():
+    """BASELINE config 5 (TransformerModel(50257, 96, 8, 1536, 3), 32 tokens): 39 gradient tensors / 5 975 761 parameters once
+    the token embedding is removed, lowered to 3 x (attention + 2 LayerNorm + 4 GEMMs) + decoder."""
+    from breaching_b200 import compiler
+
+    model = synthetic.TransformerLM(50257, 96, 8, 1536, 3)
+    params = model.attack_parameters()
+    assert len(params) == 39 and sum(p.numel() for p in params) == 5_975_761
+    prog = compiler.compile_transformer(model, 1, 32)
+    kinds = [op.kind for op in prog.ops]
+    assert kinds.count(compiler.OP_ATTENTION) == 3 and kinds.count(compiler.OP_LAYERNORM) == 6 and kinds.count(compiler.OP_POSADD) == 1
+    assert kinds.count(compiler.OP_LINEAR) == 13 and len(prog.params) == 39
+    assert prog.tensors[prog.logits].N == 32 and prog.tensors[prog.logits].C == 50257 and prog.seq_len == 32
+    assert all(op.S == 32 for op in prog.ops if op.kind in (compiler.OP_ATTENTION, compiler.OP_POSADD))
