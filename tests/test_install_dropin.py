@@ -86,3 +86,44 @@ def test_text_prologue_and_token_recovery_match_the_reference():
         expect = att._postprocess_text_data(dict(data=rec["data"].clone(), labels=rec["labels"].clone()))
         got = host.postprocess_text_data(dict(data=rec["data"].clone(), labels=rec["labels"].clone()), emb[0]["weight"].detach(), mode)
         assert torch.equal(got["data"], expect["data"]), mode
+
+
+@pytest.mark.skipif(not refshim.reference_available(), reason="needs /root/reference (build container only)")
+def test_compile_transformer_accepts_the_reference_model_class():
+    """``compiler.compile_transformer`` on an instance of the reference's own ``TransformerModel``
+    (cases/models/language_models.py:150-205): same attribute names and parameter order as ``synthetic.TransformerLM``; the
+    lowered program, run by the four-sweep interpreter, reproduces autograd's gradients through the reference module."""
+    import torch
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    from breaching_b200 import compiler, synthetic
+    from oracle import program_interp as PI
+
+    refshim.import_reference()
+    from breaching.cases.models.language_models import TransformerModel
+
+    torch.manual_seed(4)
+    model = TransformerModel(ntokens=40, ninp=16, nhead=4, nhid=24, nlayers=2, dropout=0.0, positional_embedding="learnable").double().eval()
+    mine = synthetic.TransformerLM(40, 16, 4, 24, 2).double()
+    assert [n for n, _ in model.named_parameters()] == [n for n, _ in mine.named_parameters()]
+    B, T = 2, 6
+    prog = compiler.compile_transformer(model, B, T)
+    x = torch.randn(B, T, 16, dtype=torch.double, requires_grad=True)
+    q = torch.softmax(torch.randn(B, T, 40, dtype=torch.double), dim=-1)
+    model.encoder = torch.nn.Identity()                     # what the attack does (base_attack.py:100-110)
+    params = [p for p in model.parameters()]
+    with sdpa_kernel(SDPBackend.MATH):
+        loss = synthetic.causal_loss(model(x), q)
+        G = torch.autograd.grad(loss, params)
+
+    class _Params:
+        def parameters(self):
+            return params
+
+        def named_modules(self):
+            return model.named_modules()
+
+    it = PI.ProgramInterpreter(_Params(), prog)
+    assert abs(float(it.forward(x.detach(), q)) - float(loss)) < 1e-12
+    for a, b in zip(it.backward(), G):
+        assert ((a - b).norm() / (b.norm() + 1e-300)).item() < 1e-10
