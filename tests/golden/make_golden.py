@@ -219,6 +219,25 @@ def run_reference_joint(ref, case_kwargs, attack, overrides, iters):
                 true_labels=true["labels"], weight_checksum=checksum, torch_version=torch.__version__)
 
 
+def config5_fixture(ref):
+    """BASELINE config 5 at full size (TransformerModel(50257, 96, 8, 1536, 3), 1 x 32 tokens, tag.yaml) through the reference's
+    joint attacker.  The label tensors are 1 x 32 x 50257 floats each, so the fixture keeps the candidate, the seeds from which
+    the label logits are regenerated, the objective / task loss, the candidate gradient, and a strided sample + norms of the
+    label-logit gradient."""
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    case = dict(batch=1, seq_len=32, seed=233, ntokens=50257, ninp=96, nhead=8, nhid=1536, nlayers=3)
+    with sdpa_kernel(SDPBackend.MATH):
+        fx = run_reference_joint(ref, case, "tag", {}, 3)
+    l0, gl = fx["l0"], fx["raw_grad_l0"]
+    keep = dict(case=case, attack="tag", overrides={}, iters=3, x0=fx["x0"], l0_seed=case["seed"] + 1000,
+                l0_checksum=float(l0.double().sum()), l0_abs_checksum=float(l0.double().abs().sum()),
+                objective0=fx["objective0"], task_loss0=fx["task_loss0"], raw_grad_x0=fx["raw_grad_x0"],
+                raw_grad_l0_sample=gl[:, :, ::97].clone(), raw_grad_l0_norm=float(gl.double().norm()),
+                history=fx["history"], lrs=fx["lrs"], weight_checksum=fx["weight_checksum"], torch_version=fx["torch_version"])
+    return keep
+
+
 def label_fixtures(ref):
     from breaching.attacks.base_attack import _BaseAttacker
 
@@ -294,6 +313,10 @@ def main():
             fx = run_reference_joint(ref, case_kwargs, attack, overrides, iters)
         torch.save(fx, os.path.join(HERE, f"trial_{name}.pt"))
         print(name, "history", [round(h, 5) for h in fx["history"]], "score", fx["score"])
+    if not only or "joint_tag_config5" in only:
+        fx = config5_fixture(ref)
+        torch.save(fx, os.path.join(HERE, "trial_joint_tag_config5.pt"))
+        print("joint_tag_config5 history", [round(h, 5) for h in fx["history"]])
     if only:
         return
     torch.save(label_fixtures(ref), os.path.join(HERE, "labels.pt"))

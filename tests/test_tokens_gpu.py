@@ -151,3 +151,47 @@ def test_tag_attack_through_the_attacker_api():
     cfg.optim.max_iterations = 3
     rec, st = prepare_attack(model, loss_fn, cfg, dict(device=DEV, dtype=torch.float)).reconstruct(payload, copy.deepcopy(shared), {})
     assert rec["data"].shape == true["data"].shape and rec["data"].dtype == torch.long and "raw_embeddings" in rec
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BRE_TEST_CONFIG5") != "1",
+                    reason="full-size config-5 closure on the engine: fixture and test written after the round's GPU budget was spent")
+@pytest.mark.parametrize("backend", ["simt", "tc"])
+def test_full_size_config5_closure_on_the_engine(backend):
+    """BASELINE config 5 at full size (50 257 tokens, 96 dims, 8 heads, 3 layers, 32 positions) on the CUDA engine against the
+    closure of the reference's TAG attacker (tests/golden/trial_joint_tag_config5.pt)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import case_from_fixture, cfg_from_fixture, load_golden
+    from breaching_b200 import compiler
+
+    fx = load_golden("trial_joint_tag_config5.pt")
+    gen = torch.Generator().manual_seed(fx["l0_seed"])
+    x0 = torch.randn(list(fx["x0"].shape), generator=gen)
+    l0 = torch.randn([1, 32, fx["case"]["ntokens"]], generator=gen)
+    assert torch.equal(x0, fx["x0"])
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    names = [n for n, _ in model.named_parameters()]
+    grads = list(shared[0]["gradients"])
+    grads.pop(names.index("encoder.weight"))
+    params = [p.detach() for n, p in model.named_parameters() if n != "encoder.weight"]
+    B, T, d = x0.shape
+    V = l0.shape[-1]
+    eng = E.Engine(None, (B * T, d, 1, 1), cfg, DEV, backend=backend, program=compiler.compile_transformer(model, B, T))
+    eng.load_model(params=params)
+    L = len(grads)
+    eng.load_targets([g.to(DEV) for g in grads], torch.zeros(B * T, dtype=torch.long),
+                     tensor_weights=torch.arange(L, 0, -1, dtype=torch.float32) / L)
+    q = l0.to(DEV).softmax(dim=-1)
+    eng.load_soft_labels(q.reshape(B * T, V))
+    val, gx = eng.objective_and_gradient(x0.to(DEV).reshape(B * T, d, 1, 1))
+    gq = eng.label_gradient((B, T, V))
+    gl = q * (gq - (q * gq).sum(dim=-1, keepdim=True))
+    tol_v, tol_g = (2e-4, 2e-3) if backend == "simt" else (5e-3, 3e-2)
+    assert abs(val - fx["objective0"]) < tol_v * abs(fx["objective0"]), (val, fx["objective0"], eng.last_terms())
+    assert _relerr(gx.reshape(B, T, d), fx["raw_grad_x0"]) < tol_g
+    assert _relerr(gl[:, :, ::97], fx["raw_grad_l0_sample"]) < tol_g
+    assert abs(float(gl.norm()) - fx["raw_grad_l0_norm"]) < tol_g * fx["raw_grad_l0_norm"]
+    eng.close()

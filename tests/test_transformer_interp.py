@@ -136,3 +136,52 @@ def test_config5_program_has_the_survey_dimensions():
     assert kinds.count(compiler.OP_LINEAR) == 13 and len(prog.params) == 39
     assert prog.tensors[prog.logits].N == 32 and prog.tensors[prog.logits].C == 50257 and prog.seq_len == 32
     assert all(op.S == 32 for op in prog.ops if op.kind in (compiler.OP_ATTENTION, compiler.OP_POSADD))
+
+
+def _config5_inputs(fx):
+    gen = torch.Generator().manual_seed(fx["l0_seed"])
+    x0 = torch.randn(list(fx["x0"].shape), generator=gen)
+    l0 = torch.randn([fx["x0"].shape[0], fx["x0"].shape[1], fx["case"]["ntokens"]], generator=gen)
+    assert torch.equal(x0, fx["x0"]) and abs(float(l0.double().sum()) - fx["l0_checksum"]) < 1e-6 * fx["l0_abs_checksum"]
+    return x0, l0
+
+
+def test_full_size_config5_closure_through_the_layer_program():
+    """BASELINE config 5 at full size (50 257 tokens, 96 dims, 8 heads, 3 layers, 32 positions): the lowered layer program
+    evaluated by the four-sweep interpreter against the closure of the reference's TAG attacker (objective, candidate
+    gradient, sampled label-logit gradient + its norm)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import case_from_fixture, cfg_from_fixture, load_golden
+    from breaching_b200 import compiler
+    from oracle import program_interp as PI
+    from oracle.program_interp import objective_direction  # noqa: F401
+
+    fx = load_golden("trial_joint_tag_config5.pt")
+    x0, l0 = _config5_inputs(fx)
+    model, loss_fn, payload, shared, true = case_from_fixture(fx)
+    cfg = cfg_from_fixture(fx)
+    names = [n for n, _ in model.named_parameters()]
+    g = [t.double() for t in shared[0]["gradients"]]
+    g.pop(names.index("encoder.weight"))
+    prog = compiler.compile_transformer(model, 1, 32)
+
+    class _Params:
+        def parameters(self):
+            return [p for n, p in model.named_parameters() if n != "encoder.weight"]
+
+        def named_modules(self):
+            return model.named_modules()
+
+    it = PI.ProgramInterpreter(_Params(), prog)
+    q = l0.double().softmax(dim=-1)
+    o = cfg.objective
+    val, dx, loss, G = it.matching_gradient(x0.double(), q, g, o.type, scale=o.scale, tag_scale=o.tag_scale, scale_scheme=o.scale_scheme)
+    assert abs(float(val) - fx["objective0"]) < 2e-5 * abs(fx["objective0"])
+    assert abs(float(loss) - fx["task_loss0"]) < 2e-5 * abs(fx["task_loss0"])
+    assert _relerr(dx.float(), fx["raw_grad_x0"]) < 2e-4
+    dl = q * (it.dq - (q * it.dq).sum(dim=-1, keepdim=True))
+    assert _relerr(dl[:, :, ::97].float(), fx["raw_grad_l0_sample"]) < 2e-4
+    assert abs(float(dl.norm()) - fx["raw_grad_l0_norm"]) < 2e-4 * fx["raw_grad_l0_norm"]
