@@ -1,6 +1,4 @@
 """Drop-in for ``breaching.attacks`` (reference ``attacks/__init__.py:12-37``)."""
-import os
-
 import torch
 
 from .joint_attack import OptimizationJointAttacker
@@ -21,12 +19,8 @@ def prepare_attack(model, loss, cfg_attack, setup=dict(dtype=torch.float, device
     """
     if cfg_attack.attack_type == "optimization":
         return OptimizationBasedAttacker(model, loss, cfg_attack, setup)
-    if cfg_attack.attack_type == "joint-optimization" and _loss_name(loss) == "CrossEntropyLoss":
-        # classification models (deepleakage.yaml)
-        return OptimizationJointAttacker(model, loss, cfg_attack, setup)
-    if cfg_attack.attack_type == "joint-optimization" and _loss_name(loss) == "CausalLoss" and os.environ.get("BRE_TEXT_ENGINE") == "1":
-        # token models (tag.yaml): the engine's closure for them is verified, the attacker-level glue is not yet end to end on a
-        # GPU -- opt-in until it is; otherwise fall through to the delegation below
+    if cfg_attack.attack_type == "joint-optimization" and _loss_name(loss) in ("CrossEntropyLoss", "CausalLoss"):
+        # classification models (deepleakage.yaml) and causal language models (tag.yaml, BASELINE config 5)
         return OptimizationJointAttacker(model, loss, cfg_attack, setup)
     if cfg_attack.attack_type in _OTHER_ATTACKS:
         from ..install import reference_prepare_attack

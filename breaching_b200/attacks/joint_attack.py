@@ -9,8 +9,8 @@ tangent logits of that same pass (``bre_engine_label_gradient``: the matching te
 ``dL/dq = -log_softmax(z)/N``) and is chained through the softmax here.  The loop is host-driven (two small leaves, any
 torch-style optimiser incl. L-BFGS); the fused on-device step of the single-leaf attacker is not used.
 
-Vision classification models only: the text / transformer variant (``tag.yaml``) needs
-attention / LayerNorm sweeps the engine does not have yet and raises.
+Classification models (``deepleakage.yaml``) and causal language models (``tag.yaml``, SURVEY section 8 row a15, BASELINE
+config 5: the candidate is the embedding sequence, the label leaf holds logits over the vocabulary for every position).
 """
 import logging
 import math
@@ -41,10 +41,9 @@ class OptimizationJointAttacker(OptimizationBasedAttacker):
 
     # ---- text models (tag.yaml, BASELINE config 5) ----------------------------------------------------------------
     # The closure of this path on the engine (compiler.compile_transformer program, all four sweeps, soft token labels) is
-    # verified on the B200 against the reference's TAG closure (tests/test_tokens_gpu.py).  The attacker-level glue below
-    # (prologue, loop, scoring, token recovery) was written after the round's GPU budget was spent: its host pieces are
-    # tested on the CPU against the reference (tests/test_install_dropin.py), the end-to-end call is not yet -- hence the
-    # dispatch to it is opt-in (attacks/__init__.py, BRE_TEXT_ENGINE=1).
+    # verified on the B200 against the reference's TAG closure at miniature and full size, the attacker-level glue below
+    # (prologue, loop, scoring, token recovery) against the reference trajectory (tests/test_tokens_gpu.py); its host pieces
+    # are additionally tested on the CPU against the reference (tests/test_install_dropin.py, tests/test_host_loops_cpu.py).
     def _prepare_text(self, server_payload, shared_data):
         from collections import defaultdict
 
@@ -191,9 +190,14 @@ class OptimizationJointAttacker(OptimizationBasedAttacker):
         return float(value), gx, gl, raw
 
     def _run_joint_trial(self, engine, candidate, candidate_labels, stats, trial, dryrun=False, iterations=None):
+        """optimization_with_label_attack.py:89-143.  Adam / AdamW / SGD trials run entirely on the device (both leaves stepped
+        by the engine's fused kernels from one CUDA graph, ``bre_engine_begin_joint_trial``); L-BFGS -- which branches on a few
+        scalars per inner iteration -- and engine stand-ins without that entry point are driven from the host."""
         opt = self.cfg.optim
         T = int(opt.max_iterations)
         table = lr_table(opt.step_size, cfg_get(opt, "step_size_decay"), cfg_get(opt, "warmup", 0), T)
+        if str(opt.optimizer).lower() in _OPTIMIZERS and hasattr(engine, "begin_joint_trial") and not getattr(self, "host_driven", False):
+            return self._run_joint_trial_device(engine, candidate, candidate_labels, stats, trial, table, dryrun, iterations)
         x = candidate.detach().clone().contiguous()
         ell = candidate_labels.detach().clone().contiguous()
         best, best_l, fmin = x.clone(), ell.clone(), float("inf")
@@ -233,6 +237,30 @@ class OptimizationJointAttacker(OptimizationBasedAttacker):
             history.append(value)
         stats[f"Trial_{trial}_Val"].extend(history)
         self._last_joint_state = (x.detach().clone(), ell.detach().clone())
+        return best.detach(), best_l.detach()
+
+    def _run_joint_trial_device(self, engine, candidate, candidate_labels, stats, trial, table, dryrun, iterations):
+        x = candidate.detach().contiguous()
+        if candidate_labels.dim() == 3:      # token models: the engine works on rows = batch * seq_len
+            x = x.reshape(-1, x.shape[-1], 1, 1)
+        engine.begin_joint_trial(x, candidate_labels.detach().contiguous(), table)
+        T = int(self.cfg.optim.max_iterations)
+        total = 1 if dryrun else (T if iterations is None else iterations)
+        callback = int(cfg_get(self.cfg.optim, "callback", 0) or 0)
+        done = 0
+        while done < total:
+            n = min(callback if callback > 0 else total, total - done) if done > 0 else 1
+            engine.run(n)
+            done += n
+            st = engine.status()                      # one host sync per `callback` iterations
+            if st["stopped"]:
+                log.info(f"Recovery loss is non-finite in iteration {st['recorded']}. Cancelling reconstruction!")
+                break
+        engine.sync()
+        stats[f"Trial_{trial}_Val"].extend(engine.history().tolist())
+        best = engine.best().reshape(candidate.shape)
+        best_l = engine.joint_labels(best=True)
+        self._last_joint_state = (engine.candidate().reshape(candidate.shape), engine.joint_labels(best=False))
         return best.detach(), best_l.detach()
 
     def _score_joint(self, engine, candidate, hard_labels):

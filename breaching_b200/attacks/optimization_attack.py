@@ -19,7 +19,7 @@ import torch
 
 from .. import dist as bdist
 from ..config import cfg_get
-from ..engine import OBJECTIVES, Engine, EngineError
+from ..engine import OBJECTIVES, PEARLMUTTER, Engine, EngineError
 from ..schedule import lr_table
 from . import host
 
@@ -63,9 +63,7 @@ class OptimizationBasedAttacker:
         self.model_template = copy.deepcopy(model)
         self.loss_fn = copy.deepcopy(loss_fn)
 
-        if cfg_attack.objective.type not in OBJECTIVES:
-            if cfg_attack.objective.type in ("pearlmutter-loss", "pearlmutter-cosine", "dynamic-cosine-similarity"):
-                raise NotImplementedError(f"objective {cfg_attack.objective.type} is not implemented by the B200 engine")
+        if cfg_attack.objective.type not in OBJECTIVES and cfg_attack.objective.type not in PEARLMUTTER:
             raise ValueError(f"Unknown objective type {self.cfg.objective.type} given.")  # reference :31
         self.regularizers = []
         reg = cfg_get(self.cfg, "regularization")
@@ -270,8 +268,12 @@ class OptimizationBasedAttacker:
 
     def _select_optimal_reconstruction(self, candidate_solutions, scores, stats, shape):
         """optimization_based_attack.py:206-218 + the cross-rank MINLOC select (dist.py)."""
+        t0 = time.perf_counter()
         optimal_val, optimal_index = bdist.select_best(scores)
         solution = bdist.fetch_solution(candidate_solutions, optimal_index, shape, self.setup)
+        if solution.is_cuda:
+            torch.cuda.synchronize(solution.device)
+        self.last_select_seconds = time.perf_counter() - t0   # the one cross-rank exchange of a reconstruct() call
         stats["opt_value"] = optimal_val
         if optimal_val != float("inf") and optimal_val == optimal_val:
             log.info(f"Optimal candidate solution with rec. loss {optimal_val:2.4f} selected.")

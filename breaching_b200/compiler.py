@@ -139,6 +139,29 @@ def _trace(model):
     return graph
 
 
+def _check_flatten_args(node, first):
+    """``flatten(x, 1)`` / ``x.flatten(1)`` (optionally ``end_dim=-1``) is the only flatten the layer program can express."""
+    args = list(node.args[first:])
+    start = args[0] if len(args) > 0 else node.kwargs.get("start_dim", 0)
+    end = args[1] if len(args) > 1 else node.kwargs.get("end_dim", -1)
+    if start != 1 or end not in (-1, 3):
+        raise UnsupportedModelError(f"{node.name}: only flatten(start_dim=1, end_dim=-1) is supported (got {start}, {end})")
+
+
+def _check_view_args(node, ti):
+    """``x.view(N, -1)`` / ``x.view(x.size(0), -1)`` / ``x.reshape(N, features)``: anything else would silently be mis-lowered."""
+    shape = node.args[1:]
+    if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+        shape = tuple(shape[0])
+    if len(shape) != 2:
+        raise UnsupportedModelError(f"{node.name}: only a reshape to [N, -1] is supported")
+    n, f = shape
+    ok_n = isinstance(n, torch.fx.Node) or n in (ti.N, -1)
+    ok_f = isinstance(f, torch.fx.Node) or f in (-1, ti.C * ti.H * ti.W)
+    if not (ok_n and ok_f) or (n == -1 and f == -1):
+        raise UnsupportedModelError(f"{node.name}: reshape to {shape} is not [N, -1]")
+
+
 def compile_model(model, input_shape):
     """Return the :class:`Program` for ``model`` applied to a batch of shape ``input_shape`` (N, C, H, W)."""
     N, C0, H0, W0 = [int(s) for s in input_shape]
@@ -233,8 +256,10 @@ def compile_model(model, input_shape):
                 prim.append(dict(kind="avgpool", tin=tin, tout=tout))
                 env[node] = tout
             elif isinstance(mod, torch.nn.Flatten):
+                if mod.start_dim != 1 or mod.end_dim not in (-1, 3):
+                    raise UnsupportedModelError(f"Flatten({mod.start_dim}, {mod.end_dim}) is not [N, -1]")
                 env[node] = tin  # layout handled by the consuming Linear
-            elif isinstance(mod, (torch.nn.Identity,)) or (isinstance(mod, torch.nn.Dropout) and mod.p == 0):
+            elif isinstance(mod, (torch.nn.Identity,)) or (isinstance(mod, torch.nn.Dropout) and (mod.p == 0 or not mod.training)):
                 env[node] = tin
             elif isinstance(mod, torch.nn.Linear):
                 feat = ti.C * ti.H * ti.W
@@ -242,7 +267,10 @@ def compile_model(model, input_shape):
                     raise UnsupportedModelError(f"linear {node.target}: {feat} features arrive, {mod.in_features} expected")
                 tout = new_tensor(ti.N, mod.out_features, 1, 1)
                 prim.append(dict(kind="linear", tin=tin, tout=tout, w=pidx(mod.weight), b=pidx(mod.bias)))
-                if ti.H * ti.W > 1:
+                if ti.H * ti.W > 1 and tin != 0:
+                    # internal activations are NHWC: permute the weight columns once.  The candidate itself (tensor 0) stays
+                    # NCHW, so a Linear fed directly by it (the reference's `linear` model, model_preparation.py:238,313)
+                    # keeps torch's CHW column order.
                     pd_ = prog.params[pidx(mod.weight)]
                     pd_.perm, pd_.perm_c, pd_.perm_hw = PERM_LINEAR_CHW_TO_HWC, ti.C, ti.H * ti.W
                 env[node] = tout
@@ -260,6 +288,7 @@ def compile_model(model, input_shape):
                 prim.append(dict(kind="add", tin=ta, tin2=tb, tout=tout))
                 env[node] = tout
             elif fn is torch.flatten:
+                _check_flatten_args(node, 1)
                 env[node] = arg_tid(node.args[0])
             elif fn in (torch.relu, torch.nn.functional.relu):
                 tin = arg_tid(node.args[0])
@@ -271,7 +300,13 @@ def compile_model(model, input_shape):
                 raise UnsupportedModelError(f"function {getattr(fn, '__name__', fn)} is not supported by the engine")
         elif node.op == "call_method":
             if node.target in ("flatten", "view", "reshape", "contiguous"):
+                if node.target == "flatten":
+                    _check_flatten_args(node, 1)
+                elif node.target in ("view", "reshape"):
+                    _check_view_args(node, prog.tensors[arg_tid(node.args[0])])
                 env[node] = arg_tid(node.args[0])
+            elif node.target == "size":
+                pass  # x.size(0) as an argument of view / reshape (checked there)
             else:
                 raise UnsupportedModelError(f"tensor method {node.target} is not supported by the engine")
     if out_tid is None:
@@ -394,9 +429,9 @@ def compile_transformer(model, batch, seq_len):
     has the reference's attribute names).  Parameter indices follow ``model.parameters()`` with the token embedding removed,
     i.e. the order of the shared gradient list after base_attack.py:88-95.
 
-    The program is the contract between this lowering and the sweeps; today it is executed by ``oracle/program_interp.py``
-    (CPU, float64-verified against autograd and the reference's TAG closure) -- the CUDA engine does not implement the three
-    token ops yet and rejects it.
+    The program is the contract between this lowering and the sweeps: ``csrc/engine.cu`` executes it on the GPU (token ops in
+    ``csrc/tokens.cu``), ``oracle/program_interp.py`` on the CPU (float64-verified against autograd and the reference's TAG
+    closure).
     """
     names = [n for n, _ in model.named_parameters() if n != "encoder.weight"]
     shapes = {n: tuple(p.shape) for n, p in model.named_parameters()}

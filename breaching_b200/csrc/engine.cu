@@ -105,6 +105,11 @@ struct bre_engine {
   float* soft_q_buf = nullptr;    // owned storage behind soft_q
   float* label_grad = nullptr;    // d(objective)/d(soft_q) of the last evaluation
   int n_labels = 0;
+  // joint data + label optimisation on the device (optimization_with_label_attack.py:89-143): the label logits are a second
+  // leaf [rows, classes] with their own optimiser state and best-so-far copy
+  bool joint = false;
+  float *ell = nullptr, *ell_m = nullptr, *ell_v = nullptr, *ell_best = nullptr;
+  long long n_ell = 0;
   // candidate state
   long long nx = 0;
   int xN = 0, xC = 0, xH = 0, xW = 0;
@@ -272,6 +277,7 @@ struct bre_engine {
     return PoolGeom{ti.N, ti.H, ti.W, ti.C, to.H, to.W, op.R, op.stride, op.pad};
   }
   bool need_task_grad() const { return cfg.task_regularization != 0.f; }
+  float value_task_reg() const { return cfg.objective_excludes_task ? 0.f : cfg.task_regularization; }
 
   // ---- sweeps ---------------------------------------------------------------------------------------
   int sweep_forward() {
@@ -687,6 +693,12 @@ struct bre_engine {
         BRE_LAUNCH(launch_orthogonality(x, gradx, xN, (long long)xC * xH * xW, true, sc, dpartials, dcounter, stream));
       return 0;
     }
+    if (xC != 3) {   // TV on non-RGB candidates is rejected at creation (the reference's grouped conv raises as well)
+      BRE_LAUNCH(launch_norm_prior(x, gradx, nx, cfg.norm_scale, cfg.norm_p, 1, sc, dpartials, dcounter, stream));
+      if (cfg.orthogonality != 0)
+        BRE_LAUNCH(launch_orthogonality(x, gradx, xN, (long long)xC * xH * xW, false, sc, dpartials, dcounter, stream));
+      return 0;
+    }
     PriorArgs a;
     a.x = x; a.grad = gradx; a.N = xN; a.H = xH; a.W = xW; a.accumulate = 1;
     a.tv_scale = cfg.tv_scale; a.p = cfg.tv_inner_exp; a.q = cfg.tv_outer_exp; a.eps = cfg.tv_eps;
@@ -719,12 +731,43 @@ struct bre_engine {
     return a;
   }
 
+  int label_gradient_on_device() {   // d(objective)/d(label logits) of the evaluation that just ran -> label_grad
+    const bre_tensor_desc& lt = td(logits);
+    if (seq_len > 0)
+      BRE_LAUNCH(launch_token_label_grad(t[logits].val, p, t[logits].tval, lt.N, lt.C, seq_len, cfg.task_regularization, label_grad, stream));
+    else
+      BRE_LAUNCH(launch_ce_label_grad(t[logits].val, p, t[logits].tval, lt.N, lt.C, cfg.task_regularization, label_grad, stream));
+    BRE_LAUNCH(launch_softmax_chain(soft_q_buf, label_grad, lt.N, lt.C, stream));
+    return 0;
+  }
+
+  // one iteration of the joint attacker: both leaves post-processed separately (:164-186), one optimiser steps both (:108),
+  // box projection on the data only (:111-114), best-so-far of both on the pre-step objective (:115-118)
+  int iteration_joint() {
+    const bre_tensor_desc& lt = td(logits);
+    BRE_LAUNCH(launch_row_softmax(ell, soft_q_buf, lt.N, lt.C, stream));
+    soft_q = soft_q_buf;
+    BRE_TRY(evaluate());
+    BRE_TRY(label_gradient_on_device());
+    StepArgs a = step_args();
+    if (cfg.grad_clip >= 0.f) BRE_LAUNCH(launch_grad_norm(a, sc, dpartials, dcounter, stream));
+    BRE_LAUNCH(launch_pixel_step(a, sc, stream));
+    StepArgs b = a;
+    b.x = ell; b.m = ell_m; b.v = ell_v; b.best = ell_best; b.grad = label_grad; b.grad_task = nullptr;
+    b.n = n_ell; b.C = 1; b.HW = 1; b.cfg.boxed = 0; b.cfg.noise_seed = cfg.noise_seed + 0x9E3779B97F4A7C15ull;
+    if (cfg.grad_clip >= 0.f) BRE_LAUNCH(launch_grad_norm(b, sc, dpartials, dcounter, stream));
+    BRE_LAUNCH(launch_pixel_step(b, sc, stream));
+    BRE_LAUNCH(launch_commit(sc, history, lr_cap, value_task_reg(), stream));
+    return 0;
+  }
+
   int iteration() {
+    if (joint) return iteration_joint();
     BRE_TRY(evaluate());
     StepArgs a = step_args();
     if (cfg.grad_clip >= 0.f) BRE_LAUNCH(launch_grad_norm(a, sc, dpartials, dcounter, stream));
     BRE_LAUNCH(launch_pixel_step(a, sc, stream));
-    BRE_LAUNCH(launch_commit(sc, history, lr_cap, cfg.task_regularization, stream));
+    BRE_LAUNCH(launch_commit(sc, history, lr_cap, value_task_reg(), stream));
     return 0;
   }
 };
@@ -784,6 +827,11 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
     if (op.kind == BRE_OP_LINEAR) e->feat_op = i;
   }
   if (consumers0 != 1) { set_error("the candidate must feed exactly one layer"); return fail(BRE_ERR_UNSUPPORTED); }
+  if (cfg->tv_scale != 0.f && tensors[0].C != 3) {
+    // regularizers.py:109-128 builds a grouped 3x3 convolution for 3 colour channels; on anything else it raises
+    set_error("total_variation needs a 3-channel image candidate");
+    return fail(BRE_ERR_UNSUPPORTED);
+  }
   if (tensors[logits_tensor].H * tensors[logits_tensor].W != 1) { set_error("logits must be [N, classes]"); return fail(BRE_ERR_INVALID); }
 
   // ---- parameter arenas -------------------------------------------------------------------------
@@ -1146,7 +1194,41 @@ int bre_engine_begin_trial(bre_engine* e, const float* candidate, const float* l
   BRE_CUDA_CHECK(cudaMemsetAsync(e->m, 0, e->nx * sizeof(float), e->stream));
   BRE_CUDA_CHECK(cudaMemsetAsync(e->v, 0, e->nx * sizeof(float), e->stream));
   BRE_TRY(reset_trial_state(e));
+  if (e->joint) { e->joint = false; e->graph_ready = false; }
   e->trial_begun = true;
+  return BRE_OK;
+}
+
+int bre_engine_begin_joint_trial(bre_engine* e, const float* candidate, const float* label_logits, int64_t n_label_elems,
+                                 const float* lr_table, int32_t n_lr) {
+  if (!e || !label_logits) { set_error("bre_engine_begin_joint_trial: bad arguments"); return BRE_ERR_INVALID; }
+  const bre_tensor_desc& lt = e->td(e->logits);
+  if (n_label_elems != (int64_t)lt.N * lt.C) { set_error("bre_engine_begin_joint_trial: expected N x classes label logits"); return BRE_ERR_INVALID; }
+  if (e->ms_steps > 0) { set_error("joint optimisation is not supported together with local steps"); return BRE_ERR_UNSUPPORTED; }
+  BRE_TRY(bre_engine_begin_trial(e, candidate, lr_table, n_lr));
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  if (!e->soft_q_buf) { BRE_TRY(e->alloc(&e->soft_q_buf, n_label_elems)); BRE_TRY(e->alloc(&e->label_grad, n_label_elems)); }
+  if (!e->ell) {
+    BRE_TRY(e->alloc(&e->ell, n_label_elems)); BRE_TRY(e->alloc(&e->ell_m, n_label_elems));
+    BRE_TRY(e->alloc(&e->ell_v, n_label_elems)); BRE_TRY(e->alloc(&e->ell_best, n_label_elems));
+    e->n_ell = n_label_elems;
+  }
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->ell, label_logits, n_label_elems * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->ell_best, e->ell, n_label_elems * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+  BRE_CUDA_CHECK(cudaMemsetAsync(e->ell_m, 0, n_label_elems * sizeof(float), e->stream));
+  BRE_CUDA_CHECK(cudaMemsetAsync(e->ell_v, 0, n_label_elems * sizeof(float), e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  e->soft_q = e->soft_q_buf;
+  e->joint = true;
+  e->graph_ready = false;
+  return BRE_OK;
+}
+
+int bre_engine_get_joint_labels(bre_engine* e, int32_t best, float* out) {
+  if (!e || !out || !e->ell) { set_error("bre_engine_get_joint_labels: no joint trial"); return BRE_ERR_STATE; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(out, best ? e->ell_best : e->ell, e->n_ell * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   return BRE_OK;
 }
 
@@ -1273,10 +1355,76 @@ int bre_engine_objective_and_gradient(bre_engine* e, const float* candidate, dou
   BRE_TRY(read_scalars(e, &h));
   if (objective) {
     double phi = h.match + h.tv + h.norm + h.di + h.feat;
-    if (e->cfg.task_regularization != 0.f) phi += (double)e->cfg.task_regularization * h.task_loss;
+    if (e->value_task_reg() != 0.f) phi += (double)e->value_task_reg() * h.task_loss;
     *objective = phi;
   }
   if (grad_out) BRE_TRY(copy_out(e, e->gradx, grad_out));
+  return BRE_OK;
+}
+
+// ---- user-side update production (cases/users.py:148-169) and plain forward (analysis/analysis.py:66-69) ------------------
+int bre_engine_forward(bre_engine* e, const float* data, float* logits_out) {
+  if (!e || !data || !logits_out) { set_error("bre_engine_forward: bad arguments"); return BRE_ERR_INVALID; }
+  if (!e->model_loaded) { set_error("load the model first"); return BRE_ERR_STATE; }
+  if (e->ms_steps > 0) { set_error("bre_engine_forward: not available on a multi-step engine"); return BRE_ERR_UNSUPPORTED; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->x, data, e->nx * sizeof(float), cudaMemcpyDefault, e->stream));
+  float* keep_q = e->soft_q;
+  if (e->seq_len > 0 && e->soft_q == nullptr) {   // the token loss needs targets; forward-only callers have none
+    const bre_tensor_desc& lt = e->td(e->logits);
+    if (!e->soft_q_buf) { BRE_TRY(e->alloc(&e->soft_q_buf, (long long)lt.N * lt.C)); BRE_TRY(e->alloc(&e->label_grad, (long long)lt.N * lt.C)); }
+    e->soft_q = e->soft_q_buf;
+  }
+  const int rc = e->sweep_forward();
+  e->soft_q = keep_q;
+  if (rc != 0) return rc;
+  const bre_tensor_desc& lt = e->td(e->logits);
+  BRE_CUDA_CHECK(cudaMemcpyAsync(logits_out, e->t[e->logits].val, (size_t)lt.N * lt.C * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRE_OK;
+}
+
+int bre_engine_param_gradients(bre_engine* e, const float* data, const int64_t* labels, int32_t n_labels, float* const* grads_out,
+                               int32_t n_params, double* loss_out) {
+  if (!e || !data || !labels || !grads_out) { set_error("bre_engine_param_gradients: bad arguments"); return BRE_ERR_INVALID; }
+  if (!e->model_loaded) { set_error("load the model first"); return BRE_ERR_STATE; }
+  if (e->ms_steps > 0 || e->seq_len > 0) { set_error("bre_engine_param_gradients: single-step vision programs only"); return BRE_ERR_UNSUPPORTED; }
+  if (n_labels != e->n_labels || n_params != (int)e->params.size()) { set_error("bre_engine_param_gradients: label / parameter count mismatch"); return BRE_ERR_INVALID; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->x, data, e->nx * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(e->labels, labels, n_labels * sizeof(int64_t), cudaMemcpyDefault, e->stream));
+  float* keep_q = e->soft_q;
+  e->soft_q = nullptr;                         // index labels (users.py:152)
+  int rc = e->sweep_forward();
+  if (rc == 0) rc = e->sweep_backward();
+  e->soft_q = keep_q;
+  if (rc != 0) return rc;
+  for (int i = 0; i < n_params; ++i) {
+    const ParamInfo& pi = e->params[i];
+    if (!grads_out[i]) { set_error("null output pointer"); return BRE_ERR_INVALID; }
+    const float* src = e->G + pi.off;
+    if (pi.desc.perm != BRE_PERM_NONE) {       // back to torch's OIHW / CHW-column layout
+      BRE_TRY(launch_permute(src, e->stage, pi.desc.d0, pi.desc.d1, pi.desc.d2, true, e->stream));
+      src = e->stage;
+    }
+    BRE_CUDA_CHECK(cudaMemcpyAsync(grads_out[i], src, pi.desc.numel * sizeof(float), cudaMemcpyDefault, e->stream));
+  }
+  Scalars h;
+  BRE_TRY(read_scalars(e, &h));
+  if (loss_out) *loss_out = h.task_loss;
+  return BRE_OK;
+}
+
+int bre_engine_bn_batch_stats(bre_engine* e, int32_t bn_index, float* mean_out, float* var_out) {
+  if (!e || !mean_out || !var_out || bn_index < 0 || bn_index >= (int)e->bn.size()) { set_error("bre_engine_bn_batch_stats: bad arguments"); return BRE_ERR_INVALID; }
+  bool train = false;
+  for (const bre_op_desc& op : e->ops) train = train || (op.kind == BRE_OP_BNACT && op.has_bn && op.bn_buffer == bn_index && op.bn_train);
+  if (!train) { set_error("bre_engine_bn_batch_stats: this layer normalises with running statistics"); return BRE_ERR_STATE; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  const BnBuf& b = e->bn[bn_index];
+  BRE_CUDA_CHECK(cudaMemcpyAsync(mean_out, b.di_mean, b.C * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(var_out, b.di_var, b.C * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   return BRE_OK;
 }
 
@@ -1365,7 +1513,7 @@ int bre_match_reduce(const float* G, const float* g, const float* chunk_weights,
 int bre_total_variation(const float* x, float* grad, int32_t N, int32_t H, int32_t W, float scale, float inner_exp,
                         float outer_exp, float eps, int32_t double_opponents, int32_t accumulate, double* value_host,
                         void* stream) {
-  if (!x || !grad || N <= 0 || H <= 0 || W <= 0) { set_error("bre_total_variation: bad arguments"); return BRE_ERR_INVALID; }
+  if (!x || !grad || N <= 0 || H <= 0 || W <= 0) { set_error("bre_total_variation: bad arguments (x: [N, 3, H, W], three colour channels)"); return BRE_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   Scalars* sc = nullptr; double* partials = nullptr; int* counter = nullptr;
   const long long blocks = (long long)((W + 31) / 32) * ((H + 7) / 8) * N;

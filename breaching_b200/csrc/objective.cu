@@ -308,6 +308,39 @@ __global__ void __launch_bounds__(TV_TW * TV_TH) image_priors_kernel(PriorArgs a
   }
 }
 
+// NormRegularization (regularizers.py:184-200) for candidates that are not 3-channel images (the tiled kernel above is
+// specialised for RGB): value mean(x^p) / p * scale into sc->norm, gradient accumulated into grad; sc->tv = 0.
+__global__ void __launch_bounds__(256) norm_prior_kernel(const float* __restrict__ x, float* __restrict__ grad, long long n, float scale,
+                                                         float p, int accumulate, Scalars* sc, double* partials, int* counter) {
+  pdl_prologue();
+  __shared__ double scratch[32];
+  __shared__ int s_last;
+  const float coef = scale / (float)n;
+  double sum = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    sum += (double)powx(xv, p);
+    const float gk = coef * powx(xv, p - 1.f);
+    grad[i] = accumulate ? grad[i] + gk : gk;
+  }
+  const double bs = block_sum(sum, scratch);
+  if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(counter, 1);
+    s_last = (prev == (int)gridDim.x - 1);
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double t = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += __ldcg(partials + b);
+  t = block_sum(t, scratch);
+  if (threadIdx.x == 0) { sc->norm = (double)scale / (double)p * t / (double)n; sc->tv = 0.0; }
+}
+
 // --------------------------------------------------------------------------------------------------
 // Philox4x32-10 (counter-based RNG for the Langevin noise; same draw in grad-norm and step kernels)
 // --------------------------------------------------------------------------------------------------
@@ -389,7 +422,7 @@ __global__ void __launch_bounds__(256) pixel_step_kernel(StepArgs a, Scalars* sc
       if (nrm > cfg.grad_clip) clip_mul = cfg.grad_clip / (nrm + 1e-6f);
     }
     s_c[5] = clip_mul;
-    const float phi = (float)total_objective(sc, cfg.task_regularization);
+    const float phi = (float)total_objective(sc, cfg.objective_excludes_task ? 0.f : cfg.task_regularization);
     s_c[6] = (phi < (float)sc->fmin) ? 1.f : 0.f;
   }
   __syncthreads();
@@ -424,6 +457,52 @@ __global__ void __launch_bounds__(256) pixel_step_kernel(StepArgs a, Scalars* sc
     a.x[i] = x;
     if (improved) a.best[i] = x;
   }
+}
+
+// ---- label leaf of the joint data + label optimisation (optimization_with_label_attack.py:145-189) ----------------------
+// q = softmax(label logits) per row: what the closure hands to the task loss (:154)
+__global__ void __launch_bounds__(256) row_softmax_kernel(const float* __restrict__ ell, float* __restrict__ q, int C) {
+  pdl_prologue();
+  __shared__ double scratch[32];
+  __shared__ float s_red[32];
+  __shared__ float s_b[2];
+  const float* z = ell + (long long)blockIdx.x * C;
+  float* o = q + (long long)blockIdx.x * C;
+  float mx = -3.402823466e+38f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, z[c]);
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = s_red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_red[w]);
+    s_b[0] = m;
+  }
+  __syncthreads();
+  mx = s_b[0];
+  double part = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) part += (double)expf(z[c] - mx);
+  const double tot = block_sum(part, scratch);
+  if (threadIdx.x == 0) s_b[1] = (float)(1.0 / tot);
+  __syncthreads();
+  const float inv = s_b[1];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = expf(z[c] - mx) * inv;
+}
+
+// chain d(objective)/dq through the softmax onto the label logits (what autograd does at :162): g <- q * (g - <q, g>)
+__global__ void __launch_bounds__(256) softmax_chain_kernel(const float* __restrict__ q, float* __restrict__ g, int C) {
+  pdl_prologue();
+  __shared__ double scratch[32];
+  __shared__ float s_dot;
+  const float* qq = q + (long long)blockIdx.x * C;
+  float* gg = g + (long long)blockIdx.x * C;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) part += (double)qq[c] * (double)gg[c];
+  const double tot = block_sum(part, scratch);
+  if (threadIdx.x == 0) s_dot = (float)tot;
+  __syncthreads();
+  const float dot = s_dot;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) gg[c] = qq[c] * (gg[c] - dot);
 }
 
 __global__ void commit_kernel(Scalars* sc, float* history, int max_hist, float task_reg) {
@@ -583,6 +662,15 @@ int launch_image_priors(const PriorArgs& a, Scalars* sc, double* partials, int* 
   return 0;
 }
 
+int launch_norm_prior(const float* x, float* grad, long long n, float scale, float p, int accumulate, Scalars* sc, double* partials,
+                      int* counter, cudaStream_t s) {
+  long long b = (n + 255) / 256;
+  if (b > kNumSMs * 4) b = kNumSMs * 4;
+  BRE_KLAUNCH(norm_prior_kernel, (int)b, 256, 0, s, x, grad, n, scale, p, accumulate, sc, partials, counter);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
 static inline int step_grid(long long n) {
   long long b = (n + 255) / 256;
   const long long cap = (long long)kNumSMs * 8;
@@ -596,6 +684,16 @@ int launch_grad_norm(const StepArgs& a, Scalars* sc, double* partials, int* coun
 }
 int launch_pixel_step(const StepArgs& a, Scalars* sc, cudaStream_t s) {
   BRE_KLAUNCH(pixel_step_kernel, step_grid(a.n), 256, 0, s, a, sc);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+int launch_row_softmax(const float* ell, float* q, int rows, int C, cudaStream_t s) {
+  BRE_KLAUNCH(row_softmax_kernel, rows, 256, 0, s, ell, q, C);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+int launch_softmax_chain(const float* q, float* g, int rows, int C, cudaStream_t s) {
+  BRE_KLAUNCH(softmax_chain_kernel, rows, 256, 0, s, q, g, C);
   BRE_CHECK_LAUNCH();
   return 0;
 }

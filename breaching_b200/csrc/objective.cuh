@@ -26,6 +26,9 @@ struct PriorArgs {   // TotalVariation (regularizers.py:130-147) + NormRegulariz
   float norm_scale, norm_p;
 };
 int launch_image_priors(const PriorArgs& a, Scalars* sc, double* partials, int* counter, cudaStream_t s);
+// the L^p norm prior alone, for candidates with any channel count (x, grad: n contiguous floats)
+int launch_norm_prior(const float* x, float* grad, long long n, float scale, float p, int accumulate, Scalars* sc, double* partials,
+                      int* counter, cudaStream_t s);
 // OrthogonalityRegularization (regularizers.py:169-178): sum_{i != j} mean_k (x_ik x_jk)^2 over the batch; value added to (or,
 // with overwrite, stored in) the `norm` slot of the scalar block, gradient accumulated into grad.  x, grad: [N, D].
 int launch_orthogonality(const float* x, float* grad, int N, long long D, bool overwrite, Scalars* sc, double* partials, int* counter,
@@ -41,6 +44,9 @@ struct StepArgs {   // closure tail + optimiser + projection + best-so-far (opti
 };
 int launch_grad_norm(const StepArgs& a, Scalars* sc, double* partials, int* counter, cudaStream_t s);
 int launch_pixel_step(const StepArgs& a, Scalars* sc, cudaStream_t s);
+// label leaf of the joint attacks: q = softmax(label logits) per row; g <- q * (g - <q, g>) (chain through that softmax)
+int launch_row_softmax(const float* ell, float* q, int rows, int C, cudaStream_t s);
+int launch_softmax_chain(const float* q, float* g, int rows, int C, cudaStream_t s);
 // history / fmin / iteration counter / non-finite stop flag
 int launch_commit(Scalars* sc, float* history, int max_hist, float task_reg, cudaStream_t s);
 // task_loss = mean(loss_n)

@@ -52,6 +52,7 @@ class AttackCfg(ctypes.Structure):
         ("di_scale", ctypes.c_float), ("di_first_bn_multiplier", ctypes.c_float),
         ("feat_scale", ctypes.c_float),
         ("orthogonality", ctypes.c_int32),
+        ("objective_excludes_task", ctypes.c_int32),
     ]
 
 
@@ -59,6 +60,11 @@ OBJECTIVES = {  # reference objectives.py:496-506
     "euclidean": 0, "cosine-similarity": 1, "l1": 2, "tag-euclidean": 3, "angular": 4,
     "fast-cosine-similarity": 5, "masked-cosine-similarity": 6,
 }
+# Pearlmutter* (objectives.py:279-365, 468-493) approximate d/dx <grad_W L, v> -- v = d(objective)/dG, *without* the scale --
+# by finite differences of grad_x L along W + eps v ("forward" / "backward" / "central"); the engine's tangent sweeps compute
+# that directional derivative exactly, i.e. the eps -> 0 limit of all three, at no extra cost.  (The reference versions are
+# broken under torch >= 2: `candidate.grad +=` on a None gradient)
+PEARLMUTTER = {"pearlmutter-loss": "euclidean", "pearlmutter-cosine": "cosine-similarity"}
 OPTIMIZERS = {  # reference common.py:6-17 -> (kind, beta1, beta2, eps, weight_decay, momentum, nesterov)
     "adam": (0, 0.9, 0.999, 1e-8, 0.0, 0.0, 0),
     "adam-safe": (0, 0.5, 0.99, 1e-4, 0.0, 0.0, 0),
@@ -76,6 +82,8 @@ EXPORTS = [
     "bre_total_variation", "bre_conv_gemm", "bre_last_error", "bre_version",
     "bre_engine_load_soft_labels", "bre_engine_label_gradient", "bre_engine_set_labels",
     "bre_token_layernorm", "bre_token_attention",
+    "bre_engine_param_gradients", "bre_engine_bn_batch_stats", "bre_engine_forward", "bre_image_mse",
+    "bre_engine_begin_joint_trial", "bre_engine_get_joint_labels",
 ]
 
 
@@ -124,6 +132,12 @@ def load_library(path=None):
     lib.bre_conv_gemm.argtypes = [i32, i32, vp, vp, vp, vp, vp] + [i32] * 9 + [vp]
     lib.bre_token_layernorm.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp, vp, vp]
     lib.bre_token_attention.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.bre_engine_begin_joint_trial.argtypes = [vp, vp, vp, i64, vp, i32]
+    lib.bre_engine_get_joint_labels.argtypes = [vp, i32, vp]
+    lib.bre_engine_param_gradients.argtypes = [vp, vp, vp, i32, P(vp), i32, P(ctypes.c_double)]
+    lib.bre_engine_bn_batch_stats.argtypes = [vp, i32, vp, vp]
+    lib.bre_engine_forward.argtypes = [vp, vp, vp]
+    lib.bre_image_mse.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, P(ctypes.c_double), vp]
     for name in EXPORTS:
         if name not in ("bre_last_error", "bre_version", "bre_engine_destroy"):
             getattr(lib, name).restype = ctypes.c_int
@@ -155,9 +169,17 @@ def make_cfg(cfg_attack, noise_seed=0):
     c = AttackCfg()
     obj = cfg_attack["objective"]
     kind = obj["type"]
+    if kind in PEARLMUTTER:
+        impl = cfg_get(obj, "implementation", "forward")
+        if impl not in ("forward", "backward", "central"):
+            # "upwind" mixes one-sided differences by the sign of dL/dx reduced over the batch axis (objectives.py:440-461): it has
+            # no eps -> 0 limit that a directional derivative expresses
+            raise EngineError(f"{kind}: finite-difference implementation '{impl}' is not implemented by the engine")
+        if cfg_get(obj, "level_gradients", False):
+            raise EngineError(f"{kind}: level_gradients is not implemented by the engine")
+        kind = PEARLMUTTER[kind]
+        c.objective_excludes_task = 1
     if kind not in OBJECTIVES:
-        if kind in ("pearlmutter-loss", "pearlmutter-cosine", "dynamic-cosine-similarity"):
-            raise EngineError(f"objective {kind} is not implemented by the engine")
         raise ValueError(f"Unknown objective type {kind} given.")
     c.objective = OBJECTIVES[kind]
     c.obj_scale = float(cfg_get(obj, "scale", 1.0))
@@ -281,8 +303,9 @@ class Engine:
         """``params``: list of tensors in ``model.parameters()`` order (default: the model's own)."""
         params = [_f32c(p) for p in (params if params is not None else self.model.parameters())]
         mods = self._bn_modules
-        means = [_f32c(m.running_mean) for m in mods]
-        vars_ = [_f32c(m.running_var) for m in mods]
+        # train-mode BN (no buffers anywhere, base_attack.py:192-197) has no running statistics: placeholders, never read
+        means = [_f32c(m.running_mean) if m.running_mean is not None else torch.zeros(m.num_features) for m in mods]
+        vars_ = [_f32c(m.running_var) if m.running_var is not None else torch.ones(m.num_features) for m in mods]
         torch.cuda.synchronize(self.device) if any(p.is_cuda for p in params) else None
         pa, ma, va = self._ptr_array(params), self._ptr_array(means), self._ptr_array(vars_)
         rc = self.lib.bre_engine_load_model(self.h, pa, len(params), ma, va, len(mods))
@@ -332,6 +355,22 @@ class Engine:
         if cand.is_cuda:
             torch.cuda.synchronize(self.device)
         _check(self.lib, self.lib.bre_engine_begin_trial(self.h, _ptr(cand), _ptr(lr), lr.numel()), "bre_engine_begin_trial")
+
+    def begin_joint_trial(self, candidate, label_logits, lr_table):
+        """Joint data + label optimisation on the device: ``label_logits`` [N, classes] (token models: [batch, seq, vocab])."""
+        cand, ell = _f32c(candidate, self.device), _f32c(label_logits, self.device)
+        if cand.numel() != self.numel:
+            raise EngineError(f"candidate has {cand.numel()} elements, engine expects {self.numel}")
+        lr = torch.as_tensor(lr_table, dtype=torch.float32).contiguous().cpu()
+        torch.cuda.synchronize(self.device)
+        self._label_shape = tuple(label_logits.shape)
+        _check(self.lib, self.lib.bre_engine_begin_joint_trial(self.h, _ptr(cand), _ptr(ell), ell.numel(), _ptr(lr), lr.numel()),
+               "bre_engine_begin_joint_trial")
+
+    def joint_labels(self, best=True):
+        out = torch.empty(self._label_shape, dtype=torch.float32, device=self.device)
+        _check(self.lib, self.lib.bre_engine_get_joint_labels(self.h, int(bool(best)), _ptr(out)), "bre_engine_get_joint_labels")
+        return out
 
     def run(self, n_iters):
         _check(self.lib, self.lib.bre_engine_run(self.h, int(n_iters)), "bre_engine_run")
@@ -413,6 +452,37 @@ class Engine:
         lab = labels.detach().to(device=self.device, dtype=torch.int64).contiguous()
         _check(self.lib, self.lib.bre_engine_set_labels(self.h, _ptr(lab), lab.numel()), "bre_engine_set_labels")
 
+    # ---- the steps either side of the hot path -----------------------------------------------
+    def param_gradients(self, data, labels):
+        """Gradient of the mean task loss w.r.t. every parameter at ``data`` (cases/users.py:148-156): list of device tensors in
+        ``model.parameters()`` order and torch layout, and the loss value."""
+        x = _f32c(data, self.device)
+        lab = labels.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        outs = [torch.empty(p.shape, dtype=torch.float32, device=self.device) for p in self.prog.params]
+        torch.cuda.synchronize(self.device)
+        loss = ctypes.c_double()
+        _check(self.lib, self.lib.bre_engine_param_gradients(self.h, _ptr(x), _ptr(lab), lab.numel(), self._ptr_array(outs), len(outs),
+                                                             ctypes.byref(loss)), "bre_engine_param_gradients")
+        return outs, loss.value
+
+    def bn_batch_stats(self):
+        """(mean, biased variance) per train-mode BN layer of the last forward."""
+        out = []
+        for j, mod in enumerate(self._bn_modules):
+            m = torch.empty(mod.num_features, dtype=torch.float32, device=self.device)
+            v = torch.empty_like(m)
+            _check(self.lib, self.lib.bre_engine_bn_batch_stats(self.h, j, _ptr(m), _ptr(v)), "bre_engine_bn_batch_stats")
+            out.append((m, v))
+        return out
+
+    def forward(self, data):
+        x = _f32c(data, self.device)
+        lt = self.prog.tensors[self.prog.logits]
+        out = torch.empty((lt.N, lt.C), dtype=torch.float32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        _check(self.lib, self.lib.bre_engine_forward(self.h, _ptr(x), _ptr(out)), "bre_engine_forward")
+        return out
+
     def debug_param(self, which, index):
         p = self.prog.params[index]
         out = torch.empty(p.shape, dtype=torch.float32)
@@ -461,6 +531,24 @@ def total_variation(x, scale=0.1, inner_exp=1.0, outer_exp=1.0, eps=1e-8, double
                                      eps, int(double_opponents), int(accumulate), ctypes.byref(val), ctypes.c_void_p(stream))
     _check(lib, rc, "bre_total_variation")
     return val.value, grad
+
+
+def image_mse(rec, ref, mean=None, std=None, clamp=True):
+    """Per-example MSE of the de-normalised, [0, 1]-clamped batches (analysis/analysis.py:228-242) -> list of floats."""
+    lib = load_library()
+    assert rec.is_cuda and rec.shape == ref.shape and rec.dim() == 4
+    rec, ref = _f32c(rec), _f32c(ref, rec.device)
+    N, C, H, W = rec.shape
+    mean_a = std_a = None
+    if mean is not None:
+        mean_a = (ctypes.c_float * C)(*[float(v) for v in torch.as_tensor(mean).flatten().tolist()])
+        std_a = (ctypes.c_float * C)(*[float(v) for v in torch.as_tensor(std).flatten().tolist()])
+    out = (ctypes.c_double * N)()
+    stream = torch.cuda.current_stream(rec.device).cuda_stream
+    with torch.cuda.device(rec.device):
+        rc = lib.bre_image_mse(_ptr(rec), _ptr(ref), N, C, H * W, mean_a, std_a, int(bool(clamp)), out, ctypes.c_void_p(stream))
+    _check(lib, rc, "bre_image_mse")
+    return list(out)
 
 
 def conv_gemm(mode, a, w, out, N, H, W, Ci, Co, R, S, stride, pad, a2=None, w2=None, backend=0):

@@ -71,6 +71,8 @@ def build_model(name, classes, seed=0):
         model = convnet(width=64, num_classes=classes)
     elif name == "convnet-tiny":
         model = convnet(width=8, num_classes=classes)
+    elif name == "linear":   # cases/models/model_preparation.py:236-238, :311-313 (input_dim from the CIFAR-10 shape)
+        model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 32 * 32, classes))
     elif name in ("resnet18", "resnet34", "resnet50", "resnet101"):
         model = getattr(torchvision.models, name)(weights=None)
         model.fc = torch.nn.Linear(model.fc.in_features, classes)  # cases/models/model_preparation.py:172-177

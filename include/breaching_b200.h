@@ -91,6 +91,8 @@ typedef struct bre_attack_cfg {
   float di_scale, di_first_bn_multiplier;
   float feat_scale;
   int32_t orthogonality;          /* regularizers.py:156-181 (the reference ignores its `scale`; != 0 enables the term) */
+  int32_t objective_excludes_task;/* Pearlmutter* objectives (objectives.py:279-365, 468-493): task_regularization enters the
+                                     candidate gradient (:362) but not the reported objective value */
 } bre_attack_cfg;
 
 /* ---- engine life cycle -------------------------------------------------------------------------- */
@@ -174,6 +176,33 @@ int bre_engine_debug_tensor(bre_engine* e, int32_t which, int32_t tensor, float*
 /* Number of kernel launches per iteration (for gpu_launches in bench.py) and whether graphs are used. */
 int bre_engine_launches_per_iteration(bre_engine* e, int32_t* out);
 int bre_engine_set_option(bre_engine* e, const char* name, int64_t value);
+
+/* Joint data + label optimisation on the device (OptimizationJointAttacker._run_trial, optimization_with_label_attack.py:89-143;
+ * closure :145-189): like bre_engine_begin_trial, plus the label-logit leaf [N, classes] (rows = batch * seq_len for token
+ * models).  Every bre_engine_run iteration then evaluates softmax(labels) as the soft targets of the task loss, the objective,
+ * both gradients (candidate and label logits, post-processed separately), steps both leaves with the configured optimiser,
+ * projects the candidate only, and keeps the best-so-far pair.  Pointers: device or host. */
+int bre_engine_begin_joint_trial(bre_engine* e, const float* candidate, const float* label_logits, int64_t n_label_elems,
+                                 const float* lr_table, int32_t n_lr);
+/* Label logits of the joint trial: best != 0 -> the best-so-far copy, else the current iterate. */
+int bre_engine_get_joint_labels(bre_engine* e, int32_t best, float* out);
+
+/* ---- the steps either side of the hot path ----------------------------------------- */
+/* User-side update production (cases/users.py:148-169 `_compute_batch_gradient`): one forward + backward of the loaded model
+ * on `data` (candidate layout, device or host) with index `labels` -> gradient of the mean task loss w.r.t. every parameter,
+ * written to grads_out[i] (model.parameters() order, torch layout, device or host); loss_out (host, may be NULL) = task loss. */
+int bre_engine_param_gradients(bre_engine* e, const float* data, const int64_t* labels, int32_t n_labels,
+                               float* const* grads_out, int32_t n_params, double* loss_out);
+/* Train-mode BN (user without public buffers, users.py:140-143): batch mean and *biased* variance that layer `bn_index` saw in
+ * the last forward, from which the user's shipped buffers follow (momentum None: running_mean = mean, running_var = unbiased). */
+int bre_engine_bn_batch_stats(bre_engine* e, int32_t bn_index, float* mean_out, float* var_out);
+/* Model forward only (analysis/analysis.py:66-69 feature comparison): logits [N, classes] (device or host). */
+int bre_engine_forward(bre_engine* e, const float* data, float* logits_out);
+/* Per-example mean squared error between the de-normalised ([x * std + mean], per channel; NULL = identity), optionally
+ * [0,1]-clamped reconstruction and ground truth (analysis/analysis.py:228-242); PSNR per example = 10 log10(1 / mse)
+ * (analysis/metrics.py:108-130) follows on the host.  rec, ref: device fp32 [N, C, HW]; mean / std: host [C]; mse: host [N]. */
+int bre_image_mse(const float* rec, const float* ref, int32_t N, int32_t C, int32_t HW, const float* mean, const float* std,
+                  int32_t clamp01, double* mse_host, void* stream);
 
 /* ---- stand-alone kernels (each is also a stage of the engine; exposed for parity tests + rooflines) */
 /* Multi-tensor gradient-matching reduction (objectives.py:91-95,135-141,160-164,185-196).

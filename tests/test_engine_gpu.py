@@ -488,3 +488,58 @@ def test_train_mode_batchnorm_matches_reference_fixture(name, backend):
             assert math.isclose(a, b, rel_tol=tol, abs_tol=1e-5), (engine.history().tolist(), fx["history"])
         # (soft sign early in the schedule ~ sign: a flipped near-zero gradient entry moves that pixel by 2 x 0.1 per step)
         assert (engine.candidate().cpu() - fx["candidate_final"]).abs().mean().item() < (5e-3 if "convnet" in name else 8e-2)
+
+
+@pytest.mark.parametrize("backend", ["simt", "tc"])
+def test_linear_model_on_the_candidate_and_generic_norm_prior(backend):
+    """The reference's `linear` model (Flatten -> Linear fed by the image, model_preparation.py:236-238): the candidate is NCHW in
+    the engine and the weight keeps torch's column order (ADVICE round 1: was permuted to HWC -> silently wrong gradients);
+    closure against the CPU oracle, plus the norm prior (the only image prior of the reference that takes any channel count)."""
+    from oracle import restate
+
+    model, loss_fn, payload, shared, true = synthetic.make_case("linear", "cifar", batch=2, seed=31)
+    cfg = get_attack_config("invertinggradients", {"regularization.total_variation.scale": 0.0, "regularization.norm.scale": 1e-2,
+                                                    "objective.type": "euclidean"})
+    meta = payload[0]["metadata"]
+    dm, ds = torch.tensor(meta.mean)[None, :, None, None], torch.tensor(meta.std)[None, :, None, None]
+    orc = restate.TrialOracle(model.eval(), loss_fn, cfg, shared[0]["gradients"], true["labels"], dm, ds)
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(4))
+    phi, _, raw, terms = orc.closure_gradient(x, 0, 0.1)
+    eng = _engine_for(model, cfg, shared, true["labels"], meta, (2, 3, 32, 32), backend=backend)
+    val, grad = eng.objective_and_gradient(x.to(DEV))
+    assert math.isclose(val, float(phi), rel_tol=2e-4, abs_tol=1e-7), (val, float(phi), terms, eng.last_terms())
+    assert _relerr(grad, raw) < 2e-3, _relerr(grad, raw)
+    eng.close()
+
+
+def test_total_variation_on_a_non_rgb_candidate_is_refused():
+    """regularizers.py:109-128 builds a 3-colour-channel grouped convolution; other candidates raise there and here (no
+    out-of-bounds reads)."""
+    from breaching_b200.engine import EngineError
+
+    class Gray(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.Sequential(torch.nn.Conv2d(1, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Flatten(), torch.nn.Linear(8 * 28 * 28, 10))
+
+        def forward(self, x):
+            return self.model(x)
+
+    m = Gray().to(DEV).eval()
+    with pytest.raises(EngineError):
+        Engine(m, (1, 1, 28, 28), get_attack_config("invertinggradients"), DEV)
+    cfg = get_attack_config("invertinggradients", {"regularization.total_variation.scale": 0.0, "regularization.norm.scale": 0.1})
+    eng = Engine(m, (1, 1, 28, 28), cfg, DEV, backend="simt")   # the norm prior works on one channel
+    eng.load_model()
+    x = torch.randn(1, 1, 28, 28, generator=torch.Generator().manual_seed(1))
+    y = torch.tensor([3])
+    mc = copy.deepcopy(m).cpu()
+    g = torch.autograd.grad(torch.nn.functional.cross_entropy(mc(x), y), list(mc.parameters()))
+    eng.load_targets([t.to(DEV) for t in g], y.to(DEV))
+    x2 = torch.randn(1, 1, 28, 28, generator=torch.Generator().manual_seed(2))
+    val, grad = eng.objective_and_gradient(x2.to(DEV))
+    t = eng.last_terms()
+    want = 0.1 * x2.pow(2).mean().item() / 2.0                                  # regularizers.py:197-198
+    assert math.isclose(t["norm"], want, rel_tol=1e-5), (t, want)
+    assert torch.isfinite(grad).all()
+    eng.close()

@@ -45,6 +45,50 @@ def test_compile_rejects_unsupported_graphs():
     assert not any(op.bn_train for op in compiler.compile_model(train_bn.eval(), (2, 3, 32, 32)).ops)
 
 
+def test_linear_model_on_the_candidate_keeps_torch_column_order():
+    """The reference's `linear` model (Flatten -> Linear on the image itself): the candidate stays NCHW in the engine, so the
+    weight must NOT be permuted to HWC columns; a Linear behind a feature map is."""
+    lin = synthetic.build_model("linear", 10)
+    prog = compiler.compile_model(lin, (2, 3, 32, 32))
+    assert [op.kind for op in prog.ops] == [compiler.OP_LINEAR] and prog.ops[0].tin == 0
+    assert prog.params[prog.ops[0].w].perm == compiler.PERM_NONE
+    conv = synthetic.build_model("convnet-tiny", 10)
+    prog2 = compiler.compile_model(conv, (2, 3, 32, 32))
+    head = [op for op in prog2.ops if op.kind == compiler.OP_LINEAR][-1]
+    assert prog2.params[head.w].perm == compiler.PERM_LINEAR_CHW_TO_HWC
+
+
+def test_reshapes_other_than_flatten_are_rejected_and_eval_dropout_is_identity():
+    class ViewNet(torch.nn.Module):
+        def __init__(self, how):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 4, 3, padding=1)
+            self.drop = torch.nn.Dropout(0.5)
+            self.fc = torch.nn.Linear(4 * 8 * 8, 5)
+            self.how = how
+
+        def forward(self, x):
+            h = self.drop(self.conv(x))
+            if self.how == "view":
+                h = h.view(h.size(0), -1)
+            elif self.how == "bad-view":
+                h = h.view(-1, 4 * 8 * 8 // 2).view(-1, 4 * 8 * 8)
+            elif self.how == "flatten0":
+                h = torch.flatten(h, 0).view(2, -1)
+            else:
+                h = h.flatten(1)
+            return self.fc(h)
+
+    for how in ("view", "flatten"):
+        prog = compiler.compile_model(ViewNet(how).eval(), (2, 3, 8, 8))   # Dropout(0.5) in eval mode is the identity
+        assert [op.kind for op in prog.ops] == [compiler.OP_CONV, compiler.OP_LINEAR]
+    with pytest.raises(compiler.UnsupportedModelError):
+        compiler.compile_model(ViewNet("view").train(), (2, 3, 8, 8))      # ... in train mode it is not
+    for how in ("bad-view", "flatten0"):
+        with pytest.raises(compiler.UnsupportedModelError):
+            compiler.compile_model(ViewNet(how).eval(), (2, 3, 8, 8))
+
+
 def test_reference_style_container_and_scripted_loss_are_accepted():
     class VisionContainer(torch.nn.Module):  # same shape as cases/models/model_preparation.py:152-160
         def __init__(self, model):

@@ -124,8 +124,6 @@ def test_transformer_closure_on_the_engine_matches_reference_tag_fixture(backend
     eng.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BRE_TEXT_ENGINE") != "1",
-                    reason="attacker-level text glue: written after the round's GPU budget was spent, opt-in until verified on a GPU")
 def test_tag_attack_through_the_attacker_api():
     """tag.yaml end to end (prologue in embedding space, joint loop with AdamW / clip / warm-up, scoring, token recovery)
     against the reference trajectory of the miniature config-5 fixture."""
@@ -153,8 +151,6 @@ def test_tag_attack_through_the_attacker_api():
     assert rec["data"].shape == true["data"].shape and rec["data"].dtype == torch.long and "raw_embeddings" in rec
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BRE_TEST_CONFIG5") != "1",
-                    reason="full-size config-5 closure on the engine: fixture and test written after the round's GPU budget was spent")
 @pytest.mark.parametrize("backend", ["simt", "tc"])
 def test_full_size_config5_closure_on_the_engine(backend):
     """BASELINE config 5 at full size (50 257 tokens, 96 dims, 8 heads, 3 layers, 32 positions) on the CUDA engine against the
