@@ -141,7 +141,10 @@ def candidate_shape(config, payload, shared):
     return (n, *meta.shape)
 
 
-def gemm_ops(prog):
+def gemm_ops(prog, backend="simt"):
+    """Conv / linear layers of the program as GEMM geometries.  On the tensor-core back end the candidate-fed convolution runs as
+    a 1x1 convolution over the unfolded candidate (csrc/stem_cols.cu: K = R*S*Ci padded to a multiple of 64); its *algorithmic*
+    MACs stay those of the original layer."""
     from breaching_b200 import compiler as C
 
     out = []
@@ -155,6 +158,8 @@ def gemm_ops(prog):
             g = (ti.N, ti.H, ti.W, ti.C, to.C, op.R, op.stride, op.pad)
         Ho, Wo = (to.H, to.W) if op.kind == C.OP_CONV else (1, 1)
         macs = g[0] * Ho * Wo * g[4] * g[5] * g[5] * g[3]
+        if backend == "tc" and op.kind == C.OP_CONV and op.tin == 0 and ti.C <= 4 and to.C % 64 == 0 and os.environ.get("BRE_STEM_COLS", "1") != "0":
+            g = (ti.N, Ho, Wo, ((op.R * op.R * ti.C + 63) // 64) * 64, to.C, 1, 1, 0)
         out.append(dict(first=op.tin == 0, geom=g, Ho=Ho, Wo=Wo, macs=macs))
     return out
 
@@ -184,7 +189,7 @@ def gemm_family_roofline(dev, prog, backend, local_steps=0):
 
     be = 2 if backend == "tc" else 0
     launches, flops, keep = [], 0.0, []
-    for o in gemm_ops(prog):
+    for o in gemm_ops(prog, backend):
         N, H, W, Ci, Co, R, st, pd = o["geom"]
         Ho, Wo = o["Ho"], o["Wo"]
         x, x2 = (torch.randn(N, H, W, Ci, device=dev) for _ in range(2))

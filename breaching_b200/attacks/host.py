@@ -69,112 +69,134 @@ def normalize_gradients(shared_data, fudge_factor=1e-6):
     return shared_data
 
 
-def recover_labels(strategy, user_data, setup, data_shape=None):
-    """base_attack.py:305-475 for the strategies that need no model queries.  Integer logic: bit-exact."""
-    num_data_points = user_data[0]["metadata"]["num_data_points"]
-    num_classes = user_data[0]["gradients"][-1].shape[0]
-    num_queries = len(user_data)
-    device = setup["device"]
+# ---- label recovery (base_attack.py:305-475) ----------------------------------------------------------------------------
+# One small function per strategy; every one maps the last-layer gradients of all queries to a (possibly short) label vector.
+# Integer logic on the reference's own arithmetic (same reductions in the same order): results are bit-exact
+# (tests/golden/labels.pt, 25 synthetic cases x 5 strategies).
+def _head_weight_grads(user_data):
+    return [d["gradients"][-2] for d in user_data]
 
+
+def _labels_idlg(user_data, n, classes, device):          # :319-327 -- most negative row sum of the head weight gradient
+    per_query = [g.sum(dim=-1).argmin(dim=-1).detach() for g in _head_weight_grads(user_data)]
+    return torch.stack(per_query).unique()
+
+
+def _labels_analytic(user_data, n, classes, device):      # :328-335 -- classes whose bias gradient is negative
+    per_query = [(d["gradients"][-1] < 0).nonzero() for d in user_data]
+    return torch.stack(per_query).unique()[:n]
+
+
+def _labels_yin(user_data, n, classes, device):           # :336-345 -- smallest row minima, summed over the queries
+    score = 0
+    for g in _head_weight_grads(user_data):
+        score = score + g.min(dim=-1)[0]
+    return score.argsort()[:n]
+
+
+def _labels_wainakh_simple(user_data, n, classes, device):   # :346-407
+    queries = len(user_data)
+    impact = 0
+    for g in _head_weight_grads(user_data):
+        row_sums = g.sum(dim=1)
+        negative_mass = torch.where(row_sums < 0, row_sums, torch.zeros_like(row_sums)).sum()
+        impact = impact + negative_mass * (1 + 1 / classes) / n / queries
+    residual = torch.stack([g.sum(dim=1) for g in _head_weight_grads(user_data)]).mean(dim=0)
+    found = []
+    cursor = 0
+    for cursor in range(classes):                          # stage 1: every class with negative mass, once
+        if residual[cursor] < 0:
+            found.append(torch.as_tensor(cursor, device=device))
+            residual[cursor] -= impact
+    while len(found) < n:                                  # stage 2: the reference keeps decrementing the *last stage-1 cursor*
+        found.append(torch.as_tensor(residual.argmin(), device=device))   # (:405, reproduced), so argmin never moves
+        residual[cursor] -= impact
+    return torch.stack(found)
+
+
+def _labels_bias_corrected(user_data, n, classes, device):   # :409-425
+    residual = torch.stack([d["gradients"][-1] for d in user_data]).mean(dim=0)
+    negative = (residual < 0).nonzero()                     # [k, 1], ascending class order
+    found = list(negative.squeeze(dim=-1))                  # stage 1: one label per class with a negative mean bias gradient
+    impact = residual[negative].sum() / n
+    residual[negative] = residual[negative] - impact
+    for _ in range(max(n - len(found), 0)):                 # stage 2: repeated classes, most negative residual first
+        pick = residual.argmin()
+        found.append(pick)
+        residual[pick] -= impact
+    return torch.stack(found)
+
+
+def _labels_random(user_data, n, classes, device):        # :459-461
+    return torch.randint(0, classes, (n,), device=device)
+
+
+_LABEL_STRATEGIES = {
+    "iDLG": _labels_idlg, "analytic": _labels_analytic, "yin": _labels_yin, "wainakh-simple": _labels_wainakh_simple,
+    "bias-corrected": _labels_bias_corrected, "random": _labels_random,
+}
+
+
+def recover_labels(strategy, user_data, setup, data_shape=None):
+    """base_attack.py:305-475 for the strategies that need no model queries."""
     if strategy is None:
         return None
-    if strategy == "iDLG":
-        label_list = [torch.argmin(torch.sum(d["gradients"][-2], dim=-1), dim=-1).detach() for d in user_data]
-        labels = torch.stack(label_list).unique()
-    elif strategy == "analytic":
-        label_list = [(d["gradients"][-1] < 0).nonzero() for d in user_data]
-        labels = torch.stack(label_list).unique()[:num_data_points]
-    elif strategy == "yin":
-        total_min_vals = 0
-        for d in user_data:
-            total_min_vals += d["gradients"][-2].min(dim=-1)[0]
-        labels = total_min_vals.argsort()[:num_data_points]
-    elif strategy == "wainakh-simple":
-        m_impact = 0
-        for d in user_data:
-            g_i = d["gradients"][-2].sum(dim=1)
-            m_query = torch.where(g_i < 0, g_i, torch.zeros_like(g_i)).sum() * (1 + 1 / num_classes) / num_data_points
-            m_impact += m_query / num_queries
-        label_list = []
-        g_i = torch.stack([d["gradients"][-2].sum(dim=1) for d in user_data]).mean(dim=0)
-        idx = 0
-        for idx in range(num_classes):  # stage 1
-            if g_i[idx] < 0:
-                label_list.append(torch.as_tensor(idx, device=device))
-                g_i[idx] -= m_impact
-        while len(label_list) < num_data_points:  # stage 2 (decrements g_i[idx] like the reference, :405)
-            selected_idx = g_i.argmin()
-            label_list.append(torch.as_tensor(selected_idx, device=device))
-            g_i[idx] -= m_impact
-        labels = torch.stack(label_list)
-    elif strategy == "wainakh-whitebox":
+    n = user_data[0]["metadata"]["num_data_points"]
+    classes = user_data[0]["gradients"][-1].shape[0]
+    device = setup["device"]
+    if strategy == "wainakh-whitebox":
         raise NotImplementedError("label_strategy=wainakh-whitebox (model queries per class) is not implemented")
-    elif strategy == "bias-corrected":
-        bias_per_query = [d["gradients"][-1] for d in user_data]
-        label_list = []
-        average_bias = torch.stack(bias_per_query).mean(dim=0)
-        valid_classes = (average_bias < 0).nonzero()
-        label_list += [*valid_classes.squeeze(dim=-1)]
-        m_impact = average_bias[valid_classes].sum() / num_data_points
-        average_bias[valid_classes] = average_bias[valid_classes] - m_impact
-        while len(label_list) < num_data_points:
-            selected_idx = average_bias.argmin()
-            label_list.append(selected_idx)
-            average_bias[selected_idx] -= m_impact
-        labels = torch.stack(label_list)
-    elif strategy == "random":
-        labels = torch.randint(0, num_classes, (num_data_points,), device=device)
-    elif strategy == "exhaustive":
-        raise ValueError(
-            f"Exhaustive label searching not implemented. A naive strategy would attack "
-            f"{num_classes ** num_data_points} label vectors."
-        )
-    else:
+    if strategy == "exhaustive":
+        raise ValueError(f"Exhaustive label searching not implemented. A naive strategy would attack {classes ** n} label vectors.")
+    if strategy not in _LABEL_STRATEGIES:
         raise ValueError(f"Invalid label recovery strategy {strategy} given.")
-
-    if len(labels) < num_data_points:
-        labels = torch.cat([labels, torch.randint(0, num_classes, (num_data_points - len(labels),), device=device)])
-    labels = labels.sort()[0]
+    labels = _LABEL_STRATEGIES[strategy](user_data, n, classes, device)
+    if len(labels) < n:                                     # :468-471: fill up with random classes
+        labels = torch.cat([labels, torch.randint(0, classes, (n - len(labels),), device=device)])
+    labels = labels.sort()[0]                               # :473
     log.info(f"Recovered labels {labels.tolist()} through strategy {strategy}.")
     return labels
 
 
-def initialize_data(init_type, data_shape, dm, ds, setup):
-    """base_attack.py:222-285: candidate initialisation, drawn from torch's global generator on ``setup['device']``
-    so that the draw order matches the reference trial by trial."""
-    if init_type == "randn":
-        candidate = torch.randn(data_shape, **setup)
-    elif init_type == "randn-trunc":
-        candidate = (torch.randn(data_shape, **setup) * 0.1).clamp(-0.1, 0.1)
-    elif init_type == "rand":
-        candidate = (torch.rand(data_shape, **setup) * 2) - 1.0
-    elif init_type == "zeros":
-        candidate = torch.zeros(data_shape, **setup)
-    elif any(c in init_type for c in ["red", "green", "blue", "dark", "light"]):
-        candidate = torch.zeros(data_shape, **setup)
-        if "light" in init_type:
-            candidate = torch.ones(data_shape, **setup)
-        else:
-            nonzero_channel = 0 if "red" in init_type else 1 if "green" in init_type else 2
-            candidate[:, nonzero_channel, :, :] = 1
-        if "-true" in init_type:
-            candidate = (candidate - dm) / ds
-    elif "patterned" in init_type or "wei" in init_type:
-        pattern_width = int("".join(filter(str.isdigit, init_type)))
-        if "patterned" in init_type:
-            uniform = ("rand" in init_type) and ("randn" not in init_type)
-        else:
-            uniform = "rand" in init_type
-        if uniform:
-            seed = (torch.rand([data_shape[0], 3, pattern_width, pattern_width], **setup) * 2) - 1
-        else:
-            seed = torch.randn([data_shape[0], 3, pattern_width, pattern_width], **setup)
-        x_factor = int(math.ceil(data_shape[2] / pattern_width))
-        y_factor = int(math.ceil(data_shape[3] / pattern_width))
-        candidate = torch.tile(seed, (1, 1, x_factor, y_factor))[:, :, : data_shape[2], : data_shape[3]].contiguous().clone()
+# ---- candidate initialisation (base_attack.py:222-285) --------------------------------------------------------------------
+# Draws come from torch's global generator on ``setup['device']`` in the reference's order, so trial k of a restarted attack
+# starts from the reference's trial-k candidate.
+_PLAIN_INITS = {
+    "randn": lambda shape, setup: torch.randn(shape, **setup),
+    "randn-trunc": lambda shape, setup: (torch.randn(shape, **setup) * 0.1).clamp(-0.1, 0.1),
+    "rand": lambda shape, setup: (torch.rand(shape, **setup) * 2) - 1.0,
+    "zeros": lambda shape, setup: torch.zeros(shape, **setup),
+}
+_COLOUR_WORDS = ("red", "green", "blue", "dark", "light")
+
+
+def _colour_init(init_type, shape, dm, ds, setup):          # :236-246
+    if "light" in init_type:
+        candidate = torch.ones(shape, **setup)
     else:
-        raise ValueError(f"Unknown initialization scheme {init_type} given.")
-    return candidate
+        candidate = torch.zeros(shape, **setup)
+        channel = 0 if "red" in init_type else (1 if "green" in init_type else 2)   # "dark" falls through to blue like the reference
+        candidate[:, channel, :, :] = 1
+    return (candidate - dm) / ds if "-true" in init_type else candidate
+
+
+def _pattern_init(init_type, shape, setup):                 # :247-281: one random k x k tile repeated over the image
+    width = int("".join(ch for ch in init_type if ch.isdigit()))
+    wants_uniform = "rand" in init_type and ("randn" not in init_type if "patterned" in init_type else True)
+    tile_shape = [shape[0], 3, width, width]
+    tile = (torch.rand(tile_shape, **setup) * 2) - 1 if wants_uniform else torch.randn(tile_shape, **setup)
+    reps = (1, 1, int(math.ceil(shape[2] / width)), int(math.ceil(shape[3] / width)))
+    return torch.tile(tile, reps)[:, :, : shape[2], : shape[3]].contiguous().clone()
+
+
+def initialize_data(init_type, data_shape, dm, ds, setup):
+    if init_type in _PLAIN_INITS:
+        return _PLAIN_INITS[init_type](data_shape, setup)
+    if any(word in init_type for word in _COLOUR_WORDS):
+        return _colour_init(init_type, data_shape, dm, ds, setup)
+    if "patterned" in init_type or "wei" in init_type:
+        return _pattern_init(init_type, data_shape, setup)
+    raise ValueError(f"Unknown initialization scheme {init_type} given.")
 
 
 def measured_features(shared_data, labels):

@@ -164,6 +164,35 @@ struct bre_engine {
   std::vector<BnPrep*> ms_bnprep_dev;  // per step (k >= 1): device table for the batched BN-constant refresh
   int n_bn_layers = 0;
   bool want_tangent_G = false;
+  // column path of the candidate-fed convolution on the tensor-core back end (stem_cols.cu)
+  int stem_op = -1, stem_Kp = 0;
+  float *xcol = nullptr, *dcol = nullptr, *Wcol = nullptr, *Vcol = nullptr, *Gcol = nullptr;
+  bool stem_cols_env = [] { const char* e = getenv("BRE_STEM_COLS"); return e ? atoi(e) != 0 : true; }();
+  bool use_stem_cols(size_t i) const { return gemm_backend == 1 && stem_cols_env && (int)i == stem_op; }
+  GemmArgs stem_geom(const bre_op_desc& op) const {   // the layer as a 1x1 convolution over xcol [N, Ho, Wo, Kp]
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    const bre_tensor_desc& to = td(op.tout);
+    a.g = ConvGeom{to.N, to.H, to.W, stem_Kp, to.H, to.W, to.C, 1, 1, 1, 0};
+    a.x_sN = (long long)to.H * to.W * stem_Kp; a.x_sP = stem_Kp; a.x_sC = 1;
+    a.nsrc = 1;
+    a.ws = ws; a.counters = gemm_counters; a.ws_tiles = ws_tiles; a.splits = 0;
+    return a;
+  }
+  int stem_unfold(const bre_op_desc& op) {            // candidate -> xcol
+    const bre_tensor_desc &ti = td(op.tin), &to = td(op.tout);
+    BRE_LAUNCH(launch_stem_im2col(t[0].val, xcol, ti.N, ti.C, ti.H, ti.W, to.H, to.W, op.R, op.S, op.stride, op.pad, stem_Kp, tc_round(), stream));
+    return 0;
+  }
+  int stem_pad(const float* src, float* dst, const bre_op_desc& op, cudaStream_t st) {
+    BRE_LAUNCH(launch_stem_pad_rows(src, dst, td(op.tout).C, op.R * op.S * td(op.tin).C, stem_Kp, false, tc_round(), st));
+    return 0;
+  }
+  int stem_fold(const bre_op_desc& op, float* grad_out) {   // dcol -> NCHW candidate gradient
+    const bre_tensor_desc &ti = td(op.tin), &to = td(op.tout);
+    BRE_LAUNCH(launch_stem_col2im(dcol, grad_out, ti.N, ti.C, ti.H, ti.W, to.H, to.W, op.R, op.S, op.stride, op.pad, stem_Kp, stream));
+    return 0;
+  }
   // execution
   bool use_graph = true;
   int gemm_backend = 0;  // 0 = SIMT fp32, 1 = tcgen05 TF32 where supported
@@ -192,6 +221,29 @@ struct bre_engine {
     if (tc_round()) BRE_LAUNCH(launch_round_tf32(V, Vt, P_pad, stream));
     return 0;
   }
+  // per-chunk routing of the direction write (launch_make_v): 1 = TF32 shadow only for the weights of tensor-core layers (the
+  // GEMMs read Vt, nothing reads their fp32 direction in single-step mode), 0 = fp32 only for everything else (BN / bias
+  // vectors, layers on the fp32 kernels, the stem weight that stem_pad rounds itself)
+  unsigned char* chunk_mode = nullptr;
+  bool chunk_mode_ready = false;
+  int build_chunk_modes() {
+    if (chunk_mode_ready || !tc_round()) return 0;
+    std::vector<unsigned char> host((size_t)(P_pad / kChunk), 0);
+    for (const bre_op_desc& op : ops) {
+      if ((op.kind != BRE_OP_CONV && op.kind != BRE_OP_LINEAR) || !round_val(op.tin)) continue;
+      const long long c0 = params[op.w].off / kChunk, c1 = c0 + (params[op.w].desc.numel + kChunk - 1) / kChunk;
+      for (long long c = c0; c < c1; ++c) host[(size_t)c] = 1;
+    }
+    if (!chunk_mode) BRE_TRY(alloc(&chunk_mode, P_pad / kChunk));
+    // (host vector -> pageable copy: performed before the copy call returns; no kernel of the captured iteration depends on
+    // stream order here because the first launch that reads it follows in the same stream)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone) { set_error("chunk modes must be built before graph capture"); return BRE_ERR_STATE; }
+    BRE_CUDA_CHECK(cudaMemcpy(chunk_mode, host.data(), host.size(), cudaMemcpyHostToDevice));
+    chunk_mode_ready = true;
+    return 0;
+  }
   // Which activation tensors are operands of a tensor-core GEMM: inputs (value / tangent) and output deltas of the
   // convolutions the tcgen05 back end covers.  Only those are stored TF32-rounded; layers that run on the fp32 SIMT kernels
   // (3-channel stem, narrow test networks, the classifier head) keep full fp32 operands.
@@ -207,6 +259,7 @@ struct bre_engine {
       for (int mode = 0; mode < 3; ++mode) { a.mode = mode; any = any || igemm_tc_supported(a); }
       if (any) { rnd_val[op.tin] = 1; rnd_d[op.tout] = 1; }
     }
+    if (stem_op >= 0 && stem_cols_env) rnd_d[ops[stem_op].tout] = 1;   // deltas of the stem output feed its column GEMMs
   }
   bool round_val(int tensor) { if (rnd_val.size() != t.size()) compute_round_flags(); return tc_round() && rnd_val[tensor]; }
   bool round_d(int tensor) { if (rnd_d.size() != t.size()) compute_round_flags(); return tc_round() && rnd_d[tensor]; }
@@ -291,6 +344,13 @@ struct bre_engine {
           GemmArgs a = conv_geom(op);
           a.mode = GEMM_FPROP;
           a.act[0] = t[op.tin].val; a.wgt[0] = Wg(op);
+          if (use_stem_cols(i)) {
+            BRE_TRY(stem_unfold(op));
+            if (ms_steps > 0) BRE_TRY(stem_pad(Wp(op.w), Wcol, op, stream));   // W_k changes per local step
+            a = stem_geom(op);
+            a.mode = GEMM_FPROP;
+            a.act[0] = xcol; a.wgt[0] = Wcol;
+          }
           a.bias = op.b >= 0 ? Wp(op.b) : nullptr;
           a.out = t[op.tout].val;
           if (fuses_with_next(i, a)) {
@@ -357,27 +417,32 @@ struct bre_engine {
       switch (op.kind) {
         case BRE_OP_CONV:
         case BRE_OP_LINEAR: {
-          GemmArgs a = conv_geom(op);
+          const bool cols = use_stem_cols((size_t)i);
+          GemmArgs a = cols ? stem_geom(op) : conv_geom(op);
           a.mode = GEMM_WGRAD;
-          a.act[0] = t[op.tin].val; a.wgt[0] = t[op.tout].d; a.out = Gp(op.w);
+          a.act[0] = cols ? xcol : t[op.tin].val; a.wgt[0] = t[op.tout].d; a.out = cols ? Gcol : Gp(op.w);
+          const int Kraw = op.R * op.S * td(op.tin).C;
           if (overlap_wgrad && side != nullptr) {
             BRE_CUDA_CHECK(cudaEventRecord(ev_fork[i], stream));
             BRE_CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork[i], 0));
             a.ws = ws2; a.counters = gemm_counters2;
             BRE_LAUNCH(gemm_on(a, side));
+            if (cols) BRE_LAUNCH(launch_stem_pad_rows(Gcol, Gp(op.w), to.C, Kraw, stem_Kp, true, false, side));
             if (op.b >= 0) BRE_LAUNCH(launch_channel_sum(t[op.tout].d, Pout, to.C, Gp(op.b), red_partials2, red_counters2, side));
             forked = true;
           } else {
             BRE_LAUNCH(gemm(a));
+            if (cols) BRE_LAUNCH(launch_stem_pad_rows(Gcol, Gp(op.w), to.C, Kraw, stem_Kp, true, false, stream));
             if (op.b >= 0) BRE_LAUNCH(launch_channel_sum(t[op.tout].d, Pout, to.C, Gp(op.b), red_partials, red_counters, stream));
           }
           if (op.tin != 0 || need_task_grad()) {
-            GemmArgs b = conv_geom(op);
+            GemmArgs b = cols ? stem_geom(op) : conv_geom(op);
             b.mode = GEMM_DGRAD;
-            b.act[0] = t[op.tout].d; b.wgt[0] = Wg(op);
-            b.out = op.tin == 0 ? gradx_task : t[op.tin].d;
+            b.act[0] = t[op.tout].d; b.wgt[0] = cols ? Wcol : Wg(op);
+            b.out = cols ? dcol : (op.tin == 0 ? gradx_task : t[op.tin].d);
             b.accumulate = op.tin == 0 ? 0 : op.acc_in;
             BRE_LAUNCH(gemm(b));
+            if (cols) BRE_TRY(stem_fold(op, gradx_task));
           }
           break;
         }
@@ -451,7 +516,13 @@ struct bre_engine {
         case BRE_OP_LINEAR: {
           GemmArgs a = conv_geom(op);
           a.mode = GEMM_FPROP;
-          if (op.tin == 0) {  // tangent of the candidate is zero: only the v-term
+          if (use_stem_cols(i)) {
+            if (ms_steps > 0) { BRE_TRY(stem_unfold(op)); BRE_TRY(stem_pad(Wp(op.w), Wcol, op, stream)); }   // this step's slice / weights
+            BRE_TRY(stem_pad(Vp(op.w), Vcol, op, stream));
+            a = stem_geom(op);
+            a.mode = GEMM_FPROP;
+            a.act[0] = xcol; a.wgt[0] = Vcol;
+          } else if (op.tin == 0) {  // tangent of the candidate is zero: only the v-term
             a.act[0] = t[op.tin].val; a.wgt[0] = Vg(op);
           } else {
             a.nsrc = 2;
@@ -545,21 +616,23 @@ struct bre_engine {
       switch (op.kind) {
         case BRE_OP_CONV:
         case BRE_OP_LINEAR: {
-          GemmArgs a = conv_geom(op);
+          const bool cols = use_stem_cols((size_t)i);
+          GemmArgs a = cols ? stem_geom(op) : conv_geom(op);
           a.mode = GEMM_DGRAD;
           a.nsrc = 2;
-          a.act[0] = t[op.tout].td; a.wgt[0] = Wg(op);
-          a.act[1] = t[op.tout].d; a.wgt[1] = Vg(op);
-          a.out = op.tin == 0 ? t[0].td : t[op.tin].td;
+          a.act[0] = t[op.tout].td; a.wgt[0] = cols ? Wcol : Wg(op);
+          a.act[1] = t[op.tout].d; a.wgt[1] = cols ? Vcol : Vg(op);
+          a.out = cols ? dcol : (op.tin == 0 ? t[0].td : t[op.tin].td);
           a.accumulate = op.tin == 0 ? 0 : op.acc_in;
           BRE_LAUNCH(gemm(a));
+          if (cols) BRE_TRY(stem_fold(op, t[0].td));
           if (want_tangent_G) {
             // tangent of the weight gradient: wgrad(a, delta_dot) + wgrad(a_dot, delta)   (a_dot = 0 for the candidate)
-            GemmArgs w = conv_geom(op);
+            GemmArgs w = cols ? stem_geom(op) : conv_geom(op);
             w.mode = GEMM_WGRAD;
-            w.act[0] = t[op.tin].val; w.wgt[0] = t[op.tout].td;
+            w.act[0] = cols ? xcol : t[op.tin].val; w.wgt[0] = t[op.tout].td;
             if (op.tin != 0) { w.nsrc = 2; w.act[1] = t[op.tin].tval; w.wgt[1] = t[op.tout].d; }
-            w.out = Gp(op.w);
+            w.out = cols ? Gcol : Gp(op.w);
             cudaStream_t wst = stream;
             if (overlap_wgrad && side != nullptr) {
               BRE_CUDA_CHECK(cudaEventRecord(ev_fork[i], stream));
@@ -569,6 +642,7 @@ struct bre_engine {
               forked = true;
             }
             BRE_LAUNCH(gemm_on(w, wst));
+            if (cols) BRE_LAUNCH(launch_stem_pad_rows(Gcol, Gp(op.w), to.C, op.R * op.S * td(op.tin).C, stem_Kp, true, false, wst));
             if (op.b >= 0)
               BRE_LAUNCH(launch_channel_sum(t[op.tout].td, Pout, to.C, Gp(op.b), wst == side ? red_partials2 : red_partials,
                                             wst == side ? red_counters2 : red_counters, wst));
@@ -715,8 +789,10 @@ struct bre_engine {
     BRE_TRY(sweep_forward());
     BRE_TRY(sweep_backward());
     BRE_TRY(reduce_objective(cfg.objective, cfg.obj_scale, cfg.mask_value, true));
-    BRE_LAUNCH(launch_make_v(G, g, chunk_w, V, P_pad, cfg.objective == BRE_OBJ_MASKED_COSINE ? cfg.mask_value : -1.f, sc, stream));
-    BRE_TRY(refresh_Vt());
+    // direction v and (tensor-core back end) its TF32 shadow in one pass; chunks of tensor-core conv weights get the shadow only
+    BRE_TRY(build_chunk_modes());
+    BRE_LAUNCH(launch_make_v(G, g, chunk_w, V, P_pad, cfg.objective == BRE_OBJ_MASKED_COSINE ? cfg.mask_value : -1.f, sc, stream,
+                             tc_round() ? Vt : nullptr, tc_round() ? chunk_mode : nullptr));
     BRE_TRY(sweep_tangent_forward());
     BRE_TRY(deep_inversion_stats());
     BRE_TRY(sweep_tangent_backward());
@@ -899,6 +975,18 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
       for (float** pp : ptrs) rc |= e->alloc(pp, b.C);
     }
   }
+  // ---- column path of the candidate-fed convolution (tensor-core back end; stem_cols.cu) -------------------------------------
+  for (int i = 0; i < n_ops; ++i) {
+    const bre_op_desc& op = ops[i];
+    if (op.kind == BRE_OP_CONV && op.tin == 0 && tensors[0].C <= 4 && tensors[op.tout].C % 64 == 0 && op.R * op.S <= 64) {
+      e->stem_op = i;
+      e->stem_Kp = ((op.R * op.S * tensors[0].C + 63) / 64) * 64;
+      const long long M = (long long)tensors[op.tout].N * tensors[op.tout].H * tensors[op.tout].W;
+      rc |= e->alloc(&e->xcol, M * e->stem_Kp); rc |= e->alloc(&e->dcol, M * e->stem_Kp);
+      rc |= e->alloc(&e->Wcol, (long long)tensors[op.tout].C * e->stem_Kp); rc |= e->alloc(&e->Vcol, (long long)tensors[op.tout].C * e->stem_Kp);
+      rc |= e->alloc(&e->Gcol, (long long)tensors[op.tout].C * e->stem_Kp);
+    }
+  }
   // ---- side stream for the weight-gradient GEMMs ----------------------------------------------------------
   if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(BRE_ERR_CUDA); }
   e->ev_fork.assign(n_ops, nullptr);
@@ -1003,6 +1091,10 @@ int bre_engine_load_model(bre_engine* e, const float* const* params, int32_t n_p
   }
   BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   BRE_TRY(launch_round_tf32(e->W, e->Wt, e->P_pad, e->stream));   // GEMM-operand shadow (used by the tcgen05 back end)
+  if (e->stem_op >= 0) {   // zero-padded [Co][Kp] copy of the stem weight (TF32-rounded like Wt when the tensor-core back end rounds)
+    const bre_op_desc& op = e->ops[e->stem_op];
+    BRE_TRY(launch_stem_pad_rows(e->Wp(op.w), e->Wcol, e->td(op.tout).C, op.R * op.S * e->td(op.tin).C, e->stem_Kp, false, e->tc_round_env, e->stream));
+  }
   e->model_loaded = true;
   return BRE_OK;
 }
@@ -1237,10 +1329,12 @@ int bre_engine_run(bre_engine* e, int32_t n_iters) {
   if (!e->trial_begun) { set_error("bre_engine_begin_trial must be called first"); return BRE_ERR_STATE; }
   BRE_CUDA_CHECK(cudaSetDevice(e->device));
   if (!e->use_graph) {
+    BRE_TRY(e->build_chunk_modes());
     for (int i = 0; i < n_iters; ++i) { e->launch_count = 0; BRE_TRY(e->iteration()); e->launches_per_iter = e->launch_count; }
     return BRE_OK;
   }
   if (!e->graph_ready) {
+    BRE_TRY(e->build_chunk_modes());   // host -> device table: must exist before the capture starts
     if (e->exec) { cudaGraphExecDestroy(e->exec); e->exec = nullptr; }
     cudaGraph_t graph = nullptr;
     BRE_CUDA_CHECK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
@@ -1349,6 +1443,7 @@ int bre_engine_objective_and_gradient(bre_engine* e, const float* candidate, dou
   BRE_CUDA_CHECK(cudaSetDevice(e->device));
   BRE_CUDA_CHECK(cudaMemcpyAsync(e->x, candidate, e->nx * sizeof(float), cudaMemcpyDefault, e->stream));
   e->launch_count = 0;
+  BRE_TRY(e->build_chunk_modes());
   BRE_TRY(e->evaluate());
   if (e->need_task_grad()) BRE_TRY(launch_axpy(e->gradx_task, e->gradx, e->cfg.task_regularization, e->nx, e->stream));
   Scalars h;
@@ -1482,7 +1577,7 @@ int bre_engine_set_option(bre_engine* e, const char* name, int64_t value) {
   if (n == "fuse_bnact") { e->fuse_bnact = value != 0; e->graph_ready = false; return BRE_OK; }
   if (n == "gemm_backend") {
     if (value != 0 && value != 1) { set_error("gemm_backend must be 0 (simt) or 1 (tcgen05)"); return BRE_ERR_INVALID; }
-    e->gemm_backend = (int)value; e->graph_ready = false; return BRE_OK;
+    e->gemm_backend = (int)value; e->graph_ready = false; e->chunk_mode_ready = false; return BRE_OK;
   }
   set_error("unknown option " + n);
   return BRE_ERR_INVALID;

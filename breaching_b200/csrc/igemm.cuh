@@ -58,6 +58,9 @@ struct GemmArgs {
 constexpr int IG_BM = 64, IG_BN = 64, IG_BK = 16, IG_THREADS = 256;
 
 int launch_igemm_simt(const GemmArgs& a, cudaStream_t stream);
+// linear layers on <= 16 rows (the classification head at small batch): dedicated fp32 kernels (linear_small.cu)
+bool linear_small_supported(const GemmArgs& a);
+int launch_linear_small(const GemmArgs& a, cudaStream_t stream);
 // tcgen05 TF32 back end (igemm_tc.cu); returns BRE_ERR_UNSUPPORTED (-4) for shapes it does not cover.
 int launch_igemm_tc(const GemmArgs& a, cudaStream_t stream);
 bool igemm_tc_supported(const GemmArgs& a);

@@ -119,6 +119,14 @@ int launch_ce_label_grad(const float* logits, const float* p, const float* zdot,
 // tangent of dlogits: (p*zdot - p * sum(p*zdot)) / N
 int launch_ce_tan_bwd(const float* p, const float* zdot, int N, int C, float* tdlogits, cudaStream_t s);
 
+// column path of the candidate-fed convolution (stem_cols.cu): xcol[(n,p,q)][(r,s,c)] <- NCHW candidate (K padded to Kp, optional
+// TF32 rounding); candidate gradient <- dcol by gathering; zero-padded [Co][Kp] copies of OHWI weight rows and back
+int launch_stem_im2col(const float* x, float* xcol, int N, int C, int H, int W, int Ho, int Wo, int R, int S, int stride, int pad, int Kp,
+                       bool round_out, cudaStream_t s);
+int launch_stem_col2im(const float* dcol, float* grad, int N, int C, int H, int W, int Ho, int Wo, int R, int S, int stride, int pad, int Kp,
+                       cudaStream_t s);
+int launch_stem_pad_rows(const float* src, float* dst, int Co, int K, int Kp, bool inverse, bool round_out, cudaStream_t s);
+
 // dst[(o*HW + hw)*I + i] = src[(o*I + i)*HW + hw]   (inverse=false: OIHW -> OHWI / NCHW -> NHWC)
 int launch_permute(const float* src, float* dst, int O, int I, int HW, bool inverse, cudaStream_t s);
 // y[i] += alpha * x[i]

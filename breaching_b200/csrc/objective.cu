@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(256) match_reduce_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) make_v_kernel(const float* __restrict__ G, const float* __restrict__ g,
                                                     const float* __restrict__ chunk_w, float* __restrict__ v, long long n,
-                                                    long long nchunks, float mask_value, const Scalars* sc) {
+                                                    long long nchunks, float mask_value, const Scalars* sc, float* __restrict__ vt,
+                                                    const unsigned char* __restrict__ chunk_mode) {
   pdl_prologue();
   const float c1 = sc->c1, c2 = sc->c2, c3 = sc->c3;
   const bool masked = mask_value >= 0.f;
@@ -170,10 +171,21 @@ __global__ void __launch_bounds__(256) make_v_kernel(const float* __restrict__ G
       if (masked && !(fabsf(b[j]) > mask_value)) val = 0.f;
       r[j] = val;
     }
-    if (full) *reinterpret_cast<float4*>(v + i) = make_float4(r[0], r[1], r[2], r[3]);
-    else
-      for (int j = 0; j < 4; ++j)
-        if (i + j < n) v[i + j] = r[j];
+    // chunk_mode (with vt): 0 = fp32 direction only, 1 = only its TF32-rounded shadow (operand of tensor-core GEMMs, nobody reads
+    // the fp32 value), 2 = both.  One pass instead of make_v + a separate rounding pass over the whole arena.
+    const int mode = (vt != nullptr) ? (chunk_mode != nullptr ? (int)__ldg(chunk_mode + ch) : 2) : 0;
+    if (mode != 1) {
+      if (full) *reinterpret_cast<float4*>(v + i) = make_float4(r[0], r[1], r[2], r[3]);
+      else
+        for (int j = 0; j < 4; ++j)
+          if (i + j < n) v[i + j] = r[j];
+    }
+    if (mode != 0) {
+      if (full) *reinterpret_cast<float4*>(vt + i) = make_float4(tf32_rna(r[0]), tf32_rna(r[1]), tf32_rna(r[2]), tf32_rna(r[3]));
+      else
+        for (int j = 0; j < 4; ++j)
+          if (i + j < n) vt[i + j] = tf32_rna(r[j]);
+    }
   }
 }
 
@@ -646,11 +658,11 @@ int launch_match_reduce(const float* G, const float* g, const float* chunk_w, lo
 }
 
 int launch_make_v(const float* G, const float* g, const float* chunk_w, float* v, long long n, float mask_value,
-                  const Scalars* sc, cudaStream_t s) {
+                  const Scalars* sc, cudaStream_t s, float* vt, const unsigned char* chunk_mode) {
   const long long nchunks = (n + kChunk - 1) / kChunk;
   const int cap = kNumSMs * 8;
   const int grid = (int)(nchunks < cap ? (nchunks > 0 ? nchunks : 1) : cap);
-  BRE_KLAUNCH(make_v_kernel, grid, 256, 0, s, G, g, chunk_w, v, n, nchunks, mask_value, sc);
+  BRE_KLAUNCH(make_v_kernel, grid, 256, 0, s, G, g, chunk_w, v, n, nchunks, mask_value, sc, vt, chunk_mode);
   BRE_CHECK_LAUNCH();
   return 0;
 }

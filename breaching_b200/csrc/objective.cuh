@@ -16,9 +16,11 @@ int launch_match_reduce(const float* G, const float* g, const float* chunk_w, lo
                         double* partials, int* counter, cudaStream_t s);
 constexpr int kMatchMaxBlocks = kNumSMs * 8;   // capacity of the partials buffers; the launch uses g_match_blocks_per_sm (default 4)
 
-// v = c1*g + c2*G + c3*w_chunk*sign(G-g)  (coefficients read from sc)
+// v = c1*g + c2*G + c3*w_chunk*sign(G-g)  (coefficients read from sc).  With `vt` the TF32-rounded shadow of the direction is
+// written in the same pass; `chunk_mode[chunk]` (device, may be null = 2) selects per 1024-element chunk: 0 = v only, 1 = vt only,
+// 2 = both.
 int launch_make_v(const float* G, const float* g, const float* chunk_w, float* v, long long n, float mask_value,
-                  const Scalars* sc, cudaStream_t s);
+                  const Scalars* sc, cudaStream_t s, float* vt = nullptr, const unsigned char* chunk_mode = nullptr);
 
 struct PriorArgs {   // TotalVariation (regularizers.py:130-147) + NormRegularization (:197-198)
   const float* x; float* grad; int N, H, W; int accumulate;

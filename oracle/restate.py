@@ -637,3 +637,45 @@ def select_optimal(candidates, scores):
     if val.isfinite():
         return candidates[int(idx)], float(val), int(idx)
     return torch.zeros_like(candidates[int(idx)]), float(val), int(idx)
+
+
+def pearlmutter_closure(model, loss_fn, gradients, x, labels, kind="pearlmutter-loss", scale=1.0, eps=1e-3, task_regularization=0.0,
+                        implementation="forward"):
+    """``PearlmutterEuclidean`` / ``PearlmutterCosine`` (objectives.py:279-365, 368-436, 468-493): finite-difference approximation
+    of the candidate gradient, restated without the ``candidate.grad +=`` accumulation that breaks under torch >= 2.
+    Returns ``(objective_value, task_loss, candidate_gradient)``; the model's parameters are restored (:330-332)."""
+    params = list(model.parameters())
+    original = [p.detach().clone() for p in params]
+    x = x.detach().clone().requires_grad_(True)
+    task_loss = loss_fn(model(x), labels)
+    *G, dLdx = torch.autograd.grad(task_loss, (*params, x))
+    if kind == "pearlmutter-loss":                                      # :463-466
+        first = [a - b for a, b in zip(G, gradients)]
+        value = 0.5 * scale * sum(r.pow(2).sum() for r in first)
+    else:                                                               # :471-478
+        sp = sum((a * b).sum() for a, b in zip(G, gradients))
+        gn = sum(a.pow(2).sum() for a in G).sqrt()
+        dn = sum(b.pow(2).sum() for b in gradients).sqrt()
+        first = [b / (-gn * dn) - a * (-sp / (gn.pow(3) * dn)) for a, b in zip(G, gradients)]
+        value = scale * (1 - sp / (gn * dn))
+    eps_n = eps / sum(a.pow(2).sum() for a in G).sqrt()                 # :348
+
+    def shifted(alpha):
+        with torch.no_grad():
+            for p, o, v in zip(params, original, first):
+                p.copy_(o + alpha * v)
+        (d,) = torch.autograd.grad(loss_fn(model(x), labels), (x,))
+        return d
+
+    if implementation == "forward":                                     # :349-358
+        fd = (shifted(eps_n) - dLdx) / eps_n
+    elif implementation == "backward":                                  # :380-389
+        fd = (dLdx - shifted(-eps_n)) / eps_n
+    elif implementation == "central":                                   # :405-420
+        fd = (shifted(0.5 * eps_n) - shifted(-0.5 * eps_n)) / eps_n
+    else:
+        raise ValueError(implementation)
+    with torch.no_grad():
+        for p, o in zip(params, original):
+            p.copy_(o)
+    return value.detach(), task_loss.detach(), (fd * scale + task_regularization * dLdx).detach()

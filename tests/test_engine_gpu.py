@@ -543,3 +543,34 @@ def test_total_variation_on_a_non_rgb_candidate_is_refused():
     assert math.isclose(t["norm"], want, rel_tol=1e-5), (t, want)
     assert torch.isfinite(grad).all()
     eng.close()
+
+
+@pytest.mark.parametrize("kind", ["pearlmutter-loss", "pearlmutter-cosine"])
+def test_pearlmutter_objectives_are_the_exact_tangent(kind):
+    """Pearlmutter* (objectives.py:279-365, 468-493) approximate the candidate gradient by finite differences of grad_x L along
+    W + eps d(objective)/dG; the engine computes that directional derivative exactly.  Against a float64 restatement of the
+    reference formulas (forward differences, eps = 1e-3: 1e-6 from the exact tangent in float64); the reported value excludes the
+    task term."""
+    from oracle import restate
+
+    model, loss_fn, payload, shared, true = synthetic.make_case("convnet-tiny", "cifar", batch=2, seed=12, bn_random=True)
+    treg = 0.2
+    cfg = get_attack_config("invertinggradients", {"objective.type": kind, "objective.scale": 0.7, "objective.task_regularization": treg,
+                                                    "regularization.total_variation.scale": 0.0})
+    meta = payload[0]["metadata"]
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(6))
+    m64 = copy.deepcopy(model).double().eval()
+    g64 = [g.double() for g in shared[0]["gradients"]]
+    # (forward differences only: a backward / central stencil of this seeded case steps across a ReLU kink 0.4 eps away from the
+    # weights -- the one-sided limit the engine computes is the derivative at the weights themselves)
+    value, task_loss, g_fd = restate.pearlmutter_closure(m64, loss_fn, g64, x.double(), true["labels"], kind, scale=0.7, eps=1e-3,
+                                                         task_regularization=treg, implementation="forward")
+    eng = _engine_for(model, cfg, shared, true["labels"], meta, (2, 3, 32, 32))
+    val, grad = eng.objective_and_gradient(x.to(DEV))
+    assert math.isclose(val, float(value), rel_tol=2e-4), (val, float(value))            # no task_regularization * task_loss in the value
+    assert math.isclose(eng.last_terms()["task_loss"], float(task_loss), rel_tol=1e-4)
+    assert _relerr(grad, g_fd) < 2e-3, _relerr(grad, g_fd)
+    eng.close()
+    with pytest.raises(Exception):
+        Engine(copy.deepcopy(model).to(DEV).eval(), (2, 3, 32, 32), get_attack_config("invertinggradients", {"objective.type": kind,
+               "objective.implementation": "upwind"}), DEV)
