@@ -2,10 +2,11 @@
 import torch
 
 from .joint_attack import OptimizationJointAttacker
+from .multiscale_attack import MultiScaleOptimizationAttacker
 from .optimization_attack import OptimizationBasedAttacker, _loss_name
 
 _OTHER_ATTACKS = (
-    "multiscale", "analytic", "april-analytic", "imprint-readout", "decepticon-readout", "recursive",
+    "analytic", "april-analytic", "imprint-readout", "decepticon-readout", "recursive",
     "joint-optimization", "permutation-optimization",
 )
 
@@ -22,6 +23,8 @@ def prepare_attack(model, loss, cfg_attack, setup=dict(dtype=torch.float, device
     if cfg_attack.attack_type == "joint-optimization" and _loss_name(loss) in ("CrossEntropyLoss", "CausalLoss"):
         # classification models (deepleakage.yaml) and causal language models (tag.yaml, BASELINE config 5)
         return OptimizationJointAttacker(model, loss, cfg_attack, setup)
+    if cfg_attack.attack_type == "multiscale":
+        return MultiScaleOptimizationAttacker(model, loss, cfg_attack, setup)
     if cfg_attack.attack_type in _OTHER_ATTACKS:
         from ..install import reference_prepare_attack
 
@@ -35,4 +38,4 @@ def prepare_attack(model, loss, cfg_attack, setup=dict(dtype=torch.float, device
     raise ValueError(f"Invalid type of attack {cfg_attack.attack_type} given.")
 
 
-__all__ = ["prepare_attack", "OptimizationBasedAttacker", "OptimizationJointAttacker"]
+__all__ = ["prepare_attack", "OptimizationBasedAttacker", "OptimizationJointAttacker", "MultiScaleOptimizationAttacker"]

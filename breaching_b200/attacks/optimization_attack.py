@@ -124,8 +124,10 @@ class OptimizationBasedAttacker:
             shared_data = host.normalize_gradients(shared_data)
         return rec_models, labels, stats, shared_data
 
-    def _get_engine(self, rec_models, shared_data, labels, index=0, cfg=None):
-        """Engine for model / payload ``index`` (``cfg`` overrides the attack config, used for the extra queries)."""
+    def _get_engine(self, rec_models, shared_data, labels, index=0, cfg=None, data_shape=None, primary=True):
+        """Engine for model / payload ``index`` (``cfg`` overrides the attack config, used for the extra queries; ``data_shape``
+        overrides the candidate's per-example shape and ``primary=False`` builds an additional engine next to the attacker's main
+        one -- both used by the multi-scale attacker's stages)."""
         if len(rec_models) != 1 and cfg is None:
             raise NotImplementedError("use _get_engines for several model queries")
         cfg = self.cfg if cfg is None else cfg
@@ -133,9 +135,9 @@ class OptimizationBasedAttacker:
         model = rec_models[index]
         n = shared_data[index]["metadata"]["num_data_points"]
         # FedAvg (objectives.py:48-72): the layer program is compiled for one local step's batch
-        shape = (n if local is None else int(local["data_per_step"]), *self.data_shape)
+        shape = (n if local is None else int(local["data_per_step"]), *(self.data_shape if data_shape is None else data_shape))
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if cfg_get(self.cfg.optim, "langevin_noise", 0.0) else 0
-        if self._engine is not None and index == 0:
+        if self._engine is not None and index == 0 and primary:
             self._engine.close()
         # setup["backend"]: "tc" (tcgen05 TF32, default = torch's cuDNN-TF32 numerics) or "simt" (fp32, = allow_tf32 False)
         eng = Engine(model, shape, cfg, self.setup["device"], noise_seed=seed, backend=self.backend)
@@ -159,7 +161,7 @@ class OptimizationBasedAttacker:
             eng.set_local_steps(n, int(local["steps"]), float(local["lr"]), [l for l in local["labels"][: int(local["steps"])]])
         if any(k == "features" for k, _ in self.regularizers):
             eng.load_feature_targets(host.measured_features(shared_data, labels)[0])
-        if index == 0:
+        if index == 0 and primary:
             self._engine = eng
         return eng
 

@@ -181,6 +181,18 @@ _PRESETS = {
         optim=dict(optimizer="L-BFGS", step_size=1.0, boxed=True, max_iterations=400),
         regularization=dict(total_variation=dict(scale=0.2352, inner_exp=2, outer_exp=1.25)),
     ),
+    "multiscale_ghiasi": dict(          # config/attack/multiscale_ghiasi.yaml (defaults: invertinggradients, then itself)
+        _inherits="invertinggradients",
+        attack_type="multiscale",
+        type="multiscale-invertinggradients",
+        num_stages=7,
+        augmentations=dict(continuous_shift=dict(shift=224, padding="circular"), colorjitter=dict(none=None)),
+        resize="focus",
+        scale_pyramid="linear",
+        optim=dict(optimizer="adam-safe", max_iterations=2000),
+        differentiable_augmentations=True,
+        update_augmentations="None",
+    ),
     "wei": dict(
         type="beyond-infering",
         objective=dict(type="euclidean", scale=1.0, task_regularization=1.0),
@@ -225,7 +237,14 @@ def get_attack_config(attack="invertinggradients", overrides=()):
     """
     if attack not in _PRESETS:
         raise ValueError(f"Unknown attack configuration {attack}. Known: {sorted(_PRESETS)}")
-    cfg = _wrap(_merge(copy.deepcopy(_DEFAULT), _PRESETS[attack]))
+    chain, name = [], attack
+    while name is not None:                       # hydra `defaults:` lists: base presets first
+        chain.append(name)
+        name = _PRESETS[name].get("_inherits")
+    merged = copy.deepcopy(_DEFAULT)
+    for name in reversed(chain):
+        _merge(merged, {k: v for k, v in _PRESETS[name].items() if k != "_inherits"})
+    cfg = _wrap(merged)
     if isinstance(overrides, dict):
         for key, val in overrides.items():
             _set_dotted(cfg, key, val)

@@ -81,3 +81,43 @@ extern "C" int bre_image_mse(const float* rec, const float* ref, int32_t N, int3
   if (err != cudaSuccess) { set_error(std::string("bre_image_mse failed: ") + cudaGetErrorString(err)); return BRE_ERR_CUDA; }
   return BRE_OK;
 }
+
+// ---- bilinear resize of NCHW batches (MultiScaleOptimizationAttacker, multiscale_optimization_attack.py:45-69) ---------------------
+// F.interpolate(mode="bilinear", align_corners=False): source coordinate = (dst + 0.5) * in/out - 0.5, clamped at 0; the two
+// neighbours per axis are i0 = floor, i1 = min(i0 + 1, in - 1) with weights (1 - l, l).
+namespace bre {
+namespace {
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int planes, int Hi, int Wi,
+                                                              int Ho, int Wo, float sh, float sw) {
+  const long long total = (long long)planes * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo);
+    const long long t = i / Wo;
+    const int y = (int)(t % Ho);
+    const long long pl = t / Ho;
+    float fy = ((float)y + 0.5f) * sh - 0.5f, fx = ((float)x + 0.5f) * sw - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float* p = src + pl * Hi * Wi;
+    const float top = (1.f - lx) * p[(long long)y0 * Wi + x0] + lx * p[(long long)y0 * Wi + x1];
+    const float bot = (1.f - lx) * p[(long long)y1 * Wi + x0] + lx * p[(long long)y1 * Wi + x1];
+    dst[i] = (1.f - ly) * top + ly * bot;
+  }
+}
+}  // namespace
+}  // namespace bre
+
+extern "C" int bre_resize_bilinear(const float* src, float* dst, int32_t N, int32_t C, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                                   void* stream) {
+  if (!src || !dst || N <= 0 || C <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) { set_error("bre_resize_bilinear: bad arguments"); return BRE_ERR_INVALID; }
+  const long long total = (long long)N * C * Ho * Wo;
+  long long blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  resize_bilinear_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, N * C, Hi, Wi, Ho, Wo, (float)Hi / (float)Ho, (float)Wi / (float)Wo);
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error(std::string("bre_resize_bilinear failed: ") + cudaGetErrorString(err)); return BRE_ERR_CUDA; }
+  return BRE_OK;
+}

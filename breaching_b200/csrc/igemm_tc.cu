@@ -166,6 +166,25 @@ struct TcMaps {
   CUtensorMap wgt[2];  // plain operand (tiled mode; WGRAD: dout, A operand)
 };
 
+// Strided data gradient as per-parity-class stride-1 gathers (specification + CPU check: oracle/strided_dgrad.py,
+// tests/test_strided_dgrad_spec.py).  The output pixels split into the stride x stride classes (ey, ex) = ((y + pad) % stride,
+// (x + pad) % stride); class pixels are y = stride * iy + y0, and only the taps r = ey + stride * tr reach them:
+//     din[y, x] = sum_{tr, ts} dout[iy + cy - tr, ix + cx - ts] . w[ey + stride tr, ex + stride ts]
+// i.e. an im2col load over dout with traversal stride 1, lower corner L = c - (T - 1) and filter offset (T - 1) - t.  One launch
+// covers all classes (blockIdx.x enumerates (class, m-tile) pairs); a class no tap reaches writes zeros.  Replaces the cp.async
+// producer with its 4x zero-filled taps (round 1: 10 % of a config-2 and 13 % of a config-3 iteration).
+constexpr int TC_MAXCLS = 4;   // stride 2
+struct ClsPlan {
+  int ncls, stride;
+  int tile0[TC_MAXCLS + 1];                                  // first m-tile of each class, tile0[ncls] = all tiles
+  int Hc[TC_MAXCLS], Wc[TC_MAXCLS], y0[TC_MAXCLS], x0[TC_MAXCLS];   // class pixel grid and its first pixel
+  int Ty[TC_MAXCLS], Tx[TC_MAXCLS], Ly[TC_MAXCLS], Lx[TC_MAXCLS], ey[TC_MAXCLS], ex[TC_MAXCLS];
+};
+struct TcMapsCls {
+  CUtensorMap act[2 * TC_MAXCLS];  // [class][source]: im2col maps over dout with the class's corners
+  CUtensorMap wgt[2];
+};
+
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -218,8 +237,10 @@ __device__ long long g_tc_trace[16];
 #define TC_MARK(i, cond) do { } while (0)
 #endif
 
-template <int MODE, int BN, bool TMA>
-__global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d, int proxy_fence, const __grid_constant__ TcMaps maps) {
+template <int MODE, int BN, bool TMA, bool CLS = false>
+__global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d, int proxy_fence,
+                                                            const __grid_constant__ std::conditional_t<CLS, TcMapsCls, TcMaps> maps, ClsPlan plan) {
+  static_assert(!CLS || (MODE == GEMM_DGRAD && TMA), "per-class gathers: strided dgrad with the TMA producer only");
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;                                  // [STAGES][A_BYTES]
@@ -234,10 +255,25 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   pdl_launch_dependents();   // the successor may start its own prologue; it blocks in its griddepcontrol.wait
   const ConvGeom g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN, z = blockIdx.z;
-  const int kb_begin = z * d.kblocks_per_split;
-  const int kb_end = min(d.total_kblocks, kb_begin + d.kblocks_per_split);
+  const int n0 = blockIdx.y * BN, z = blockIdx.z;
+  int m0 = blockIdx.x * TC_BM;
+  int kb_begin = z * d.kblocks_per_split;
+  int kb_end = min(d.total_kblocks, kb_begin + d.kblocks_per_split);
   const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+  // per-class view (CLS): which class this CTA serves, its pixel grid / taps, and its own k-block range
+  int cls = 0, cHc = 0, cWc = 0, cTy = 0, cTx = 0, cls_kps = 0, Mrows = d.M;
+  if (CLS) {
+#pragma unroll
+    for (int c = 1; c < TC_MAXCLS; ++c)
+      if (c < plan.ncls && (int)blockIdx.x >= plan.tile0[c]) cls = c;
+    m0 = ((int)blockIdx.x - plan.tile0[cls]) * TC_BM;
+    cHc = plan.Hc[cls]; cWc = plan.Wc[cls]; cTy = plan.Ty[cls]; cTx = plan.Tx[cls];
+    Mrows = g.N * cHc * cWc;
+    cls_kps = cTy * cTx * (g.Co / TC_BK);
+    const int total = cls_kps * a.nsrc, per = (total + (int)gridDim.z - 1) / (int)gridDim.z;
+    kb_begin = z * per;
+    kb_end = min(total, kb_begin + per);
+  }
 
   if (tid == 0) {
 #pragma unroll
@@ -315,7 +351,7 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   // predecessor kernel is read.
   if (TMA && tid == 0 && (proxy_fence & 2)) {
     for (int sidx = 0; sidx < a.nsrc; ++sidx) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.act[sidx])) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.act[(CLS ? 2 * cls : 0) + sidx])) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.wgt[sidx])) : "memory");
     }
   }
@@ -423,7 +459,13 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   // TMA producer (one thread): the CTA's first GEMM row fixes the base pixel of every im2col load; per k-block only the
   // filter-tap offsets and the channel coordinate change.
   int base_n = 0, base_h = 0, base_w = 0;
-  if (TMA && MODE != GEMM_WGRAD) {
+  if (CLS) {
+    const int per = cHc * cWc;
+    base_n = m0 / per;
+    const int rem = m0 - base_n * per;
+    const int iy0 = rem / cWc, ix0 = rem - iy0 * cWc;
+    base_h = iy0 + plan.Ly[cls]; base_w = ix0 + plan.Lx[cls];
+  } else if (TMA && MODE != GEMM_WGRAD) {
     const int per = (MODE == GEMM_FPROP) ? HoWo : HW, wid = (MODE == GEMM_FPROP) ? g.Wo : g.W;
     base_n = m0 / per;
     const int rem = m0 - base_n * per;
@@ -437,6 +479,16 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   auto kb_init = [&](int kb) {
     KbState st;
     const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
+    if (CLS) {   // k = (source, class tap (tr, ts), channel); st.r / st.s hold the class-tap indices, st.rs the weight's filter cell
+      st.src = cls_kps > 0 ? kb / cls_kps : 0;
+      const int rem = kb - st.src * cls_kps, cpb = g.Co / TC_BK;
+      const int tap = rem / cpb;
+      st.c0 = (rem - tap * cpb) * TC_BK;
+      st.r = cTx > 0 ? tap / cTx : 0; st.s = tap - st.r * cTx;
+      st.rs = (plan.ey[cls] + plan.stride * st.r) * g.S + plan.ex[cls] + plan.stride * st.s;
+      st.img = st.p = st.q = 0;
+      return st;
+    }
     st.src = kb / d.kblocks_per_src;
     const int kbase = (kb - st.src * d.kblocks_per_src) * TC_BK;
     if (MODE == GEMM_WGRAD) {
@@ -454,6 +506,14 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   auto kb_advance = [&](KbState& st) {
     const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
     st.c0 += TC_BK;
+    if (CLS) {
+      if (st.c0 >= kch) {
+        st.c0 = 0;
+        if (++st.s == cTx) { st.s = 0; if (++st.r == cTy) { st.r = 0; ++st.src; } }
+        st.rs = (plan.ey[cls] + plan.stride * st.r) * g.S + plan.ex[cls] + plan.stride * st.s;
+      }
+      return;
+    }
     if (MODE == GEMM_WGRAD) {
       if (st.c0 >= d.kblocks_per_src * TC_BK) { st.c0 = 0; ++st.src; st.img = st.p = st.q = 0; }
       else {
@@ -483,7 +543,8 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
       tma_im2col(pa, &maps.act[st.src], bar, st.c0, base_w, base_h, base_n, st.s, st.r);
       tma_tile2d(pb, &maps.wgt[st.src], bar, st.rs * g.Ci + st.c0, n0);
     } else if (MODE == GEMM_DGRAD) {
-      tma_im2col(pa, &maps.act[st.src], bar, st.c0, base_w, base_h, base_n, g.S - 1 - st.s, g.R - 1 - st.r);
+      if (CLS) tma_im2col(pa, &maps.act[2 * cls + st.src], bar, st.c0, base_w, base_h, base_n, cTx - 1 - st.s, cTy - 1 - st.r);
+      else tma_im2col(pa, &maps.act[st.src], bar, st.c0, base_w, base_h, base_n, g.S - 1 - st.s, g.R - 1 - st.r);
 #pragma unroll
       for (int h = 0; h < BN / 32; ++h) tma_tile3d(pb + h * 4096, &maps.wgt[st.src], bar, n0 + 32 * h, st.rs, st.c0);
     } else {
@@ -564,10 +625,16 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
   float v[32];
   const int m = m0 + tid;
-  const bool row_ok = m < d.M;
+  const bool row_ok = m < Mrows;
   const bool is_loader = warp < TC_THREADS / 32;
   auto out_row = [&](int mm, long long& row, int& cs) {
-    if (MODE == GEMM_DGRAD) {
+    if (CLS) {   // class pixel (img, iy, ix) -> input pixel (y0 + stride * iy, x0 + stride * ix)
+      const int per = cHc * cWc;
+      const int img = mm / per, rem = mm - img * per;
+      const int iy = rem / cWc, ix = rem - iy * cWc;
+      row = img * a.x_sN + (long long)((plan.y0[cls] + plan.stride * iy) * g.W + plan.x0[cls] + plan.stride * ix) * a.x_sP;
+      cs = a.x_sC;
+    } else if (MODE == GEMM_DGRAD) {
       const int img = mm / HW;
       row = img * a.x_sN + (long long)(mm - img * HW) * a.x_sP;
       cs = a.x_sC;
@@ -584,7 +651,11 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
     if (row_ok) out_row(m, row, cs);
 #pragma unroll
     for (int c = 0; c < BN; c += 32) {
-      tmem_ld32(lane_base + c, v);  // warp-collective: executed by all lanes, also for rows beyond M
+      if (nkb > 0) tmem_ld32(lane_base + c, v);  // warp-collective: executed by all lanes, also for rows beyond M
+      else {                                    // (a class no filter tap reaches: zeros)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
       if (!row_ok) continue;
       const int n = n0 + c;
       if (MODE == GEMM_FPROP && a.bias != nullptr) {
@@ -665,7 +736,7 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
 #pragma unroll
         for (int sl = 0; sl < SLOTS; ++sl) {
           const int r = rr[sl], c4 = cc[sl];
-          if (m0 + r >= d.M) continue;
+          if (m0 + r >= Mrows) continue;
           float4 acc4 = t[sl][0];
 #pragma unroll
           for (int q = 1; q < S; ++q) { acc4.x += t[sl][q].x; acc4.y += t[sl][q].y; acc4.z += t[sl][q].z; acc4.w += t[sl][q].w; }
@@ -848,10 +919,88 @@ bool build_maps(const GemmArgs& a, int BN, TcMaps* maps) {
   return true;
 }
 
-template <int MODE, int BN, bool TMA>
-int launch_tc(const GemmArgs& a, const TcDims& d0, const TcMaps& maps, cudaStream_t stream) {
+// ---- per-class plan of a strided dgrad (oracle/strided_dgrad.py class_plan, per axis) ---------------------------------------------
+struct AxisPlan { bool any; int y0, Hc, T, L, U; };
+inline AxisPlan axis_plan(int H, int Ho, int R, int stride, int pad, int e) {
+  AxisPlan p{false, 0, 0, 0, 0, 0};
+  p.y0 = ((e - pad) % stride + stride) % stride;
+  if (p.y0 >= H) return p;                       // no input pixel of this parity
+  p.any = true;
+  p.Hc = (H - p.y0 + stride - 1) / stride;
+  if (e >= R) return p;                          // pixels exist, no tap reaches them: T = 0
+  p.T = (R - e + stride - 1) / stride;
+  const int c = (p.y0 + pad - e) / stride;
+  p.L = c - (p.T - 1);
+  p.U = p.Hc - Ho + p.L;
+  return p;
+}
+
+bool cls_eligible(const GemmArgs& a) {
+  static const int env = [] { const char* e = getenv("BRE_TC_STRIDED_TMA"); return e ? atoi(e) : 1; }();
+  const ConvGeom& g = a.g;
+  if (!env || a.mode != GEMM_DGRAD || g.stride != 2 || !tma_api().ok) return false;
+  static const int tma_env = [] { const char* e = getenv("BRE_TC_TMA"); return e ? atoi(e) : 1; }();
+  if (!tma_env || g.R > 16 || g.S > 16) return false;
+  for (int ey = 0; ey < 2; ++ey)
+    for (int horiz = 0; horiz < 2; ++horiz) {
+      const AxisPlan p = horiz ? axis_plan(g.W, g.Wo, g.S, 2, g.pad, ey) : axis_plan(g.H, g.Ho, g.R, 2, g.pad, ey);
+      if (p.any && p.T > 0 && (p.L < -128 || p.L > 127 || p.U < -128 || p.U > 127)) return false;
+    }
+  return true;
+}
+
+bool build_cls(const GemmArgs& a, ClsPlan* plan, TcMapsCls* maps) {
+  const ConvGeom& g = a.g;
+  memset(plan, 0, sizeof(*plan));
+  plan->stride = g.stride;
+  int tiles = 0, n = 0;
+  for (int ey = 0; ey < g.stride; ++ey) {
+    const AxisPlan py = axis_plan(g.H, g.Ho, g.R, g.stride, g.pad, ey);
+    if (!py.any) continue;
+    for (int ex = 0; ex < g.stride; ++ex) {
+      const AxisPlan px = axis_plan(g.W, g.Wo, g.S, g.stride, g.pad, ex);
+      if (!px.any) continue;
+      if (n >= TC_MAXCLS) return false;
+      const bool taps = py.T > 0 && px.T > 0;
+      plan->Hc[n] = py.Hc; plan->Wc[n] = px.Hc; plan->y0[n] = py.y0; plan->x0[n] = px.y0;
+      plan->Ty[n] = taps ? py.T : 0; plan->Tx[n] = taps ? px.T : 0;
+      plan->Ly[n] = py.L; plan->Lx[n] = px.L; plan->ey[n] = ey; plan->ex[n] = ex;
+      plan->tile0[n] = tiles;
+      tiles += ceil_div((long long)g.N * py.Hc * px.Hc, TC_BM);
+      for (int s = 0; s < a.nsrc && taps; ++s)
+        if (!im2col_map(&maps->act[2 * n + s], a.act[s], g.N, g.Ho, g.Wo, g.Co, (long long)g.Ho * g.Wo * g.Co, g.Co, px.L, py.L, px.U, py.U, 1,
+                        TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B))
+          return false;
+      if (!taps)   // never dereferenced (the class has no k-blocks), but a valid descriptor keeps prefetch.tensormap well defined
+        for (int s = 0; s < a.nsrc; ++s) maps->act[2 * n + s] = maps->act[s];
+      ++n;
+    }
+  }
+  plan->ncls = n;
+  plan->tile0[n] = tiles;
+  for (int s = 0; s < a.nsrc; ++s) {
+    const long long dims[3] = {g.Ci, (long long)g.R * g.S, g.Co}, strides[2] = {g.Ci, (long long)g.R * g.S * g.Ci};
+    const int box[3] = {32, 1, TC_BK};
+    if (!tiled_map(&maps->wgt[s], a.wgt[s], 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
+  }
+  return n > 0;
+}
+
+template <int MODE, int BN, bool TMA, bool CLS = false>
+int launch_tc(const GemmArgs& a, const TcDims& d0, const std::conditional_t<CLS, TcMapsCls, TcMaps>& maps, cudaStream_t stream,
+              const ClsPlan* plan_in = nullptr) {
   TcDims d = d0;
-  const int tm = ceil_div(d.M, TC_BM), tn = d.Nc / BN;
+  ClsPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  if (CLS) plan = *plan_in;
+  // CLS: the m-tiles of all classes side by side; the k extent that sizes the split is the largest class's
+  const int tm = CLS ? plan.tile0[plan.ncls] : ceil_div(d.M, TC_BM), tn = d.Nc / BN;
+  if (CLS) {
+    int kmax = 0;
+    for (int c = 0; c < plan.ncls; ++c) kmax = kmax > plan.Ty[c] * plan.Tx[c] ? kmax : plan.Ty[c] * plan.Tx[c];
+    d.total_kblocks = kmax * (a.g.Co / TC_BK) * a.nsrc;
+    if (d.total_kblocks < 1) d.total_kblocks = 1;
+  }
   const long long tiles = (long long)tm * tn;
   // split-K factor = cluster size along z: a power of two <= 8 (portable cluster limit) that brings the grid to ~100 CTAs
   static const int max_splits_env = [] { const char* e = getenv("BRE_TC_MAX_SPLITS"); return e ? atoi(e) : 0; }();
@@ -875,8 +1024,8 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, const TcMaps& maps, cudaStrea
   const size_t smem = (size_t)TC_STAGES * (TC_BM + BN) * TC_BK * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN, TMA>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN, TMA, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN, TMA, CLS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_done = true;
   }
   static const int proxy_fence_env = [] {
@@ -888,8 +1037,8 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, const TcMaps& maps, cudaStrea
     return (e && atoi(e) ? 1 : 0) | ((pf ? atoi(pf) : 1) ? 2 : 0) | (nprod << 2);
   }();
   {
-    cudaError_t lerr = launch_kernel(igemm_tc_kernel<MODE, BN, TMA>, dim3(tm, tn, splits), dim3(TC_BLOCK), smem, stream, splits, a, d,
-                                     proxy_fence_env, maps);
+    cudaError_t lerr = launch_kernel(igemm_tc_kernel<MODE, BN, TMA, CLS>, dim3(tm, tn, splits), dim3(TC_BLOCK), smem, stream, splits, a, d,
+                                     proxy_fence_env, maps, plan);
     if (lerr != cudaSuccess) { set_error(std::string("igemm_tc launch failed: ") + cudaGetErrorString(lerr)); return -2; }
   }
   BRE_CHECK_LAUNCH();
@@ -926,6 +1075,12 @@ int launch_igemm_tc(const GemmArgs& a, cudaStream_t stream) {
   // kernel (still tcgen05, still on the GPU: a different loader, not a fallback to another implementation)
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
+  if (cls_eligible(a)) {   // strided dgrad: per-parity-class gathers through im2col tensor maps
+    ClsPlan plan;
+    TcMapsCls cmaps;
+    memset(&cmaps, 0, sizeof(cmaps));
+    if (build_cls(a, &plan, &cmaps)) return launch_tc<GEMM_DGRAD, 64, true, true>(a, d, cmaps, stream, &plan);
+  }
   const bool tma = tma_eligible(a) && build_maps(a, 64, &maps);
   if (a.mode == GEMM_FPROP) return tma ? launch_tc<GEMM_FPROP, 64, true>(a, d, maps, stream) : launch_tc<GEMM_FPROP, 64, false>(a, d, maps, stream);
   if (a.mode == GEMM_DGRAD) return tma ? launch_tc<GEMM_DGRAD, 64, true>(a, d, maps, stream) : launch_tc<GEMM_DGRAD, 64, false>(a, d, maps, stream);

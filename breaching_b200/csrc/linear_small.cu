@@ -52,11 +52,13 @@ __global__ void __launch_bounds__(256) linear_small_fprop_kernel(GemmArgs a, int
   }
 }
 
-// ---- dgrad: block = 32 input channels x 8 groups of output channels; fixed-order reduction over the groups -----------------------
+// ---- dgrad: block = 32 input channels x 32 groups of output channels (one warp per group, lanes along ci: coalesced 128-byte
+//      rows of W); every thread keeps four independent weight loads in flight; fixed-order reduction over the groups ----------------
 template <int NB>
-__global__ void __launch_bounds__(256) linear_small_dgrad_kernel(GemmArgs a) {
+__global__ void __launch_bounds__(1024) linear_small_dgrad_kernel(GemmArgs a) {
   pdl_prologue();
-  __shared__ float part[8][NB][33];
+  constexpr int G = NB >= 16 ? 8 : (NB >= 8 ? 16 : 32);   // groups of output channels = warps per block (17 KB of partials)
+  __shared__ float part[G][NB][33];
   const int cx = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int ci = blockIdx.x * 32 + cx;
   const int Co = a.g.Co, Ci = a.g.Ci, N = a.g.N;
@@ -67,7 +69,19 @@ __global__ void __launch_bounds__(256) linear_small_dgrad_kernel(GemmArgs a) {
     for (int s = 0; s < a.nsrc; ++s) {
       const float* __restrict__ w = a.wgt[s];
       const float* __restrict__ dy = a.act[s];
-      for (int co = grp; co < Co; co += 8) {
+      int co = grp;
+      for (; co + 3 * G < Co; co += 4 * G) {
+        float wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wv[u] = __ldg(w + (long long)(co + u * G) * Ci + ci);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int n = 0; n < NB; ++n)
+            if (n < N) acc[n] = fmaf(wv[u], __ldg(dy + (long long)n * Co + co + u * G), acc[n]);
+        }
+      }
+      for (; co < Co; co += G) {
         const float wv = __ldg(w + (long long)co * Ci + ci);
 #pragma unroll
         for (int n = 0; n < NB; ++n)
@@ -78,14 +92,13 @@ __global__ void __launch_bounds__(256) linear_small_dgrad_kernel(GemmArgs a) {
 #pragma unroll
   for (int n = 0; n < NB; ++n) part[grp][n][cx] = acc[n];
   __syncthreads();
-  // threads (grp = n mod 8 ...) : thread t handles (n, cx) pairs in a fixed order
-  for (int idx = threadIdx.x; idx < NB * 32; idx += 256) {
+  for (int idx = threadIdx.x; idx < NB * 32; idx += 32 * G) {
     const int n = idx >> 5, c = idx & 31;
     const int cc = blockIdx.x * 32 + c;
     if (n >= N || cc >= Ci) continue;
     float t = 0.f;
 #pragma unroll
-    for (int g2 = 0; g2 < 8; ++g2) t += part[g2][n][c];
+    for (int g2 = 0; g2 < G; ++g2) t += part[g2][n][c];
     float* o = a.out + (long long)n * a.x_sN + (long long)cc * a.x_sC;
     *o = a.accumulate ? *o + t : t;
   }
@@ -120,7 +133,7 @@ int launch_nb(const GemmArgs& a, cudaStream_t stream) {
     for (int s = 0; s < a.nsrc; ++s) vec = vec && al16(a.act[s]) && al16(a.wgt[s]);
     BRE_KLAUNCH((linear_small_fprop_kernel<NB>), ceil_div((long long)Co * 32, 256), 256, 0, stream, a, vec);
   } else if (a.mode == GEMM_DGRAD) {
-    BRE_KLAUNCH((linear_small_dgrad_kernel<NB>), ceil_div(Ci, 32), 256, 0, stream, a);
+    BRE_KLAUNCH((linear_small_dgrad_kernel<NB>), ceil_div(Ci, 32), 32 * (NB >= 16 ? 8 : (NB >= 8 ? 16 : 32)), 0, stream, a);
   } else {
     long long blocks = ((long long)Co * Ci + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;

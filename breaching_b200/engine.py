@@ -83,7 +83,7 @@ EXPORTS = [
     "bre_engine_load_soft_labels", "bre_engine_label_gradient", "bre_engine_set_labels",
     "bre_token_layernorm", "bre_token_attention",
     "bre_engine_param_gradients", "bre_engine_bn_batch_stats", "bre_engine_forward", "bre_image_mse",
-    "bre_engine_begin_joint_trial", "bre_engine_get_joint_labels",
+    "bre_engine_begin_joint_trial", "bre_engine_get_joint_labels", "bre_resize_bilinear",
 ]
 
 
@@ -137,6 +137,7 @@ def load_library(path=None):
     lib.bre_engine_param_gradients.argtypes = [vp, vp, vp, i32, P(vp), i32, P(ctypes.c_double)]
     lib.bre_engine_bn_batch_stats.argtypes = [vp, i32, vp, vp]
     lib.bre_engine_forward.argtypes = [vp, vp, vp]
+    lib.bre_resize_bilinear.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.bre_image_mse.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, P(ctypes.c_double), vp]
     for name in EXPORTS:
         if name not in ("bre_last_error", "bre_version", "bre_engine_destroy"):
@@ -531,6 +532,20 @@ def total_variation(x, scale=0.1, inner_exp=1.0, outer_exp=1.0, eps=1e-8, double
                                      eps, int(double_opponents), int(accumulate), ctypes.byref(val), ctypes.c_void_p(stream))
     _check(lib, rc, "bre_total_variation")
     return val.value, grad
+
+
+def resize_bilinear(x, size):
+    """``F.interpolate(x, size=size, mode="bilinear", align_corners=False)`` for an NCHW fp32 batch on the device."""
+    lib = load_library()
+    assert x.is_cuda and x.dim() == 4
+    x = _f32c(x)
+    Ho, Wo = (int(size), int(size)) if not isinstance(size, (tuple, list)) else (int(size[0]), int(size[1]))
+    out = torch.empty((x.shape[0], x.shape[1], Ho, Wo), dtype=torch.float32, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        rc = lib.bre_resize_bilinear(_ptr(x), _ptr(out), x.shape[0], x.shape[1], x.shape[2], x.shape[3], Ho, Wo, ctypes.c_void_p(stream))
+    _check(lib, rc, "bre_resize_bilinear")
+    return out
 
 
 def image_mse(rec, ref, mean=None, std=None, clamp=True):

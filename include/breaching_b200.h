@@ -204,6 +204,10 @@ int bre_engine_forward(bre_engine* e, const float* data, float* logits_out);
 int bre_image_mse(const float* rec, const float* ref, int32_t N, int32_t C, int32_t HW, const float* mean, const float* std,
                   int32_t clamp01, double* mse_host, void* stream);
 
+/* Bilinear resize of an NCHW fp32 batch on the device, F.interpolate(mode="bilinear", align_corners=False) semantics: the
+ * stage-to-stage up-sampling of MultiScaleOptimizationAttacker (multiscale_optimization_attack.py:45-69). */
+int bre_resize_bilinear(const float* src, float* dst, int32_t N, int32_t C, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, void* stream);
+
 /* ---- stand-alone kernels (each is also a stage of the engine; exposed for parity tests + rooflines) */
 /* Multi-tensor gradient-matching reduction (objectives.py:91-95,135-141,160-164,185-196).
  * G, g: device fp32 [n]; chunk_weights: device fp32 [ceil(n/1024)] or NULL.  sums5 (host, double):

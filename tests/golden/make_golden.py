@@ -266,6 +266,30 @@ def label_fixtures(ref):
     return out
 
 
+INIT_TYPES = ["randn", "randn-trunc", "rand", "zeros", "red", "green-true", "blue", "dark", "light-true", "patterned-4", "rand-patterned-8",
+              "randn-patterned-3", "wei-4", "rand-wei-5"]
+
+
+def init_fixtures(ref):
+    """Candidate initialisations of the reference (`_BaseAttacker._initialize_data`, base_attack.py:222-285) from a seeded global
+    generator, for every scheme incl. the `patterned-k` / `wei-k` tiles and the colour fills."""
+    from breaching.attacks.base_attack import _BaseAttacker
+
+    out = []
+    dm = torch.tensor(synthetic.IMAGENET["mean"])[None, :, None, None]
+    ds = torch.tensor(synthetic.IMAGENET["std"])[None, :, None, None]
+    for init in INIT_TYPES:
+        att = _BaseAttacker.__new__(_BaseAttacker)
+        att.cfg = refshim.load_reference_attack_cfg("invertinggradients", {"init": init})
+        att.setup = dict(device=torch.device("cpu"), dtype=torch.float)
+        att.dm, att.ds = dm, ds
+        att.memory_format = torch.contiguous_format
+        torch.manual_seed(4321)
+        cand = att._initialize_data([2, 3, 19, 21])
+        out.append(dict(init=init, shape=[2, 3, 19, 21], seed=4321, candidate=cand.detach().clone()))
+    return out
+
+
 def lr_fixtures(ref):
     from breaching.attacks.auxiliaries.common import optimizer_lookup
     from oracle.restate import lr_table_by_stepping
@@ -283,7 +307,7 @@ def lr_fixtures(ref):
 
 def config_fixtures():
     names = ["invertinggradients", "modern", "seethroughgradients", "clsattack", "legacy", "sanitycheck", "tag",
-             "deepleakage", "beyondinfering", "wei", "_default_optimization_attack"]
+             "deepleakage", "beyondinfering", "wei", "multiscale_ghiasi", "_default_optimization_attack"]
 
     def plain(node):
         if isinstance(node, dict):
@@ -317,6 +341,10 @@ def main():
         fx = config5_fixture(ref)
         torch.save(fx, os.path.join(HERE, "trial_joint_tag_config5.pt"))
         print("joint_tag_config5 history", [round(h, 5) for h in fx["history"]])
+    if "configs" in only:
+        torch.save(config_fixtures(), os.path.join(HERE, "attack_configs.pt"))
+    if not only or "inits" in only:
+        torch.save(init_fixtures(ref), os.path.join(HERE, "inits.pt"))
     if only:
         return
     torch.save(label_fixtures(ref), os.path.join(HERE, "labels.pt"))

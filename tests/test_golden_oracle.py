@@ -101,6 +101,29 @@ def test_label_recovery_bit_exact():
         assert orc.tolist() == fx["recovered"].tolist(), fx["strategy"]
 
 
+def test_candidate_initialisation_equals_the_reference():
+    """Every initialisation scheme (base_attack.py:222-285, incl. `patterned-k` / `wei-k` tiles and colour fills) from the same
+    seeded generator: the product's host code and the oracle draw exactly what the reference drew."""
+    from breaching_b200 import synthetic
+    from breaching_b200.attacks import host
+    from oracle import restate
+
+    setup = dict(device=torch.device("cpu"), dtype=torch.float)
+    dm = torch.tensor(synthetic.IMAGENET["mean"])[None, :, None, None]
+    ds = torch.tensor(synthetic.IMAGENET["std"])[None, :, None, None]
+    fixtures = load_golden("inits.pt")
+    assert len(fixtures) >= 14
+    for fx in fixtures:
+        torch.manual_seed(fx["seed"])
+        ours = host.initialize_data(fx["init"], fx["shape"], dm, ds, setup)
+        assert torch.equal(ours, fx["candidate"]), fx["init"]
+        torch.manual_seed(fx["seed"])
+        orc = restate.initialize_data(fx["init"], fx["shape"], dm, ds)
+        assert torch.equal(orc, fx["candidate"]), fx["init"]
+    with pytest.raises(ValueError):
+        host.initialize_data("no-such-scheme", [1, 3, 4, 4], dm, ds, setup)
+
+
 def test_attack_presets_equal_reference_yaml():
     from breaching_b200 import config as bcfg
 

@@ -114,3 +114,41 @@ def test_report_mse_psnr_label_accuracy():
     assert math.isclose(out["feat_mse"], want, rel_tol=2e-2), (out["feat_mse"], want)   # default back end = TF32 products
     mean_psnr, max_psnr = analysis.psnr_compute(a.to(DEV), b.to(DEV), factor=1.0)
     assert math.isclose(mean_psnr, psnr.mean().item(), rel_tol=1e-5) and math.isclose(max_psnr, psnr.max().item(), rel_tol=1e-5)
+
+
+@pytest.mark.parametrize("shape,size", [((2, 3, 16, 16), 32), ((1, 3, 32, 32), 20), ((2, 3, 9, 13), (17, 7)), ((1, 1, 7, 7), 7)])
+def test_bilinear_resize_equals_interpolate(shape, size):
+    from breaching_b200.engine import resize_bilinear
+
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(3))
+    want = torch.nn.functional.interpolate(x, size=size, mode="bilinear", align_corners=False)
+    got = resize_bilinear(x.to(DEV), size)
+    assert got.shape == want.shape and (got.cpu() - want).abs().max().item() < 1e-5
+
+
+def test_multiscale_attack_runs_its_stages_on_the_engine():
+    """MultiScaleOptimizationAttacker (multiscale_optimization_attack.py:18-122; preset multiscale_ghiasi.yaml without its
+    augmentations): two stages of a log pyramid on a ResNet-18 -- every stage is a trial of a layer program compiled for that
+    resolution, candidates move between stages through bre_resize_bilinear, the history concatenates the stages, and a
+    one-stage `trivial` pyramid equals the plain attacker's trial from the same initial candidate."""
+    from breaching_b200 import get_attack_config
+    from breaching_b200.attacks import prepare_attack
+    from breaching_b200.attacks.multiscale_attack import scale_pyramid
+
+    assert scale_pyramid("linear", 7, 224) == [32, 64, 96, 128, 160, 192, 224]      # :32-33
+    assert scale_pyramid("log", 3, 64) == [16, 32, 64] and scale_pyramid("trivial", 2, 8) == [8, 8]
+    model, loss_fn, payload, shared, true = synthetic.make_case("resnet18", "imagenet", batch=1, seed=4, bn_random=True, image_size=64, classes=10)
+    over = {"augmentations": None, "num_stages": 2, "scale_pyramid": "log", "resize": "upsampling", "optim.max_iterations": 6, "optim.callback": 3}
+    cfg = get_attack_config("multiscale_ghiasi", over)
+    attacker = prepare_attack(model, loss_fn, cfg, dict(SETUP, backend="simt"))
+    assert type(attacker).__name__ == "MultiScaleOptimizationAttacker"
+    torch.manual_seed(0)
+    rec, stats = attacker.reconstruct(payload, copy.deepcopy(shared), {})
+    assert rec["data"].shape == (1, 3, 64, 64) and torch.isfinite(rec["data"]).all()
+    hist = stats["Trial_0_Val"]
+    assert len(hist) == 12 and hist[5] < hist[0] and hist[11] < hist[6]                # two stages of 6 iterations, each optimising
+    assert sorted(attacker._stage_engines) == [32]                                     # the 64x64 stage runs on the attacker's main engine
+    # `focus` pasting and a trivial pyramid
+    cfg2 = get_attack_config("multiscale_ghiasi", dict(over, resize="focus", scale_pyramid="trivial", num_stages=1))
+    rec2, stats2 = prepare_attack(model, loss_fn, cfg2, dict(SETUP, backend="simt")).reconstruct(payload, copy.deepcopy(shared), {})
+    assert len(stats2["Trial_0_Val"]) == 6 and rec2["data"].shape == (1, 3, 64, 64)
