@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const int chunk = ((c + j) >> 2) ^ (tid & 15);
+        const int chunk = ((c + j) >> 2) ^ (tid & (BN / 4 - 1) & 15);
         *reinterpret_cast<float4*>(part + tid * BN + chunk * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     }
@@ -720,7 +720,8 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
       // trip is ~0.5 us; one slot at a time made this phase 2.2 us), then summed in fixed rank order.
       auto reduce_rows = [&](auto s_tag) {
         constexpr int S = decltype(s_tag)::value;
-        constexpr int C4 = BN / 4, SLOTS = (TC_BM / S) * C4 / TC_THREADS;
+        constexpr int C4 = BN / 4, SLOTS = (TC_BM / S) * C4 / TC_THREADS > 0 ? (TC_BM / S) * C4 / TC_THREADS : 1;
+        static_assert(BN >= 64 || S <= 8, "narrow tiles: at most 8 splits");
         const uint32_t part_s = smem_u32(sA);
         float4 t[SLOTS][S];
         int rr[SLOTS], cc[SLOTS];
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
           const int slot = tid + sl * TC_THREADS;
           rr[sl] = z * (TC_BM / S) + slot / C4;
           cc[sl] = slot % C4;
-          const uint32_t local = part_s + (uint32_t)(rr[sl] * BN + ((cc[sl] ^ (rr[sl] & 15)) << 2)) * 4u;
+          const uint32_t local = part_s + (uint32_t)(rr[sl] * BN + ((cc[sl] ^ (rr[sl] & (BN / 4 - 1) & 15)) << 2)) * 4u;
 #pragma unroll
           for (int q = 0; q < S; ++q) t[sl][q] = ld_dsmem4(local, (uint32_t)q);
         }
@@ -773,7 +774,9 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
         case 2: reduce_rows(std::integral_constant<int, 2>{}); break;
         case 4: reduce_rows(std::integral_constant<int, 4>{}); break;
         case 8: reduce_rows(std::integral_constant<int, 8>{}); break;
-        default: reduce_rows(std::integral_constant<int, 16>{}); break;
+        default:
+          if constexpr (BN >= 64) reduce_rows(std::integral_constant<int, 16>{});
+          break;
       }
     }
     TC_MARK(9, tid == 0);
@@ -1006,7 +1009,7 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, const std::conditional_t<CLS,
   static const int max_splits_env = [] { const char* e = getenv("BRE_TC_MAX_SPLITS"); return e ? atoi(e) : 0; }();
   static const int target_ctas_env = [] { const char* e = getenv("BRE_TC_TARGET_CTAS"); return e ? atoi(e) : 0; }();
   const int target = target_ctas_env > 0 ? target_ctas_env : 144;   // re-tuned with the TMA producer: 96 -> 144 is +2 % on config 2, 288 is -4 %
-  constexpr int kMaxCluster = 16;  // non-portable cluster size (8 is the portable limit); opted in below
+  constexpr int kMaxCluster = BN >= 64 ? 16 : 8;  // non-portable cluster size 16 (8 is the portable limit; narrow tiles: see reduce_rows)
   int splits = a.splits;
   if (splits <= 0) {
     splits = 1;
@@ -1047,6 +1050,14 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, const std::conditional_t<CLS,
 
 }  // namespace
 
+static bool narrow_tiles_ok(const GemmArgs& a) {
+  static const int env = [] { const char* e = getenv("BRE_TC_NARROW"); return e ? atoi(e) : 1; }();
+  if (!env || !tma_eligible(a)) return false;
+  if (a.mode == GEMM_DGRAD && a.g.stride != 1) return false;
+  if (a.mode == GEMM_WGRAD && (a.g.Ci % 32 != 0)) return false;
+  return true;
+}
+
 bool igemm_tc_supported(const GemmArgs& a) {
   const ConvGeom& g = a.g;
   int M, Nc, K;
@@ -1055,7 +1066,9 @@ bool igemm_tc_supported(const GemmArgs& a) {
     if (!aligned16(a.act[s]) || !aligned16(a.wgt[s])) return false;
   if (!aligned16(a.out) || (a.splits == 0 && a.ws == nullptr)) return false;
   const bool x_nhwc = a.x_sC == 1 && a.x_sP % 4 == 0 && a.x_sN % 4 == 0;
-  if (Nc % 64 != 0) return false;
+  // output tiles are 128 x 64; widths that are only a multiple of 32 (token models: d = 96, 3 d = 288) run 128 x 32 tiles, which
+  // exist for the TMA producer only
+  if (Nc % 64 != 0 && !(Nc % 32 == 0 && narrow_tiles_ok(a))) return false;
   switch (a.mode) {
     case GEMM_FPROP: return x_nhwc && g.Ci % TC_BK == 0 && g.R * g.S <= 64;  // k-block inside one (r, s) cell
     case GEMM_DGRAD: return x_nhwc && g.Co % TC_BK == 0 && g.Ci % 64 == 0 && g.R * g.S <= 64;
@@ -1080,6 +1093,12 @@ int launch_igemm_tc(const GemmArgs& a, cudaStream_t stream) {
     TcMapsCls cmaps;
     memset(&cmaps, 0, sizeof(cmaps));
     if (build_cls(a, &plan, &cmaps)) return launch_tc<GEMM_DGRAD, 64, true, true>(a, d, cmaps, stream, &plan);
+  }
+  if (d.Nc % 64 != 0) {   // 128 x 32 tiles (TMA producer only, see igemm_tc_supported)
+    if (!build_maps(a, 32, &maps)) { set_error("igemm_tc: tensor-map encoding failed for a narrow-tile shape"); return -4; }
+    if (a.mode == GEMM_FPROP) return launch_tc<GEMM_FPROP, 32, true>(a, d, maps, stream);
+    if (a.mode == GEMM_DGRAD) return launch_tc<GEMM_DGRAD, 32, true>(a, d, maps, stream);
+    return launch_tc<GEMM_WGRAD, 32, true>(a, d, maps, stream);
   }
   const bool tma = tma_eligible(a) && build_maps(a, 64, &maps);
   if (a.mode == GEMM_FPROP) return tma ? launch_tc<GEMM_FPROP, 64, true>(a, d, maps, stream) : launch_tc<GEMM_FPROP, 64, false>(a, d, maps, stream);

@@ -2,6 +2,7 @@
 // one deterministic cross-block reduction per kernel (last-arriving block sums the partials in order), no atomics
 // on data, no host synchronisation: every scalar the next stage needs stays in the device-resident Scalars block.
 #include "objective.cuh"
+#include "cluster_rows.cuh"
 
 namespace bre {
 
@@ -472,49 +473,38 @@ __global__ void __launch_bounds__(256) pixel_step_kernel(StepArgs a, Scalars* sc
 }
 
 // ---- label leaf of the joint data + label optimisation (optimization_with_label_attack.py:145-189) ----------------------
+// One thread-block cluster per row (cluster_rows.cuh): token models have 50 257 classes per row.
 // q = softmax(label logits) per row: what the closure hands to the task loss (:154)
-__global__ void __launch_bounds__(256) row_softmax_kernel(const float* __restrict__ ell, float* __restrict__ q, int C) {
+__global__ void __launch_bounds__(kRowThreads) row_softmax_kernel(const float* __restrict__ ell, float* __restrict__ q, int C) {
   pdl_prologue();
-  __shared__ double scratch[32];
-  __shared__ float s_red[32];
-  __shared__ float s_b[2];
+  __shared__ RowReduce ws;
+  int c0, c1;
+  row_segment(C, c0, c1);
   const float* z = ell + (long long)blockIdx.x * C;
   float* o = q + (long long)blockIdx.x * C;
   float mx = -3.402823466e+38f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, z[c]);
-  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float m = s_red[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_red[w]);
-    s_b[0] = m;
-  }
-  __syncthreads();
-  mx = s_b[0];
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) mx = fmaxf(mx, z[c]);
+  mx = (float)row_allreduce<ROW_MAX>((double)mx, ws, 0);
   double part = 0.0;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) part += (double)expf(z[c] - mx);
-  const double tot = block_sum(part, scratch);
-  if (threadIdx.x == 0) s_b[1] = (float)(1.0 / tot);
-  __syncthreads();
-  const float inv = s_b[1];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = expf(z[c] - mx) * inv;
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) part += (double)expf(z[c] - mx);
+  const float inv = (float)(1.0 / row_allreduce<ROW_SUM>(part, ws, 1));
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) o[c] = expf(z[c] - mx) * inv;
+  cluster_exit();
 }
 
 // chain d(objective)/dq through the softmax onto the label logits (what autograd does at :162): g <- q * (g - <q, g>)
-__global__ void __launch_bounds__(256) softmax_chain_kernel(const float* __restrict__ q, float* __restrict__ g, int C) {
+__global__ void __launch_bounds__(kRowThreads) softmax_chain_kernel(const float* __restrict__ q, float* __restrict__ g, int C) {
   pdl_prologue();
-  __shared__ double scratch[32];
-  __shared__ float s_dot;
+  __shared__ RowReduce ws;
+  int c0, c1;
+  row_segment(C, c0, c1);
   const float* qq = q + (long long)blockIdx.x * C;
   float* gg = g + (long long)blockIdx.x * C;
   double part = 0.0;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) part += (double)qq[c] * (double)gg[c];
-  const double tot = block_sum(part, scratch);
-  if (threadIdx.x == 0) s_dot = (float)tot;
-  __syncthreads();
-  const float dot = s_dot;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) gg[c] = qq[c] * (gg[c] - dot);
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) part += (double)qq[c] * (double)gg[c];
+  const float dot = (float)row_allreduce<ROW_SUM>(part, ws, 0);
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) gg[c] = qq[c] * (gg[c] - dot);
+  cluster_exit();
 }
 
 __global__ void commit_kernel(Scalars* sc, float* history, int max_hist, float task_reg) {
@@ -700,12 +690,12 @@ int launch_pixel_step(const StepArgs& a, Scalars* sc, cudaStream_t s) {
   return 0;
 }
 int launch_row_softmax(const float* ell, float* q, int rows, int C, cudaStream_t s) {
-  BRE_KLAUNCH(row_softmax_kernel, rows, 256, 0, s, ell, q, C);
+  if (launch_row_kernel(row_softmax_kernel, rows, C, s, ell, q, C) != cudaSuccess) { set_error("row softmax: launch failed"); return -2; }
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_softmax_chain(const float* q, float* g, int rows, int C, cudaStream_t s) {
-  BRE_KLAUNCH(softmax_chain_kernel, rows, 256, 0, s, q, g, C);
+  if (launch_row_kernel(softmax_chain_kernel, rows, C, s, q, g, C) != cudaSuccess) { set_error("softmax chain: launch failed"); return -2; }
   BRE_CHECK_LAUNCH();
   return 0;
 }

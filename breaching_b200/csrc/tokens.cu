@@ -12,6 +12,7 @@
 #include <float.h>
 
 #include "tokens.cuh"
+#include "cluster_rows.cuh"
 
 namespace bre {
 namespace {
@@ -115,104 +116,128 @@ __global__ void layernorm_param_grad_kernel(const float* __restrict__ x, const f
 }
 
 // ---- multi-head self-attention (no mask) ---------------------------------------------------------------------------
-// One block per (sequence b, head h), T threads (thread i = query / key row i).  Shared memory: Q, K, V [T][dh] (+ their
-// tangents), probabilities P [T][T] and scratch matrices.  P (and the tangent P') are also kept in global memory
-// [B, heads, T, T] between sweeps.
+// One block of 256 threads per (sequence b, head h); Q, K, V [T][dh] (+ their tangents), the probabilities P [T][T] and scratch
+// matrices live in shared memory; P (and the tangent P') are also kept in global memory [B, heads, T, T] between sweeps.
+// Every sweep has two phases: (A) one warp per query row, lanes along the key index -- scores, the row reductions of the softmax
+// and of its first / second derivative via warp shuffles; (B) all threads over the (row, channel) outputs, each a T-long dot
+// product.  (Round 1 ran one *thread* per query row: 48 us per launch, 21 % of a config-5 iteration.)
 //   sweep 0 (F):  O = P V                                  writes out [rows, d], P
 //   sweep 1 (B):  d(qkv) from dO (= in1 [rows, d])          writes out [rows, 3 d]
 //   sweep 2 (TF): O' from (qkv)' (= in1 [rows, 3 d])        writes out [rows, d], P'
 //   sweep 3 (TB): d(qkv)' from dO' (= in1), dO (= in2), (qkv)' (= in3), P, P'     writes out [rows, 3 d]
-__global__ void attention_kernel(int sweep, const float* __restrict__ qkv, const float* __restrict__ in1, const float* __restrict__ in2,
-                                 const float* __restrict__ in3, int T, int heads, int dh, float* __restrict__ P, float* __restrict__ Pd,
-                                 float* __restrict__ out, int accumulate) {
+constexpr int ATT_THREADS = 256;
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(int sweep, const float* __restrict__ qkv, const float* __restrict__ in1,
+                                                              const float* __restrict__ in2, const float* __restrict__ in3, int T, int heads,
+                                                              int dh, float* __restrict__ P, float* __restrict__ Pd, float* __restrict__ out,
+                                                              int accumulate) {
   extern __shared__ float sm[];
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-  const int i = threadIdx.x, d = heads * dh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = ATT_THREADS / 32;
+  const int d = heads * dh;
   const float scale = 1.0f / sqrtf((float)dh);
   float* sQ = sm;                 // [T][dh]
   float* sK = sQ + T * dh;
   float* sV = sK + T * dh;
   float* sA = sV + T * dh;        // [T][dh]  dO  /  Q'
-  float* sB = sA + T * dh;        // [T][dh]  dO' /  K'
+  float* sB = sA + T * dh;        // [T][dh]         K'
   float* sC = sB + T * dh;        // [T][dh]         V'
   float* sP = sC + T * dh;        // [T][T]
-  float* sM = sP + T * T;         // [T][T]  dS  (B, TB)  /  P' (TF, TB)
+  float* sM = sP + T * T;         // [T][T]  dS  (B)  /  P' (TF, TB)
   float* sN = sM + T * T;         // [T][T]  dS' (TB)
-  const long long row = (long long)b * T + i;
-  const long long pbase = ((long long)blockIdx.x * T + i) * T;
+  float* sdO = sN + T * T;        // [T][dh] dO  (TB)
+  float* sdOd = sdO + T * dh;     // [T][dh] dO' (TB)
+  float* sdS = sdOd + T * dh;     // [T][T]  dS  (TB)
+  const long long row0 = (long long)b * T;
+  const long long pb = (long long)blockIdx.x * T * T;
   auto load_qkv = [&](const float* src, float* q, float* k, float* v) {
-    for (int c = 0; c < dh; ++c) {
-      q[i * dh + c] = src[row * 3 * d + h * dh + c];
-      k[i * dh + c] = src[row * 3 * d + d + h * dh + c];
-      v[i * dh + c] = src[row * 3 * d + 2 * d + h * dh + c];
+    for (int e = tid; e < T * dh; e += ATT_THREADS) {
+      const int i = e / dh, c = e - i * dh;
+      const float* r = src + (row0 + i) * 3 * d + h * dh + c;
+      q[e] = r[0]; k[e] = r[d]; v[e] = r[2 * d];
     }
+  };
+  auto load_rows = [&](const float* src, float* dst) {   // [rows, d] -> this head's [T][dh]
+    for (int e = tid; e < T * dh; e += ATT_THREADS) {
+      const int i = e / dh, c = e - i * dh;
+      dst[e] = src[(row0 + i) * d + h * dh + c];
+    }
+  };
+  auto dot = [&](const float* x, const float* y) {
+    float s = 0.f;
+    for (int c = 0; c < dh; ++c) s = fmaf(x[c], y[c], s);
+    return s;
+  };
+  auto store_qkv_grad = [&](int i, int c, float dq, float dk, float dv) {
+    float* o = out + (row0 + i) * 3 * d + h * dh + c;
+    const float vq = dq * scale, vk = dk * scale;
+    o[0] = accumulate ? o[0] + vq : vq;
+    o[d] = accumulate ? o[d] + vk : vk;
+    o[2 * d] = accumulate ? o[2 * d] + dv : dv;
   };
   load_qkv(qkv, sQ, sK, sV);
   if (sweep == 0) {
     __syncthreads();
-    float mx = -3.0e38f;
-    for (int j = 0; j < T; ++j) {
-      float s = 0.f;
-      for (int c = 0; c < dh; ++c) s = fmaf(sQ[i * dh + c], sK[j * dh + c], s);
-      s *= scale;
-      sP[i * T + j] = s;
-      mx = fmaxf(mx, s);
+    for (int i = warp; i < T; i += nwarps) {                      // (A) softmax of row i
+      float mx = -3.0e38f;
+      for (int j = lane; j < T; j += 32) { const float sc = dot(sQ + i * dh, sK + j * dh) * scale; sP[i * T + j] = sc; mx = fmaxf(mx, sc); }
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float den = 0.f;
+      for (int j = lane; j < T; j += 32) { const float e = expf(sP[i * T + j] - mx); sP[i * T + j] = e; den += e; }
+      den = warp_sum(den);
+      const float rden = 1.0f / den;
+      for (int j = lane; j < T; j += 32) { const float p = sP[i * T + j] * rden; sP[i * T + j] = p; P[pb + i * T + j] = p; }
     }
-    float den = 0.f;
-    for (int j = 0; j < T; ++j) { const float e = expf(sP[i * T + j] - mx); sP[i * T + j] = e; den += e; }
-    const float rden = 1.0f / den;
-    for (int j = 0; j < T; ++j) { sP[i * T + j] *= rden; P[pbase + j] = sP[i * T + j]; }
-    for (int c = 0; c < dh; ++c) {
+    __syncthreads();
+    for (int e = tid; e < T * dh; e += ATT_THREADS) {             // (B) O = P V
+      const int i = e / dh, c = e - i * dh;
       float o = 0.f;
       for (int j = 0; j < T; ++j) o = fmaf(sP[i * T + j], sV[j * dh + c], o);
-      out[row * d + h * dh + c] = o;
+      out[(row0 + i) * d + h * dh + c] = o;
     }
     return;
   }
-  for (int j = 0; j < T; ++j) sP[i * T + j] = P[pbase + j];
+  for (int e = tid; e < T * T; e += ATT_THREADS) sP[e] = P[pb + e];
   if (sweep == 1) {
-    for (int c = 0; c < dh; ++c) sA[i * dh + c] = in1[row * d + h * dh + c];    // dO
+    load_rows(in1, sA);                                           // dO
     __syncthreads();
-    float r = 0.f;
-    for (int j = 0; j < T; ++j) {
-      float dp = 0.f;
-      for (int c = 0; c < dh; ++c) dp = fmaf(sA[i * dh + c], sV[j * dh + c], dp);
-      sM[i * T + j] = dp;
-      r = fmaf(dp, sP[i * T + j], r);
+    for (int i = warp; i < T; i += nwarps) {                      // (A) dS = P (dP - r), dP_ij = dO_i . V_j, r = sum_j dP_ij P_ij
+      float r = 0.f;
+      for (int j = lane; j < T; j += 32) { const float dp = dot(sA + i * dh, sV + j * dh); sM[i * T + j] = dp; r = fmaf(dp, sP[i * T + j], r); }
+      r = warp_sum(r);
+      for (int j = lane; j < T; j += 32) sM[i * T + j] = sP[i * T + j] * (sM[i * T + j] - r);
     }
-    for (int j = 0; j < T; ++j) sM[i * T + j] = sP[i * T + j] * (sM[i * T + j] - r);   // dS
     __syncthreads();
-    for (int c = 0; c < dh; ++c) {
+    for (int e = tid; e < T * dh; e += ATT_THREADS) {             // (B)
+      const int i = e / dh, c = e - i * dh;
       float dq = 0.f, dk = 0.f, dv = 0.f;
       for (int j = 0; j < T; ++j) {
         dq = fmaf(sM[i * T + j], sK[j * dh + c], dq);
         dk = fmaf(sM[j * T + i], sQ[j * dh + c], dk);
         dv = fmaf(sP[j * T + i], sA[j * dh + c], dv);
       }
-      float* o = out + row * 3 * d + h * dh + c;
-      const float vq = dq * scale, vk = dk * scale;
-      o[0] = accumulate ? o[0] + vq : vq;
-      o[d] = accumulate ? o[d] + vk : vk;
-      o[2 * d] = accumulate ? o[2 * d] + dv : dv;
+      store_qkv_grad(i, c, dq, dk, dv);
     }
     return;
   }
   if (sweep == 2) {
     load_qkv(in1, sA, sB, sC);   // Q', K', V'
     __syncthreads();
-    float acc = 0.f;
-    for (int j = 0; j < T; ++j) {
-      float s = 0.f;
-      for (int c = 0; c < dh; ++c) s += sA[i * dh + c] * sK[j * dh + c] + sQ[i * dh + c] * sB[j * dh + c];
-      s *= scale;
-      sM[i * T + j] = s;
-      acc = fmaf(sP[i * T + j], s, acc);
+    for (int i = warp; i < T; i += nwarps) {                      // (A) P' = P (S' - sum_j P S')
+      float acc = 0.f;
+      for (int j = lane; j < T; j += 32) {
+        const float sd = (dot(sA + i * dh, sK + j * dh) + dot(sQ + i * dh, sB + j * dh)) * scale;
+        sM[i * T + j] = sd;
+        acc = fmaf(sP[i * T + j], sd, acc);
+      }
+      acc = warp_sum(acc);
+      for (int j = lane; j < T; j += 32) { const float pd = sP[i * T + j] * (sM[i * T + j] - acc); sM[i * T + j] = pd; Pd[pb + i * T + j] = pd; }
     }
-    for (int j = 0; j < T; ++j) { sM[i * T + j] = sP[i * T + j] * (sM[i * T + j] - acc); Pd[pbase + j] = sM[i * T + j]; }
-    for (int c = 0; c < dh; ++c) {
+    __syncthreads();
+    for (int e = tid; e < T * dh; e += ATT_THREADS) {             // (B) O' = P' V + P V'
+      const int i = e / dh, c = e - i * dh;
       float o = 0.f;
       for (int j = 0; j < T; ++j) o += sM[i * T + j] * sV[j * dh + c] + sP[i * T + j] * sC[j * dh + c];
-      out[row * d + h * dh + c] = o;
+      out[(row0 + i) * d + h * dh + c] = o;
     }
     return;
   }
@@ -220,44 +245,38 @@ __global__ void attention_kernel(int sweep, const float* __restrict__ qkv, const
   float* sQd = sA; float* sKd = sB; float* sVd = sC;
   load_qkv(in3, sQd, sKd, sVd);
   float* sPd = sM;                    // P'
-  for (int j = 0; j < T; ++j) sPd[i * T + j] = Pd[pbase + j];
+  for (int e = tid; e < T * T; e += ATT_THREADS) sPd[e] = Pd[pb + e];
+  load_rows(in2, sdO);
+  load_rows(in1, sdOd);
   __syncthreads();
-  // row-wise pieces: dP_ij = dO_i . V_j ; dP'_ij = dO'_i . V_j + dO_i . V'_j ; r, r'
-  float* sdO = sN + T * T;            // [T][dh]
-  float* sdOd = sdO + T * dh;         // [T][dh]
-  float* sdS = sdOd + T * dh;         // [T][T]
-  for (int c = 0; c < dh; ++c) { sdO[i * dh + c] = in2[row * d + h * dh + c]; sdOd[i * dh + c] = in1[row * d + h * dh + c]; }
-  __syncthreads();
-  float r = 0.f, rd = 0.f;
-  for (int j = 0; j < T; ++j) {
-    float dp = 0.f, dpd = 0.f;
-    for (int c = 0; c < dh; ++c) {
-      dp = fmaf(sdO[i * dh + c], sV[j * dh + c], dp);
-      dpd += sdOd[i * dh + c] * sV[j * dh + c] + sdO[i * dh + c] * sVd[j * dh + c];
+  for (int i = warp; i < T; i += nwarps) {                        // (A) dS, dS' of row i
+    float r = 0.f, rd = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float dp = dot(sdO + i * dh, sV + j * dh);
+      const float dpd = dot(sdOd + i * dh, sV + j * dh) + dot(sdO + i * dh, sVd + j * dh);
+      sdS[i * T + j] = dp;       // dP for now
+      sN[i * T + j] = dpd;       // dP' for now
+      r = fmaf(dp, sP[i * T + j], r);
+      rd += dpd * sP[i * T + j] + dp * sPd[i * T + j];
     }
-    sdS[i * T + j] = dp;       // dP for now
-    sN[i * T + j] = dpd;       // dP' for now
-    r = fmaf(dp, sP[i * T + j], r);
-    rd += dpd * sP[i * T + j] + dp * sPd[i * T + j];
-  }
-  for (int j = 0; j < T; ++j) {
-    const float dp = sdS[i * T + j], dpd = sN[i * T + j];
-    sN[i * T + j] = sPd[i * T + j] * (dp - r) + sP[i * T + j] * (dpd - rd);   // dS'
-    sdS[i * T + j] = sP[i * T + j] * (dp - r);                               // dS
+    r = warp_sum(r);
+    rd = warp_sum(rd);
+    for (int j = lane; j < T; j += 32) {
+      const float dp = sdS[i * T + j], dpd = sN[i * T + j];
+      sN[i * T + j] = sPd[i * T + j] * (dp - r) + sP[i * T + j] * (dpd - rd);   // dS'
+      sdS[i * T + j] = sP[i * T + j] * (dp - r);                               // dS
+    }
   }
   __syncthreads();
-  for (int c = 0; c < dh; ++c) {
+  for (int e = tid; e < T * dh; e += ATT_THREADS) {               // (B)
+    const int i = e / dh, c = e - i * dh;
     float dq = 0.f, dk = 0.f, dv = 0.f;
     for (int j = 0; j < T; ++j) {
       dq += sN[i * T + j] * sK[j * dh + c] + sdS[i * T + j] * sKd[j * dh + c];
       dk += sN[j * T + i] * sQ[j * dh + c] + sdS[j * T + i] * sQd[j * dh + c];
       dv += sPd[j * T + i] * sdO[j * dh + c] + sP[j * T + i] * sdOd[j * dh + c];
     }
-    float* o = out + row * 3 * d + h * dh + c;
-    const float vq = dq * scale, vk = dk * scale;
-    o[0] = accumulate ? o[0] + vq : vq;
-    o[d] = accumulate ? o[d] + vk : vk;
-    o[2 * d] = accumulate ? o[2 * d] + dv : dv;
+    store_qkv_grad(i, c, dq, dk, dv);
   }
 }
 
@@ -305,19 +324,33 @@ __device__ __forceinline__ void row_softmax_stats(const float* z, int V, double*
   sum_out = s_sum;
 }
 
-__global__ void token_ce_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ q, int rows, int V, int T, float* p,
-                                    float* loss_n, float* dlogits) {
-  __shared__ double scratch[32];
+// softmax statistics of the row this cluster serves: (max, sum of exp) over all segments
+__device__ __forceinline__ void cluster_softmax_stats(const float* z, int c0, int c1, RowReduce& ws, int slot0, float& mx_out, float& sum_out) {
+  float mx = -FLT_MAX;
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) mx = fmaxf(mx, z[c]);
+  mx = (float)row_allreduce<ROW_MAX>((double)mx, ws, slot0);
+  double part = 0.0;
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) part += (double)expf(z[c] - mx);
+  sum_out = (float)row_allreduce<ROW_SUM>(part, ws, slot0 + 1);
+  mx_out = mx;
+}
+
+__global__ void __launch_bounds__(kRowThreads) token_ce_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ q, int rows, int V,
+                                                                  int T, float* p, float* loss_n, float* dlogits) {
+  pdl_prologue();
+  __shared__ RowReduce ws;
   const int row = blockIdx.x;
+  int c0, c1;
+  row_segment(V, c0, c1);
   const float* z = logits + (long long)row * V;
   float mx, sum;
-  row_softmax_stats(z, V, scratch, mx, sum);
+  cluster_softmax_stats(z, c0, c1, ws, 0, mx, sum);
   const bool scored = (row % T) != T - 1;
   const float invM = 1.0f / (float)(rows - rows / T);
   const float lse = mx + logf(sum);
   const float* qn = q + (long long)(row + 1) * V;   // target of the next position (never read for the last position)
   double lpart = 0.0;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) {
     const float pc = expf(z[c] - mx) / sum;
     p[(long long)row * V + c] = pc;
     if (scored) {
@@ -328,34 +361,40 @@ __global__ void token_ce_fwd_kernel(const float* __restrict__ logits, const floa
       dlogits[(long long)row * V + c] = 0.f;
     }
   }
-  const double ltot = block_sum(lpart, scratch);
-  if (threadIdx.x == 0) loss_n[row] = scored ? (float)(ltot * (double)rows * (double)invM) : 0.f;
+  const double ltot = row_allreduce<ROW_SUM>(lpart, ws, 2);
+  if (threadIdx.x == 0 && cluster_rank() == 0) loss_n[row] = scored ? (float)(ltot * (double)rows * (double)invM) : 0.f;
+  cluster_exit();
 }
 
-__global__ void token_ce_tan_bwd_kernel(const float* __restrict__ p, const float* __restrict__ zdot, int rows, int V, int T, float* tdl) {
-  __shared__ double scratch[32];
-  __shared__ float s_dot;
+__global__ void __launch_bounds__(kRowThreads) token_ce_tan_bwd_kernel(const float* __restrict__ p, const float* __restrict__ zdot, int rows, int V,
+                                                                      int T, float* tdl) {
+  pdl_prologue();
+  __shared__ RowReduce ws;
   const int row = blockIdx.x;
+  int c0, c1;
+  row_segment(V, c0, c1);
   const float* pp = p + (long long)row * V;
   const float* zz = zdot + (long long)row * V;
   double part = 0.0;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) part += (double)pp[c] * (double)zz[c];
-  const double tot = block_sum(part, scratch);
-  if (threadIdx.x == 0) s_dot = (float)tot;
-  __syncthreads();
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) part += (double)pp[c] * (double)zz[c];
+  const float dot = (float)row_allreduce<ROW_SUM>(part, ws, 0);
   const bool scored = (row % T) != T - 1;
-  const float dot = s_dot, invM = 1.0f / (float)(rows - rows / T);
-  for (int c = threadIdx.x; c < V; c += blockDim.x) tdl[(long long)row * V + c] = scored ? pp[c] * (zz[c] - dot) * invM : 0.f;
+  const float invM = 1.0f / (float)(rows - rows / T);
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) tdl[(long long)row * V + c] = scored ? pp[c] * (zz[c] - dot) * invM : 0.f;
+  cluster_exit();
 }
 
-__global__ void token_label_grad_kernel(const float* __restrict__ logits, const float* __restrict__ p, const float* __restrict__ zdot, int rows,
-                                        int V, int T, float task_reg, float* __restrict__ out) {
-  __shared__ double scratch[32];
-  __shared__ float s_dot;
+__global__ void __launch_bounds__(kRowThreads) token_label_grad_kernel(const float* __restrict__ logits, const float* __restrict__ p,
+                                                                      const float* __restrict__ zdot, int rows, int V, int T, float task_reg,
+                                                                      float* __restrict__ out) {
+  pdl_prologue();
+  __shared__ RowReduce ws;
   const int row = blockIdx.x;                      // output row = target position (b, t); source = logits row (b, t - 1)
+  int c0, c1;
+  row_segment(V, c0, c1);
   float* o = out + (long long)row * V;
-  if (row % T == 0) {                              // position 0 is never a target
-    for (int c = threadIdx.x; c < V; c += blockDim.x) o[c] = 0.f;
+  if (row % T == 0) {                              // position 0 is never a target (uniform over the cluster: no barrier is skipped)
+    for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) o[c] = 0.f;
     return;
   }
   const long long src = row - 1;
@@ -363,19 +402,18 @@ __global__ void token_label_grad_kernel(const float* __restrict__ logits, const 
   const float* pp = p + src * V;
   const float* zz = zdot + src * V;
   double part = 0.0;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) part += (double)pp[c] * (double)zz[c];
-  const double tot = block_sum(part, scratch);
-  if (threadIdx.x == 0) s_dot = (float)tot;
-  __syncthreads();
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) part += (double)pp[c] * (double)zz[c];
+  const float dot = (float)row_allreduce<ROW_SUM>(part, ws, 0);
   float mx = 0.f, sum = 1.f;
-  if (task_reg != 0.f) row_softmax_stats(z, V, scratch, mx, sum);
-  const float dot = s_dot, invM = 1.0f / (float)(rows - rows / T);
+  if (task_reg != 0.f) cluster_softmax_stats(z, c0, c1, ws, 1, mx, sum);
+  const float invM = 1.0f / (float)(rows - rows / T);
   const float lse = mx + logf(sum);
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) {
     float v = -(zz[c] - dot) * invM;
     if (task_reg != 0.f) v -= task_reg * (z[c] - lse) * invM;
     o[c] = v;
   }
+  cluster_exit();
 }
 
 }  // namespace
@@ -412,7 +450,7 @@ int launch_token_attention(int sweep, const float* qkv, const float* in1, const 
     }
     attr_done = true;
   }
-  attention_kernel<<<B * heads, T, smem, s>>>(sweep, qkv, in1, in2, in3, T, heads, dh, P, Pd, out, accumulate);
+  attention_kernel<<<B * heads, ATT_THREADS, smem, s>>>(sweep, qkv, in1, in2, in3, T, heads, dh, P, Pd, out, accumulate);
   return check_launch("token attention");
 }
 int launch_token_posadd(const float* x, const float* pos, float* out, int rows, int C, int T, cudaStream_t s) {
@@ -425,16 +463,16 @@ int launch_token_pos_grad(const float* d, float* g_pos, int rows, int C, int T, 
   return check_launch("token positional gradient");
 }
 int launch_token_ce_fwd(const float* logits, const float* q, int rows, int V, int T, float* p, float* loss_n, float* dlogits, cudaStream_t s) {
-  token_ce_fwd_kernel<<<rows, 256, 0, s>>>(logits, q, rows, V, T, p, loss_n, dlogits);
+  if (launch_row_kernel(token_ce_fwd_kernel, rows, V, s, logits, q, rows, V, T, p, loss_n, dlogits) != cudaSuccess) { set_error("token cross-entropy: launch failed"); return -2; }
   return check_launch("token cross-entropy");
 }
 int launch_token_ce_tan_bwd(const float* p, const float* zdot, int rows, int V, int T, float* tdlogits, cudaStream_t s) {
-  token_ce_tan_bwd_kernel<<<rows, 256, 0, s>>>(p, zdot, rows, V, T, tdlogits);
+  if (launch_row_kernel(token_ce_tan_bwd_kernel, rows, V, s, p, zdot, rows, V, T, tdlogits) != cudaSuccess) { set_error("token cross-entropy tangent: launch failed"); return -2; }
   return check_launch("token cross-entropy tangent");
 }
 int launch_token_label_grad(const float* logits, const float* p, const float* zdot, int rows, int V, int T, float task_reg, float* out,
                             cudaStream_t s) {
-  token_label_grad_kernel<<<rows, 256, 0, s>>>(logits, p, zdot, rows, V, T, task_reg, out);
+  if (launch_row_kernel(token_label_grad_kernel, rows, V, s, logits, p, zdot, rows, V, T, task_reg, out) != cudaSuccess) { set_error("token label gradient: launch failed"); return -2; }
   return check_launch("token label gradient");
 }
 
