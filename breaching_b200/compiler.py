@@ -55,6 +55,7 @@ class ParamDesc:
     perm: int = PERM_NONE
     perm_c: int = 0  # for PERM_LINEAR_CHW_TO_HWC: (C, H*W) of the flattened feature map
     perm_hw: int = 0
+    alloc_numel: int = 0  # > numel: the engine reserves this many elements (zero tail), e.g. rows of a padded vocabulary
 
     @property
     def numel(self):
@@ -98,6 +99,7 @@ class Program:
     logits: int = -1  # tensor id of the network output
     num_classes: int = 0
     seq_len: int = 0  # > 0: token-sequence program (rows = batch * seq_len), causal next-token loss over rows
+    logits_valid: int = 0  # > 0: number of real classes when the logits tensor is padded to the GEMM tile width
 
     def describe(self):
         lines = []
@@ -421,7 +423,7 @@ def bn_modules(model, prog):
     return [modules[op.bn_module] if (op.kind == OP_BNACT and op.has_bn) else None for op in prog.ops]
 
 
-def compile_transformer(model, batch, seq_len):
+def compile_transformer(model, batch, seq_len, pad_vocab=True):
     """Lower the reference's ``TransformerModel`` (cases/models/language_models.py:150-205) *as the attack runs it* -- token
     embedding bypassed, the candidate is the embedding sequence [batch, seq_len, d] (base_attack.py:76-128) -- to the layer
     program: learnable positional embedding added, post-norm encoder layers (self-attention without mask, ReLU FFN), linear
@@ -473,9 +475,18 @@ def compile_transformer(model, batch, seq_len):
         prog.ops.append(Op(OP_BNACT, f2, r2, res=n1))
         cur = new_tensor(d)
         prog.ops.append(Op(OP_LAYERNORM, r2, cur, gamma=pidx[pre + "norm2.weight"], beta=pidx[pre + "norm2.bias"], eps=float(layer.norm2.eps)))
-    logits = new_tensor(model.decoder.out_features)
+    # the vocabulary is padded to the GEMM tile width (50 257 -> 50 304) so that the decoder -- the contraction that dominates this
+    # model -- runs on the tensor-core kernels: extra logit columns exist in the logits-shaped tensors only
+    # (zero weight rows / bias entries, never read by the loss: ``logits_valid``); labels stay [rows, vocabulary]
+    V = model.decoder.out_features
+    Vp = ((V + 63) // 64) * 64 if pad_vocab else V
+    logits = new_tensor(Vp)
     prog.ops.append(Op(OP_LINEAR, cur, logits, w=pidx["decoder.weight"], b=pidx["decoder.bias"]))
-    prog.logits, prog.num_classes = logits, model.decoder.out_features
+    prog.logits, prog.num_classes, prog.logits_valid = logits, V, V
+    if Vp != V:
+        prog.params[pidx["decoder.weight"]].alloc_numel = Vp * d
+        if "decoder.bias" in pidx:
+            prog.params[pidx["decoder.bias"]].alloc_numel = Vp
     written = set()
     for op in reversed(prog.ops):
         op.acc_in = op.tin in written

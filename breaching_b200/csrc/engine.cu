@@ -105,6 +105,10 @@ struct bre_engine {
   float* soft_q_buf = nullptr;    // owned storage behind soft_q
   float* label_grad = nullptr;    // d(objective)/d(soft_q) of the last evaluation
   int n_labels = 0;
+  // token models: the vocabulary may be padded to the GEMM tile width -- logits-shaped tensors then have td(logits).C columns of
+  // which the first `logits_valid` are real classes (0 = all of them); label-shaped tensors are dense [rows, classes]
+  int logits_valid = 0;
+  int classes() const { return logits_valid > 0 ? logits_valid : td(logits).C; }
   // joint data + label optimisation on the device (optimization_with_label_attack.py:89-143): the label logits are a second
   // leaf [rows, classes] with their own optimiser state and best-so-far copy
   bool joint = false;
@@ -399,10 +403,11 @@ struct bre_engine {
     const bre_tensor_desc& lt = td(logits);
     if (seq_len > 0) {   // next-token loss over rows with class-probability targets (joint attacker on a causal language model)
       if (soft_q == nullptr) { set_error("token programs need soft labels (bre_engine_load_soft_labels)"); return BRE_ERR_STATE; }
-      BRE_LAUNCH(launch_token_ce_fwd(t[logits].val, soft_q, lt.N, lt.C, seq_len, p, loss_n, t[logits].d, stream));
+      BRE_LAUNCH(launch_token_ce_fwd(t[logits].val, soft_q, lt.N, classes(), lt.C, seq_len, p, loss_n, t[logits].d, stream));
       BRE_LAUNCH(launch_loss_mean(loss_n, lt.N, sc, stream));
       return 0;
     }
+    if (classes() != lt.C) { set_error("padded class dimension is only supported for token programs"); return BRE_ERR_UNSUPPORTED; }
     BRE_LAUNCH(launch_ce_fwd(t[logits].val, labels, soft_q, lt.N, lt.C, p, loss_n, t[logits].d, stream));
     BRE_LAUNCH(launch_loss_mean(loss_n, lt.N, sc, stream));
     return 0;
@@ -606,7 +611,7 @@ struct bre_engine {
   int sweep_tangent_backward() {
     bool forked = false;
     const bre_tensor_desc& lt = td(logits);
-    if (seq_len > 0) BRE_LAUNCH(launch_token_ce_tan_bwd(p, t[logits].tval, lt.N, lt.C, seq_len, t[logits].td, stream));
+    if (seq_len > 0) BRE_LAUNCH(launch_token_ce_tan_bwd(p, t[logits].tval, lt.N, classes(), lt.C, seq_len, t[logits].td, stream));
     else BRE_LAUNCH(launch_ce_tan_bwd(p, t[logits].tval, lt.N, lt.C, t[logits].td, stream));
     const bool di = cfg.di_scale > 0.f && n_di > 0;
     for (int i = (int)ops.size() - 1; i >= 0; --i) {
@@ -810,10 +815,10 @@ struct bre_engine {
   int label_gradient_on_device() {   // d(objective)/d(label logits) of the evaluation that just ran -> label_grad
     const bre_tensor_desc& lt = td(logits);
     if (seq_len > 0)
-      BRE_LAUNCH(launch_token_label_grad(t[logits].val, p, t[logits].tval, lt.N, lt.C, seq_len, cfg.task_regularization, label_grad, stream));
+      BRE_LAUNCH(launch_token_label_grad(t[logits].val, p, t[logits].tval, lt.N, classes(), lt.C, seq_len, cfg.task_regularization, label_grad, stream));
     else
       BRE_LAUNCH(launch_ce_label_grad(t[logits].val, p, t[logits].tval, lt.N, lt.C, cfg.task_regularization, label_grad, stream));
-    BRE_LAUNCH(launch_softmax_chain(soft_q_buf, label_grad, lt.N, lt.C, stream));
+    BRE_LAUNCH(launch_softmax_chain(soft_q_buf, label_grad, lt.N, classes(), stream));
     return 0;
   }
 
@@ -821,7 +826,7 @@ struct bre_engine {
   // box projection on the data only (:111-114), best-so-far of both on the pre-step objective (:115-118)
   int iteration_joint() {
     const bre_tensor_desc& lt = td(logits);
-    BRE_LAUNCH(launch_row_softmax(ell, soft_q_buf, lt.N, lt.C, stream));
+    BRE_LAUNCH(launch_row_softmax(ell, soft_q_buf, lt.N, classes(), stream));
     soft_q = soft_q_buf;
     BRE_TRY(evaluate());
     BRE_TRY(label_gradient_on_device());
@@ -916,7 +921,9 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
   for (int i = 0; i < n_params; ++i) {
     e->params[i].desc = params[i];
     e->params[i].off = off;
-    off += ((params[i].numel + kChunk - 1) / kChunk) * kChunk;
+    // perm NONE: d0 = allocated element count when larger than numel (zero tail: rows of a padded vocabulary)
+    const long long alloc_n = (params[i].perm == BRE_PERM_NONE && params[i].d0 > params[i].numel) ? params[i].d0 : params[i].numel;
+    off += ((alloc_n + kChunk - 1) / kChunk) * kChunk;
     if (params[i].numel > e->max_param) e->max_param = params[i].numel;
   }
   e->P_pad = off;
@@ -1151,7 +1158,7 @@ int bre_engine_load_soft_labels(bre_engine* e, const float* probabilities, int64
   e->graph_ready = false;
   if (probabilities == nullptr) { e->soft_q = nullptr; return BRE_OK; }   // back to index labels
   const bre_tensor_desc& lt = e->td(e->logits);
-  if (numel != (int64_t)lt.N * lt.C) { set_error("bre_engine_load_soft_labels: expected N x classes probabilities"); return BRE_ERR_INVALID; }
+  if (numel != (int64_t)lt.N * e->classes()) { set_error("bre_engine_load_soft_labels: expected N x classes probabilities"); return BRE_ERR_INVALID; }
   if (e->ms_steps > 0) { set_error("soft labels are not supported together with local steps"); return BRE_ERR_UNSUPPORTED; }
   if (!e->soft_q_buf) { BRE_TRY(e->alloc(&e->soft_q_buf, numel)); BRE_TRY(e->alloc(&e->label_grad, numel)); }
   BRE_CUDA_CHECK(cudaMemcpyAsync(e->soft_q_buf, probabilities, numel * sizeof(float), cudaMemcpyDefault, e->stream));
@@ -1173,12 +1180,12 @@ int bre_engine_label_gradient(bre_engine* e, float* grad_out) {
   BRE_CUDA_CHECK(cudaSetDevice(e->device));
   const bre_tensor_desc& lt = e->td(e->logits);
   if (e->seq_len > 0)
-    BRE_TRY(launch_token_label_grad(e->t[e->logits].val, e->p, e->t[e->logits].tval, lt.N, lt.C, e->seq_len, e->cfg.task_regularization,
-                                    e->label_grad, e->stream));
+    BRE_TRY(launch_token_label_grad(e->t[e->logits].val, e->p, e->t[e->logits].tval, lt.N, e->classes(), lt.C, e->seq_len,
+                                    e->cfg.task_regularization, e->label_grad, e->stream));
   else
     BRE_TRY(launch_ce_label_grad(e->t[e->logits].val, e->p, e->t[e->logits].tval, lt.N, lt.C, e->cfg.task_regularization, e->label_grad,
                                  e->stream));
-  BRE_CUDA_CHECK(cudaMemcpyAsync(grad_out, e->label_grad, (size_t)lt.N * lt.C * sizeof(float), cudaMemcpyDefault, e->stream));
+  BRE_CUDA_CHECK(cudaMemcpyAsync(grad_out, e->label_grad, (size_t)lt.N * e->classes() * sizeof(float), cudaMemcpyDefault, e->stream));
   BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   return BRE_OK;
 }
@@ -1295,7 +1302,7 @@ int bre_engine_begin_joint_trial(bre_engine* e, const float* candidate, const fl
                                  const float* lr_table, int32_t n_lr) {
   if (!e || !label_logits) { set_error("bre_engine_begin_joint_trial: bad arguments"); return BRE_ERR_INVALID; }
   const bre_tensor_desc& lt = e->td(e->logits);
-  if (n_label_elems != (int64_t)lt.N * lt.C) { set_error("bre_engine_begin_joint_trial: expected N x classes label logits"); return BRE_ERR_INVALID; }
+  if (n_label_elems != (int64_t)lt.N * e->classes()) { set_error("bre_engine_begin_joint_trial: expected N x classes label logits"); return BRE_ERR_INVALID; }
   if (e->ms_steps > 0) { set_error("joint optimisation is not supported together with local steps"); return BRE_ERR_UNSUPPORTED; }
   BRE_TRY(bre_engine_begin_trial(e, candidate, lr_table, n_lr));
   BRE_CUDA_CHECK(cudaSetDevice(e->device));
@@ -1575,6 +1582,11 @@ int bre_engine_set_option(bre_engine* e, const char* name, int64_t value) {
   if (n == "pdl") { bre::set_pdl(value != 0); e->graph_ready = false; return BRE_OK; }
   if (n == "overlap_wgrad") { e->overlap_wgrad = value != 0; e->graph_ready = false; return BRE_OK; }
   if (n == "fuse_bnact") { e->fuse_bnact = value != 0; e->graph_ready = false; return BRE_OK; }
+  if (n == "logits_valid") {
+    if (value < 1 || value > e->td(e->logits).C) { set_error("logits_valid must be in [1, logits columns]"); return BRE_ERR_INVALID; }
+    if (e->soft_q_buf != nullptr) { set_error("logits_valid must be set before soft labels are loaded"); return BRE_ERR_STATE; }
+    e->logits_valid = (int)value; e->graph_ready = false; return BRE_OK;
+  }
   if (n == "gemm_backend") {
     if (value != 0 && value != 1) { set_error("gemm_backend must be 0 (simt) or 1 (tcgen05)"); return BRE_ERR_INVALID; }
     e->gemm_backend = (int)value; e->graph_ready = false; e->chunk_mode_ready = false; return BRE_OK;

@@ -1071,7 +1071,7 @@ bool igemm_tc_supported(const GemmArgs& a) {
   if (Nc % 64 != 0 && !(Nc % 32 == 0 && narrow_tiles_ok(a))) return false;
   switch (a.mode) {
     case GEMM_FPROP: return x_nhwc && g.Ci % TC_BK == 0 && g.R * g.S <= 64;  // k-block inside one (r, s) cell
-    case GEMM_DGRAD: return x_nhwc && g.Co % TC_BK == 0 && g.Ci % 64 == 0 && g.R * g.S <= 64;
+    case GEMM_DGRAD: return x_nhwc && g.Co % TC_BK == 0 && g.R * g.S <= 64;   // (Nc = Ci: tile-width rule above)
     case GEMM_WGRAD: return x_nhwc && g.Co % 4 == 0 && g.Ci % 4 == 0 && g.R * g.S <= 64;
     default: return false;
   }

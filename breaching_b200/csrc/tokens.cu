@@ -336,13 +336,13 @@ __device__ __forceinline__ void cluster_softmax_stats(const float* z, int c0, in
 }
 
 __global__ void __launch_bounds__(kRowThreads) token_ce_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ q, int rows, int V,
-                                                                  int T, float* p, float* loss_n, float* dlogits) {
+                                                                  int Vs, int T, float* p, float* loss_n, float* dlogits) {
   pdl_prologue();
   __shared__ RowReduce ws;
   const int row = blockIdx.x;
   int c0, c1;
   row_segment(V, c0, c1);
-  const float* z = logits + (long long)row * V;
+  const float* z = logits + (long long)row * Vs;   // logits-shaped tensors: row stride Vs >= V (vocabulary padded for the GEMM tiles)
   float mx, sum;
   cluster_softmax_stats(z, c0, c1, ws, 0, mx, sum);
   const bool scored = (row % T) != T - 1;
@@ -352,13 +352,13 @@ __global__ void __launch_bounds__(kRowThreads) token_ce_fwd_kernel(const float* 
   double lpart = 0.0;
   for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) {
     const float pc = expf(z[c] - mx) / sum;
-    p[(long long)row * V + c] = pc;
+    p[(long long)row * Vs + c] = pc;
     if (scored) {
       const float qc = qn[c];
-      dlogits[(long long)row * V + c] = (pc - qc) * invM;
+      dlogits[(long long)row * Vs + c] = (pc - qc) * invM;
       lpart -= (double)qc * (double)(z[c] - lse);
     } else {
-      dlogits[(long long)row * V + c] = 0.f;
+      dlogits[(long long)row * Vs + c] = 0.f;
     }
   }
   const double ltot = row_allreduce<ROW_SUM>(lpart, ws, 2);
@@ -367,26 +367,26 @@ __global__ void __launch_bounds__(kRowThreads) token_ce_fwd_kernel(const float* 
 }
 
 __global__ void __launch_bounds__(kRowThreads) token_ce_tan_bwd_kernel(const float* __restrict__ p, const float* __restrict__ zdot, int rows, int V,
-                                                                      int T, float* tdl) {
+                                                                      int Vs, int T, float* tdl) {
   pdl_prologue();
   __shared__ RowReduce ws;
   const int row = blockIdx.x;
   int c0, c1;
   row_segment(V, c0, c1);
-  const float* pp = p + (long long)row * V;
-  const float* zz = zdot + (long long)row * V;
+  const float* pp = p + (long long)row * Vs;
+  const float* zz = zdot + (long long)row * Vs;
   double part = 0.0;
   for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) part += (double)pp[c] * (double)zz[c];
   const float dot = (float)row_allreduce<ROW_SUM>(part, ws, 0);
   const bool scored = (row % T) != T - 1;
   const float invM = 1.0f / (float)(rows - rows / T);
-  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) tdl[(long long)row * V + c] = scored ? pp[c] * (zz[c] - dot) * invM : 0.f;
+  for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) tdl[(long long)row * Vs + c] = scored ? pp[c] * (zz[c] - dot) * invM : 0.f;
   cluster_exit();
 }
 
 __global__ void __launch_bounds__(kRowThreads) token_label_grad_kernel(const float* __restrict__ logits, const float* __restrict__ p,
-                                                                      const float* __restrict__ zdot, int rows, int V, int T, float task_reg,
-                                                                      float* __restrict__ out) {
+                                                                      const float* __restrict__ zdot, int rows, int V, int Vs, int T,
+                                                                      float task_reg, float* __restrict__ out) {
   pdl_prologue();
   __shared__ RowReduce ws;
   const int row = blockIdx.x;                      // output row = target position (b, t); source = logits row (b, t - 1)
@@ -398,9 +398,9 @@ __global__ void __launch_bounds__(kRowThreads) token_label_grad_kernel(const flo
     return;
   }
   const long long src = row - 1;
-  const float* z = logits + src * V;
-  const float* pp = p + src * V;
-  const float* zz = zdot + src * V;
+  const float* z = logits + src * Vs;
+  const float* pp = p + src * Vs;
+  const float* zz = zdot + src * Vs;
   double part = 0.0;
   for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) part += (double)pp[c] * (double)zz[c];
   const float dot = (float)row_allreduce<ROW_SUM>(part, ws, 0);
@@ -462,17 +462,17 @@ int launch_token_pos_grad(const float* d, float* g_pos, int rows, int C, int T, 
   pos_grad_kernel<<<(T * C + 255) / 256, 256, 0, s>>>(d, g_pos, rows, C, T);
   return check_launch("token positional gradient");
 }
-int launch_token_ce_fwd(const float* logits, const float* q, int rows, int V, int T, float* p, float* loss_n, float* dlogits, cudaStream_t s) {
-  if (launch_row_kernel(token_ce_fwd_kernel, rows, V, s, logits, q, rows, V, T, p, loss_n, dlogits) != cudaSuccess) { set_error("token cross-entropy: launch failed"); return -2; }
+int launch_token_ce_fwd(const float* logits, const float* q, int rows, int V, int Vs, int T, float* p, float* loss_n, float* dlogits, cudaStream_t s) {
+  if (launch_row_kernel(token_ce_fwd_kernel, rows, V, s, logits, q, rows, V, Vs, T, p, loss_n, dlogits) != cudaSuccess) { set_error("token cross-entropy: launch failed"); return -2; }
   return check_launch("token cross-entropy");
 }
-int launch_token_ce_tan_bwd(const float* p, const float* zdot, int rows, int V, int T, float* tdlogits, cudaStream_t s) {
-  if (launch_row_kernel(token_ce_tan_bwd_kernel, rows, V, s, p, zdot, rows, V, T, tdlogits) != cudaSuccess) { set_error("token cross-entropy tangent: launch failed"); return -2; }
+int launch_token_ce_tan_bwd(const float* p, const float* zdot, int rows, int V, int Vs, int T, float* tdlogits, cudaStream_t s) {
+  if (launch_row_kernel(token_ce_tan_bwd_kernel, rows, V, s, p, zdot, rows, V, Vs, T, tdlogits) != cudaSuccess) { set_error("token cross-entropy tangent: launch failed"); return -2; }
   return check_launch("token cross-entropy tangent");
 }
-int launch_token_label_grad(const float* logits, const float* p, const float* zdot, int rows, int V, int T, float task_reg, float* out,
-                            cudaStream_t s) {
-  if (launch_row_kernel(token_label_grad_kernel, rows, V, s, logits, p, zdot, rows, V, T, task_reg, out) != cudaSuccess) { set_error("token label gradient: launch failed"); return -2; }
+int launch_token_label_grad(const float* logits, const float* p, const float* zdot, int rows, int V, int Vs, int T, float task_reg,
+                            float* out, cudaStream_t s) {
+  if (launch_row_kernel(token_label_grad_kernel, rows, V, s, logits, p, zdot, rows, V, Vs, T, task_reg, out) != cudaSuccess) { set_error("token label gradient: launch failed"); return -2; }
   return check_launch("token label gradient");
 }
 

@@ -19,10 +19,12 @@ int launch_token_pos_grad(const float* d, float* g_pos, int rows, int C, int T, 
 // CausalLoss (losses.py:7-26) with class-probability targets q [rows, V]: row (b, t) is scored against q of row (b, t + 1),
 // the last position of every sequence has no target; mean over the M = rows - rows / T scored rows.
 // loss_n[row] is pre-scaled by rows / M so that the engine's mean over rows is that mean.
-int launch_token_ce_fwd(const float* logits, const float* q, int rows, int V, int T, float* p, float* loss_n, float* dlogits, cudaStream_t s);
-int launch_token_ce_tan_bwd(const float* p, const float* zdot, int rows, int V, int T, float* tdlogits, cudaStream_t s);
+// V = vocabulary size, Vs >= V = row stride of the logits-shaped tensors (vocabulary padded to the GEMM tile width); the label-shaped
+// tensors (q, label gradient) are dense [rows, V]
+int launch_token_ce_fwd(const float* logits, const float* q, int rows, int V, int Vs, int T, float* p, float* loss_n, float* dlogits, cudaStream_t s);
+int launch_token_ce_tan_bwd(const float* p, const float* zdot, int rows, int V, int Vs, int T, float* tdlogits, cudaStream_t s);
 // d objective / d q [rows, V]: row (b, t + 1) receives -(zdot - <p, zdot>) / M (+ task_reg * dL/dq) of the logits row (b, t)
-int launch_token_label_grad(const float* logits, const float* p, const float* zdot, int rows, int V, int T, float task_reg, float* out,
-                            cudaStream_t s);
+int launch_token_label_grad(const float* logits, const float* p, const float* zdot, int rows, int V, int Vs, int T, float task_reg,
+                            float* out, cudaStream_t s);
 
 }  // namespace bre

@@ -255,8 +255,8 @@ class Engine:
                 pds.append(ParamDesc(p.numel, 1, p.shape[0], p.shape[1], p.shape[2] * p.shape[3]))
             elif p.perm == C.PERM_LINEAR_CHW_TO_HWC:
                 pds.append(ParamDesc(p.numel, 1, p.shape[0], p.perm_c, p.perm_hw))
-            else:
-                pds.append(ParamDesc(p.numel, 0, 0, 0, 0))
+            else:   # plain layout; d0 carries the reserved element count when a zero tail is wanted (padded vocabulary)
+                pds.append(ParamDesc(p.numel, 0, int(getattr(p, "alloc_numel", 0) or 0), 0, 0))
         self._bn_modules = []
         ops = []
         mods = C.bn_modules(model, prog) if program is None else [None] * len(prog.ops)
@@ -280,6 +280,9 @@ class Engine:
             raise ValueError(f"unknown GEMM backend {backend}")
         self.backend = backend
         self.set_option("gemm_backend", 1 if backend == "tc" else 0)
+        valid = getattr(prog, "logits_valid", 0)
+        if valid and valid != prog.tensors[prog.logits].C:
+            self.set_option("logits_valid", valid)
         self.numel = 1
         for s in self.input_shape:
             self.numel *= s

@@ -48,7 +48,8 @@ typedef struct bre_tensor_desc { int32_t N, C, H, W; } bre_tensor_desc; /* tenso
 typedef struct bre_param_desc {
   int64_t numel;
   int32_t perm;          /* bre_param_perm: engine-internal layout of this tensor */
-  int32_t d0, d1, d2;    /* OIHW->OHWI: d0=O, d1=I, d2=H*W ; LINEAR: d0=out, d1=C, d2=H*W */
+  int32_t d0, d1, d2;    /* OIHW->OHWI: d0=O, d1=I, d2=H*W ; LINEAR: d0=out, d1=C, d2=H*W ; NONE: d0 = elements to reserve if > numel
+                            (zero tail, e.g. the rows of a vocabulary padded to the GEMM tile width; see option "logits_valid") */
 } bre_param_desc;
 
 typedef struct bre_op_desc {

@@ -107,7 +107,7 @@ def test_compile_transformer_accepts_the_reference_model_class():
     mine = synthetic.TransformerLM(40, 16, 4, 24, 2).double()
     assert [n for n, _ in model.named_parameters()] == [n for n, _ in mine.named_parameters()]
     B, T = 2, 6
-    prog = compiler.compile_transformer(model, B, T)
+    prog = compiler.compile_transformer(model, B, T, pad_vocab=False)   # the torch interpreter runs the un-padded program
     x = torch.randn(B, T, 16, dtype=torch.double, requires_grad=True)
     q = torch.softmax(torch.randn(B, T, 40, dtype=torch.double), dim=-1)
     model.encoder = torch.nn.Identity()                     # what the attack does (base_attack.py:100-110)

@@ -96,7 +96,7 @@ def test_transformer_layer_program_reproduces_the_reference_tag_closure():
     g = [t.double() for t in shared[0]["gradients"]]
     g.pop(names.index("encoder.weight"))
     B, T, d = fx["x0"].shape
-    prog = compiler.compile_transformer(model, B, T)
+    prog = compiler.compile_transformer(model, B, T, pad_vocab=False)   # the torch interpreter runs the un-padded program
     assert prog.seq_len == T and len(prog.params) == len(g)
 
     class _Params:  # the interpreter reads parameters in program order (token embedding removed)
@@ -134,7 +134,12 @@ def test_config5_program_has_the_survey_dimensions():
     kinds = [op.kind for op in prog.ops]
     assert kinds.count(compiler.OP_ATTENTION) == 3 and kinds.count(compiler.OP_LAYERNORM) == 6 and kinds.count(compiler.OP_POSADD) == 1
     assert kinds.count(compiler.OP_LINEAR) == 13 and len(prog.params) == 39
-    assert prog.tensors[prog.logits].N == 32 and prog.tensors[prog.logits].C == 50257 and prog.seq_len == 32
+    # the vocabulary is padded to the GEMM tile width for the engine (50 257 -> 50 304 logit columns, 50 257 real classes)
+    assert prog.tensors[prog.logits].N == 32 and prog.tensors[prog.logits].C == 50304 and prog.logits_valid == 50257 and prog.seq_len == 32
+    dec = [p for p in prog.params if p.shape == (50257, 96)][0]
+    assert dec.alloc_numel == 50304 * 96 and [p for p in prog.params if p.shape == (50257,)][0].alloc_numel == 50304
+    plain = compiler.compile_transformer(model, 1, 32, pad_vocab=False)
+    assert plain.tensors[plain.logits].C == 50257 and all(p.alloc_numel == 0 for p in plain.params)
     assert all(op.S == 32 for op in prog.ops if op.kind in (compiler.OP_ATTENTION, compiler.OP_POSADD))
 
 
@@ -166,7 +171,7 @@ def test_full_size_config5_closure_through_the_layer_program():
     names = [n for n, _ in model.named_parameters()]
     g = [t.double() for t in shared[0]["gradients"]]
     g.pop(names.index("encoder.weight"))
-    prog = compiler.compile_transformer(model, 1, 32)
+    prog = compiler.compile_transformer(model, 1, 32, pad_vocab=False)
 
     class _Params:
         def parameters(self):
