@@ -1005,7 +1005,8 @@ int bre_engine_create(const bre_tensor_desc* tensors, int32_t n_tensors, const b
   e->ws_tiles = 1024;
   rc |= e->alloc(&e->ws, (long long)e->ws_tiles * IG_BM * IG_BN);
   rc |= e->alloc(&e->gemm_counters, 1 << 16);
-  const long long redp = (long long)(16384 > 2 * maxC + 64 ? 16384 : 2 * maxC + 64) * 2 * 2;
+  long long redp = (long long)(16384 > 2 * maxC + 64 ? 16384 : 2 * maxC + 64) * 2 * 2;
+  if (redp < kSlabPartialFloats) redp = kSlabPartialFloats;
   rc |= e->alloc(&e->red_partials, redp);
   rc |= e->alloc(&e->red_counters, maxC / 32 + 8);
   rc |= e->alloc(&e->ws2, (long long)e->ws_tiles * IG_BM * IG_BN);

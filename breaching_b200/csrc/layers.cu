@@ -1,5 +1,7 @@
 // Non-GEMM layer kernels (see layers.cuh).  All HBM-bound: coalesced along the channel dimension of the
 // NHWC activations (32 consecutive channels = one 128-byte line per warp row), grid sized from the SM count.
+#include <stdlib.h>
+
 #include "layers.cuh"
 
 #include <float.h>
@@ -14,6 +16,12 @@ inline int ew_grid(long long n) {
   long long b = (n + kEwThreads - 1) / kEwThreads;
   const long long cap = (long long)kNumSMs * 16;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// 128-bit kernels: every channel count of the conv nets is a multiple of 4 (BRE_VEC_EW=0 falls back to the scalar kernels)
+inline bool vec_ok(int C) {
+  static const bool env = [] { const char* e = getenv("BRE_VEC_EW"); return e ? atoi(e) != 0 : true; }();
+  return env && C % 4 == 0 && C >= 4;
 }
 
 // ---- BN constants -------------------------------------------------------------------------------
@@ -256,6 +264,241 @@ __global__ void channel_stats_kernel(const float* __restrict__ x, long long P, i
     const float m = tot[0] / (float)P;
     mean[c] = m + sh;
     var[c] = fmaxf(tot[1] / (float)P - m * m, 0.f);
+  }
+}
+
+
+// ======================================================================================================================
+// 128-bit variants of the BN / residual / ReLU sweeps (C % 4 == 0, which every conv net here satisfies).  The scalar kernels
+// above moved 4 bytes per thread and instruction and reached 20-40 % of the HBM rate on the batch-8 tensors of config 3
+// (profiles/launches_r2*: 33 % of that iteration); these move 16 bytes per thread with several independent loads in flight.
+// Same expressions, element by element.
+// ======================================================================================================================
+__device__ __forceinline__ float4 ld4(const float* p, long long i4) { return __ldg(reinterpret_cast<const float4*>(p) + i4); }
+__device__ __forceinline__ float4 ldc4(const float* p, int c4) { return __ldg(reinterpret_cast<const float4*>(p) + c4); }
+__device__ __forceinline__ void st4(float* p, long long i4, float4 v) { reinterpret_cast<float4*>(p)[i4] = v; }
+__device__ __forceinline__ float4 rna4(float4 v) { return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w)); }
+#define BRE_F4(expr_x, expr_y, expr_z, expr_w) make_float4(expr_x, expr_y, expr_z, expr_w)
+
+__global__ void __launch_bounds__(256) bnact_fwd_vec_kernel(const float* __restrict__ in, const float* __restrict__ res, float* __restrict__ out,
+                                                            long long total4, int C4, bool has_bn, bool relu, BnConsts bn, bool round_out) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    float4 u = ld4(in, i);
+    if (has_bn) {
+      const float4 sc = ldc4(bn.scale, c4), sh = ldc4(bn.shift, c4);
+      u = BRE_F4(fmaf(u.x, sc.x, sh.x), fmaf(u.y, sc.y, sh.y), fmaf(u.z, sc.z, sh.z), fmaf(u.w, sc.w, sh.w));
+    }
+    if (res != nullptr) { const float4 r = ld4(res, i); u.x += r.x; u.y += r.y; u.z += r.z; u.w += r.w; }
+    if (relu) u = BRE_F4(fmaxf(u.x, 0.f), fmaxf(u.y, 0.f), fmaxf(u.z, 0.f), fmaxf(u.w, 0.f));
+    st4(out, i, round_out ? rna4(u) : u);
+  }
+}
+
+__global__ void __launch_bounds__(256) bnact_tan_fwd_vec_kernel(BnActTanFwdArgs a, long long total4, int C4) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    float4 u = a.tin != nullptr ? ld4(a.tin, i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.has_bn) {
+      const float4 z = ld4(a.in, i), inv = ldc4(a.bn.inv, c4), nrm = ldc4(a.bn.nrm, c4), sc = ldc4(a.bn.scale, c4);
+      const float4 vg = ldc4(a.v_gamma, c4), vb = ldc4(a.v_beta, c4);
+      u.x = fmaf(sc.x, u.x, fmaf(vg.x, fmaf(z.x, inv.x, nrm.x), vb.x));
+      u.y = fmaf(sc.y, u.y, fmaf(vg.y, fmaf(z.y, inv.y, nrm.y), vb.y));
+      u.z = fmaf(sc.z, u.z, fmaf(vg.z, fmaf(z.z, inv.z, nrm.z), vb.z));
+      u.w = fmaf(sc.w, u.w, fmaf(vg.w, fmaf(z.w, inv.w, nrm.w), vb.w));
+    }
+    if (a.tres != nullptr) { const float4 r = ld4(a.tres, i); u.x += r.x; u.y += r.y; u.z += r.z; u.w += r.w; }
+    if (a.relu) {
+      const float4 o = ld4(a.out, i);
+      if (!(o.x > 0.f)) u.x = 0.f;
+      if (!(o.y > 0.f)) u.y = 0.f;
+      if (!(o.z > 0.f)) u.z = 0.f;
+      if (!(o.w > 0.f)) u.w = 0.f;
+    }
+    st4(a.tout, i, a.round_out ? rna4(u) : u);
+  }
+}
+
+__global__ void __launch_bounds__(256) bnact_tan_bwd_vec_kernel(BnActTanBwdArgs a, long long total4, int C4) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    float4 tdu = ld4(a.tdout, i), du = ld4(a.dout, i);
+    if (a.relu) {
+      const float4 o = ld4(a.out, i);
+      if (!(o.x > 0.f)) { tdu.x = 0.f; du.x = 0.f; }
+      if (!(o.y > 0.f)) { tdu.y = 0.f; du.y = 0.f; }
+      if (!(o.z > 0.f)) { tdu.z = 0.f; du.z = 0.f; }
+      if (!(o.w > 0.f)) { tdu.w = 0.f; du.w = 0.f; }
+    }
+    float4 tdi = tdu;
+    if (a.has_bn) {
+      const float4 sc = ldc4(a.bn.scale, c4), vg = ldc4(a.v_gamma, c4), inv = ldc4(a.bn.inv, c4);
+      tdi = BRE_F4(fmaf(sc.x, tdu.x, vg.x * inv.x * du.x), fmaf(sc.y, tdu.y, vg.y * inv.y * du.y), fmaf(sc.z, tdu.z, vg.z * inv.z * du.z),
+                   fmaf(sc.w, tdu.w, vg.w * inv.w * du.w));
+      if (a.di_cm != nullptr) {
+        const float4 z = ld4(a.in, i), cv = ldc4(a.di_cv, c4), mn = ldc4(a.di_mean, c4), cm = ldc4(a.di_cm, c4);
+        tdi.x += fmaf(cv.x, z.x - mn.x, cm.x); tdi.y += fmaf(cv.y, z.y - mn.y, cm.y);
+        tdi.z += fmaf(cv.z, z.z - mn.z, cm.z); tdi.w += fmaf(cv.w, z.w - mn.w, cm.w);
+      }
+    }
+    if (a.tdin != nullptr) {
+      if (a.acc_in) { const float4 o = ld4(a.tdin, i); tdi.x += o.x; tdi.y += o.y; tdi.z += o.z; tdi.w += o.w; }
+      st4(a.tdin, i, a.round_din ? rna4(tdi) : tdi);
+    }
+    if (a.tdres != nullptr) {
+      float4 r = tdu;
+      if (a.acc_res) { const float4 o = ld4(a.tdres, i); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+      st4(a.tdres, i, r);
+    }
+  }
+}
+
+// ---- (LX float4 columns) x (pixel slab) reductions: block of 256 threads = LX x LY, blockIdx.x = column group, blockIdx.y = slab --
+// Per thread NV x 4 partial sums; rows of the block are summed in shared memory in fixed order, then the last-arriving block of a
+// column group sums the slabs in fixed order (deterministic, like slab_reduce).
+template <int NV>
+__device__ __forceinline__ bool slab_reduce4(float (&v)[NV][4], int LX, int LY, float* partials, int* counters, int Cpad, int C,
+                                             float (&total)[NV][4]) {
+  __shared__ float sm4[NV * 4][257];
+  __shared__ int s_last4;
+  const int tid = threadIdx.x, lx = tid % LX;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sm4[k * 4 + j][tid] = v[k][j];
+  __syncthreads();
+  const int c0 = (blockIdx.x * LX + lx) * 4;
+  if (tid < LX && c0 < C) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+        for (int y = 0; y < LY; ++y) s += sm4[k * 4 + j][y * LX + lx];
+        partials[((long long)blockIdx.y * Cpad + c0 + j) * NV + k] = s;
+      }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(counters + blockIdx.x, 1);
+    s_last4 = (prev == (int)gridDim.y - 1);
+    if (s_last4) counters[blockIdx.x] = 0;
+  }
+  __syncthreads();
+  if (!s_last4) return false;
+  __threadfence();
+  if (tid < LX && c0 < C) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+        for (int sl = 0; sl < (int)gridDim.y; ++sl) s += __ldcg(partials + ((long long)sl * Cpad + c0 + j) * NV + k);
+        total[k][j] = s;
+      }
+    return true;
+  }
+  return false;
+}
+
+inline void slab_grid4(long long P, int C, dim3& grid, int& LX, int& LY, long long& pps) {
+  const int C4 = C / 4;
+  LX = C4 < 32 ? C4 : 32;
+  while (256 % LX != 0) --LX;          // C4 = 16, 32, 64 ... in practice; keep LX a divisor of 256 for odd widths
+  LY = 256 / LX;
+  const int cg = ceil_div(C4, LX);
+  long long slabs = (4LL * kNumSMs + cg - 1) / cg;
+  const long long max_slabs = (P + LY - 1) / LY;
+  if (slabs > max_slabs) slabs = max_slabs;
+  const long long cap = kSlabPartialFloats / (2LL * cg * LX * 4);   // partials: slabs x Cpad x (<= 2 quantities)
+  if (slabs > cap) slabs = cap;
+  if (slabs < 1) slabs = 1;
+  pps = (P + slabs - 1) / slabs;
+  slabs = (P + pps - 1) / pps;
+  grid = dim3(cg, (unsigned)slabs);
+}
+
+__global__ void __launch_bounds__(256) bnact_bwd_vec_kernel(BnActBwdArgs a, long long pps, int Cpad, int LX, int LY) {
+  pdl_prologue();
+  const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
+  const int c4 = blockIdx.x * LX + lx, C4 = a.C / 4;
+  const bool cv = c4 < C4;
+  const long long p0 = blockIdx.y * pps;
+  const long long p1 = (p0 + pps < a.P) ? p0 + pps : a.P;
+  float v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float4 inv = make_float4(0.f, 0.f, 0.f, 0.f), nrm = inv, scale = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (cv && a.has_bn) { inv = ldc4(a.bn.inv, c4); nrm = ldc4(a.bn.nrm, c4); scale = ldc4(a.bn.scale, c4); }
+  if (cv) {
+    for (long long p = p0 + ly; p < p1; p += LY) {
+      const long long o = p * C4 + c4;
+      float4 du = ld4(a.dout, o);
+      if (a.relu) {
+        const float4 y = ld4(a.out, o);
+        if (!(y.x > 0.f)) du.x = 0.f;
+        if (!(y.y > 0.f)) du.y = 0.f;
+        if (!(y.z > 0.f)) du.z = 0.f;
+        if (!(y.w > 0.f)) du.w = 0.f;
+      }
+      float4 di = du;
+      if (a.has_bn) {
+        const float4 z = ld4(a.in, o);
+        v[0][0] = fmaf(du.x, fmaf(z.x, inv.x, nrm.x), v[0][0]); v[0][1] = fmaf(du.y, fmaf(z.y, inv.y, nrm.y), v[0][1]);
+        v[0][2] = fmaf(du.z, fmaf(z.z, inv.z, nrm.z), v[0][2]); v[0][3] = fmaf(du.w, fmaf(z.w, inv.w, nrm.w), v[0][3]);
+        v[1][0] += du.x; v[1][1] += du.y; v[1][2] += du.z; v[1][3] += du.w;
+        di = BRE_F4(scale.x * du.x, scale.y * du.y, scale.z * du.z, scale.w * du.w);
+      }
+      if (a.din != nullptr) {
+        if (a.acc_in) { const float4 q = ld4(a.din, o); di.x += q.x; di.y += q.y; di.z += q.z; di.w += q.w; }
+        st4(a.din, o, a.round_din ? rna4(di) : di);
+      }
+      if (a.dres != nullptr) {
+        float4 r = du;
+        if (a.acc_res) { const float4 q = ld4(a.dres, o); r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w; }
+        st4(a.dres, o, r);
+      }
+    }
+  }
+  if (!a.has_bn || a.g_gamma == nullptr) return;  // uniform across the grid
+  float tot[2][4];
+  if (slab_reduce4<2>(v, LX, LY, a.partials, a.counters, Cpad, a.C, tot)) {
+    st4(a.g_gamma, c4, make_float4(tot[0][0], tot[0][1], tot[0][2], tot[0][3]));
+    st4(a.g_beta, c4, make_float4(tot[1][0], tot[1][1], tot[1][2], tot[1][3]));
+  }
+}
+
+__global__ void __launch_bounds__(256) channel_stats_vec_kernel(const float* __restrict__ x, long long P, int C, float* mean, float* var,
+                                                                float* partials, int* counters, long long pps, int Cpad, int LX, int LY) {
+  pdl_prologue();
+  const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
+  const int c4 = blockIdx.x * LX + lx, C4 = C / 4;
+  const long long p0 = blockIdx.y * pps;
+  const long long p1 = (p0 + pps < P) ? p0 + pps : P;
+  // shifted sums (shift = first element of the channel) keep E[x^2] - E[x]^2 well conditioned in fp32
+  const float4 sh = c4 < C4 ? ldc4(x, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  if (c4 < C4)
+    for (long long p = p0 + ly; p < p1; p += LY) {
+      const float4 t = ld4(x, p * C4 + c4);
+      const float a0 = t.x - sh.x, a1 = t.y - sh.y, a2 = t.z - sh.z, a3 = t.w - sh.w;
+      v[0][0] += a0; v[0][1] += a1; v[0][2] += a2; v[0][3] += a3;
+      v[1][0] = fmaf(a0, a0, v[1][0]); v[1][1] = fmaf(a1, a1, v[1][1]); v[1][2] = fmaf(a2, a2, v[1][2]); v[1][3] = fmaf(a3, a3, v[1][3]);
+    }
+  float tot[2][4];
+  if (slab_reduce4<2>(v, LX, LY, partials, counters, Cpad, C, tot)) {
+    const float shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    float m[4], vr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mj = tot[0][j] / (float)P;
+      m[j] = mj + shv[j];
+      vr[j] = fmaxf(tot[1][j] / (float)P - mj * mj, 0.f);
+    }
+    st4(mean, c4, make_float4(m[0], m[1], m[2], m[3]));
+    st4(var, c4, make_float4(vr[0], vr[1], vr[2], vr[3]));
   }
 }
 
@@ -592,6 +835,11 @@ int launch_bn_prepare(const float* gamma, const float* beta, const float* rm, co
 int launch_bnact_fwd(const float* in, const float* res, float* out, long long P, int C, bool has_bn, bool relu,
                      BnConsts bn, bool round_out, cudaStream_t s) {
   const long long total = P * C;
+  if (vec_ok(C)) {
+    BRE_KLAUNCH(bnact_fwd_vec_kernel, ew_grid(total / 4), kEwThreads, 0, s, in, res, out, total / 4, C / 4, has_bn, relu, bn, round_out);
+    BRE_CHECK_LAUNCH();
+    return 0;
+  }
   BRE_KLAUNCH(bnact_fwd_kernel, ew_grid(total), kEwThreads, 0, s, in, res, out, total, C, has_bn, relu, bn, round_out);
   BRE_CHECK_LAUNCH();
   return 0;
@@ -600,6 +848,13 @@ int launch_bnact_fwd(const float* in, const float* res, float* out, long long P,
 int launch_bnact_bwd(const BnActBwdArgs& a, cudaStream_t s) {
   dim3 grid, block;
   long long pps;
+  if (vec_ok(a.C)) {
+    int LX, LY;
+    slab_grid4(a.P, a.C, grid, LX, LY, pps);
+    BRE_KLAUNCH(bnact_bwd_vec_kernel, grid, 256, 0, s, a, pps, (int)(grid.x * LX * 4), LX, LY);
+    BRE_CHECK_LAUNCH();
+    return 0;
+  }
   slab_grid(a.P, a.C, grid, block, pps);
   BRE_KLAUNCH(bnact_bwd_kernel, grid, block, 0, s, a, pps, grid.x * 32);
   BRE_CHECK_LAUNCH();
@@ -608,6 +863,11 @@ int launch_bnact_bwd(const BnActBwdArgs& a, cudaStream_t s) {
 
 int launch_bnact_tan_fwd(const BnActTanFwdArgs& a, cudaStream_t s) {
   const long long total = a.P * a.C;
+  if (vec_ok(a.C)) {
+    BRE_KLAUNCH(bnact_tan_fwd_vec_kernel, ew_grid(total / 4), kEwThreads, 0, s, a, total / 4, a.C / 4);
+    BRE_CHECK_LAUNCH();
+    return 0;
+  }
   BRE_KLAUNCH(bnact_tan_fwd_kernel, ew_grid(total), kEwThreads, 0, s, a, total);
   BRE_CHECK_LAUNCH();
   return 0;
@@ -634,6 +894,11 @@ int launch_bnact_tan_bwd(const BnActTanBwdArgs& a, cudaStream_t s) {
     return 0;
   }
   const long long total = a.P * a.C;
+  if (vec_ok(a.C)) {
+    BRE_KLAUNCH(bnact_tan_bwd_vec_kernel, ew_grid(total / 4), kEwThreads, 0, s, a, total / 4, a.C / 4);
+    BRE_CHECK_LAUNCH();
+    return 0;
+  }
   BRE_KLAUNCH(bnact_tan_bwd_kernel, ew_grid(total), kEwThreads, 0, s, a, total);
   BRE_CHECK_LAUNCH();
   return 0;
@@ -687,6 +952,13 @@ int launch_channel_stats(const float* x, long long P, int C, float* mean, float*
                          cudaStream_t s) {
   dim3 grid, block;
   long long pps;
+  if (vec_ok(C)) {
+    int LX, LY;
+    slab_grid4(P, C, grid, LX, LY, pps);
+    BRE_KLAUNCH(channel_stats_vec_kernel, grid, 256, 0, s, x, P, C, mean, var, partials, counters, pps, (int)(grid.x * LX * 4), LX, LY);
+    BRE_CHECK_LAUNCH();
+    return 0;
+  }
   slab_grid(P, C, grid, block, pps);
   BRE_KLAUNCH(channel_stats_kernel, grid, block, 0, s, x, P, C, mean, var, partials, counters, pps, grid.x * 32);
   BRE_CHECK_LAUNCH();

@@ -5,6 +5,9 @@
 
 namespace bre {
 
+// capacity (floats) callers must provide for the `partials` scratch of the slab reductions below
+constexpr long long kSlabPartialFloats = 1 << 18;
+
 struct BnConsts {          // per-channel constants of an eval-mode BN (weights are fixed during an attack)
   const float* scale;      // gamma * inv
   const float* shift;      // beta - gamma * mean * inv
