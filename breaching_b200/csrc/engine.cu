@@ -172,7 +172,7 @@ struct bre_engine {
   int stem_op = -1, stem_Kp = 0;
   float *xcol = nullptr, *dcol = nullptr, *Wcol = nullptr, *Vcol = nullptr, *Gcol = nullptr;
   bool stem_cols_env = [] { const char* e = getenv("BRE_STEM_COLS"); return e ? atoi(e) != 0 : true; }();
-  bool use_stem_cols(size_t i) const { return gemm_backend == 1 && stem_cols_env && (int)i == stem_op; }
+  bool use_stem_cols(size_t i) { return gemm_backend == 1 && stem_cols_env && (int)i == stem_op && !is_precise(i); }
   GemmArgs stem_geom(const bre_op_desc& op) const {   // the layer as a 1x1 convolution over xcol [N, Ho, Wo, Kp]
     GemmArgs a;
     memset(&a, 0, sizeof(a));
@@ -197,6 +197,22 @@ struct bre_engine {
     BRE_LAUNCH(launch_stem_col2im(dcol, grad_out, ti.N, ti.C, ti.H, ti.W, to.H, to.W, op.R, op.S, op.stride, op.pad, stem_Kp, stream));
     return 0;
   }
+  // precision knob of the tensor-core back end: the first `precise_first` and last `precise_last` conv / linear layers (program
+  // order) run on the fp32 kernels with unrounded operands -- for badly conditioned cases (config 3: random-init ResNet-50 whose
+  // BN-statistics prior differences amplify TF32 rounding) at the price of those layers' tensor-core speed
+  int precise_first = [] { const char* e = getenv("BRE_PRECISE_FIRST"); return e ? atoi(e) : 0; }();
+  int precise_last = [] { const char* e = getenv("BRE_PRECISE_LAST"); return e ? atoi(e) : 0; }();
+  mutable std::vector<char> precise_op;
+  bool is_precise(size_t i) const {
+    if (precise_op.size() != ops.size()) {
+      precise_op.assign(ops.size(), 0);
+      std::vector<int> gemm_ops_idx;
+      for (size_t j = 0; j < ops.size(); ++j) if (ops[j].kind == BRE_OP_CONV || ops[j].kind == BRE_OP_LINEAR) gemm_ops_idx.push_back((int)j);
+      const int n = (int)gemm_ops_idx.size();
+      for (int j = 0; j < n; ++j) if (j < precise_first || j >= n - precise_last) precise_op[gemm_ops_idx[j]] = 1;
+    }
+    return gemm_backend == 1 && precise_op[i] != 0;
+  }
   // execution
   bool use_graph = true;
   int gemm_backend = 0;  // 0 = SIMT fp32, 1 = tcgen05 TF32 where supported
@@ -219,8 +235,9 @@ struct bre_engine {
   // conv / linear weights as GEMM operands: the TF32-rounded shadow for the layers the tcgen05 back end covers, the fp32
   // master for the layers that run on the SIMT kernels (so that a network with no eligible layer is bit-identical on both
   // back ends)
-  const float* Wg(const bre_op_desc& op) { return (round_val(op.tin) ? Wt : W) + params[op.w].off; }
-  const float* Vg(const bre_op_desc& op) { return (round_val(op.tin) ? Vt : V) + params[op.w].off; }
+  size_t op_index(const bre_op_desc& op) const { return (size_t)(&op - ops.data()); }
+  const float* Wg(const bre_op_desc& op) { return (round_val(op.tin) && !is_precise(op_index(op)) ? Wt : W) + params[op.w].off; }
+  const float* Vg(const bre_op_desc& op) { return (round_val(op.tin) && !is_precise(op_index(op)) ? Vt : V) + params[op.w].off; }
   int refresh_Vt() {
     if (tc_round()) BRE_LAUNCH(launch_round_tf32(V, Vt, P_pad, stream));
     return 0;
@@ -234,7 +251,7 @@ struct bre_engine {
     if (chunk_mode_ready || !tc_round()) return 0;
     std::vector<unsigned char> host((size_t)(P_pad / kChunk), 0);
     for (const bre_op_desc& op : ops) {
-      if ((op.kind != BRE_OP_CONV && op.kind != BRE_OP_LINEAR) || !round_val(op.tin)) continue;
+      if ((op.kind != BRE_OP_CONV && op.kind != BRE_OP_LINEAR) || !round_val(op.tin) || is_precise(op_index(op))) continue;
       const long long c0 = params[op.w].off / kChunk, c1 = c0 + (params[op.w].desc.numel + kChunk - 1) / kChunk;
       for (long long c = c0; c < c1; ++c) host[(size_t)c] = 1;
     }
@@ -255,15 +272,17 @@ struct bre_engine {
   void compute_round_flags() {
     rnd_val.assign(t.size(), 0);
     rnd_d.assign(t.size(), 0);
-    for (const bre_op_desc& op : ops) {
+    for (size_t oi = 0; oi < ops.size(); ++oi) {
+      const bre_op_desc& op = ops[oi];
       if (op.kind != BRE_OP_CONV && op.kind != BRE_OP_LINEAR) continue;
+      if (is_precise(oi)) continue;
       GemmArgs a = conv_geom(op);
       a.act[0] = t[op.tin].val; a.wgt[0] = Wp(op.w); a.out = t[op.tout].val;
       bool any = false;
       for (int mode = 0; mode < 3; ++mode) { a.mode = mode; any = any || igemm_tc_supported(a); }
       if (any) { rnd_val[op.tin] = 1; rnd_d[op.tout] = 1; }
     }
-    if (stem_op >= 0 && stem_cols_env) rnd_d[ops[stem_op].tout] = 1;   // deltas of the stem output feed its column GEMMs
+    if (stem_op >= 0 && stem_cols_env && !is_precise((size_t)stem_op)) rnd_d[ops[stem_op].tout] = 1;   // deltas of the stem output feed its column GEMMs
   }
   bool round_val(int tensor) { if (rnd_val.size() != t.size()) compute_round_flags(); return tc_round() && rnd_val[tensor]; }
   bool round_d(int tensor) { if (rnd_d.size() != t.size()) compute_round_flags(); return tc_round() && rnd_d[tensor]; }
@@ -286,11 +305,12 @@ struct bre_engine {
     }
     a.nsrc = 1;
     a.ws = ws; a.counters = gemm_counters; a.ws_tiles = ws_tiles; a.splits = 0;
+    a.force_fp32 = is_precise(op_index(op)) ? 1 : 0;
     return a;
   }
   int gemm(const GemmArgs& a) { return gemm_on(a, stream); }
   int gemm_on(const GemmArgs& a, cudaStream_t st) {
-    if (gemm_backend == 1 && igemm_tc_supported(a)) {
+    if (gemm_backend == 1 && !a.force_fp32 && igemm_tc_supported(a)) {
       return launch_igemm_tc(a, st);
     }
     return launch_igemm_simt(a, st);
@@ -1583,6 +1603,11 @@ int bre_engine_set_option(bre_engine* e, const char* name, int64_t value) {
   if (n == "pdl") { bre::set_pdl(value != 0); e->graph_ready = false; return BRE_OK; }
   if (n == "overlap_wgrad") { e->overlap_wgrad = value != 0; e->graph_ready = false; return BRE_OK; }
   if (n == "fuse_bnact") { e->fuse_bnact = value != 0; e->graph_ready = false; return BRE_OK; }
+  if (n == "precise_first" || n == "precise_last") {
+    (n == "precise_first" ? e->precise_first : e->precise_last) = (int)value;
+    e->precise_op.clear(); e->rnd_val.clear(); e->rnd_d.clear(); e->chunk_mode_ready = false; e->graph_ready = false;
+    return BRE_OK;
+  }
   if (n == "logits_valid") {
     if (value < 1 || value > e->td(e->logits).C) { set_error("logits_valid must be in [1, logits columns]"); return BRE_ERR_INVALID; }
     if (e->soft_q_buf != nullptr) { set_error("logits_valid must be set before soft labels are loaded"); return BRE_ERR_STATE; }

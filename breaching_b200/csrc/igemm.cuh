@@ -53,6 +53,7 @@ struct GemmArgs {
   int* counters;          // >= max tiles ints, zero-initialised, self-resetting
   int ws_tiles;
   int splits;             // 0 = choose automatically
+  int force_fp32;         // engine: run this contraction on the fp32 kernels even on the tensor-core back end (precision knob)
 };
 
 constexpr int IG_BM = 64, IG_BN = 64, IG_BK = 16, IG_THREADS = 256;

@@ -275,6 +275,7 @@ __global__ void channel_stats_kernel(const float* __restrict__ x, long long P, i
 // Same expressions, element by element.
 // ======================================================================================================================
 __device__ __forceinline__ float4 ld4(const float* p, long long i4) { return __ldg(reinterpret_cast<const float4*>(p) + i4); }
+__device__ __forceinline__ float4 ldrw4(const float* p, long long i4) { return reinterpret_cast<const float4*>(p)[i4]; }   // buffers this kernel also writes
 __device__ __forceinline__ float4 ldc4(const float* p, int c4) { return __ldg(reinterpret_cast<const float4*>(p) + c4); }
 __device__ __forceinline__ void st4(float* p, long long i4, float4 v) { reinterpret_cast<float4*>(p)[i4] = v; }
 __device__ __forceinline__ float4 rna4(float4 v) { return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w)); }
@@ -345,12 +346,12 @@ __global__ void __launch_bounds__(256) bnact_tan_bwd_vec_kernel(BnActTanBwdArgs 
       }
     }
     if (a.tdin != nullptr) {
-      if (a.acc_in) { const float4 o = ld4(a.tdin, i); tdi.x += o.x; tdi.y += o.y; tdi.z += o.z; tdi.w += o.w; }
+      if (a.acc_in) { const float4 o = ldrw4(a.tdin, i); tdi.x += o.x; tdi.y += o.y; tdi.z += o.z; tdi.w += o.w; }
       st4(a.tdin, i, a.round_din ? rna4(tdi) : tdi);
     }
     if (a.tdres != nullptr) {
       float4 r = tdu;
-      if (a.acc_res) { const float4 o = ld4(a.tdres, i); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+      if (a.acc_res) { const float4 o = ldrw4(a.tdres, i); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
       st4(a.tdres, i, r);
     }
   }
@@ -391,15 +392,32 @@ __device__ __forceinline__ bool slab_reduce4(float (&v)[NV][4], int LX, int LY, 
   __syncthreads();
   if (!s_last4) return false;
   __threadfence();
+  // all 256 threads: one (quantity, channel) sum over the slabs each, in slab order (fixed), then handed to the column's owner
+  __shared__ float tot4[NV][128];
+  const int cols = LX * 4;
+  for (int idx = tid; idx < cols * NV; idx += 256) {
+    const int k = idx / cols, col = idx - k * cols;
+    const int c = blockIdx.x * cols + col;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four interleaved chains (loads overlap), combined in a fixed order
+    if (c < C) {
+      const int ns = (int)gridDim.y;
+      int sl = 0;
+      for (; sl + 3 < ns; sl += 4) {
+        s0 += __ldcg(partials + ((long long)sl * Cpad + c) * NV + k);
+        s1 += __ldcg(partials + ((long long)(sl + 1) * Cpad + c) * NV + k);
+        s2 += __ldcg(partials + ((long long)(sl + 2) * Cpad + c) * NV + k);
+        s3 += __ldcg(partials + ((long long)(sl + 3) * Cpad + c) * NV + k);
+      }
+      for (; sl < ns; ++sl) s0 += __ldcg(partials + ((long long)sl * Cpad + c) * NV + k);
+    }
+    tot4[k][col] = (s0 + s1) + (s2 + s3);
+  }
+  __syncthreads();
   if (tid < LX && c0 < C) {
 #pragma unroll
     for (int k = 0; k < NV; ++k)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float s = 0.f;
-        for (int sl = 0; sl < (int)gridDim.y; ++sl) s += __ldcg(partials + ((long long)sl * Cpad + c0 + j) * NV + k);
-        total[k][j] = s;
-      }
+      for (int j = 0; j < 4; ++j) total[k][j] = tot4[k][lx * 4 + j];
     return true;
   }
   return false;
@@ -411,7 +429,7 @@ inline void slab_grid4(long long P, int C, dim3& grid, int& LX, int& LY, long lo
   while (256 % LX != 0) --LX;          // C4 = 16, 32, 64 ... in practice; keep LX a divisor of 256 for odd widths
   LY = 256 / LX;
   const int cg = ceil_div(C4, LX);
-  long long slabs = (4LL * kNumSMs + cg - 1) / cg;
+  long long slabs = (2LL * kNumSMs + cg - 1) / cg;
   const long long max_slabs = (P + LY - 1) / LY;
   if (slabs > max_slabs) slabs = max_slabs;
   const long long cap = kSlabPartialFloats / (2LL * cg * LX * 4);   // partials: slabs x Cpad x (<= 2 quantities)
@@ -433,32 +451,47 @@ __global__ void __launch_bounds__(256) bnact_bwd_vec_kernel(BnActBwdArgs a, long
   float4 inv = make_float4(0.f, 0.f, 0.f, 0.f), nrm = inv, scale = make_float4(1.f, 1.f, 1.f, 1.f);
   if (cv && a.has_bn) { inv = ldc4(a.bn.inv, c4); nrm = ldc4(a.bn.nrm, c4); scale = ldc4(a.bn.scale, c4); }
   if (cv) {
-    for (long long p = p0 + ly; p < p1; p += LY) {
-      const long long o = p * C4 + c4;
-      float4 du = ld4(a.dout, o);
-      if (a.relu) {
-        const float4 y = ld4(a.out, o);
-        if (!(y.x > 0.f)) du.x = 0.f;
-        if (!(y.y > 0.f)) du.y = 0.f;
-        if (!(y.z > 0.f)) du.z = 0.f;
-        if (!(y.w > 0.f)) du.w = 0.f;
+    // four pixel rows per trip, every load issued before the first use: the block count only gives ~16 warps per SM, and the stores
+    // (which the compiler must assume to alias the loads) would otherwise serialise one row per memory round trip
+    constexpr int U = 4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long p = p0 + ly; p < p1; p += (long long)LY * U) {
+      float4 du[U], y[U], z[U], qi[U], qr[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pp = p + (long long)u * LY;
+        ok[u] = pp < p1;
+        const long long o = pp * C4 + c4;
+        du[u] = ok[u] ? ld4(a.dout, o) : zero4;
+        y[u] = (ok[u] && a.relu) ? ld4(a.out, o) : make_float4(1.f, 1.f, 1.f, 1.f);
+        z[u] = (ok[u] && a.has_bn) ? ld4(a.in, o) : zero4;
+        qi[u] = (ok[u] && a.din != nullptr && a.acc_in) ? ldrw4(a.din, o) : zero4;
+        qr[u] = (ok[u] && a.dres != nullptr && a.acc_res) ? ldrw4(a.dres, o) : zero4;
       }
-      float4 di = du;
-      if (a.has_bn) {
-        const float4 z = ld4(a.in, o);
-        v[0][0] = fmaf(du.x, fmaf(z.x, inv.x, nrm.x), v[0][0]); v[0][1] = fmaf(du.y, fmaf(z.y, inv.y, nrm.y), v[0][1]);
-        v[0][2] = fmaf(du.z, fmaf(z.z, inv.z, nrm.z), v[0][2]); v[0][3] = fmaf(du.w, fmaf(z.w, inv.w, nrm.w), v[0][3]);
-        v[1][0] += du.x; v[1][1] += du.y; v[1][2] += du.z; v[1][3] += du.w;
-        di = BRE_F4(scale.x * du.x, scale.y * du.y, scale.z * du.z, scale.w * du.w);
-      }
-      if (a.din != nullptr) {
-        if (a.acc_in) { const float4 q = ld4(a.din, o); di.x += q.x; di.y += q.y; di.z += q.z; di.w += q.w; }
-        st4(a.din, o, a.round_din ? rna4(di) : di);
-      }
-      if (a.dres != nullptr) {
-        float4 r = du;
-        if (a.acc_res) { const float4 q = ld4(a.dres, o); r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w; }
-        st4(a.dres, o, r);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const long long o = (p + (long long)u * LY) * C4 + c4;
+        float4 d = du[u];
+        if (a.relu) {
+          if (!(y[u].x > 0.f)) d.x = 0.f;
+          if (!(y[u].y > 0.f)) d.y = 0.f;
+          if (!(y[u].z > 0.f)) d.z = 0.f;
+          if (!(y[u].w > 0.f)) d.w = 0.f;
+        }
+        float4 di = d;
+        if (a.has_bn) {
+          v[0][0] = fmaf(d.x, fmaf(z[u].x, inv.x, nrm.x), v[0][0]); v[0][1] = fmaf(d.y, fmaf(z[u].y, inv.y, nrm.y), v[0][1]);
+          v[0][2] = fmaf(d.z, fmaf(z[u].z, inv.z, nrm.z), v[0][2]); v[0][3] = fmaf(d.w, fmaf(z[u].w, inv.w, nrm.w), v[0][3]);
+          v[1][0] += d.x; v[1][1] += d.y; v[1][2] += d.z; v[1][3] += d.w;
+          di = BRE_F4(scale.x * d.x, scale.y * d.y, scale.z * d.z, scale.w * d.w);
+        }
+        if (a.din != nullptr) {
+          di.x += qi[u].x; di.y += qi[u].y; di.z += qi[u].z; di.w += qi[u].w;
+          st4(a.din, o, a.round_din ? rna4(di) : di);
+        }
+        if (a.dres != nullptr) st4(a.dres, o, BRE_F4(d.x + qr[u].x, d.y + qr[u].y, d.z + qr[u].z, d.w + qr[u].w));
       }
     }
   }
@@ -480,13 +513,23 @@ __global__ void __launch_bounds__(256) channel_stats_vec_kernel(const float* __r
   // shifted sums (shift = first element of the channel) keep E[x^2] - E[x]^2 well conditioned in fp32
   const float4 sh = c4 < C4 ? ldc4(x, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
   float v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  if (c4 < C4)
-    for (long long p = p0 + ly; p < p1; p += LY) {
-      const float4 t = ld4(x, p * C4 + c4);
-      const float a0 = t.x - sh.x, a1 = t.y - sh.y, a2 = t.z - sh.z, a3 = t.w - sh.w;
-      v[0][0] += a0; v[0][1] += a1; v[0][2] += a2; v[0][3] += a3;
-      v[1][0] = fmaf(a0, a0, v[1][0]); v[1][1] = fmaf(a1, a1, v[1][1]); v[1][2] = fmaf(a2, a2, v[1][2]); v[1][3] = fmaf(a3, a3, v[1][3]);
+  if (c4 < C4) {
+    constexpr int U = 8;   // eight independent 128-bit loads in flight per thread
+    for (long long p = p0 + ly; p < p1; p += (long long)LY * U) {
+      float4 t[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pp = p + (long long)u * LY;
+        t[u] = pp < p1 ? ld4(x, pp * C4 + c4) : sh;   // (a padded row contributes x - shift = 0 to both sums)
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float a0 = t[u].x - sh.x, a1 = t[u].y - sh.y, a2 = t[u].z - sh.z, a3 = t[u].w - sh.w;
+        v[0][0] += a0; v[0][1] += a1; v[0][2] += a2; v[0][3] += a3;
+        v[1][0] = fmaf(a0, a0, v[1][0]); v[1][1] = fmaf(a1, a1, v[1][1]); v[1][2] = fmaf(a2, a2, v[1][2]); v[1][3] = fmaf(a3, a3, v[1][3]);
+      }
     }
+  }
   float tot[2][4];
   if (slab_reduce4<2>(v, LX, LY, partials, counters, Cpad, C, tot)) {
     const float shv[4] = {sh.x, sh.y, sh.z, sh.w};

@@ -34,9 +34,9 @@ def _engine(fx, backend):
     return eng, cfg
 
 
-def _reference_tf32_deviation(fx):
+def _reference_tf32_deviation(fx, with_score=False):
     """rel. l2 distance between the reference algorithm run in eager PyTorch on the GPU with TF32 convolutions (the
-    reference's default GPU numerics) and the fp32 fixture."""
+    reference's default GPU numerics) and the fp32 fixture (optionally also its score of the fixture's best candidate)."""
     from oracle import restate
 
     model, loss_fn, payload, shared, true = case_from_fixture(fx)
@@ -52,10 +52,11 @@ def _reference_tf32_deviation(fx):
         orc = restate.TrialOracle(copy.deepcopy(model).to(DEV).eval(), loss_fn, cfg, [g.to(DEV) for g in shared[0]["gradients"]],
                                   torch.cat(local["labels"]), dm, ds, local_hyperparams=local)
         _, _, raw, _ = orc.closure_gradient(fx["x0"].to(DEV), 0, 0.0)
+        score = orc.score(fx["best"].to(DEV), fx["scoring"]) if with_score else None
         orc.close()
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
-    return _relerr(raw, fx["raw_grad0"])
+    return (_relerr(raw, fx["raw_grad0"]), score) if with_score else _relerr(raw, fx["raw_grad0"])
 
 
 @pytest.mark.parametrize("backend", ["simt", "tc"])
@@ -76,10 +77,14 @@ def test_fedavg_closure_matches_reference_fixture(name, backend):
         # (eager PyTorch, cuDNN TF32 convolutions = torch's default) is 27 % away from its fp32 CPU result on the
         # ResNet-18 fixture, step by step in the same pattern as the TF32 engine (profiles/experiments/diag_fedavg_tc.py).
         # The TF32 back end is therefore held to the reference's TF32 deviation, the fp32 back end to the fp32 fixture.
-        tol_g = max(tol_g, 1.5 * _reference_tf32_deviation(fx))
+        ref_dev, ref_score = _reference_tf32_deviation(fx, with_score=True)
+        tol_g = max(tol_g, 1.5 * ref_dev)
     assert rel < tol_g, rel
     score = eng.score(fx["best"].to(DEV), fx["scoring"])
-    assert math.isclose(score, fx["score"], rel_tol=2e-2 if backend == "simt" else 5e-2, abs_tol=1e-5), (score, fx["score"])
+    tol_s = 2e-2 * abs(fx["score"]) if backend == "simt" else max(5e-2 * abs(fx["score"]), 1.5 * abs(ref_score - fx["score"]))
+    # (the score of a converged candidate is a small difference of two nearly equal updates: under TF32 the reference's own GPU run moves it
+    # by ten per cent and more on the narrow ConvNet fixture, whose 32-channel layers run on the 128 x 32 tensor-core tiles)
+    assert abs(score - fx["score"]) <= tol_s + 1e-5, (score, fx["score"], tol_s)
     eng.close()
 
 
