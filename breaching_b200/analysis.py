@@ -72,7 +72,7 @@ def report(reconstructed_user_data, true_user_data, server_payload, model_templa
                     for b, src in zip(m.buffers(), buffers):
                         b.copy_(src.to(dev))
             m.eval()
-            eng = E.Engine(m, tuple(rec.shape), get_attack_config("invertinggradients"), dev)
+            eng = E.Engine(m, tuple(rec.shape), get_attack_config("invertinggradients"), dev, backend="simt")   # metric: fp32 forward
             eng.load_model()
             fr, ft = eng.forward(rec), eng.forward(ref)
             eng.close()

@@ -73,9 +73,7 @@ class OptimizationBasedAttacker:
                     if key not in _REGULARIZERS:
                         raise KeyError(key)
                     self.regularizers.append((key, dict(reg[key])))
-        aug = cfg_get(self.cfg, "augmentations")
-        if aug is not None and len(list(aug.keys())) > 0:
-            raise NotImplementedError("candidate augmentations are not implemented by the B200 engine")
+        self._aug_plans = {}   # candidate augmentations (attacks/augment.py), built per batch size on first use
         if self.setup["dtype"] != torch.float32:
             raise NotImplementedError("the B200 engine computes in fp32 (cfg.impl.dtype=float)")
         if cfg_get(self.cfg.impl, "mixed_precision", False):
@@ -228,6 +226,11 @@ class OptimizationBasedAttacker:
             best, history = lbfgs.run_trial(engine, candidate, self.cfg, table, -dm / ds, (1 - dm) / ds, dryrun)
             stats[f"Trial_{trial}_Val"].extend(history)
             return best.detach()
+        if hasattr(engine, "set_augmentations"):
+            plan = self._augmentation_plan(candidate)
+            if plan is not None or getattr(engine, "_aug_active", False):   # (re-setting invalidates the captured graph: only when needed)
+                engine.set_augmentations(plan)
+                engine._aug_active = plan is not None
         engine.begin_trial(candidate, table)
         callback = int(cfg_get(opt, "callback", 0) or 0)
         chunk = callback if callback > 0 else T
@@ -256,6 +259,16 @@ class OptimizationBasedAttacker:
         engine.sync()
         stats[f"Trial_{trial}_Val"].extend(engine.history().tolist())
         return engine.best().detach()
+
+    def _augmentation_plan(self, candidate):
+        """cfg.augmentations -> the engine's view pipeline (optimization_based_attack.py:42-48); colour constants are drawn once per
+        attacker and batch size, like the reference module's ``shuffled`` flag."""
+        from . import augment
+
+        key = (candidate.shape[0], candidate.shape[1])
+        if key not in self._aug_plans:
+            self._aug_plans[key] = augment.build_plan(self.cfg, candidate.shape[0], candidate.shape[1], self.setup)
+        return self._aug_plans[key]
 
     def _score_trial(self, engine, candidate):
         """optimization_based_attack.py:191-204."""

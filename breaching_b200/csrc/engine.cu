@@ -16,6 +16,7 @@
 #include "layers.cuh"
 #include "tokens.cuh"
 #include "objective.cuh"
+#include "augment.cuh"
 
 namespace bre {
 void set_pdl(bool on);
@@ -213,6 +214,28 @@ struct bre_engine {
     }
     return gemm_backend == 1 && precise_op[i] != 0;
   }
+  // candidate augmentations (augment.cu; optimization_based_attack.py:149-153): the model and the priors see view(x); the
+  // gradient is pulled back through the transposed view (differentiable mode) or x itself is replaced by its view (the
+  // reference's non-differentiable mode, which assigns candidate.data)
+  bool aug_on = false, aug_diff = false;
+  AugPlan aug;
+  AugDraws* aug_draws = nullptr;
+  float *x_aug = nullptr, *gradx_aug = nullptr, *aug_tmp = nullptr, *cj_scale = nullptr, *cj_shift = nullptr;
+  float* input_x() const { return aug_on && aug_diff ? x_aug : x; }          // what the first layer and the priors read
+  float* input_grad() const { return aug_on && aug_diff ? gradx_aug : gradx; }
+  void bind_input() { t[0].val = input_x(); t[0].td = input_grad(); }
+  int augment_forward() {
+    BRE_LAUNCH(launch_aug_draw(aug, sc, aug_draws, xN, stream));
+    BRE_LAUNCH(launch_aug_view(x, x_aug, xN, xC, xH, xW, aug, aug_draws, stream));
+    if (!aug_diff) BRE_CUDA_CHECK(cudaMemcpyAsync(x, x_aug, nx * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    return 0;
+  }
+  int augment_pull() {   // gradx <- view^T (gradx_aug + task_regularization * gradx_task)
+    if (need_task_grad()) BRE_LAUNCH(launch_axpy(gradx_task, gradx_aug, cfg.task_regularization, nx, stream));
+    BRE_LAUNCH(launch_aug_pull(gradx_aug, aug_tmp, gradx, xN, xC, xH, xW, aug, aug_draws, stream));
+    return 0;
+  }
+  bool task_grad_folded() const { return aug_on && aug_diff; }   // the task-gradient term already sits inside gradx
   // execution
   bool use_graph = true;
   int gemm_backend = 0;  // 0 = SIMT fp32, 1 = tcgen05 TF32 where supported
@@ -789,28 +812,29 @@ struct bre_engine {
     const bool image_terms = cfg.tv_scale != 0.f || cfg.norm_scale != 0.f;
     if (!image_terms) {
       if (cfg.orthogonality != 0)
-        BRE_LAUNCH(launch_orthogonality(x, gradx, xN, (long long)xC * xH * xW, true, sc, dpartials, dcounter, stream));
+        BRE_LAUNCH(launch_orthogonality(input_x(), input_grad(), xN, (long long)xC * xH * xW, true, sc, dpartials, dcounter, stream));
       return 0;
     }
     if (xC != 3) {   // TV on non-RGB candidates is rejected at creation (the reference's grouped conv raises as well)
-      BRE_LAUNCH(launch_norm_prior(x, gradx, nx, cfg.norm_scale, cfg.norm_p, 1, sc, dpartials, dcounter, stream));
+      BRE_LAUNCH(launch_norm_prior(input_x(), input_grad(), nx, cfg.norm_scale, cfg.norm_p, 1, sc, dpartials, dcounter, stream));
       if (cfg.orthogonality != 0)
-        BRE_LAUNCH(launch_orthogonality(x, gradx, xN, (long long)xC * xH * xW, false, sc, dpartials, dcounter, stream));
+        BRE_LAUNCH(launch_orthogonality(input_x(), input_grad(), xN, (long long)xC * xH * xW, false, sc, dpartials, dcounter, stream));
       return 0;
     }
     PriorArgs a;
-    a.x = x; a.grad = gradx; a.N = xN; a.H = xH; a.W = xW; a.accumulate = 1;
+    a.x = input_x(); a.grad = input_grad(); a.N = xN; a.H = xH; a.W = xW; a.accumulate = 1;
     a.tv_scale = cfg.tv_scale; a.p = cfg.tv_inner_exp; a.q = cfg.tv_outer_exp; a.eps = cfg.tv_eps;
     a.double_opponents = cfg.tv_double_opponents; a.norm_scale = cfg.norm_scale; a.norm_p = cfg.norm_p;
     BRE_LAUNCH(launch_image_priors(a, sc, dpartials, dcounter, stream));
     if (cfg.orthogonality != 0)
-      BRE_LAUNCH(launch_orthogonality(x, gradx, xN, (long long)xC * xH * xW, false, sc, dpartials, dcounter, stream));
+      BRE_LAUNCH(launch_orthogonality(input_x(), input_grad(), xN, (long long)xC * xH * xW, false, sc, dpartials, dcounter, stream));
     return 0;
   }
 
   // objective + its gradient w.r.t. the candidate (closure body, optimization_based_attack.py:146-165)
   int evaluate() {
     if (ms_steps > 0) return evaluate_multistep();
+    if (aug_on) BRE_TRY(augment_forward());
     BRE_TRY(sweep_forward());
     BRE_TRY(sweep_backward());
     BRE_TRY(reduce_objective(cfg.objective, cfg.obj_scale, cfg.mask_value, true));
@@ -822,12 +846,13 @@ struct bre_engine {
     BRE_TRY(deep_inversion_stats());
     BRE_TRY(sweep_tangent_backward());
     BRE_TRY(priors());
+    if (aug_on && aug_diff) BRE_TRY(augment_pull());
     return 0;
   }
 
   StepArgs step_args() const {
     StepArgs a;
-    a.x = x; a.m = m; a.v = v; a.best = best; a.grad = gradx; a.grad_task = need_task_grad() ? gradx_task : nullptr;
+    a.x = x; a.m = m; a.v = v; a.best = best; a.grad = gradx; a.grad_task = (need_task_grad() && !task_grad_folded()) ? gradx_task : nullptr;
     a.lr_table = lr_table; a.n_lr = n_lr; a.lo = lo; a.hi = hi; a.n = nx; a.C = xC; a.HW = xH * xW; a.cfg = cfg;
     return a;
   }
@@ -1454,8 +1479,11 @@ int bre_engine_score(bre_engine* e, const float* candidate, int32_t scoring, dou
                                 e->sc, e->dpartials, e->dcounter, e->stream));
     e->bind_step(0);
   } else {
-    BRE_TRY(e->sweep_forward());
-    BRE_TRY(e->sweep_backward());
+    e->t[0].val = e->x;                 // scores are taken on the candidate itself, not on an augmented view (:191-204)
+    int rc = e->sweep_forward();
+    if (rc == 0) rc = e->sweep_backward();
+    e->bind_input();
+    if (rc != 0) return rc;
     BRE_TRY(e->reduce_objective(scoring, 1.0f, -1.f, true));
   }
   Scalars h;
@@ -1473,7 +1501,7 @@ int bre_engine_objective_and_gradient(bre_engine* e, const float* candidate, dou
   e->launch_count = 0;
   BRE_TRY(e->build_chunk_modes());
   BRE_TRY(e->evaluate());
-  if (e->need_task_grad()) BRE_TRY(launch_axpy(e->gradx_task, e->gradx, e->cfg.task_regularization, e->nx, e->stream));
+  if (e->need_task_grad() && !e->task_grad_folded()) BRE_TRY(launch_axpy(e->gradx_task, e->gradx, e->cfg.task_regularization, e->nx, e->stream));
   Scalars h;
   BRE_TRY(read_scalars(e, &h));
   if (objective) {
@@ -1548,6 +1576,52 @@ int bre_engine_bn_batch_stats(bre_engine* e, int32_t bn_index, float* mean_out, 
   BRE_CUDA_CHECK(cudaMemcpyAsync(mean_out, b.di_mean, b.C * sizeof(float), cudaMemcpyDefault, e->stream));
   BRE_CUDA_CHECK(cudaMemcpyAsync(var_out, b.di_var, b.C * sizeof(float), cudaMemcpyDefault, e->stream));
   BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRE_OK;
+}
+
+int bre_engine_set_augmentations(bre_engine* e, int32_t n_steps, const int32_t* kinds, const float* params, int32_t cs_enabled, float cs_shift,
+                                 int32_t cs_circular, const float* cj_scale, const float* cj_shift, int32_t differentiable, uint64_t seed) {
+  if (!e || n_steps < 0 || n_steps > AUG_MAX_STEPS || (n_steps > 0 && (!kinds || !params))) { set_error("bre_engine_set_augmentations: bad arguments"); return BRE_ERR_INVALID; }
+  if (e->ms_steps > 0) { set_error("augmentations are not supported together with local steps"); return BRE_ERR_UNSUPPORTED; }
+  if (e->xN > AUG_MAX_BATCH) { set_error("augmentations: batch too large"); return BRE_ERR_UNSUPPORTED; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  e->graph_ready = false;
+  const bool any = n_steps > 0 || cs_enabled || cj_scale != nullptr;
+  memset(&e->aug, 0, sizeof(e->aug));
+  e->aug_on = any;
+  e->aug_diff = any && differentiable != 0;
+  if (any) {
+    for (int s = 0; s < n_steps; ++s) {
+      if (kinds[s] != AUG_SHIFT && kinds[s] != AUG_FLIP) { set_error("unknown augmentation step"); return BRE_ERR_INVALID; }
+      e->aug.kind[s] = kinds[s]; e->aug.p0[s] = params[s];
+    }
+    e->aug.n_steps = n_steps; e->aug.cs_enabled = cs_enabled; e->aug.cs_shift = cs_shift; e->aug.cs_circular = cs_circular; e->aug.seed = seed;
+    if (cs_enabled && e->xH != e->xW) { set_error("continuous_shift needs square images (the reference builds an S x S grid from shape[2])"); return BRE_ERR_UNSUPPORTED; }
+    if (!e->x_aug) {
+      BRE_TRY(e->alloc(&e->x_aug, e->nx)); BRE_TRY(e->alloc(&e->gradx_aug, e->nx)); BRE_TRY(e->alloc(&e->aug_tmp, e->nx));
+      BRE_TRY(e->alloc(&e->aug_draws, 1));
+      BRE_TRY(e->alloc(&e->cj_scale, (long long)e->xN * e->xC)); BRE_TRY(e->alloc(&e->cj_shift, (long long)e->xN * e->xC));
+    }
+    if (cj_scale != nullptr) {
+      if (!cj_shift) { set_error("colour scale and shift go together"); return BRE_ERR_INVALID; }
+      BRE_CUDA_CHECK(cudaMemcpyAsync(e->cj_scale, cj_scale, (size_t)e->xN * e->xC * sizeof(float), cudaMemcpyDefault, e->stream));
+      BRE_CUDA_CHECK(cudaMemcpyAsync(e->cj_shift, cj_shift, (size_t)e->xN * e->xC * sizeof(float), cudaMemcpyDefault, e->stream));
+      BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      e->aug.cj_scale = e->cj_scale; e->aug.cj_shift = e->cj_shift;
+    }
+  }
+  e->bind_input();
+  return BRE_OK;
+}
+
+int bre_engine_last_augmentation(bre_engine* e, int32_t* o1, int32_t* o2, float* sx, float* sy) {
+  if (!e || !e->aug_draws) { set_error("bre_engine_last_augmentation: no augmentations configured"); return BRE_ERR_STATE; }
+  BRE_CUDA_CHECK(cudaSetDevice(e->device));
+  AugDraws h;
+  BRE_CUDA_CHECK(cudaMemcpyAsync(&h, e->aug_draws, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  BRE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  for (int s = 0; s < AUG_MAX_STEPS; ++s) { if (o1) o1[s] = h.o1[s]; if (o2) o2[s] = h.o2[s]; }
+  for (int n = 0; n < e->xN && n < AUG_MAX_BATCH; ++n) { if (sx) sx[n] = h.sx[n]; if (sy) sy[n] = h.sy[n]; }
   return BRE_OK;
 }
 

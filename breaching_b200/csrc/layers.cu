@@ -88,7 +88,13 @@ __device__ __forceinline__ bool slab_reduce(float (&v)[NV], float* partials, int
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       float s = 0.f;
-      for (int sl = 0; sl < (int)gridDim.y; ++sl) s += __ldcg(partials + ((long long)sl * Cpad + c) * NV + k);
+      for (int base = 0; base < (int)gridDim.y; base += 16) {   // 16 independent loads per round trip, summed in slab order
+        float r[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) r[u] = base + u < (int)gridDim.y ? __ldcg(partials + ((long long)(base + u) * Cpad + c) * NV + k) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s += r[u];
+      }
       total[k] = s;
     }
   }
@@ -398,19 +404,19 @@ __device__ __forceinline__ bool slab_reduce4(float (&v)[NV][4], int LX, int LY, 
   for (int idx = tid; idx < cols * NV; idx += 256) {
     const int k = idx / cols, col = idx - k * cols;
     const int c = blockIdx.x * cols + col;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four interleaved chains (loads overlap), combined in a fixed order
+    // slabs in batches of 32 independent loads (one L2 round trip per batch instead of one per few slabs), summed in slab order
+    float sum = 0.f;
     if (c < C) {
       const int ns = (int)gridDim.y;
-      int sl = 0;
-      for (; sl + 3 < ns; sl += 4) {
-        s0 += __ldcg(partials + ((long long)sl * Cpad + c) * NV + k);
-        s1 += __ldcg(partials + ((long long)(sl + 1) * Cpad + c) * NV + k);
-        s2 += __ldcg(partials + ((long long)(sl + 2) * Cpad + c) * NV + k);
-        s3 += __ldcg(partials + ((long long)(sl + 3) * Cpad + c) * NV + k);
+      for (int base = 0; base < ns; base += 32) {
+        float r[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) r[u] = base + u < ns ? __ldcg(partials + ((long long)(base + u) * Cpad + c) * NV + k) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) sum += r[u];
       }
-      for (; sl < ns; ++sl) s0 += __ldcg(partials + ((long long)sl * Cpad + c) * NV + k);
     }
-    tot4[k][col] = (s0 + s1) + (s2 + s3);
+    tot4[k][col] = sum;
   }
   __syncthreads();
   if (tid < LX && c0 < C) {

@@ -84,6 +84,7 @@ EXPORTS = [
     "bre_token_layernorm", "bre_token_attention",
     "bre_engine_param_gradients", "bre_engine_bn_batch_stats", "bre_engine_forward", "bre_image_mse",
     "bre_engine_begin_joint_trial", "bre_engine_get_joint_labels", "bre_resize_bilinear",
+    "bre_engine_set_augmentations", "bre_engine_last_augmentation", "bre_augment_view",
 ]
 
 
@@ -137,6 +138,9 @@ def load_library(path=None):
     lib.bre_engine_param_gradients.argtypes = [vp, vp, vp, i32, P(vp), i32, P(ctypes.c_double)]
     lib.bre_engine_bn_batch_stats.argtypes = [vp, i32, vp, vp]
     lib.bre_engine_forward.argtypes = [vp, vp, vp]
+    lib.bre_engine_set_augmentations.argtypes = [vp, i32, P(i32), P(f32), i32, f32, i32, vp, vp, i32, ctypes.c_uint64]
+    lib.bre_engine_last_augmentation.argtypes = [vp, P(i32), P(i32), P(f32), P(f32)]
+    lib.bre_augment_view.argtypes = [vp, vp, i32, i32, i32, i32, i32, P(i32), P(i32), P(i32), f32, i32, P(f32), P(f32), vp, vp, i32, vp, vp]
     lib.bre_resize_bilinear.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.bre_image_mse.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, P(ctypes.c_double), vp]
     for name in EXPORTS:
@@ -376,6 +380,30 @@ class Engine:
         _check(self.lib, self.lib.bre_engine_get_joint_labels(self.h, int(bool(best)), _ptr(out)), "bre_engine_get_joint_labels")
         return out
 
+    def set_augmentations(self, plan):
+        """``plan`` (attacks/augment.py ``AugmentationPlan``) or ``None`` to switch augmentations off."""
+        if plan is None:
+            _check(self.lib, self.lib.bre_engine_set_augmentations(self.h, 0, None, None, 0, 0.0, 0, None, None, 0, 0), "bre_engine_set_augmentations")
+            return
+        n = len(plan.steps)
+        kinds = (ctypes.c_int32 * max(n, 1))(*[k for k, _ in plan.steps])
+        params = (ctypes.c_float * max(n, 1))(*[float(p) for _, p in plan.steps])
+        scale = None if plan.colour_scale is None else _f32c(plan.colour_scale, self.device)
+        shift = None if plan.colour_shift is None else _f32c(plan.colour_shift, self.device)
+        torch.cuda.synchronize(self.device)
+        self._aug_keep = (scale, shift)
+        _check(self.lib, self.lib.bre_engine_set_augmentations(self.h, n, kinds, params, int(plan.continuous_shift is not None),
+                                                               float(plan.continuous_shift or 0.0), int(plan.circular), _ptr(scale), _ptr(shift),
+                                                               int(plan.differentiable), int(plan.seed) & 0xFFFFFFFFFFFFFFFF),
+               "bre_engine_set_augmentations")
+
+    def last_augmentation(self):
+        o1, o2 = (ctypes.c_int32 * 4)(), (ctypes.c_int32 * 4)()
+        sx, sy = (ctypes.c_float * 64)(), (ctypes.c_float * 64)()
+        _check(self.lib, self.lib.bre_engine_last_augmentation(self.h, o1, o2, sx, sy), "bre_engine_last_augmentation")
+        n = self.input_shape[0]
+        return list(o1), list(o2), list(sx)[:n], list(sy)[:n]
+
     def run(self, n_iters):
         _check(self.lib, self.lib.bre_engine_run(self.h, int(n_iters)), "bre_engine_run")
 
@@ -535,6 +563,32 @@ def total_variation(x, scale=0.1, inner_exp=1.0, outer_exp=1.0, eps=1e-8, double
                                      eps, int(double_opponents), int(accumulate), ctypes.byref(val), ctypes.c_void_p(stream))
     _check(lib, rc, "bre_total_variation")
     return val.value, grad
+
+
+def augment_view(x, steps=(), offsets=(), continuous_shift=None, circular=True, uniforms=None, colour_scale=None, colour_shift=None,
+                 transpose=False):
+    """Stand-alone augmentation view (or its transpose) with explicit draws: ``steps`` = [(kind, param)], ``offsets`` = [(o1, o2)] per
+    step (roll offsets; flip: (flag, 0)), ``uniforms`` = (sx, sy) lists per image for the continuous shift."""
+    lib = load_library()
+    x = _f32c(x).clone()
+    N, C, H, W = x.shape
+    out = torch.empty_like(x)
+    n = len(steps)
+    kinds = (ctypes.c_int32 * max(n, 1))(*[k for k, _ in steps])
+    o1 = (ctypes.c_int32 * max(n, 1))(*[int(a) for a, _ in offsets])
+    o2 = (ctypes.c_int32 * max(n, 1))(*[int(b) for _, b in offsets])
+    sx = sy = None
+    if continuous_shift is not None:
+        sx, sy = (ctypes.c_float * N)(*[float(v) for v in uniforms[0]]), (ctypes.c_float * N)(*[float(v) for v in uniforms[1]])
+    scratch = torch.empty_like(x)
+    cs, csh = (None if colour_scale is None else _f32c(colour_scale, x.device)), (None if colour_shift is None else _f32c(colour_shift, x.device))
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        torch.cuda.synchronize(x.device)
+        rc = lib.bre_augment_view(_ptr(x), _ptr(out), N, C, H, W, n, kinds, o1, o2, float(continuous_shift or 0.0), int(circular), sx, sy, _ptr(cs),
+                                  _ptr(csh), int(transpose), _ptr(scratch), ctypes.c_void_p(stream))
+    _check(lib, rc, "bre_augment_view")
+    return out
 
 
 def resize_bilinear(x, size):

@@ -188,6 +188,24 @@ int bre_engine_begin_joint_trial(bre_engine* e, const float* candidate, const fl
 /* Label logits of the joint trial: best != 0 -> the best-so-far copy, else the current iterate. */
 int bre_engine_get_joint_labels(bre_engine* e, int32_t best, float* out);
 
+/* Candidate augmentations of the closure (optimization_based_attack.py:149-153, auxiliaries/augmentations.py): the model and the
+ * priors see view(candidate); `differentiable` != 0 pulls the gradient back through the transposed view, 0 replaces the candidate
+ * by its view every iteration (the reference assigns candidate.data).  Pipeline: up to 4 permutation steps in config order
+ * (kinds[s]: 1 = discrete_shift with params[s] = lim, 2 = flip with params[s] = p), then the optional continuous_shift
+ * (bilinear grid sample, shift in pixels, "circular" wrap as in the reference), then the composite colour affine per (image,
+ * channel): out = in * cj_scale + cj_shift (colorjitter; NULL = none; device or host [N * C]).  Random draws: Philox(seed,
+ * iteration).  n_steps = 0, cs_enabled = 0 and cj_scale = NULL switch augmentations off. */
+int bre_engine_set_augmentations(bre_engine* e, int32_t n_steps, const int32_t* kinds, const float* params, int32_t cs_enabled,
+                                 float cs_shift, int32_t cs_circular, const float* cj_scale, const float* cj_shift,
+                                 int32_t differentiable, uint64_t seed);
+/* The draws of the last evaluation (for parity tests): roll offsets / flip flags per step, continuous-shift uniforms per image. */
+int bre_engine_last_augmentation(bre_engine* e, int32_t* o1, int32_t* o2, float* sx, float* sy);
+/* Stand-alone view (transpose = 0) or pull-back (transpose = 1: x is the gradient w.r.t. the view and is clobbered when the
+ * continuous shift is on; scratch: same size) with explicit draws o1 / o2 per step and sx / sy per image (NULL = no continuous shift). */
+int bre_augment_view(const float* x, float* out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t n_steps, const int32_t* kinds,
+                     const int32_t* o1, const int32_t* o2, float cs_shift, int32_t cs_circular, const float* sx, const float* sy,
+                     const float* cj_scale, const float* cj_shift, int32_t transpose, float* scratch, void* stream);
+
 /* ---- the steps either side of the hot path ----------------------------------------- */
 /* User-side update production (cases/users.py:148-169 `_compute_batch_gradient`): one forward + backward of the loaded model
  * on `data` (candidate layout, device or host) with index `labels` -> gradient of the mean task loss w.r.t. every parameter,

@@ -679,3 +679,32 @@ def pearlmutter_closure(model, loss_fn, gradients, x, labels, kind="pearlmutter-
         for p, o in zip(params, original):
             p.copy_(o)
     return value.detach(), task_loss.detach(), (fd * scale + task_regularization * dLdx).detach()
+
+
+# --------------------------------------------------------------------------------------
+# candidate augmentations  (attacks/auxiliaries/augmentations.py; closure: optimization_based_attack.py:149-153)
+# --------------------------------------------------------------------------------------
+def augment_candidate(x, steps=(), offsets=(), continuous_shift=None, circular=True, uniforms=None, colour_mean=None, colour_std=None):
+    """The reference's augmentation modules applied with *given* random draws (the modules draw from torch's global generator):
+    ``steps`` = [(kind, param)] with kind 1 = ``Jitter`` (:9-18, roll by ``offsets[s]``), 2 = ``Flip`` (:57-64, flipped iff
+    ``offsets[s][0]``), then ``RandomTransform`` (:141-205, ``shift`` = ``continuous_shift``, ``uniforms`` = (randgen[:, 0],
+    randgen[:, 1])), then ``ColorJitter`` (:70-89) with per-(image, channel) ``colour_mean`` / ``colour_std`` [N, 3, 1, 1]."""
+    for (kind, _), (a, b) in zip(steps, offsets):
+        if kind == 1:
+            x = torch.roll(x, shifts=(int(a), int(b)), dims=(2, 3))            # :18
+        elif kind == 2:
+            x = torch.flip(x, dims=(3,)) if a else x                           # :64
+    if continuous_shift is not None:
+        S = x.shape[2]
+        direct = torch.linspace(-1, 1.0, S, dtype=x.dtype).unsqueeze(0).repeat(S, 1).unsqueeze(-1)   # build_grid(S, S): k = 1 (:165-170)
+        grid = torch.cat([direct, direct.transpose(1, 0)], dim=2).unsqueeze(0).repeat(x.shape[0], 1, 1, 1)
+        randgen = torch.stack([torch.as_tensor(uniforms[0], dtype=x.dtype), torch.as_tensor(uniforms[1], dtype=x.dtype)], dim=1)
+        delta = continuous_shift / (S - 1)                                      # :179
+        grid[:, :, :, 0] = grid[:, :, :, 0] + ((randgen[:, 0] - 0.5) * 2 * delta)[:, None, None]
+        grid[:, :, :, 1] = grid[:, :, :, 1] + ((randgen[:, 1] - 0.5) * 2 * delta)[:, None, None]
+        if circular:                                                            # :197-199
+            grid = (grid + 1) % 1 - 1
+        x = F.grid_sample(x, grid, align_corners=True, mode="bilinear", padding_mode="zeros")   # :203 (self.align = True, :157)
+    if colour_mean is not None:
+        x = (x - colour_mean) / colour_std                                      # :89
+    return x
