@@ -236,6 +236,38 @@ struct bre_engine {
     return 0;
   }
   bool task_grad_folded() const { return aug_on && aug_diff; }   // the task-gradient term already sits inside gradx
+  // deferred finalisation of the BN parameter gradients (layers.cu bn_grad_finalize_kernel): per-layer partial regions + table
+  bool defer_bn_env = [] { const char* e = getenv("BRE_DEFER_BN"); return e ? atoi(e) != 0 : true; }();
+  std::vector<float*> bn_partials;      // per op (BNACT with eval-mode BN), null otherwise
+  BnGradSlot* bn_slots_dev = nullptr;
+  int bn_slots = 0, bn_slot_blocks = 0;
+  bool bn_slots_built = false;
+  int build_bn_slots() {
+    if (bn_slots_built) return 0;
+    bn_slots_built = true;
+    if (!defer_bn_env) return 0;
+    std::vector<BnGradSlot> table;
+    bn_partials.assign(ops.size(), nullptr);
+    int blocks = 0;
+    for (size_t i = 0; i < ops.size(); ++i) {
+      const bre_op_desc& op = ops[i];
+      if (op.kind != BRE_OP_BNACT || !op.has_bn || op.bn_train) continue;
+      const bre_tensor_desc& to = td(op.tout);
+      int slabs = 0, Cpad = 0;
+      bnact_bwd_plan((long long)to.N * to.H * to.W, to.C, &slabs, &Cpad);
+      float* buf = nullptr;
+      BRE_TRY(alloc(&buf, (long long)slabs * Cpad * 2));
+      bn_partials[i] = buf;
+      table.push_back(BnGradSlot{buf, slabs, Cpad, to.C, blocks, nullptr, nullptr});   // gradient pointers: filled per sweep (G arena is fixed)
+      table.back().g_gamma = Gp(op.gamma); table.back().g_beta = Gp(op.beta);
+      blocks += (to.C + 127) / 128;
+    }
+    bn_slots = (int)table.size(); bn_slot_blocks = blocks;
+    if (bn_slots == 0) return 0;
+    BRE_TRY(alloc(&bn_slots_dev, (long long)table.size()));
+    BRE_CUDA_CHECK(cudaMemcpy(bn_slots_dev, table.data(), table.size() * sizeof(BnGradSlot), cudaMemcpyHostToDevice));
+    return 0;
+  }
   // execution
   bool use_graph = true;
   int gemm_backend = 0;  // 0 = SIMT fp32, 1 = tcgen05 TF32 where supported
@@ -457,7 +489,7 @@ struct bre_engine {
   }
 
   int sweep_backward() {
-    bool forked = false;
+    bool forked = false, deferred_bn = false;
     for (int i = (int)ops.size() - 1; i >= 0; --i) {
       const bre_op_desc& op = ops[i];
       const bre_tensor_desc& to = td(op.tout);
@@ -501,7 +533,8 @@ struct bre_engine {
           a.din = t[op.tin].d; a.acc_in = op.acc_in != 0; a.round_din = round_d(op.tin);
           a.dres = op.res >= 0 ? t[op.res].d : nullptr; a.acc_res = op.acc_res != 0;
           a.g_gamma = op.has_bn ? Gp(op.gamma) : nullptr; a.g_beta = op.has_bn ? Gp(op.beta) : nullptr;
-          a.partials = red_partials; a.counters = red_counters;
+          a.partials = red_partials; a.counters = red_counters; a.defer = 0;
+          if (op.has_bn && !op.bn_train && !bn_partials.empty() && bn_partials[i] != nullptr) { a.partials = bn_partials[i]; a.defer = 1; deferred_bn = true; }
           // (splitting this op into an element-wise kernel on the main stream and the gamma / beta reductions on the side
           // stream was measured: config 2 unchanged, configs 1 and 3 3-5 % slower -- the side stream is already full)
           if (op.has_bn && op.bn_train) {
@@ -540,6 +573,7 @@ struct bre_engine {
         default: break;
       }
     }
+    if (deferred_bn) BRE_LAUNCH(launch_bn_grad_finalize(bn_slots_dev, bn_slots, bn_slot_blocks, stream));   // gamma / beta gradients of all layers
     if (forked) {
       BRE_CUDA_CHECK(cudaEventRecord(ev_join, side));
       BRE_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));
@@ -637,17 +671,54 @@ struct bre_engine {
     return 0;
   }
 
-  int deep_inversion_stats() {
+  // DeepInversion statistics of every BN input of this forward pass: one batched launch pair (layers.cu) + per-layer finalisation
+  StatSlot* di_stat_slots = nullptr;
+  double* di_layer_values = nullptr;
+  int di_stat_blocks = 0, di_stat_groups = 0;
+  bool di_batched = false, di_tables_built = false;
+  int build_di_tables() {
+    if (di_tables_built) return 0;
+    di_tables_built = true;
     if (cfg.di_scale <= 0.f || n_di == 0) return 0;
-    for (size_t i = 0; i < ops.size(); ++i) {
-      const bre_op_desc& op = ops[i];
+    BRE_TRY(alloc(&di_layer_values, n_di));
+    static const bool env = [] { const char* e = getenv("BRE_DI_BATCHED"); return e ? atoi(e) != 0 : true; }();
+    if (!env || ms_steps > 0) return 0;
+    std::vector<StatSlot> table;
+    int blocks = 0, groups = 0;
+    for (const bre_op_desc& op : ops) {
       if (op.kind != BRE_OP_BNACT || !op.has_bn) continue;
       const bre_tensor_desc& ti = td(op.tin);
+      StatSlot sl;
+      memset(&sl, 0, sizeof(sl));
+      if (!channel_stats_plan((long long)ti.N * ti.H * ti.W, ti.C, &sl)) return 0;   // odd channel count somewhere: per-layer kernels
       BnBuf& b = bn[op.bn_buffer];
-      BRE_LAUNCH(launch_channel_stats(t[op.tin].val, (long long)ti.N * ti.H * ti.W, ti.C, b.di_mean, b.di_var, red_partials,
-                                      red_counters, stream));
+      sl.x = t[op.tin].val; sl.mean = b.di_mean; sl.var = b.di_var;
+      BRE_TRY(alloc(&sl.partials, (long long)sl.slabs * sl.Cpad * 2));
+      sl.first_block = blocks; sl.first_group = groups;
+      blocks += sl.cg * sl.slabs; groups += (ti.C + 255) / 256;
+      table.push_back(sl);
     }
-    BRE_LAUNCH(launch_di_finalize(di_layers_dev, n_di, sc, stream));
+    if (table.empty()) return 0;
+    BRE_TRY(alloc(&di_stat_slots, (long long)table.size()));
+    BRE_CUDA_CHECK(cudaMemcpy(di_stat_slots, table.data(), table.size() * sizeof(StatSlot), cudaMemcpyHostToDevice));
+    di_stat_blocks = blocks; di_stat_groups = groups; di_batched = true;
+    return 0;
+  }
+  int deep_inversion_stats() {
+    if (cfg.di_scale <= 0.f || n_di == 0) return 0;
+    if (di_batched) {
+      BRE_LAUNCH(launch_channel_stats_batched(di_stat_slots, n_di, di_stat_blocks, di_stat_groups, stream));
+    } else {
+      for (size_t i = 0; i < ops.size(); ++i) {
+        const bre_op_desc& op = ops[i];
+        if (op.kind != BRE_OP_BNACT || !op.has_bn) continue;
+        const bre_tensor_desc& ti = td(op.tin);
+        BnBuf& b = bn[op.bn_buffer];
+        BRE_LAUNCH(launch_channel_stats(t[op.tin].val, (long long)ti.N * ti.H * ti.W, ti.C, b.di_mean, b.di_var, red_partials,
+                                        red_counters, stream));
+      }
+    }
+    BRE_LAUNCH(launch_di_finalize(di_layers_dev, n_di, di_layer_values, sc, stream));
     return 0;
   }
 
@@ -1383,11 +1454,15 @@ int bre_engine_run(bre_engine* e, int32_t n_iters) {
   BRE_CUDA_CHECK(cudaSetDevice(e->device));
   if (!e->use_graph) {
     BRE_TRY(e->build_chunk_modes());
+    BRE_TRY(e->build_bn_slots());
+    BRE_TRY(e->build_di_tables());
     for (int i = 0; i < n_iters; ++i) { e->launch_count = 0; BRE_TRY(e->iteration()); e->launches_per_iter = e->launch_count; }
     return BRE_OK;
   }
   if (!e->graph_ready) {
-    BRE_TRY(e->build_chunk_modes());   // host -> device table: must exist before the capture starts
+    BRE_TRY(e->build_chunk_modes());   // host -> device tables: must exist before the capture starts
+    BRE_TRY(e->build_bn_slots());
+    BRE_TRY(e->build_di_tables());
     if (e->exec) { cudaGraphExecDestroy(e->exec); e->exec = nullptr; }
     cudaGraph_t graph = nullptr;
     BRE_CUDA_CHECK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
@@ -1500,6 +1575,8 @@ int bre_engine_objective_and_gradient(bre_engine* e, const float* candidate, dou
   BRE_CUDA_CHECK(cudaMemcpyAsync(e->x, candidate, e->nx * sizeof(float), cudaMemcpyDefault, e->stream));
   e->launch_count = 0;
   BRE_TRY(e->build_chunk_modes());
+  BRE_TRY(e->build_bn_slots());
+  BRE_TRY(e->build_di_tables());
   BRE_TRY(e->evaluate());
   if (e->need_task_grad() && !e->task_grad_folded()) BRE_TRY(launch_axpy(e->gradx_task, e->gradx, e->cfg.task_regularization, e->nx, e->stream));
   Scalars h;

@@ -57,7 +57,7 @@ __global__ void bnact_fwd_kernel(const float* __restrict__ in, const float* __re
 // Block (32, 8); blockIdx.x = channel group, blockIdx.y = slab.  Returns per-thread partial sums reduced over
 // threadIdx.y into row 0, then the last-arriving block of a channel group reduces the slabs in fixed order.
 template <int NV>
-__device__ __forceinline__ bool slab_reduce(float (&v)[NV], float* partials, int* counters, int Cpad, float (&total)[NV]) {
+__device__ __forceinline__ bool slab_reduce(float (&v)[NV], float* partials, int* counters, int Cpad, float (&total)[NV], bool defer = false) {
   __shared__ float sm[NV][8][33];
   __shared__ int s_last;
   const int x = threadIdx.x, y = threadIdx.y;
@@ -74,6 +74,7 @@ __device__ __forceinline__ bool slab_reduce(float (&v)[NV], float* partials, int
       partials[((long long)blockIdx.y * Cpad + c) * NV + k] = s;
     }
   }
+  if (defer) return false;   // the slabs are summed later by one batched kernel for all layers (launch_bn_grad_finalize)
   __threadfence();
   __syncthreads();
   if (x == 0 && y == 0) {
@@ -144,7 +145,7 @@ __global__ void bnact_bwd_kernel(BnActBwdArgs a, long long pps, int Cpad) {
   }
   if (!a.has_bn || a.g_gamma == nullptr) return;  // uniform across the grid
   float tot[2];
-  if (slab_reduce<2>(v, a.partials, a.counters, Cpad, tot) && cv) {
+  if (slab_reduce<2>(v, a.partials, a.counters, Cpad, tot, a.defer != 0) && cv) {
     a.g_gamma[c] = tot[0];
     a.g_beta[c] = tot[1];
   }
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256) bnact_tan_bwd_vec_kernel(BnActTanBwdArgs 
 // column group sums the slabs in fixed order (deterministic, like slab_reduce).
 template <int NV>
 __device__ __forceinline__ bool slab_reduce4(float (&v)[NV][4], int LX, int LY, float* partials, int* counters, int Cpad, int C,
-                                             float (&total)[NV][4]) {
+                                             float (&total)[NV][4], bool defer = false) {
   __shared__ float sm4[NV * 4][257];
   __shared__ int s_last4;
   const int tid = threadIdx.x, lx = tid % LX;
@@ -388,6 +389,7 @@ __device__ __forceinline__ bool slab_reduce4(float (&v)[NV][4], int LX, int LY, 
         partials[((long long)blockIdx.y * Cpad + c0 + j) * NV + k] = s;
       }
   }
+  if (defer) return false;   // summed over the slabs later, batched over all layers (launch_bn_grad_finalize)
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(256) bnact_bwd_vec_kernel(BnActBwdArgs a, long
   }
   if (!a.has_bn || a.g_gamma == nullptr) return;  // uniform across the grid
   float tot[2][4];
-  if (slab_reduce4<2>(v, LX, LY, a.partials, a.counters, Cpad, a.C, tot)) {
+  if (slab_reduce4<2>(v, LX, LY, a.partials, a.counters, Cpad, a.C, tot, a.defer != 0)) {
     st4(a.g_gamma, c4, make_float4(tot[0][0], tot[0][1], tot[0][2], tot[0][3]));
     st4(a.g_beta, c4, make_float4(tot[1][0], tot[1][1], tot[1][2], tot[1][3]));
   }
@@ -549,6 +551,109 @@ __global__ void __launch_bounds__(256) channel_stats_vec_kernel(const float* __r
     st4(mean, c4, make_float4(m[0], m[1], m[2], m[3]));
     st4(var, c4, make_float4(vr[0], vr[1], vr[2], vr[3]));
   }
+}
+
+// ---- per-channel statistics of many tensors in one launch (DeepInversion: every BN input of the forward pass) --------------------
+// 53 separate slab reductions (ResNet-50) cost ~8 us of fixed two-phase overhead each; batched: one launch writes the slab partials
+// of all layers (blockIdx.x -> (layer, channel group, slab) through a prefix table), one launch turns them into mean / variance.
+__global__ void __launch_bounds__(256) channel_stats_batched_kernel(const StatSlot* __restrict__ table, int n_layers) {
+  pdl_prologue();
+  __shared__ float sm4[8][257];
+  int layer = 0;
+  while (layer + 1 < n_layers && (int)blockIdx.x >= table[layer + 1].first_block) ++layer;
+  const StatSlot e = table[layer];
+  const int local = (int)blockIdx.x - e.first_block;
+  const int bx = local % e.cg, by = local / e.cg;
+  const int LX = e.LX, LY = e.LY, C4 = e.C / 4;
+  const int tid = threadIdx.x, lx = tid % LX, ly = tid / LX;
+  const int c4 = bx * LX + lx;
+  const long long p0 = by * e.pps;
+  const long long p1 = (p0 + e.pps < e.P) ? p0 + e.pps : e.P;
+  const float4 sh = c4 < C4 ? ldc4(e.x, c4) : make_float4(0.f, 0.f, 0.f, 0.f);   // shift = first element of the channel (conditioning)
+  float v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  if (c4 < C4) {
+    constexpr int U = 8;
+    for (long long p = p0 + ly; p < p1; p += (long long)LY * U) {
+      float4 t[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pp = p + (long long)u * LY;
+        t[u] = pp < p1 ? ld4(e.x, pp * C4 + c4) : sh;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float a0 = t[u].x - sh.x, a1 = t[u].y - sh.y, a2 = t[u].z - sh.z, a3 = t[u].w - sh.w;
+        v[0][0] += a0; v[0][1] += a1; v[0][2] += a2; v[0][3] += a3;
+        v[1][0] = fmaf(a0, a0, v[1][0]); v[1][1] = fmaf(a1, a1, v[1][1]); v[1][2] = fmaf(a2, a2, v[1][2]); v[1][3] = fmaf(a3, a3, v[1][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sm4[k * 4 + j][tid] = v[k][j];
+  __syncthreads();
+  const int c0 = c4 * 4;
+  if (tid < LX && c0 < e.C) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float sum = 0.f;
+        for (int y = 0; y < LY; ++y) sum += sm4[k * 4 + j][y * LX + lx];
+        e.partials[((long long)by * e.Cpad + c0 + j) * 2 + k] = sum;
+      }
+  }
+}
+
+__global__ void __launch_bounds__(256) channel_stats_batched_finalize_kernel(const StatSlot* __restrict__ table, int n_layers) {
+  pdl_prologue();
+  int layer = 0;
+  while (layer + 1 < n_layers && (int)blockIdx.x >= table[layer + 1].first_group) ++layer;
+  const StatSlot e = table[layer];
+  const int c = ((int)blockIdx.x - e.first_group) * 256 + threadIdx.x;
+  if (c >= e.C) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (int base = 0; base < e.slabs; base += 16) {
+    float r0[16], r1[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const bool ok = base + u < e.slabs;
+      const float* q = e.partials + ((long long)(base + u) * e.Cpad + c) * 2;
+      r0[u] = ok ? __ldcg(q) : 0.f;
+      r1[u] = ok ? __ldcg(q + 1) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { s0 += r0[u]; s1 += r1[u]; }
+  }
+  const float sh = e.x[c];
+  const float m = s0 / (float)e.P;
+  e.mean[c] = m + sh;
+  e.var[c] = fmaxf(s1 / (float)e.P - m * m, 0.f);
+}
+
+// ---- deferred, batched finalisation of the BN parameter gradients ---------------------------------------------------------------
+// Every bnact_bwd launch used to end with a serial tail: atomic ticket, the last block of each channel group re-reads the slab
+// partials and sums them (5-8 us of a 9-20 us launch, on the critical path of the backward sweep 20-53 times per iteration).  With
+// `defer` the kernels stop after writing their partials; one launch at the end of the sweep sums the slabs of *all* layers (one
+// block per 128 channels of a layer, fixed slab order) -- the gradients of gamma / beta are only read by the matching reduction.
+__global__ void __launch_bounds__(256) bn_grad_finalize_kernel(const BnGradSlot* __restrict__ table, int n_layers) {
+  pdl_prologue();
+  int layer = 0;
+  while (layer + 1 < n_layers && (int)blockIdx.x >= table[layer + 1].first_block) ++layer;
+  const BnGradSlot e = table[layer];
+  const int group = (int)blockIdx.x - e.first_block;
+  const int k = threadIdx.x >> 7, c = group * 128 + (threadIdx.x & 127);   // 128 channels x 2 quantities
+  if (c >= e.C) return;
+  float sum = 0.f;
+  for (int base = 0; base < e.slabs; base += 32) {
+    float r[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) r[u] = base + u < e.slabs ? __ldcg(e.partials + ((long long)(base + u) * e.Cpad + c) * 2 + k) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) sum += r[u];
+  }
+  (k == 0 ? e.g_gamma : e.g_beta)[c] = sum;
 }
 
 // ---- train-mode BatchNorm (rules in layers.cuh) -------------------------------------------------------------
@@ -890,6 +995,46 @@ int launch_bnact_fwd(const float* in, const float* res, float* out, long long P,
     return 0;
   }
   BRE_KLAUNCH(bnact_fwd_kernel, ew_grid(total), kEwThreads, 0, s, in, res, out, total, C, has_bn, relu, bn, round_out);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+// fills the geometry fields of a StatSlot (x, partials, mean, var and the block / group offsets are the caller's); false if the
+// 128-bit path does not apply to this channel count
+bool channel_stats_plan(long long P, int C, StatSlot* slot) {
+  if (!vec_ok(C)) return false;
+  dim3 grid;
+  int LX, LY;
+  long long pps;
+  slab_grid4(P, C, grid, LX, LY, pps);
+  slot->P = P; slot->pps = pps; slot->C = C; slot->LX = LX; slot->LY = LY; slot->cg = (int)grid.x; slot->slabs = (int)grid.y;
+  slot->Cpad = (int)(grid.x * LX * 4);
+  return true;
+}
+int launch_channel_stats_batched(const StatSlot* table_dev, int n_layers, int total_blocks, int total_groups, cudaStream_t s) {
+  BRE_KLAUNCH(channel_stats_batched_kernel, total_blocks, 256, 0, s, table_dev, n_layers);
+  BRE_KLAUNCH(channel_stats_batched_finalize_kernel, total_groups, 256, 0, s, table_dev, n_layers);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
+
+void bnact_bwd_plan(long long P, int C, int* slabs, int* Cpad) {
+  dim3 grid, block;
+  long long pps;
+  if (vec_ok(C)) {
+    int LX, LY;
+    slab_grid4(P, C, grid, LX, LY, pps);
+    *Cpad = (int)(grid.x * LX * 4);
+  } else {
+    slab_grid(P, C, grid, block, pps);
+    *Cpad = (int)(grid.x * 32);
+  }
+  *slabs = (int)grid.y;
+}
+
+int launch_bn_grad_finalize(const BnGradSlot* table_dev, int n_layers, int total_blocks, cudaStream_t s) {
+  if (n_layers <= 0 || total_blocks <= 0) return 0;
+  BRE_KLAUNCH(bn_grad_finalize_kernel, total_blocks, 256, 0, s, table_dev, n_layers);
   BRE_CHECK_LAUNCH();
   return 0;
 }

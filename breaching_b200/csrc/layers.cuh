@@ -35,8 +35,13 @@ struct BnActBwdArgs {
   bool round_din;              // store din on the TF32 grid (GEMM operand of dgrad / wgrad)
   float* g_gamma; float* g_beta;  // parameter-gradient outputs (may be null)
   float* partials; int* counters; // scratch: >= slabs*Cpad*2 floats, >= Cgroups ints (zeroed, self-resetting)
+  int defer;                      // != 0: stop after writing the slab partials; launch_bn_grad_finalize sums them later
 };
 int launch_bnact_bwd(const BnActBwdArgs& a, cudaStream_t s);
+// deferred finalisation of g_gamma / g_beta for all BN layers of a sweep in one launch
+struct BnGradSlot { const float* partials; int slabs, Cpad, C, first_block; float* g_gamma; float* g_beta; };
+void bnact_bwd_plan(long long P, int C, int* slabs, int* Cpad);   // slab count / padded channel count launch_bnact_bwd will use
+int launch_bn_grad_finalize(const BnGradSlot* table_dev, int n_layers, int total_blocks, cudaStream_t s);
 
 struct BnActTanFwdArgs {
   long long P; int C; bool has_bn, relu;
@@ -104,6 +109,14 @@ int launch_channel_sum(const float* x, long long P, int C, float* out, float* pa
 // per-channel mean / biased variance over pixels (DeepInversion statistics, deepinversion.py:96-98)
 int launch_channel_stats(const float* x, long long P, int C, float* mean, float* var, float* partials, int* counters,
                          cudaStream_t s);
+
+// one launch for the statistics of many tensors (DeepInversion): table entry per tensor
+struct StatSlot {
+  const float* x; long long P, pps; int C, LX, LY, cg, slabs, Cpad, first_block, first_group;
+  float* partials; float* mean; float* var;
+};
+bool channel_stats_plan(long long P, int C, StatSlot* slot);
+int launch_channel_stats_batched(const StatSlot* table_dev, int n_layers, int total_blocks, int total_groups, cudaStream_t s);
 
 struct PoolGeom { int N, H, W, C, Ho, Wo, k, stride, pad; };
 int launch_maxpool_fwd(const float* in, float* out, int* idx, PoolGeom g, cudaStream_t s);

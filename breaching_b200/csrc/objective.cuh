@@ -56,7 +56,8 @@ int launch_loss_mean(const float* loss_n, int N, Scalars* sc, cudaStream_t s);
 
 struct DiLayer { const float* mean; const float* var; const float* rm; const float* rv; float* cm; float* cv; int C; float M; float mult; };
 // DeepInversion value + per-channel adjoint coefficients for all BN layers (one block, layers in order)
-int launch_di_finalize(const DiLayer* layers_dev, int n_layers, Scalars* sc, cudaStream_t s);
+// `layer_values`: device scratch of n_layers doubles (two launches: one block per layer, then the ordered sum)
+int launch_di_finalize(const DiLayer* layers_dev, int n_layers, double* layer_values, Scalars* sc, cudaStream_t s);
 // features regulariser: value into sc->feat, adjoint accumulated into tdelta
 int launch_feature_reg(const float* feat, const float* measured, float* tdelta, long long n, float scale, Scalars* sc,
                        cudaStream_t s);
