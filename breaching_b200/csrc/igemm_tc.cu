@@ -32,13 +32,15 @@ namespace {
 
 constexpr int TC_BM = 128;      // UMMA M
 constexpr int TC_BK = 32;       // k-block per pipeline stage (4 MMAs of K = 8)
-constexpr int TC_STAGES = 4;       // ring depth (power of two: stage / phase of k-block i are i & 3, (i >> 2) & 1)
+constexpr int TC_STAGES = 4;       // default ring depth
+constexpr int TC_MAX_STAGES = 8;   // deep ring (chosen per launch, TcDims::stage_shift): stage / phase of k-block i are i & (n - 1), (i >> log2 n) & 1
 constexpr int TC_THREADS = 128;       // loader / epilogue threads (warps 0-3 <-> TMEM lane quadrants)
 constexpr int TC_BLOCK = TC_THREADS + 32;  // + one MMA-issuer warp
 
 struct TcDims {
   int M, Nc, K;
   int kblocks_per_src, total_kblocks, kblocks_per_split;
+  int stage_shift;   // log2 of the ring depth of this launch (2 or 3)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
@@ -244,10 +246,10 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;                                  // [STAGES][A_BYTES]
-  constexpr int nst = TC_STAGES;
+  const int nst = 1 << d.stage_shift, stage_mask = nst - 1;
   uint8_t* sB = smem + nst * A_BYTES;                  // [stages][B_BYTES]
-  __shared__ __align__(8) uint64_t bar_full[TC_STAGES];   // loaders -> MMA issuer (cp.async completion, 128 arrivals)
-  __shared__ __align__(8) uint64_t bar_empty[TC_STAGES];  // MMA issuer -> loaders (tcgen05.commit)
+  __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];   // loaders -> MMA issuer (cp.async completion, 128 arrivals)
+  __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];  // MMA issuer -> loaders (tcgen05.commit)
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ uint32_t s_tmem;
 
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], TMA ? 1 : TC_THREADS); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(&bar_full[s], TMA ? 1 : TC_THREADS); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_done, 1);
     fence_barrier_init();
   }
@@ -569,8 +571,8 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
       const uint64_t bdesc0 = b_mn ? make_desc(smem_u32(sB), 4096, 512, 1) : make_desc(smem_u32(sB), 16, 1024, 2);
       constexpr uint32_t a_step = (a_mn ? 1024u : 32u) >> 4, b_step = (b_mn ? 1024u : 32u) >> 4;
       for (int i = 0; i < nkb; ++i) {
-        const int stage = i & (TC_STAGES - 1);
-        mbar_wait(&bar_full[stage], (uint32_t)((i >> 2) & 1));
+        const int stage = i & stage_mask;
+        mbar_wait(&bar_full[stage], (uint32_t)((i >> d.stage_shift) & 1));
         TC_MARK(4, i == 0);
         TC_MARK(11, i == nkb - 1);
         // The mbarrier phase completes only after every cp.async of this stage has been performed, so the data is in
@@ -598,8 +600,8 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
       if ((tid & 31) == 0 && warp < nprod && warp < nkb) {
         KbState st = kb_init(kb_begin + warp);
         for (int i = warp; i < nkb; i += nprod) {
-          const int stage = i & (TC_STAGES - 1);
-          if (i >= nst) mbar_wait(&bar_empty[stage], (uint32_t)(((i >> 2) - 1) & 1));
+          const int stage = i & stage_mask;
+          if (i >= nst) mbar_wait(&bar_empty[stage], (uint32_t)(((i >> d.stage_shift) - 1) & 1));
           issue_block_tma(stage, st);
           TC_MARK(3, i == (nkb < nst ? nkb : nst) - 1);
           for (int u = 0; u < nprod; ++u) kb_advance(st);
@@ -608,8 +610,8 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
       __syncwarp();
     } else {
       for (int i = 0; i < nkb; ++i) {
-        const int stage = i & (TC_STAGES - 1);
-        if (i >= nst) mbar_wait(&bar_empty[stage], (uint32_t)(((i >> 2) - 1) & 1));
+        const int stage = i & stage_mask;
+        if (i >= nst) mbar_wait(&bar_empty[stage], (uint32_t)(((i >> d.stage_shift) - 1) & 1));
         issue_block(stage);
         cp_async_arrive(&bar_full[stage]);
       }
@@ -1024,10 +1026,19 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, const std::conditional_t<CLS,
   if (tn > 65535) { set_error("igemm_tc: grid too large"); return -1; }
   // (an 8-deep ring for single-wave launches was tried: 192 KB of shared memory per CTA stops the next kernel's CTAs from
   // becoming resident during this one's tail -- programmatic dependent launch loses its overlap -- and layer4 got 2x slower)
-  const size_t smem = (size_t)TC_STAGES * (TC_BM + BN) * TC_BK * 4;
+  // Ring depth: 4 stages (96 KB: two CTAs per SM, and the next kernel's CTAs become resident during this one's tail -- what
+  // programmatic dependent launch needs for the single-wave launches of batch 1) or 8 stages when the launch is several waves
+  // deep and every CTA walks a long k range (more bytes in flight per CTA; BRE_TC_STAGES=4|8 forces one).
+  static const int stages_env = [] { const char* e = getenv("BRE_TC_STAGES"); return e ? atoi(e) : 0; }();
+  int stages = TC_STAGES;
+  if (stages_env == 8 || (stages_env == 0 && tiles * splits >= 2LL * kNumSMs && d.kblocks_per_split >= 16)) stages = TC_MAX_STAGES;
+  if (stages_env == 4) stages = TC_STAGES;
+  d.stage_shift = stages == TC_MAX_STAGES ? 3 : 2;
+  const size_t smem = (size_t)stages * (TC_BM + BN) * TC_BK * 4;
+  const size_t smem_max = (size_t)TC_MAX_STAGES * (TC_BM + BN) * TC_BK * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN, TMA, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN, TMA, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     BRE_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<MODE, BN, TMA, CLS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_done = true;
   }
