@@ -1027,13 +1027,12 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, const std::conditional_t<CLS,
   // (an 8-deep ring for single-wave launches was tried: 192 KB of shared memory per CTA stops the next kernel's CTAs from
   // becoming resident during this one's tail -- programmatic dependent launch loses its overlap -- and layer4 got 2x slower)
   // Ring depth: 4 stages (96 KB: two CTAs per SM, and the next kernel's CTAs become resident during this one's tail -- what
-  // programmatic dependent launch needs for the single-wave launches of batch 1) or 8 stages when the launch is several waves
-  // deep and every CTA walks a long k range (more bytes in flight per CTA; BRE_TC_STAGES=4|8 forces one).
+  // programmatic dependent launch needs).  Measured on the B200 (profiles/README.md): an 8-deep ring (192 KB, one CTA per SM) is
+  // 25-30 % slower on config 2 *and* on the multi-wave batch-8 launches of config 3 -- occupancy beats ring depth.
+  // BRE_TC_STAGES=2|4|8 forces a depth for experiments.
   static const int stages_env = [] { const char* e = getenv("BRE_TC_STAGES"); return e ? atoi(e) : 0; }();
-  int stages = TC_STAGES;
-  if (stages_env == 8 || (stages_env == 0 && tiles * splits >= 2LL * kNumSMs && d.kblocks_per_split >= 16)) stages = TC_MAX_STAGES;
-  if (stages_env == 4) stages = TC_STAGES;
-  d.stage_shift = stages == TC_MAX_STAGES ? 3 : 2;
+  const int stages = (stages_env == 8 || stages_env == 2) ? stages_env : TC_STAGES;
+  d.stage_shift = stages == 8 ? 3 : (stages == 2 ? 1 : 2);
   const size_t smem = (size_t)stages * (TC_BM + BN) * TC_BK * 4;
   const size_t smem_max = (size_t)TC_MAX_STAGES * (TC_BM + BN) * TC_BK * 4;
   static bool attr_done = false;
