@@ -275,9 +275,9 @@ def matching_reduction_roofline(dev, n_params):
     ms = e0.elapsed_time(e1) / (reps * replays)
     out = dict(bound="hbm", achieved=8.0 * n_params / (ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s", kernel="match_reduce_kernel",
                ms=ms, peak_source=peaks["source"], algorithmic_bytes=8 * n_params,
-               traffic=(91086336 + 2996736) if n_params == 11_380_173 else None,
+               traffic=(91086080 + 2710784) if n_params == 11_380_173 else None,
                note=f"mean of {replays} graph replays of {reps} launches over {npairs} rotating buffer pairs (cold in L2); includes "
-                    "inter-kernel gaps; traffic = dram read+write bytes of one ncu --set full capture (profiles/)")
+                    "inter-kernel gaps; traffic = dram read+write bytes of one ncu --set full capture (profiles/r2_match_reduce_summary.txt)")
     out["frac"] = out["achieved"] / out["peak"]
     return out
 
@@ -534,7 +534,7 @@ def product_arm(args):
     fam = gemm_family_roofline(dev, prog, args.backend, local_steps)
     peak = peaks["bf16_tflops_sustained"]
     roof = dict(bound="tensor", achieved=fam["tflops"], peak=peak, unit="TFLOP/s", frac=fam["tflops"] / peak,
-                traffic=2042624 if config == 2 else None, peak_source=peaks["source"],
+                traffic=2059008 if config == 2 else None, peak_source=peaks["source"],
                 kernel="igemm_tc_kernel (tcgen05 kind::tf32) + SIMT kernels for the shapes it does not cover",
                 launches_per_step=fam["n_launches"], avg_launch_us=1e3 * fam["ms_per_launch"], algorithmic_gflop_per_step=fam["flops"] / 1e9,
                 peak_tf32_equivalent=peak / 2, frac_of_tf32_peak=fam["tflops"] / (peak / 2), share_of_step=fam["ms_total"] / (ms_max / args.steps),
@@ -542,7 +542,7 @@ def product_arm(args):
                 note="achieved = algorithmic conv+linear FLOPs of one iteration (SURVEY 8d) / live CUDA-event time of exactly those GEMM "
                      "launches (one graph replay through the C ABI); peak = the measured sustained bf16 cuBLAS rate (the only measured "
                      "tensor peak; the work is TF32, whose dense peak is half of it -> frac_of_tf32_peak); traffic = dram bytes of one "
-                     "captured launch (profiles/) where available")
+                     "captured launch (the batch-1 layer2 tangent GEMM, profiles/r2_tc_fprop_dual_b1_summary.txt: = its algorithmic operand bytes)")
     match = matching_reduction_roofline(dev, n_params)
     threads, sweep = cpu_thread_sweep(config, case)
     cpu_its, cpu_dt = oracle_iters_per_sec(config, case, "cpu", 1, args.cpu_steps if args.cpu_steps > 0 else w["ref_steps"])

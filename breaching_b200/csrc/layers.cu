@@ -431,13 +431,15 @@ __device__ __forceinline__ bool slab_reduce4(float (&v)[NV][4], int LX, int LY, 
   return false;
 }
 
-inline void slab_grid4(long long P, int C, dim3& grid, int& LX, int& LY, long long& pps) {
+inline void slab_grid4(long long P, int C, dim3& grid, int& LX, int& LY, long long& pps, int waves = 2) {
   const int C4 = C / 4;
   LX = C4 < 32 ? C4 : 32;
   while (256 % LX != 0) --LX;          // C4 = 16, 32, 64 ... in practice; keep LX a divisor of 256 for odd widths
   LY = 256 / LX;
   const int cg = ceil_div(C4, LX);
-  long long slabs = (2LL * kNumSMs + cg - 1) / cg;
+  // `waves` x 148 blocks: 2 when the last block of a column group sums the slabs itself (a longer tail per slab), 4 when the slabs are
+  // summed by a later batched kernel (deferred BN gradients, batched statistics)
+  long long slabs = ((long long)waves * kNumSMs + cg - 1) / cg;
   const long long max_slabs = (P + LY - 1) / LY;
   if (slabs > max_slabs) slabs = max_slabs;
   const long long cap = kSlabPartialFloats / (2LL * cg * LX * 4);   // partials: slabs x Cpad x (<= 2 quantities)
@@ -448,7 +450,7 @@ inline void slab_grid4(long long P, int C, dim3& grid, int& LX, int& LY, long lo
   grid = dim3(cg, (unsigned)slabs);
 }
 
-__global__ void __launch_bounds__(256) bnact_bwd_vec_kernel(BnActBwdArgs a, long long pps, int Cpad, int LX, int LY) {
+__global__ void __launch_bounds__(256, 2) bnact_bwd_vec_kernel(BnActBwdArgs a, long long pps, int Cpad, int LX, int LY) {
   pdl_prologue();
   const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
   const int c4 = blockIdx.x * LX + lx, C4 = a.C / 4;
@@ -1006,7 +1008,7 @@ bool channel_stats_plan(long long P, int C, StatSlot* slot) {
   dim3 grid;
   int LX, LY;
   long long pps;
-  slab_grid4(P, C, grid, LX, LY, pps);
+  slab_grid4(P, C, grid, LX, LY, pps, 4);
   slot->P = P; slot->pps = pps; slot->C = C; slot->LX = LX; slot->LY = LY; slot->cg = (int)grid.x; slot->slabs = (int)grid.y;
   slot->Cpad = (int)(grid.x * LX * 4);
   return true;
@@ -1018,12 +1020,12 @@ int launch_channel_stats_batched(const StatSlot* table_dev, int n_layers, int to
   return 0;
 }
 
-void bnact_bwd_plan(long long P, int C, int* slabs, int* Cpad) {
+void bnact_bwd_plan(long long P, int C, int* slabs, int* Cpad) {   // geometry of a *deferred* launch_bnact_bwd
   dim3 grid, block;
   long long pps;
   if (vec_ok(C)) {
     int LX, LY;
-    slab_grid4(P, C, grid, LX, LY, pps);
+    slab_grid4(P, C, grid, LX, LY, pps, 4);
     *Cpad = (int)(grid.x * LX * 4);
   } else {
     slab_grid(P, C, grid, block, pps);
@@ -1044,7 +1046,7 @@ int launch_bnact_bwd(const BnActBwdArgs& a, cudaStream_t s) {
   long long pps;
   if (vec_ok(a.C)) {
     int LX, LY;
-    slab_grid4(a.P, a.C, grid, LX, LY, pps);
+    slab_grid4(a.P, a.C, grid, LX, LY, pps, a.defer ? 4 : 2);
     BRE_KLAUNCH(bnact_bwd_vec_kernel, grid, 256, 0, s, a, pps, (int)(grid.x * LX * 4), LX, LY);
     BRE_CHECK_LAUNCH();
     return 0;
