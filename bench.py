@@ -32,9 +32,9 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     1: dict(name="BASELINE config 1: invertinggradients, ConvNet(width 64, 10 classes, random init), synthetic 3x32x32 batch=1",
-            metric="reconstruction iters/sec (ConvNet-64 32x32, invertinggradients)", attack="invertinggradients", e2e_steps=8000, ref_steps=40),
+            metric="reconstruction iters/sec (ConvNet-64 32x32, invertinggradients)", attack="invertinggradients", e2e_steps=24000, ref_steps=40),
     2: dict(name="BASELINE config 2: invertinggradients, torchvision ResNet-18 (397 classes, random init), synthetic 3x224x224 batch=1",
-            metric="reconstruction iters/sec (ResNet-18 224x224, invertinggradients)", attack="invertinggradients", e2e_steps=8000, ref_steps=20),
+            metric="reconstruction iters/sec (ResNet-18 224x224, invertinggradients)", attack="invertinggradients", e2e_steps=24000, ref_steps=20),
     3: dict(name="BASELINE config 3: see-through-gradients (euclidean, TV, norm, DeepInversion on 53 BN layers, yin labels), torchvision "
                  "ResNet-50 (397 classes, random init, user buffers), synthetic 3x224x224 batch=8",
             metric="reconstruction iters/sec (ResNet-50 224x224 batch 8, see-through-gradients)", attack="seethroughgradients", e2e_steps=800,
@@ -567,6 +567,7 @@ def product_arm(args):
                          "configurations; no explicit flush"},
         "e2e": {"value": e2e_iters / e2e_dt, "unit": "it/s", "h2d_bytes_per_step": world * h2d / e2e_iters, "d2h_bytes_per_step": world * d2h / e2e_iters,
                 "steps": e2e_steps, "trials": world, "iterations_executed": e2e_iters, "seconds": e2e_dt, "select_seconds": select_s,
+                "phase_seconds_rank0": {k: round(float(v), 4) for k, v in getattr(attacker, "last_timing", {}).items()},
                 "what": "prepare_attack(...).reconstruct(host payload, host shared_data) with restarts.num_trials = n_gpus: model rebuild, "
                         "program compile, engine create, H2D of parameters+gradients from pinned memory, every rank runs its own trial for "
                         "all iterations, scoring, cross-rank MIN select + broadcast of the winner (select_seconds), D2H of the result; value "

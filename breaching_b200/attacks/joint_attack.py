@@ -14,6 +14,7 @@ config 5: the candidate is the embedding sequence, the label leaf holds logits o
 """
 import logging
 import math
+import time
 
 import torch
 
@@ -90,10 +91,14 @@ class OptimizationJointAttacker(OptimizationBasedAttacker):
         return eng
 
     def _reconstruct_text(self, server_payload, shared_data, server_secrets, initial_data, dryrun):
+        clock, t0 = self.last_timing, time.perf_counter()
+        clock.clear()
         rec_models, labels, stats, shared_data = self._prepare_text(server_payload, shared_data)
+        clock["prologue"], t0 = time.perf_counter() - t0, time.perf_counter()
         if len(rec_models) != 1 or self.regularizers:
             raise NotImplementedError("text models: one model query, no regularisers (the reference's TAG / DLG presets configure none)")
         engine = self._get_text_engine(rec_models, shared_data)
+        clock["engine"], t0 = time.perf_counter() - t0, time.perf_counter()
         num_trials = self.cfg.restarts.num_trials
         rank, world = bdist.rank_and_world()
         scores = torch.full((num_trials,), float("inf"))
@@ -112,9 +117,12 @@ class OptimizationJointAttacker(OptimizationBasedAttacker):
             q_hard = torch.nn.functional.one_hot(hard_labels, labels.shape[-1]).to(**self.setup)
             engine.load_soft_labels(q_hard.reshape(-1, labels.shape[-1]))
             scores[trial] = engine.score(data.reshape(-1, data.shape[-1], 1, 1), self.cfg.restarts.scoring)
+        clock["trials"], t0 = time.perf_counter() - t0, time.perf_counter()
         optimal_solution = self._select_optimal_reconstruction(candidate_solutions, scores, stats, shape)
+        clock["select"], t0 = self.last_select_seconds, time.perf_counter()
         reconstructed = dict(data=optimal_solution, labels=hard_labels)
         reconstructed = host.postprocess_text_data(reconstructed, self.embeddings[0]["weight"].detach(), self.cfg.token_recovery)
+        clock["token_recovery"] = time.perf_counter() - t0
         reconstructed["raw_embeddings"] = optimal_solution                # :80
         return reconstructed, stats
 

@@ -74,6 +74,8 @@ class OptimizationBasedAttacker:
                         raise KeyError(key)
                     self.regularizers.append((key, dict(reg[key])))
         self._aug_plans = {}   # candidate augmentations (attacks/augment.py), built per batch size on first use
+        self.last_timing = {}  # seconds per phase of the last reconstruct() call
+        self.last_select_seconds = 0.0
         if self.setup["dtype"] != torch.float32:
             raise NotImplementedError("the B200 engine computes in fp32 (cfg.impl.dtype=float)")
         if cfg_get(self.cfg.impl, "mixed_precision", False):
@@ -182,9 +184,15 @@ class OptimizationBasedAttacker:
         return [first] + self._extra_engines
 
     def reconstruct(self, server_payload, shared_data, server_secrets=None, initial_data=None, dryrun=False):
+        # wall-clock seconds per phase of the last call (host clock, no extra device syncs: asynchronous work lands in the phase
+        # that first waits for it): prologue = prepare_attack, engine = compile + create + uploads, trials, select
+        clock, t0 = self.last_timing, time.perf_counter()
+        clock.clear()
         rec_models, labels, stats, shared_data = self.prepare_attack(server_payload, shared_data)
+        clock["prologue"], t0 = time.perf_counter() - t0, time.perf_counter()
         multi = len(rec_models) > 1
         engine = _EngineSum(self._get_engines(rec_models, shared_data, labels)) if multi else self._get_engine(rec_models, shared_data, labels)
+        clock["engine"], t0 = time.perf_counter() - t0, time.perf_counter()
         num_trials = self.cfg.restarts.num_trials
         rank, world = bdist.rank_and_world()
         scores = torch.full((num_trials,), float("inf"))
@@ -202,7 +210,9 @@ class OptimizationBasedAttacker:
                 scores[trial] = self._score_trial(engine, candidate_solutions[trial])
         except KeyboardInterrupt:
             print("Trial procedure manually interruped.")
+        clock["trials"] = time.perf_counter() - t0
         optimal_solution = self._select_optimal_reconstruction(candidate_solutions, scores, stats, shape)
+        clock["select"] = self.last_select_seconds
         reconstructed_data = dict(data=optimal_solution, labels=labels)
         if server_secrets is not None and "ClassAttack" in server_secrets:  # :82-87
             true_num_data = server_secrets["ClassAttack"]["true_num_data"]

@@ -40,6 +40,11 @@ constexpr int kNumSMs = 148;  // B200
 // records the edges as programmatic dependencies of the CUDA graph.  Without the launch attribute both instructions
 // are no-ops.  BRE_PDL=0 disables it.
 bool use_pdl();
+// The next launch_kernel() on this thread is issued without the programmatic attribute: it starts only after its predecessor has
+// completed and flushed, so every later kernel -- also the part that runs ahead of its own griddepcontrol.wait -- sees the
+// predecessor's output (the engine puts this after make_v: weight-side loads of the tangent sweeps may then run ahead).
+void serialize_next_launch();
+bool consume_serialize_once();
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
@@ -60,7 +65,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     attrs[n].val.clusterDim.x = 1; attrs[n].val.clusterDim.y = 1; attrs[n].val.clusterDim.z = (unsigned)cluster_z;
     ++n;
   }
-  if (use_pdl()) {
+  if (use_pdl() && !consume_serialize_once()) {
     attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

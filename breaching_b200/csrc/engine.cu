@@ -31,6 +31,9 @@ bool use_pdl() {
   return g_pdl != 0;
 }
 void set_pdl(bool on) { g_pdl = on ? 1 : 0; }
+static thread_local bool g_serialize_once = false;
+void serialize_next_launch() { g_serialize_once = true; }
+bool consume_serialize_once() { const bool r = g_serialize_once; g_serialize_once = false; return r; }
 }  // namespace bre
 
 using namespace bre;
@@ -364,9 +367,28 @@ struct bre_engine {
     return a;
   }
   int gemm(const GemmArgs& a) { return gemm_on(a, stream); }
+  // Weight operands the tensor-core kernels may load ahead of griddepcontrol.wait: the model weights (and their TF32 shadow /
+  // column copy) of a single-step user never change during a run; the direction v and its shadow are final once the serialised
+  // launch after make_v has started (evaluate()).  FedAvg users (ms_steps > 0) rewrite W_k and v inside the iteration: none.
+  bool weight_prefetch = [] { const char* e = getenv("BRE_TC_WPREFETCH"); return e ? atoi(e) != 0 : true; }();
+  bool v_settled = false;
+  bool inside(const float* p, const float* base, long long n) const { return base != nullptr && p >= base && p < base + n; }
+  unsigned static_weights(const GemmArgs& a) const {
+    if (!weight_prefetch || ms_steps > 0 || a.mode == GEMM_WGRAD) return 0u;
+    unsigned mask = 0;
+    for (int s = 0; s < a.nsrc; ++s) {
+      const float* p = a.wgt[s];
+      const bool model = inside(p, W, P_pad) || inside(p, Wt, P_pad) || (Wcol != nullptr && p == Wcol);
+      const bool direction = v_settled && (inside(p, V, P_pad) || inside(p, Vt, P_pad));
+      if (model || direction) mask |= 1u << s;
+    }
+    return mask;
+  }
   int gemm_on(const GemmArgs& a, cudaStream_t st) {
     if (gemm_backend == 1 && !a.force_fp32 && igemm_tc_supported(a)) {
-      return launch_igemm_tc(a, st);
+      GemmArgs b = a;
+      b.wgt_static = static_weights(a);
+      return launch_igemm_tc(b, st);
     }
     return launch_igemm_simt(a, st);
   }
@@ -913,9 +935,12 @@ struct bre_engine {
     BRE_TRY(build_chunk_modes());
     BRE_LAUNCH(launch_make_v(G, g, chunk_w, V, P_pad, cfg.objective == BRE_OBJ_MASKED_COSINE ? cfg.mask_value : -1.f, sc, stream,
                              tc_round() ? Vt : nullptr, tc_round() ? chunk_mode : nullptr));
+    serialize_next_launch();   // v is complete and visible before anything of the tangent sweeps starts
+    v_settled = true;
     BRE_TRY(sweep_tangent_forward());
     BRE_TRY(deep_inversion_stats());
     BRE_TRY(sweep_tangent_backward());
+    v_settled = false;
     BRE_TRY(priors());
     if (aug_on && aug_diff) BRE_TRY(augment_pull());
     return 0;

@@ -54,6 +54,9 @@ struct GemmArgs {
   int ws_tiles;
   int splits;             // 0 = choose automatically
   int force_fp32;         // engine: run this contraction on the fp32 kernels even on the tensor-core back end (precision knob)
+  // bit s: wgt[s] (fprop / dgrad) was fully written before the *predecessor* kernel of this launch started, so the tcgen05 back end
+  // may start loading it before griddepcontrol.wait (model weights; the direction v once a serialised launch follows make_v)
+  unsigned wgt_static;
 };
 
 constexpr int IG_BM = 64, IG_BN = 64, IG_BK = 16, IG_THREADS = 256;

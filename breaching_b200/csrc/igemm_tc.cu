@@ -349,14 +349,149 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
     it_c0 = (MODE == GEMM_WGRAD) ? kbase : kbase - it_rs * kch;
   }
 
-  // Everything above touched only kernel parameters, shared memory and TMEM; from here on global memory written by the
-  // predecessor kernel is read.
+  const int nkb = kb_end > kb_begin ? kb_end - kb_begin : 0;  // a trailing split may be empty: it contributes zeros
+  // TMA producer (one thread): the CTA's first GEMM row fixes the base pixel of every im2col load; per k-block only the
+  // filter-tap offsets and the channel coordinate change.
+  int base_n = 0, base_h = 0, base_w = 0;
+  if (CLS) {
+    const int per = cHc * cWc;
+    base_n = m0 / per;
+    const int rem = m0 - base_n * per;
+    const int iy0 = rem / cWc, ix0 = rem - iy0 * cWc;
+    base_h = iy0 + plan.Ly[cls]; base_w = ix0 + plan.Lx[cls];
+  } else if (TMA && MODE != GEMM_WGRAD) {
+    const int per = (MODE == GEMM_FPROP) ? HoWo : HW, wid = (MODE == GEMM_FPROP) ? g.Wo : g.W;
+    base_n = m0 / per;
+    const int rem = m0 - base_n * per;
+    const int p0 = rem / wid, q0 = rem - p0 * wid;
+    if (MODE == GEMM_FPROP) { base_h = p0 * g.stride - g.pad; base_w = q0 * g.stride - g.pad; }
+    else { base_h = p0 + g.pad - (g.R - 1); base_w = q0 + g.pad - (g.S - 1); }   // stride-1 dgrad: flipped taps
+  }
+  // Running decode of the producer's k-block sequence.  The producer lane is a single thread on the critical path of the
+  // whole CTA: no divisions inside the loop (an integer division costs it ~100 cycles), everything advances incrementally.
+  struct KbState { int src, rs, r, s, c0, img, p, q; };
+  auto kb_init = [&](int kb) {
+    KbState st;
+    const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
+    if (CLS) {   // k = (source, class tap (tr, ts), channel); st.r / st.s hold the class-tap indices, st.rs the weight's filter cell
+      st.src = cls_kps > 0 ? kb / cls_kps : 0;
+      const int rem = kb - st.src * cls_kps, cpb = g.Co / TC_BK;
+      const int tap = rem / cpb;
+      st.c0 = (rem - tap * cpb) * TC_BK;
+      st.r = cTx > 0 ? tap / cTx : 0; st.s = tap - st.r * cTx;
+      st.rs = (plan.ey[cls] + plan.stride * st.r) * g.S + plan.ex[cls] + plan.stride * st.s;
+      st.img = st.p = st.q = 0;
+      return st;
+    }
+    st.src = kb / d.kblocks_per_src;
+    const int kbase = (kb - st.src * d.kblocks_per_src) * TC_BK;
+    if (MODE == GEMM_WGRAD) {
+      st.rs = st.r = st.s = 0; st.c0 = kbase;
+      st.img = kbase / HoWo;
+      const int rem = kbase - st.img * HoWo;
+      st.p = rem / g.Wo; st.q = rem - st.p * g.Wo;
+    } else {
+      st.rs = kbase / kch; st.c0 = kbase - st.rs * kch;
+      st.r = st.rs / g.S; st.s = st.rs - st.r * g.S;
+      st.img = st.p = st.q = 0;
+    }
+    return st;
+  };
+  auto kb_advance = [&](KbState& st) {
+    const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
+    st.c0 += TC_BK;
+    if (CLS) {
+      if (st.c0 >= kch) {
+        st.c0 = 0;
+        if (++st.s == cTx) { st.s = 0; if (++st.r == cTy) { st.r = 0; ++st.src; } }
+        st.rs = (plan.ey[cls] + plan.stride * st.r) * g.S + plan.ex[cls] + plan.stride * st.s;
+      }
+      return;
+    }
+    if (MODE == GEMM_WGRAD) {
+      if (st.c0 >= d.kblocks_per_src * TC_BK) { st.c0 = 0; ++st.src; st.img = st.p = st.q = 0; }
+      else {
+        st.q += TC_BK;
+        while (st.q >= g.Wo) { st.q -= g.Wo; if (++st.p == g.Ho) { st.p = 0; ++st.img; } }
+      }
+    } else if (st.c0 >= kch) {
+      st.c0 = 0; ++st.rs;
+      if (++st.s == g.S) { st.s = 0; if (++st.r == g.R) { st.r = 0; st.rs = 0; ++st.src; } }
+    }
+  };
+  // WGRAD: the filter tap / channel of the CTA's B columns are fixed
+  int wg_c[BN / 32], wg_r[BN / 32], wg_s[BN / 32];
+  if (TMA && MODE == GEMM_WGRAD) {
+#pragma unroll
+    for (int h = 0; h < BN / 32; ++h) {
+      const int n = n0 + 32 * h;
+      const int rs = n / g.Ci;
+      wg_c[h] = n - rs * g.Ci; wg_r[h] = rs / g.S; wg_s[h] = rs - wg_r[h] * g.S;
+    }
+  }
+  // One k-block = the weight-side loads and the activation-side loads on the same stage barrier.  They are separate calls because
+  // the weight side of the first ring stages is issued *before* griddepcontrol.wait (below): weights do not depend on the
+  // predecessor kernel, so their HBM / L2 round trip overlaps the predecessor's tail.
+  auto issue_wgt_tma = [&](int stage, const KbState& st) {
+    uint64_t* bar = &bar_full[stage];
+    const uint32_t pb = smem_u32(sB) + stage * B_BYTES;
+    if (MODE == GEMM_FPROP) {
+      tma_tile2d(pb, &maps.wgt[st.src], bar, st.rs * g.Ci + st.c0, n0);
+    } else if (MODE == GEMM_DGRAD) {
+#pragma unroll
+      for (int h = 0; h < BN / 32; ++h) tma_tile3d(pb + h * 4096, &maps.wgt[st.src], bar, n0 + 32 * h, st.rs, st.c0);
+    } else {
+      const uint32_t pa = smem_u32(sA) + stage * A_BYTES;
+#pragma unroll
+      for (int h = 0; h < TC_BM / 32; ++h) tma_tile2d(pa + h * 4096, &maps.wgt[st.src], bar, m0 + 32 * h, st.c0);   // k = pixel
+    }
+  };
+  auto issue_act_tma = [&](int stage, const KbState& st) {
+    uint64_t* bar = &bar_full[stage];
+    const uint32_t pa = smem_u32(sA) + stage * A_BYTES, pb = smem_u32(sB) + stage * B_BYTES;
+    if (MODE == GEMM_FPROP) {
+      tma_im2col(pa, &maps.act[st.src], bar, st.c0, base_w, base_h, base_n, st.s, st.r);
+    } else if (MODE == GEMM_DGRAD) {
+      if (CLS) tma_im2col(pa, &maps.act[2 * cls + st.src], bar, st.c0, base_w, base_h, base_n, cTx - 1 - st.s, cTy - 1 - st.r);
+      else tma_im2col(pa, &maps.act[st.src], bar, st.c0, base_w, base_h, base_n, g.S - 1 - st.s, g.R - 1 - st.r);
+    } else {
+#pragma unroll
+      for (int h = 0; h < BN / 32; ++h)
+        tma_im2col(pb + h * 4096, &maps.act[st.src], bar, wg_c[h], st.q * g.stride - g.pad, st.p * g.stride - g.pad, st.img, wg_s[h], wg_r[h]);
+    }
+  };
+
   if (TMA && tid == 0 && (proxy_fence & 2)) {
     for (int sidx = 0; sidx < a.nsrc; ++sidx) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.act[(CLS ? 2 * cls : 0) + sidx])) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.wgt[sidx])) : "memory");
     }
   }
+  // `nprod` producer lanes (lane 0 of loader warps 0..nprod-1, default 2), k-blocks dealt round-robin: a cp.async.bulk.tensor
+  // costs its issuing thread ~140 cycles (profiles/experiments/tc_trace.py); two issuers keep up with the six loads per
+  // k-block of the wgrad form, more make no difference
+  const int nprod = (proxy_fence >> 2) & 7;
+  const bool producer = TMA && (tid & 31) == 0 && warp < nprod && warp < nkb;
+  KbState pst;
+  memset(&pst, 0, sizeof(pst));
+  uint32_t pre_wgt = 0;   // ring stages whose weight loads are already in flight when the wait below returns
+  if (producer) {
+    pst = kb_init(kb_begin + warp);
+    if (MODE != GEMM_WGRAD && a.wgt_static != 0) {
+      KbState st = pst;
+      for (int i = warp; i < nkb && i < nst; i += nprod) {
+        if ((a.wgt_static >> st.src) & 1) {
+          mbar_expect_tx(&bar_full[i], A_BYTES + B_BYTES);
+          issue_wgt_tma(i, st);
+          pre_wgt |= 1u << i;
+        }
+        for (int u = 0; u < nprod; ++u) kb_advance(st);
+      }
+    }
+  }
+
+  // Everything above touched only kernel parameters, shared memory, TMEM and weights the caller declared constant across the
+  // predecessor (GemmArgs::wgt_static); from here on global memory written by the predecessor kernel is read.
   pdl_wait();
   TC_MARK(2, threadIdx.x == 0);
 
@@ -458,111 +593,10 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
     }
   };
 
-  // TMA producer (one thread): the CTA's first GEMM row fixes the base pixel of every im2col load; per k-block only the
-  // filter-tap offsets and the channel coordinate change.
-  int base_n = 0, base_h = 0, base_w = 0;
-  if (CLS) {
-    const int per = cHc * cWc;
-    base_n = m0 / per;
-    const int rem = m0 - base_n * per;
-    const int iy0 = rem / cWc, ix0 = rem - iy0 * cWc;
-    base_h = iy0 + plan.Ly[cls]; base_w = ix0 + plan.Lx[cls];
-  } else if (TMA && MODE != GEMM_WGRAD) {
-    const int per = (MODE == GEMM_FPROP) ? HoWo : HW, wid = (MODE == GEMM_FPROP) ? g.Wo : g.W;
-    base_n = m0 / per;
-    const int rem = m0 - base_n * per;
-    const int p0 = rem / wid, q0 = rem - p0 * wid;
-    if (MODE == GEMM_FPROP) { base_h = p0 * g.stride - g.pad; base_w = q0 * g.stride - g.pad; }
-    else { base_h = p0 + g.pad - (g.R - 1); base_w = q0 + g.pad - (g.S - 1); }   // stride-1 dgrad: flipped taps
-  }
-  // Running decode of the producer's k-block sequence.  The producer lane is a single thread on the critical path of the
-  // whole CTA: no divisions inside the loop (an integer division costs it ~100 cycles), everything advances incrementally.
-  struct KbState { int src, rs, r, s, c0, img, p, q; };
-  auto kb_init = [&](int kb) {
-    KbState st;
-    const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
-    if (CLS) {   // k = (source, class tap (tr, ts), channel); st.r / st.s hold the class-tap indices, st.rs the weight's filter cell
-      st.src = cls_kps > 0 ? kb / cls_kps : 0;
-      const int rem = kb - st.src * cls_kps, cpb = g.Co / TC_BK;
-      const int tap = rem / cpb;
-      st.c0 = (rem - tap * cpb) * TC_BK;
-      st.r = cTx > 0 ? tap / cTx : 0; st.s = tap - st.r * cTx;
-      st.rs = (plan.ey[cls] + plan.stride * st.r) * g.S + plan.ex[cls] + plan.stride * st.s;
-      st.img = st.p = st.q = 0;
-      return st;
-    }
-    st.src = kb / d.kblocks_per_src;
-    const int kbase = (kb - st.src * d.kblocks_per_src) * TC_BK;
-    if (MODE == GEMM_WGRAD) {
-      st.rs = st.r = st.s = 0; st.c0 = kbase;
-      st.img = kbase / HoWo;
-      const int rem = kbase - st.img * HoWo;
-      st.p = rem / g.Wo; st.q = rem - st.p * g.Wo;
-    } else {
-      st.rs = kbase / kch; st.c0 = kbase - st.rs * kch;
-      st.r = st.rs / g.S; st.s = st.rs - st.r * g.S;
-      st.img = st.p = st.q = 0;
-    }
-    return st;
-  };
-  auto kb_advance = [&](KbState& st) {
-    const int kch = (MODE == GEMM_DGRAD) ? g.Co : g.Ci;
-    st.c0 += TC_BK;
-    if (CLS) {
-      if (st.c0 >= kch) {
-        st.c0 = 0;
-        if (++st.s == cTx) { st.s = 0; if (++st.r == cTy) { st.r = 0; ++st.src; } }
-        st.rs = (plan.ey[cls] + plan.stride * st.r) * g.S + plan.ex[cls] + plan.stride * st.s;
-      }
-      return;
-    }
-    if (MODE == GEMM_WGRAD) {
-      if (st.c0 >= d.kblocks_per_src * TC_BK) { st.c0 = 0; ++st.src; st.img = st.p = st.q = 0; }
-      else {
-        st.q += TC_BK;
-        while (st.q >= g.Wo) { st.q -= g.Wo; if (++st.p == g.Ho) { st.p = 0; ++st.img; } }
-      }
-    } else if (st.c0 >= kch) {
-      st.c0 = 0; ++st.rs;
-      if (++st.s == g.S) { st.s = 0; if (++st.r == g.R) { st.r = 0; st.rs = 0; ++st.src; } }
-    }
-  };
-  // WGRAD: the filter tap / channel of the CTA's B columns are fixed
-  int wg_c[BN / 32], wg_r[BN / 32], wg_s[BN / 32];
-  if (TMA && MODE == GEMM_WGRAD) {
-#pragma unroll
-    for (int h = 0; h < BN / 32; ++h) {
-      const int n = n0 + 32 * h;
-      const int rs = n / g.Ci;
-      wg_c[h] = n - rs * g.Ci; wg_r[h] = rs / g.S; wg_s[h] = rs - wg_r[h] * g.S;
-    }
-  }
-  auto issue_block_tma = [&](int stage, const KbState& st) {
-    uint64_t* bar = &bar_full[stage];
-    const uint32_t pa = smem_u32(sA) + stage * A_BYTES, pb = smem_u32(sB) + stage * B_BYTES;
-    mbar_expect_tx(bar, A_BYTES + B_BYTES);
-    if (MODE == GEMM_FPROP) {
-      tma_im2col(pa, &maps.act[st.src], bar, st.c0, base_w, base_h, base_n, st.s, st.r);
-      tma_tile2d(pb, &maps.wgt[st.src], bar, st.rs * g.Ci + st.c0, n0);
-    } else if (MODE == GEMM_DGRAD) {
-      if (CLS) tma_im2col(pa, &maps.act[2 * cls + st.src], bar, st.c0, base_w, base_h, base_n, cTx - 1 - st.s, cTy - 1 - st.r);
-      else tma_im2col(pa, &maps.act[st.src], bar, st.c0, base_w, base_h, base_n, g.S - 1 - st.s, g.R - 1 - st.r);
-#pragma unroll
-      for (int h = 0; h < BN / 32; ++h) tma_tile3d(pb + h * 4096, &maps.wgt[st.src], bar, n0 + 32 * h, st.rs, st.c0);
-    } else {
-#pragma unroll
-      for (int h = 0; h < TC_BM / 32; ++h) tma_tile2d(pa + h * 4096, &maps.wgt[st.src], bar, m0 + 32 * h, st.c0);   // k = pixel
-#pragma unroll
-      for (int h = 0; h < BN / 32; ++h)
-        tma_im2col(pb + h * 4096, &maps.act[st.src], bar, wg_c[h], st.q * g.stride - g.pad, st.p * g.stride - g.pad, st.img, wg_s[h], wg_r[h]);
-    }
-  };
-
   // ---- main loop, warp-specialised: warps 0-3 stream k-blocks into a TC_STAGES-deep ring with cp.async and signal
   //      "full" through cp.async.mbarrier.arrive; one thread of warp 4 waits for "full", issues the four tcgen05.mma of
   //      the k-block and lets tcgen05.commit signal "empty" when the tensor core has consumed the stage.  No CTA-wide
   //      barrier inside the loop.
-  const int nkb = kb_end > kb_begin ? kb_end - kb_begin : 0;  // a trailing split may be empty: it contributes zeros
   if (warp == TC_THREADS / 32) {
     if (tid == TC_THREADS) {
       // descriptors of stage 0 / MMA slice 0; the 14-bit address field counts 16-byte units, so stage and slice offsets are
@@ -593,16 +627,16 @@ __global__ void __launch_bounds__(TC_BLOCK) igemm_tc_kernel(GemmArgs a, TcDims d
     __syncwarp();
   } else {
     if (TMA) {
-      // `nprod` producer lanes (lane 0 of loader warps 0..nprod-1, default 2), k-blocks dealt round-robin: a cp.async.bulk.tensor
-      // costs its issuing thread ~140 cycles (profiles/experiments/tc_trace.py); two issuers keep up with the six loads per
-      // k-block of the wgrad form, more make no difference
-      const int nprod = (proxy_fence >> 2) & 7;
-      if ((tid & 31) == 0 && warp < nprod && warp < nkb) {
-        KbState st = kb_init(kb_begin + warp);
+      if (producer) {
+        KbState st = pst;
         for (int i = warp; i < nkb; i += nprod) {
           const int stage = i & stage_mask;
           if (i >= nst) mbar_wait(&bar_empty[stage], (uint32_t)(((i >> d.stage_shift) - 1) & 1));
-          issue_block_tma(stage, st);
+          if (i >= nst || !((pre_wgt >> i) & 1u)) {
+            mbar_expect_tx(&bar_full[stage], A_BYTES + B_BYTES);
+            issue_wgt_tma(stage, st);
+          }
+          issue_act_tma(stage, st);
           TC_MARK(3, i == (nkb < nst ? nkb : nst) - 1);
           for (int u = 0; u < nprod; ++u) kb_advance(st);
         }

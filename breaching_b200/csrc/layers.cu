@@ -821,6 +821,97 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int* __
   }
 }
 
+// 128-bit forms of the three pooling kernels (C % 4 == 0, 16-byte aligned tensors, < 2^31 elements): a thread owns four adjacent
+// channels of one pixel, so the index arithmetic is paid once per 16 bytes and every access is a full-width load / store.  The
+// scalar kernels above spend most of their time in 64-bit divisions (batch 8: 78 us for a 40 MB sweep).
+__device__ __forceinline__ void take_max(float v, int at, float& best, int& bi) {
+  if (v > best || v != v || bi < 0) { best = v; bi = at; }
+}
+__global__ void __launch_bounds__(kEwThreads) maxpool_fwd_vec_kernel(const float4* __restrict__ in, float4* __restrict__ out, int4* __restrict__ idx,
+                                                                     PoolGeom g, int total4) {
+  pdl_prologue();
+  const int C4 = g.C >> 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    int t = i / C4;
+    const int q = t % g.Wo; t /= g.Wo;
+    const int p = t % g.Ho;
+    const int n = t / g.Ho;
+    const int h0 = p * g.stride - g.pad, w0 = q * g.stride - g.pad;
+    float4 best = make_float4(-FLT_MAX * 2.f, -FLT_MAX * 2.f, -FLT_MAX * 2.f, -FLT_MAX * 2.f);  // -inf
+    int4 bi = make_int4(-1, -1, -1, -1);
+    for (int r = 0; r < g.k; ++r) {
+      const int h = h0 + r;
+      if (h < 0 || h >= g.H) continue;
+      for (int s = 0; s < g.k; ++s) {
+        const int w = w0 + s;
+        if (w < 0 || w >= g.W) continue;
+        const int at = h * g.W + w;
+        const float4 v = in[(long long)(n * g.H * g.W + at) * C4 + c4];
+        take_max(v.x, at, best.x, bi.x); take_max(v.y, at, best.y, bi.y);
+        take_max(v.z, at, best.z, bi.z); take_max(v.w, at, best.w, bi.w);
+      }
+    }
+    out[i] = best;
+    idx[i] = bi;
+  }
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(kEwThreads) maxpool_bwd_vec_kernel(const float4* __restrict__ dout, const int4* __restrict__ idx,
+                                                                     float4* __restrict__ din, PoolGeom g, int total4) {
+  pdl_prologue();
+  const int C4 = g.C >> 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    int t = i / C4;
+    const int w = t % g.W; t /= g.W;
+    const int h = t % g.H;
+    const int n = t / g.H;
+    const int me = h * g.W + w;
+    int p_lo = h + g.pad - g.k + 1; p_lo = p_lo > 0 ? (p_lo + g.stride - 1) / g.stride : 0;
+    int q_lo = w + g.pad - g.k + 1; q_lo = q_lo > 0 ? (q_lo + g.stride - 1) / g.stride : 0;
+    int p_hi = (h + g.pad) / g.stride; if (p_hi > g.Ho - 1) p_hi = g.Ho - 1;
+    int q_hi = (w + g.pad) / g.stride; if (q_hi > g.Wo - 1) q_hi = g.Wo - 1;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = p_lo; p <= p_hi; ++p)
+      for (int q = q_lo; q <= q_hi; ++q) {
+        const long long o = (long long)((n * g.Ho + p) * g.Wo + q) * C4 + c4;
+        const int4 ix = idx[o];
+        const float4 d = dout[o];
+        if (ix.x == me) s.x += d.x;
+        if (ix.y == me) s.y += d.y;
+        if (ix.z == me) s.z += d.z;
+        if (ix.w == me) s.w += d.w;
+      }
+    if (ACC) { const float4 o = din[i]; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+    din[i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads) maxpool_gather_vec_kernel(const float* __restrict__ tin, const int4* __restrict__ idx,
+                                                                        float4* __restrict__ tout, PoolGeom g, int total4) {
+  pdl_prologue();
+  const int C4 = g.C >> 2;
+  const int per = C4 * g.Ho * g.Wo;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const int c = (i % C4) * 4;
+    const long long base = (long long)(i / per) * g.H * g.W;
+    const int4 ix = idx[i];
+    float4 v;
+    v.x = tin[(base + ix.x) * g.C + c];
+    v.y = tin[(base + ix.y) * g.C + c + 1];
+    v.z = tin[(base + ix.z) * g.C + c + 2];
+    v.w = tin[(base + ix.w) * g.C + c + 3];
+    tout[i] = v;
+  }
+}
+
+inline bool pool_vec_ok(const PoolGeom& g, const void* a, const void* b, const void* c) {
+  const long long big = (long long)g.N * g.H * g.W * g.C;
+  return vec_ok(g.C) && big < (1LL << 31) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+
 __global__ void maxpool_gather_kernel(const float* __restrict__ tin, const int* __restrict__ idx, float* __restrict__ tout,
                                       PoolGeom g, long long total) {
   pdl_prologue();
@@ -1163,18 +1254,38 @@ int launch_channel_stats(const float* x, long long P, int C, float* mean, float*
 
 int launch_maxpool_fwd(const float* in, float* out, int* idx, PoolGeom g, cudaStream_t s) {
   const long long total = (long long)g.N * g.Ho * g.Wo * g.C;
+  if (pool_vec_ok(g, in, out, idx)) {
+    BRE_KLAUNCH(maxpool_fwd_vec_kernel, ew_grid(total / 4), kEwThreads, 0, s, reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
+                reinterpret_cast<int4*>(idx), g, (int)(total / 4));
+    BRE_CHECK_LAUNCH();
+    return 0;
+  }
   BRE_KLAUNCH(maxpool_fwd_kernel, ew_grid(total), kEwThreads, 0, s, in, out, idx, g, total);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_maxpool_bwd(const float* dout, const int* idx, float* din, bool acc, PoolGeom g, cudaStream_t s) {
   const long long total = (long long)g.N * g.H * g.W * g.C;
+  if (pool_vec_ok(g, dout, idx, din)) {
+    const float4* d4 = reinterpret_cast<const float4*>(dout);
+    const int4* i4 = reinterpret_cast<const int4*>(idx);
+    if (acc) BRE_KLAUNCH(maxpool_bwd_vec_kernel<true>, ew_grid(total / 4), kEwThreads, 0, s, d4, i4, reinterpret_cast<float4*>(din), g, (int)(total / 4));
+    else BRE_KLAUNCH(maxpool_bwd_vec_kernel<false>, ew_grid(total / 4), kEwThreads, 0, s, d4, i4, reinterpret_cast<float4*>(din), g, (int)(total / 4));
+    BRE_CHECK_LAUNCH();
+    return 0;
+  }
   BRE_KLAUNCH(maxpool_bwd_kernel, ew_grid(total), kEwThreads, 0, s, dout, idx, din, acc, g, total);
   BRE_CHECK_LAUNCH();
   return 0;
 }
 int launch_maxpool_gather(const float* tin, const int* idx, float* tout, PoolGeom g, cudaStream_t s) {
   const long long total = (long long)g.N * g.Ho * g.Wo * g.C;
+  if (pool_vec_ok(g, tin, idx, tout)) {
+    BRE_KLAUNCH(maxpool_gather_vec_kernel, ew_grid(total / 4), kEwThreads, 0, s, tin, reinterpret_cast<const int4*>(idx), reinterpret_cast<float4*>(tout), g,
+                (int)(total / 4));
+    BRE_CHECK_LAUNCH();
+    return 0;
+  }
   BRE_KLAUNCH(maxpool_gather_kernel, ew_grid(total), kEwThreads, 0, s, tin, idx, tout, g, total);
   BRE_CHECK_LAUNCH();
   return 0;

@@ -403,11 +403,11 @@ __global__ void __launch_bounds__(256) grad_norm_kernel(StepArgs a, Scalars* sc,
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(partials + b);
-    sc->grad_norm_sq = s;
-  }
+  // last block: all 256 threads fold the per-block partials (fixed order: thread-strided, then the block tree)
+  double s = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += __ldcg(partials + b);
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) sc->grad_norm_sq = s;
 }
 
 __global__ void __launch_bounds__(256) pixel_step_kernel(StepArgs a, Scalars* sc) {

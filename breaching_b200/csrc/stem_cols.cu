@@ -46,6 +46,49 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   }
 }
 
+// Same unfold with the k -> (r, s, c) decode done once per block into shared memory (Kp <= 256: the 7x7x3 stem pads to 192, a
+// 3x3x3 first conv to 64) and 32-bit index arithmetic: the generic kernel above spends its time in the per-element divisions
+// (batch 8: 84 us for a 77 MB write).
+__global__ void __launch_bounds__(256) stem_im2col_lut_kernel(const float* __restrict__ x, float* __restrict__ xcol, ColGeom g, int total, int round_out) {
+  __shared__ int tap_off[256];   // c * H * W + r * W + s
+  __shared__ int tap_rs[256];    // r | s << 8, -1 for the zero padding of K
+  pdl_launch_dependents();
+  for (int k = threadIdx.x; k < g.Kp; k += blockDim.x) {
+    if (k < g.K) {
+      const int rs = k / g.C, c = k - rs * g.C;
+      const int r = rs / g.S, sx = rs - r * g.S;
+      tap_off[k] = (c * g.H + r) * g.W + sx;
+      tap_rs[k] = r | (sx << 8);
+    } else {
+      tap_off[k] = 0;
+      tap_rs[k] = -1;
+    }
+  }
+  __syncthreads();
+  pdl_wait();
+  const int gran = g.Kp >> 2, HoWo = g.Ho * g.Wo, plane = g.C * g.H * g.W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int m = i / gran;
+    const int k0 = (i - m * gran) << 2;
+    const int n = m / HoWo, rem = m - n * HoWo;
+    const int p = rem / g.Wo, q = rem - p * g.Wo;
+    const int y0 = p * g.stride - g.pad, x0 = q * g.stride - g.pad;
+    const float* __restrict__ base = x + (long long)n * plane + y0 * g.W + x0;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = tap_rs[k0 + j];
+      float val = 0.f;
+      if (t >= 0) {
+        const int yy = y0 + (t & 255), xx = x0 + (t >> 8);
+        if (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) val = __ldg(base + tap_off[k0 + j]);
+      }
+      v[j] = round_out ? tf32_rna(val) : val;
+    }
+    reinterpret_cast<float4*>(xcol)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // grad[n][c][y][x] = sum over taps (r, s) with (y + pad - r) % stride == 0, (x + pad - s) % stride == 0 of dcol[(n, p, q)][(r, s, c)]
 __global__ void __launch_bounds__(256) stem_col2im_kernel(const float* __restrict__ dcol, float* __restrict__ grad, ColGeom g, long long total) {
   pdl_prologue();
@@ -101,6 +144,11 @@ int launch_stem_im2col(const float* x, float* xcol, int N, int C, int H, int W, 
                        bool round_out, cudaStream_t s) {
   const ColGeom g{N, C, H, W, Ho, Wo, R, S, stride, pad, R * S * C, Kp};
   const long long total = (long long)N * Ho * Wo * (Kp / 4);
+  if (Kp <= 256 && R < 256 && S < 256 && total < (1LL << 31) && (long long)N * C * H * W < (1LL << 31)) {
+    BRE_KLAUNCH(stem_im2col_lut_kernel, grid_for(total), 256, 0, s, x, xcol, g, (int)total, round_out ? 1 : 0);
+    BRE_CHECK_LAUNCH();
+    return 0;
+  }
   BRE_KLAUNCH(stem_im2col_kernel, grid_for(total), 256, 0, s, x, xcol, g, total, round_out ? 1 : 0);
   BRE_CHECK_LAUNCH();
   return 0;

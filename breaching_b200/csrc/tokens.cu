@@ -28,6 +28,7 @@ __global__ void layernorm_kernel(int sweep, const float* __restrict__ x, const f
                                  const float* __restrict__ in3, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ v_gamma, const float* __restrict__ v_beta, float eps, int rows, int C,
                                  float* __restrict__ stats, float* __restrict__ out, int accumulate) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -103,6 +104,7 @@ __global__ void layernorm_kernel(int sweep, const float* __restrict__ x, const f
 // gamma / beta gradients of LayerNorm: G_gamma[c] = sum_rows dy xh, G_beta[c] = sum_rows dy  (one thread per column, rows in order)
 __global__ void layernorm_param_grad_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stats,
                                             int rows, int C, float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float sg = 0.f, sb = 0.f;
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(int sweep, const
                                                               const float* __restrict__ in2, const float* __restrict__ in3, int T, int heads,
                                                               int dh, float* __restrict__ P, float* __restrict__ Pd, float* __restrict__ out,
                                                               int accumulate) {
+  pdl_prologue();
   extern __shared__ float sm[];
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = ATT_THREADS / 32;
@@ -282,6 +285,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(int sweep, const
 
 // ---- positional embedding ------------------------------------------------------------------------------------------
 __global__ void posadd_kernel(const float* __restrict__ x, const float* __restrict__ pos, float* __restrict__ out, long long total, int C, int T) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / C;
     const int c = (int)(i - row * C);
@@ -291,6 +295,7 @@ __global__ void posadd_kernel(const float* __restrict__ x, const float* __restri
 }
 
 __global__ void pos_grad_kernel(const float* __restrict__ d, float* __restrict__ g_pos, int rows, int C, int T) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (t, c)
   if (i >= T * C) return;
   const int t = i / C, c = i - t * C;
@@ -428,13 +433,15 @@ int launch_token_layernorm(int sweep, const float* x, const float* in1, const fl
                            const float* beta, const float* v_gamma, const float* v_beta, float eps, int rows, int C, float* stats, float* out,
                            int accumulate, cudaStream_t s) {
   const int warps = 4;
-  layernorm_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(sweep, x, in1, in2, in3, gamma, beta, v_gamma, v_beta, eps, rows, C, stats,
-                                                                     out, accumulate);
+  const cudaError_t lerr = launch_kernel(layernorm_kernel, dim3((rows + warps - 1) / warps), dim3(warps * 32), 0, s, 1, sweep, x, in1, in2, in3, gamma, beta,
+                                         v_gamma, v_beta, eps, rows, C, stats, out, accumulate);
+  if (lerr != cudaSuccess) { set_error(std::string("token layernorm: ") + cudaGetErrorString(lerr)); return -2; }
   return check_launch("token layernorm");
 }
 int launch_token_ln_param_grad(const float* x, const float* dy, const float* stats, int rows, int C, float* g_gamma, float* g_beta,
                                cudaStream_t s) {
-  layernorm_param_grad_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, dy, stats, rows, C, g_gamma, g_beta);
+  const cudaError_t lerr = launch_kernel(layernorm_param_grad_kernel, dim3((C + 127) / 128), dim3(128), 0, s, 1, x, dy, stats, rows, C, g_gamma, g_beta);
+  if (lerr != cudaSuccess) { set_error(std::string("token layernorm parameter gradient: ") + cudaGetErrorString(lerr)); return -2; }
   return check_launch("token layernorm parameter gradient");
 }
 int launch_token_attention(int sweep, const float* qkv, const float* in1, const float* in2, const float* in3, int B, int T, int heads, int dh,
@@ -450,16 +457,20 @@ int launch_token_attention(int sweep, const float* qkv, const float* in1, const 
     }
     attr_done = true;
   }
-  attention_kernel<<<B * heads, ATT_THREADS, smem, s>>>(sweep, qkv, in1, in2, in3, T, heads, dh, P, Pd, out, accumulate);
+  const cudaError_t lerr = launch_kernel(attention_kernel, dim3(B * heads), dim3(ATT_THREADS), smem, s, 1, sweep, qkv, in1, in2, in3, T, heads, dh, P, Pd, out,
+                                         accumulate);
+  if (lerr != cudaSuccess) { set_error(std::string("token attention: ") + cudaGetErrorString(lerr)); return -2; }
   return check_launch("token attention");
 }
 int launch_token_posadd(const float* x, const float* pos, float* out, int rows, int C, int T, cudaStream_t s) {
   const long long total = (long long)rows * C;
-  posadd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, pos, out, total, C, T);
+  const cudaError_t lerr = launch_kernel(posadd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, 1, x, pos, out, total, C, T);
+  if (lerr != cudaSuccess) { set_error(std::string("token posadd: ") + cudaGetErrorString(lerr)); return -2; }
   return check_launch("token posadd");
 }
 int launch_token_pos_grad(const float* d, float* g_pos, int rows, int C, int T, cudaStream_t s) {
-  pos_grad_kernel<<<(T * C + 255) / 256, 256, 0, s>>>(d, g_pos, rows, C, T);
+  const cudaError_t lerr = launch_kernel(pos_grad_kernel, dim3((T * C + 255) / 256), dim3(256), 0, s, 1, d, g_pos, rows, C, T);
+  if (lerr != cudaSuccess) { set_error(std::string("token positional gradient: ") + cudaGetErrorString(lerr)); return -2; }
   return check_launch("token positional gradient");
 }
 int launch_token_ce_fwd(const float* logits, const float* q, int rows, int V, int Vs, int T, float* p, float* loss_n, float* dlogits, cudaStream_t s) {
