@@ -385,6 +385,7 @@ struct bre_engine {
     return mask;
   }
   int gemm_on(const GemmArgs& a, cudaStream_t st) {
+    if (linear_tall_supported(a)) return launch_linear_tall(a, st);
     if (gemm_backend == 1 && !a.force_fp32 && igemm_tc_supported(a)) {
       GemmArgs b = a;
       b.wgt_static = static_weights(a);
@@ -1856,6 +1857,7 @@ int bre_conv_gemm(int32_t mode, int32_t backend, const float* a, const float* w,
   static thread_local int* counters = nullptr;
   if (!ws) { BRE_TRY(dev_alloc(&ws, 1024LL * IG_BM * IG_BN)); BRE_TRY(dev_alloc(&counters, 1 << 16)); }
   g.ws = ws; g.counters = counters; g.ws_tiles = 1024;
+  if (linear_tall_supported(g)) return launch_linear_tall(g, s) == 0 ? BRE_OK : BRE_ERR_CUDA;   // the engine's dispatch rule (gemm_on)
   if (backend == 1) {
     if (!igemm_tc_supported(g)) { set_error("tcgen05 back end does not cover this shape"); return BRE_ERR_UNSUPPORTED; }
     return launch_igemm_tc(g, s);

@@ -65,6 +65,10 @@ int launch_igemm_simt(const GemmArgs& a, cudaStream_t stream);
 // linear layers on <= 16 rows (the classification head at small batch): dedicated fp32 kernels (linear_small.cu)
 bool linear_small_supported(const GemmArgs& a);
 int launch_linear_small(const GemmArgs& a, cudaStream_t stream);
+// dgrad of a linear layer with <= 32 rows, <= 128 inputs and >= 8192 outputs (the token models' decoder): chunked reduction in
+// fp32 registers + a fixed-order fold (linear_small.cu); uses a.ws for the per-chunk partial sums
+bool linear_tall_supported(const GemmArgs& a);
+int launch_linear_tall(const GemmArgs& a, cudaStream_t stream);
 // tcgen05 TF32 back end (igemm_tc.cu); returns BRE_ERR_UNSUPPORTED (-4) for shapes it does not cover.
 int launch_igemm_tc(const GemmArgs& a, cudaStream_t stream);
 bool igemm_tc_supported(const GemmArgs& a);

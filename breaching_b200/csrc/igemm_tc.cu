@@ -1065,7 +1065,11 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, const std::conditional_t<CLS,
   // 25-30 % slower on config 2 *and* on the multi-wave batch-8 launches of config 3 -- occupancy beats ring depth.
   // BRE_TC_STAGES=2|4|8 forces a depth for experiments.
   static const int stages_env = [] { const char* e = getenv("BRE_TC_STAGES"); return e ? atoi(e) : 0; }();
-  const int stages = (stages_env == 8 || stages_env == 2) ? stages_env : TC_STAGES;
+  // Short reductions on many tiles (the token models' decoder fprop: 786 tiles x 3-6 k-blocks): a 2-deep ring halves the shared
+  // memory so four CTAs share an SM and the per-CTA prologue / epilogue overlap: config 5 1187 -> 1220 it/s (BRE_TC_SHORTK_STAGES=4 turns it off)
+  static const int shortk_env = [] { const char* e = getenv("BRE_TC_SHORTK_STAGES"); return e ? atoi(e) : 2; }();
+  const bool shortk = shortk_env == 2 && d.kblocks_per_split <= 6 && tiles * splits > 2LL * kNumSMs;
+  const int stages = (stages_env == 8 || stages_env == 2) ? stages_env : (shortk ? 2 : TC_STAGES);
   d.stage_shift = stages == 8 ? 3 : (stages == 2 ? 1 : 2);
   const size_t smem = (size_t)stages * (TC_BM + BN) * TC_BK * 4;
   const size_t smem_max = (size_t)TC_MAX_STAGES * (TC_BM + BN) * TC_BK * 4;

@@ -143,7 +143,128 @@ int launch_nb(const GemmArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+// ---- tall-K dgrad: din[n][ci] = sum_co dy[n][co] W[co][ci] with few rows (n <= 32), a narrow input (ci <= 128) and a very long
+//      reduction (the 96 -> 50257 decoder of the token models: Co = 50304).  As an implicit GEMM this is one row of 128 x 32 output
+//      tiles whose split-K is capped by the cluster size: 24 CTAs streamed the 19 MB weight matrix in 65 us (123 us for the
+//      two-source tangent form), 19 % of a config-5 iteration.  Here the reduction is cut into ~2 chunks per SM; a block keeps all
+//      n x ci partial sums of its chunk in registers (warp = 8 rows x one half of the chunk's output channels, lanes along ci, so the
+//      weight rows are read as coalesced 128-byte lines exactly once per block) and a second small kernel adds the per-chunk
+//      partials in a fixed order.  Same products as the GEMM back ends (the operands are the same arrays), fp32 accumulation.
+constexpr int LT_ROWS = 32, LT_SUB = 64, LT_PITCH = LT_ROWS + 4;
+
+template <int CJ>   // CJ = Ci / 32
+__global__ void __launch_bounds__(256) linear_tall_dgrad_kernel(GemmArgs a, int chunk, float* __restrict__ partials) {
+  __shared__ __align__(16) float dy_s[LT_SUB][LT_PITCH];       // [co][n], rows 16-byte aligned for the 128-bit broadcast reads
+  __shared__ float fold[4][8][CJ * 32];                         // second co-half of every row group, folded at the end
+  pdl_prologue();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = warp >> 2, r0 = (warp & 3) * 8;              // warps 0-3: even output channels, 4-7: odd; 8 rows each
+  const int Co = a.g.Co, Ci = a.g.Ci, N = a.g.N;
+  const int co_begin = blockIdx.x * chunk, co_end = min(Co, co_begin + chunk);
+  float acc[8][CJ];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int j = 0; j < CJ; ++j) acc[r][j] = 0.f;
+  for (int s = 0; s < a.nsrc; ++s) {
+    const float* __restrict__ w = a.wgt[s];
+    const float* __restrict__ dy = a.act[s];
+    for (int c0 = co_begin; c0 < co_end; c0 += LT_SUB) {
+      const int cn = min(LT_SUB, co_end - c0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < LT_SUB * LT_ROWS; i += 256) {   // coalesced along co, transposed into [co][n]
+        const int n = i / LT_SUB, c = i - n * LT_SUB;
+        dy_s[c][n] = (n < N && c < cn) ? __ldg(dy + (long long)n * Co + c0 + c) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 2
+      for (int c = half; c < cn; c += 2) {
+        float wv[CJ];
+        const float* __restrict__ wr = w + (long long)(c0 + c) * Ci + lane;
+#pragma unroll
+        for (int j = 0; j < CJ; ++j) wv[j] = __ldg(wr + 32 * j);
+        const float4 d0 = *reinterpret_cast<const float4*>(&dy_s[c][r0]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&dy_s[c][r0 + 4]);
+        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int j = 0; j < CJ; ++j) acc[r][j] = fmaf(dv[r], wv[j], acc[r][j]);
+      }
+    }
+  }
+  if (half == 1) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int j = 0; j < CJ; ++j) fold[warp & 3][r][32 * j + lane] = acc[r][j];
+  }
+  __syncthreads();
+  if (half == 0) {
+    float* __restrict__ dst = partials + (long long)blockIdx.x * LT_ROWS * Ci;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int j = 0; j < CJ; ++j) dst[(r0 + r) * Ci + 32 * j + lane] = acc[r][j] + fold[warp][r][32 * j + lane];
+  }
+}
+
+// out[n][ci] (+)= sum over chunks of partials[chunk][n][ci]: block = 32 adjacent outputs x 8 interleaved slices of the chunk list
+__global__ void __launch_bounds__(256) linear_tall_fold_kernel(const float* __restrict__ partials, int chunks, int Ci, int N, long long x_sN,
+                                                               int accumulate, float* __restrict__ out) {
+  __shared__ float part[8][32];
+  pdl_prologue();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + lane;                 // index into [LT_ROWS][Ci]
+  const long long per = (long long)LT_ROWS * Ci;
+  float t = 0.f;
+  for (int c = warp; c < chunks; c += 8) t += __ldcg(partials + c * per + o);
+  part[warp][lane] = t;
+  __syncthreads();
+  if (warp == 0) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += part[k][lane];
+    const int n = o / Ci, ci = o - n * Ci;
+    if (n < N) {
+      float* dst = out + (long long)n * x_sN + ci;
+      *dst = accumulate ? *dst + sum : sum;
+    }
+  }
+}
+
+inline int tall_chunk(int Co) {
+  int chunk = ceil_div(Co, 2 * kNumSMs);
+  chunk += chunk & 1;
+  return chunk < 2 ? 2 : chunk;
+}
+
 }  // namespace
+
+bool linear_tall_supported(const GemmArgs& a) {
+  static const bool env = [] { const char* e = getenv("BRE_LINEAR_TALL"); return e ? atoi(e) != 0 : true; }();
+  const ConvGeom& g = a.g;
+  if (!env || a.mode != GEMM_DGRAD) return false;
+  if (!(g.R == 1 && g.S == 1 && g.H == 1 && g.W == 1 && g.Ho == 1 && g.Wo == 1 && g.stride == 1 && g.pad == 0)) return false;
+  if (g.N < 1 || g.N > LT_ROWS || g.Ci % 32 != 0 || g.Ci > 128 || g.Co < 8192 || a.x_sC != 1 || a.epi.kind != 0) return false;
+  if (a.nsrc < 1 || a.nsrc > 2 || a.ws == nullptr) return false;
+  const long long need = (long long)ceil_div(g.Co, tall_chunk(g.Co)) * LT_ROWS * g.Ci;
+  return need <= (long long)a.ws_tiles * IG_BM * IG_BN;
+}
+
+int launch_linear_tall(const GemmArgs& a, cudaStream_t stream) {
+  const int Co = a.g.Co, Ci = a.g.Ci;
+  const int chunk = tall_chunk(Co), chunks = ceil_div(Co, chunk);
+  switch (Ci / 32) {
+    case 1: BRE_KLAUNCH((linear_tall_dgrad_kernel<1>), chunks, 256, 0, stream, a, chunk, a.ws); break;
+    case 2: BRE_KLAUNCH((linear_tall_dgrad_kernel<2>), chunks, 256, 0, stream, a, chunk, a.ws); break;
+    case 3: BRE_KLAUNCH((linear_tall_dgrad_kernel<3>), chunks, 256, 0, stream, a, chunk, a.ws); break;
+    default: BRE_KLAUNCH((linear_tall_dgrad_kernel<4>), chunks, 256, 0, stream, a, chunk, a.ws); break;
+  }
+  BRE_KLAUNCH(linear_tall_fold_kernel, LT_ROWS * Ci / 32, 256, 0, stream, (const float*)a.ws, chunks, Ci, a.g.N, a.x_sN, a.accumulate, a.out);
+  BRE_CHECK_LAUNCH();
+  return 0;
+}
 
 bool linear_small_supported(const GemmArgs& a) {
   const ConvGeom& g = a.g;

@@ -101,20 +101,34 @@ __global__ void layernorm_kernel(int sweep, const float* __restrict__ x, const f
   }
 }
 
-// gamma / beta gradients of LayerNorm: G_gamma[c] = sum_rows dy xh, G_beta[c] = sum_rows dy  (one thread per column, rows in order)
-__global__ void layernorm_param_grad_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stats,
-                                            int rows, int C, float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+// gamma / beta gradients of LayerNorm: G_gamma[c] = sum_rows dy xh, G_beta[c] = sum_rows dy.  Block = 32 columns x 8 row slices
+// (warp w takes rows w, w + 8, ...: coalesced 128-byte row segments, 8 independent chains), folded over the slices in a fixed order.
+// (One thread per column walking all rows serially was 10 us per launch at 32 rows.)
+__global__ void __launch_bounds__(256) layernorm_param_grad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                   const float* __restrict__ stats, int rows, int C,
+                                                                   float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+  __shared__ float fg[8][32], fb[8][32];
   pdl_prologue();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float sg = 0.f, sb = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    const float d = dy[(long long)r * C + c];
-    sg = fmaf(d, (x[(long long)r * C + c] - stats[2 * r]) * stats[2 * r + 1], sg);
-    sb += d;
+  if (c < C) {
+    for (int r = warp; r < rows; r += 8) {
+      const float d = dy[(long long)r * C + c];
+      sg = fmaf(d, (x[(long long)r * C + c] - stats[2 * r]) * stats[2 * r + 1], sg);
+      sb += d;
+    }
   }
-  g_gamma[c] = sg;
-  g_beta[c] = sb;
+  fg[warp][lane] = sg;
+  fb[warp][lane] = sb;
+  __syncthreads();
+  if (warp == 0 && c < C) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { tg += fg[k][lane]; tb += fb[k][lane]; }
+    g_gamma[c] = tg;
+    g_beta[c] = tb;
+  }
 }
 
 // ---- multi-head self-attention (no mask) ---------------------------------------------------------------------------
@@ -440,7 +454,7 @@ int launch_token_layernorm(int sweep, const float* x, const float* in1, const fl
 }
 int launch_token_ln_param_grad(const float* x, const float* dy, const float* stats, int rows, int C, float* g_gamma, float* g_beta,
                                cudaStream_t s) {
-  const cudaError_t lerr = launch_kernel(layernorm_param_grad_kernel, dim3((C + 127) / 128), dim3(128), 0, s, 1, x, dy, stats, rows, C, g_gamma, g_beta);
+  const cudaError_t lerr = launch_kernel(layernorm_param_grad_kernel, dim3((C + 31) / 32), dim3(256), 0, s, 1, x, dy, stats, rows, C, g_gamma, g_beta);
   if (lerr != cudaSuccess) { set_error(std::string("token layernorm parameter gradient: ") + cudaGetErrorString(lerr)); return -2; }
   return check_launch("token layernorm parameter gradient");
 }

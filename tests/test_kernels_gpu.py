@@ -173,3 +173,30 @@ def test_conv_tcgen05_tf32_backend(shape):
         E.conv_gemm(2, _nhwc(x), _nhwc(dy), dw, N, H, W, Ci, Co, R, R, st, pd, a2=_nhwc(x2), w2=_nhwc(dy2), backend=1)
         refw2 = refw + torch.nn.grad.conv2d_weight(x2.double(), (Co, Ci, R, R), dy2.double(), stride=st, padding=pd)
         assert _relerr(dw.permute(0, 3, 1, 2), refw2) < tol, "wgrad dual"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,Ci,Co,dual", [(32, 96, 50304, False), (32, 96, 50304, True), (5, 64, 9000, True), (17, 128, 8192, False)])
+def test_tall_linear_dgrad_matches_float64(rows, Ci, Co, dual):
+    """dgrad of a linear layer with a very long reduction (the token models' 96 -> 50257 decoder, tag.yaml / BASELINE config 5):
+    chunked fp32 register reduction + fixed-order fold (csrc/linear_small.cu) against float64; run twice: bitwise reproducible."""
+    from breaching_b200 import engine as E
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(rows * 1000 + Ci)
+    dy = torch.randn(rows, Co, generator=g).to(dev)
+    w = (torch.randn(Co, Ci, generator=g) / 8).to(dev)
+    dy2 = torch.randn(rows, Co, generator=g).to(dev) if dual else None
+    w2 = (torch.randn(Co, Ci, generator=g) / 8).to(dev) if dual else None
+    want = dy.double() @ w.double()
+    if dual:
+        want = want + dy2.double() @ w2.double()
+    for backend in (0, 1):
+        out = torch.full((rows, Ci), float("nan"), device=dev)
+        E.conv_gemm(1, dy, w, out, rows, 1, 1, Ci, Co, 1, 1, 1, 0, a2=dy2, w2=w2, backend=backend)
+        again = torch.empty_like(out)
+        E.conv_gemm(1, dy, w, again, rows, 1, 1, Ci, Co, 1, 1, 1, 0, a2=dy2, w2=w2, backend=backend)
+        torch.cuda.synchronize()
+        assert torch.equal(out, again)
+        rel = ((out.double() - want).norm() / want.norm()).item()
+        assert rel < 2e-6, (backend, rel)
