@@ -81,6 +81,81 @@ __device__ __forceinline__ double row_allreduce(double v, RowReduce& ws, int slo
 }
 __device__ __forceinline__ void cluster_exit() { cluster_barrier(); }
 
+// ---- register-resident row segments ------------------------------------------------------------------------------------------------
+// A CTA's segment of a 50 257-wide row is ~6 300 elements = 25 per thread.  The row kernels make two or three passes over it; with the
+// plain loops every pass is a chain of dependent L2 round trips (ncu: 15 long-scoreboard stalls per issue, 27 us for a 25 MB
+// cross-entropy).  When the segment fits, each thread loads its elements once, all loads in flight together, and the passes run out of
+// registers.  `seg_fits` depends only on the row width and the cluster size, so it is uniform over the cluster (the barriers inside the
+// reductions need every CTA on the same path).
+constexpr int kSegCache = 26;
+struct SegCache { float v[kSegCache]; };
+__device__ __forceinline__ bool seg_fits(int C) {
+  const int n = (int)cluster_size();
+  const int per = (((C + n - 1) / n) + 3) & ~3;
+  return per <= kSegCache * kRowThreads;
+}
+__device__ __forceinline__ void seg_load(SegCache& s, const float* __restrict__ row, int c0, int c1, float fill) {
+#pragma unroll
+  for (int k = 0; k < kSegCache; ++k) {
+    const int c = c0 + k * kRowThreads + (int)threadIdx.x;
+    s.v[k] = c < c1 ? row[c] : fill;
+  }
+}
+
+// (max, sum of exp(. - max)) of a row in ONE cluster-wide reduction: every thread brings the pair of its own elements, pairs are merged
+// as (M, s exp(m - M) + s' exp(m' - M)) -- lanes, warps and CTAs in a fixed order.  Uses slots `slot` and `slot + 1`.
+__device__ __forceinline__ void merge_softmax(float& m, double& s, float m2, double s2) {
+  const float M = fmaxf(m, m2);
+  s = s * (double)expf(m - M) + s2 * (double)expf(m2 - M);
+  m = M;
+}
+__device__ __forceinline__ void row_allreduce_softmax(float& m, double& s, RowReduce& ws, int slot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const double s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    merge_softmax(m, s, m2, s2);
+  }
+  __syncthreads();
+  if (lane == 0) { ws.scratch[warp] = (double)m; ws.scratch[8 + warp] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tm = (float)ws.scratch[0];
+    double ts = ws.scratch[8];
+    for (int w = 1; w < kRowThreads / 32; ++w) merge_softmax(tm, ts, (float)ws.scratch[w], ws.scratch[8 + w]);
+    ws.slot[slot] = (double)tm;
+    ws.slot[slot + 1] = ts;
+  }
+  cluster_barrier();
+  if (threadIdx.x == 0) {
+    const unsigned n = cluster_size();
+    float tm = (float)ld_cluster_f64(&ws.slot[slot], 0);
+    double ts = ld_cluster_f64(&ws.slot[slot + 1], 0);
+    for (unsigned r = 1; r < n; ++r) merge_softmax(tm, ts, (float)ld_cluster_f64(&ws.slot[slot], r), ld_cluster_f64(&ws.slot[slot + 1], r));
+    ws.scratch[16] = (double)tm;
+    ws.bcast = ts;
+  }
+  __syncthreads();
+  m = (float)ws.scratch[16];
+  s = ws.bcast;
+  __syncthreads();
+}
+// the pair of one thread's cached elements (elements beyond the segment hold -FLT_MAX: exp underflows to 0)
+__device__ __forceinline__ void seg_softmax_pair(const SegCache& z, float& m, double& s) {
+  m = -3.402823466e+38f;
+#pragma unroll
+  for (int k = 0; k < kSegCache; ++k) m = fmaxf(m, z.v[k]);
+  float acc = 0.f;
+  double tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < kSegCache; ++k) {
+    acc += expf(z.v[k] - m);
+    if ((k & 3) == 3) { tot += (double)acc; acc = 0.f; }   // short fp32 runs folded into the double total
+  }
+  s = tot + (double)acc;
+}
+
 // cluster size for rows of C elements: enough CTAs that a segment is a few thousand elements, at most the portable 8
 inline int row_cluster_size(int C) {
   int cs = 1;

@@ -263,7 +263,7 @@ struct bre_engine {
       bn_partials[i] = buf;
       table.push_back(BnGradSlot{buf, slabs, Cpad, to.C, blocks, nullptr, nullptr});   // gradient pointers: filled per sweep (G arena is fixed)
       table.back().g_gamma = Gp(op.gamma); table.back().g_beta = Gp(op.beta);
-      blocks += (to.C + 127) / 128;
+      blocks += (to.C + 31) / 32;     // bn_grad_finalize_kernel: one block per 32 channels
     }
     bn_slots = (int)table.size(); bn_slot_blocks = blocks;
     if (bn_slots == 0) return 0;
@@ -708,12 +708,19 @@ struct bre_engine {
     if (!env || ms_steps > 0) return 0;
     std::vector<StatSlot> table;
     int blocks = 0, groups = 0;
+    // one launch covers every BN input: ~16 blocks per SM in total, dealt to the tensors in proportion to their size
+    double all_elems = 0.0;
+    for (const bre_op_desc& op : ops)
+      if (op.kind == BRE_OP_BNACT && op.has_bn) { const bre_tensor_desc& ti = td(op.tin); all_elems += (double)ti.N * ti.H * ti.W * ti.C; }
     for (const bre_op_desc& op : ops) {
       if (op.kind != BRE_OP_BNACT || !op.has_bn) continue;
       const bre_tensor_desc& ti = td(op.tin);
       StatSlot sl;
       memset(&sl, 0, sizeof(sl));
-      if (!channel_stats_plan((long long)ti.N * ti.H * ti.W, ti.C, &sl)) return 0;   // odd channel count somewhere: per-layer kernels
+      const double share = (double)ti.N * ti.H * ti.W * ti.C / all_elems;
+      long long target = (long long)(share * 16.0 * kNumSMs + 0.5);
+      if (target < 4) target = 4;
+      if (!channel_stats_plan((long long)ti.N * ti.H * ti.W, ti.C, &sl, target)) return 0;   // odd channel count somewhere: per-layer kernels
       BnBuf& b = bn[op.bn_buffer];
       sl.x = t[op.tin].val; sl.mean = b.di_mean; sl.var = b.di_var;
       BRE_TRY(alloc(&sl.partials, (long long)sl.slabs * sl.Cpad * 2));

@@ -1068,7 +1068,7 @@ int launch_tc(const GemmArgs& a, const TcDims& d0, const std::conditional_t<CLS,
   // Short reductions on many tiles (the token models' decoder fprop: 786 tiles x 3-6 k-blocks): a 2-deep ring halves the shared
   // memory so four CTAs share an SM and the per-CTA prologue / epilogue overlap: config 5 1187 -> 1220 it/s (BRE_TC_SHORTK_STAGES=4 turns it off)
   static const int shortk_env = [] { const char* e = getenv("BRE_TC_SHORTK_STAGES"); return e ? atoi(e) : 2; }();
-  const bool shortk = shortk_env == 2 && d.kblocks_per_split <= 6 && tiles * splits > 2LL * kNumSMs;
+  const bool shortk = shortk_env == 2 && d.kblocks_per_split <= 6 && tm == 1 && tiles * splits > 2LL * kNumSMs;   // (with full 128-row tiles -- config 3's 1x1 convolutions -- it costs 1 %)
   const int stages = (stages_env == 8 || stages_env == 2) ? stages_env : (shortk ? 2 : TC_STAGES);
   d.stage_shift = stages == 8 ? 3 : (stages == 2 ? 1 : 2);
   const size_t smem = (size_t)stages * (TC_BM + BN) * TC_BK * 4;

@@ -431,7 +431,7 @@ __device__ __forceinline__ bool slab_reduce4(float (&v)[NV][4], int LX, int LY, 
   return false;
 }
 
-inline void slab_grid4(long long P, int C, dim3& grid, int& LX, int& LY, long long& pps, int waves = 2) {
+inline void slab_grid4(long long P, int C, dim3& grid, int& LX, int& LY, long long& pps, int waves = 2, long long target_blocks = 0) {
   const int C4 = C / 4;
   LX = C4 < 32 ? C4 : 32;
   while (256 % LX != 0) --LX;          // C4 = 16, 32, 64 ... in practice; keep LX a divisor of 256 for odd widths
@@ -439,7 +439,9 @@ inline void slab_grid4(long long P, int C, dim3& grid, int& LX, int& LY, long lo
   const int cg = ceil_div(C4, LX);
   // `waves` x 148 blocks: 2 when the last block of a column group sums the slabs itself (a longer tail per slab), 4 when the slabs are
   // summed by a later batched kernel (deferred BN gradients, batched statistics)
-  long long slabs = ((long long)waves * kNumSMs + cg - 1) / cg;
+  // (a batched launch over many tensors passes this tensor's share of the whole grid as `target_blocks` instead)
+  const long long want = target_blocks > 0 ? target_blocks : (long long)waves * kNumSMs;
+  long long slabs = (want + cg - 1) / cg;
   const long long max_slabs = (P + LY - 1) / LY;
   if (slabs > max_slabs) slabs = max_slabs;
   const long long cap = kSlabPartialFloats / (2LL * cg * LX * 4);   // partials: slabs x Cpad x (<= 2 quantities)
@@ -638,24 +640,37 @@ __global__ void __launch_bounds__(256) channel_stats_batched_finalize_kernel(con
 // Every bnact_bwd launch used to end with a serial tail: atomic ticket, the last block of each channel group re-reads the slab
 // partials and sums them (5-8 us of a 9-20 us launch, on the critical path of the backward sweep 20-53 times per iteration).  With
 // `defer` the kernels stop after writing their partials; one launch at the end of the sweep sums the slabs of *all* layers (one
-// block per 128 channels of a layer, fixed slab order) -- the gradients of gamma / beta are only read by the matching reduction.
-__global__ void __launch_bounds__(256) bn_grad_finalize_kernel(const BnGradSlot* __restrict__ table, int n_layers) {
+// block per 32 channels of a layer, fixed summation order) -- the gradients of gamma / beta are only read by the matching reduction.
+__global__ void __launch_bounds__(1024) bn_grad_finalize_kernel(const BnGradSlot* __restrict__ table, int n_layers) {
+  // block = 32 channels x 2 quantities (64 adjacent floats of a slab row: coalesced) x 16 interleaved slices of the slab list; the
+  // slices are folded in a fixed order.  (One thread per (channel, quantity) walking all slabs was 25 us at ~600 slabs.)
+  __shared__ float part[16][64];
   pdl_prologue();
   int layer = 0;
   while (layer + 1 < n_layers && (int)blockIdx.x >= table[layer + 1].first_block) ++layer;
   const BnGradSlot e = table[layer];
   const int group = (int)blockIdx.x - e.first_block;
-  const int k = threadIdx.x >> 7, c = group * 128 + (threadIdx.x & 127);   // 128 channels x 2 quantities
-  if (c >= e.C) return;
+  const int q = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int c = group * 32 + (q >> 1), k = q & 1;
   float sum = 0.f;
-  for (int base = 0; base < e.slabs; base += 32) {
-    float r[32];
-#pragma unroll
-    for (int u = 0; u < 32; ++u) r[u] = base + u < e.slabs ? __ldcg(e.partials + ((long long)(base + u) * e.Cpad + c) * 2 + k) : 0.f;
-#pragma unroll
-    for (int u = 0; u < 32; ++u) sum += r[u];
+  if (c < e.C) {
+    const float* __restrict__ src = e.partials + (long long)c * 2 + k;
+    const long long pitch = (long long)e.Cpad * 2;
+    int sl = slice;
+    for (; sl + 48 < e.slabs; sl += 64) {
+      const float v0 = __ldcg(src + sl * pitch), v1 = __ldcg(src + (sl + 16) * pitch), v2 = __ldcg(src + (sl + 32) * pitch), v3 = __ldcg(src + (sl + 48) * pitch);
+      sum += v0; sum += v1; sum += v2; sum += v3;
+    }
+    for (; sl < e.slabs; sl += 16) sum += __ldcg(src + sl * pitch);
   }
-  (k == 0 ? e.g_gamma : e.g_beta)[c] = sum;
+  part[slice][q] = sum;
+  __syncthreads();
+  if (slice == 0 && c < e.C) {
+    float t = 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) t += part[u][q];
+    (k == 0 ? e.g_gamma : e.g_beta)[c] = t;
+  }
 }
 
 // ---- train-mode BatchNorm (rules in layers.cuh) -------------------------------------------------------------
@@ -1094,12 +1109,12 @@ int launch_bnact_fwd(const float* in, const float* res, float* out, long long P,
 
 // fills the geometry fields of a StatSlot (x, partials, mean, var and the block / group offsets are the caller's); false if the
 // 128-bit path does not apply to this channel count
-bool channel_stats_plan(long long P, int C, StatSlot* slot) {
+bool channel_stats_plan(long long P, int C, StatSlot* slot, long long target_blocks) {
   if (!vec_ok(C)) return false;
   dim3 grid;
   int LX, LY;
   long long pps;
-  slab_grid4(P, C, grid, LX, LY, pps, 4);
+  slab_grid4(P, C, grid, LX, LY, pps, 4, target_blocks);
   slot->P = P; slot->pps = pps; slot->C = C; slot->LX = LX; slot->LY = LY; slot->cg = (int)grid.x; slot->slabs = (int)grid.y;
   slot->Cpad = (int)(grid.x * LX * 4);
   return true;
@@ -1127,7 +1142,7 @@ void bnact_bwd_plan(long long P, int C, int* slabs, int* Cpad) {   // geometry o
 
 int launch_bn_grad_finalize(const BnGradSlot* table_dev, int n_layers, int total_blocks, cudaStream_t s) {
   if (n_layers <= 0 || total_blocks <= 0) return 0;
-  BRE_KLAUNCH(bn_grad_finalize_kernel, total_blocks, 256, 0, s, table_dev, n_layers);
+  BRE_KLAUNCH(bn_grad_finalize_kernel, total_blocks, 1024, 0, s, table_dev, n_layers);
   BRE_CHECK_LAUNCH();
   return 0;
 }

@@ -115,7 +115,7 @@ struct StatSlot {
   const float* x; long long P, pps; int C, LX, LY, cg, slabs, Cpad, first_block, first_group;
   float* partials; float* mean; float* var;
 };
-bool channel_stats_plan(long long P, int C, StatSlot* slot);
+bool channel_stats_plan(long long P, int C, StatSlot* slot, long long target_blocks);   // target_blocks: this tensor's share of the batched grid
 int launch_channel_stats_batched(const StatSlot* table_dev, int n_layers, int total_blocks, int total_groups, cudaStream_t s);
 
 struct PoolGeom { int N, H, W, C, Ho, Wo, k, stride, pad; };

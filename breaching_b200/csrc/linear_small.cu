@@ -150,46 +150,51 @@ int launch_nb(const GemmArgs& a, cudaStream_t stream) {
 //      n x ci partial sums of its chunk in registers (warp = 8 rows x one half of the chunk's output channels, lanes along ci, so the
 //      weight rows are read as coalesced 128-byte lines exactly once per block) and a second small kernel adds the per-chunk
 //      partials in a fixed order.  Same products as the GEMM back ends (the operands are the same arrays), fp32 accumulation.
-constexpr int LT_ROWS = 32, LT_SUB = 64, LT_PITCH = LT_ROWS + 4;
+constexpr int LT_ROWS = 32, LT_MAXC = 96, LT_PITCH = LT_ROWS + 4;
 
 template <int CJ>   // CJ = Ci / 32
-__global__ void __launch_bounds__(256) linear_tall_dgrad_kernel(GemmArgs a, int chunk, float* __restrict__ partials) {
-  __shared__ __align__(16) float dy_s[LT_SUB][LT_PITCH];       // [co][n], rows 16-byte aligned for the 128-bit broadcast reads
+__global__ void __launch_bounds__(256, (CJ <= 3 ? 4 : 3)) linear_tall_dgrad_kernel(GemmArgs a, int chunk, float* __restrict__ partials) {
+  __shared__ __align__(16) float dy_s[LT_MAXC][LT_PITCH];      // [co][n], rows 16-byte aligned for the 128-bit broadcast reads
   __shared__ float fold[4][8][CJ * 32];                         // second co-half of every row group, folded at the end
   pdl_prologue();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = warp >> 2, r0 = (warp & 3) * 8;              // warps 0-3: even output channels, 4-7: odd; 8 rows each
   const int Co = a.g.Co, Ci = a.g.Ci, N = a.g.N;
-  const int co_begin = blockIdx.x * chunk, co_end = min(Co, co_begin + chunk);
+  const int c0 = blockIdx.x * chunk, cn = min(chunk, Co - c0);
   float acc[8][CJ];
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
     for (int j = 0; j < CJ; ++j) acc[r][j] = 0.f;
   for (int s = 0; s < a.nsrc; ++s) {
-    const float* __restrict__ w = a.wgt[s];
-    const float* __restrict__ dy = a.act[s];
-    for (int c0 = co_begin; c0 < co_end; c0 += LT_SUB) {
-      const int cn = min(LT_SUB, co_end - c0);
-      __syncthreads();
-      for (int i = threadIdx.x; i < LT_SUB * LT_ROWS; i += 256) {   // coalesced along co, transposed into [co][n]
-        const int n = i / LT_SUB, c = i - n * LT_SUB;
-        dy_s[c][n] = (n < N && c < cn) ? __ldg(dy + (long long)n * Co + c0 + c) : 0.f;
-      }
-      __syncthreads();
-#pragma unroll 2
-      for (int c = half; c < cn; c += 2) {
-        float wv[CJ];
-        const float* __restrict__ wr = w + (long long)(c0 + c) * Ci + lane;
+    const float* __restrict__ w = a.wgt[s] + (long long)c0 * Ci + lane;
+    const float* __restrict__ dy = a.act[s] + c0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < chunk * LT_ROWS; i += 256) {   // the whole chunk at once: coalesced along co, transposed into [co][n]
+      const int n = i / chunk, c = i - n * chunk;
+      dy_s[c][n] = (n < N && c < cn) ? __ldg(dy + (long long)n * Co + c) : 0.f;
+    }
+    __syncthreads();
+    // four output channels per trip (c, c + 2, c + 4, c + 6 of this half): 4 CJ independent 128-byte weight loads in flight per
+    // thread, 32 warps per SM -- the kernel is bound by the latency of these loads, not by their volume
+    for (int c = half; c < cn; c += 8) {
+      float wv[4][CJ];
 #pragma unroll
-        for (int j = 0; j < CJ; ++j) wv[j] = __ldg(wr + 32 * j);
-        const float4 d0 = *reinterpret_cast<const float4*>(&dy_s[c][r0]);
-        const float4 d1 = *reinterpret_cast<const float4*>(&dy_s[c][r0 + 4]);
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = c + 2 * u < cn;
+#pragma unroll
+        for (int j = 0; j < CJ; ++j) wv[u][j] = ok ? __ldg(w + (long long)(c + 2 * u) * Ci + 32 * j) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cc = c + 2 * u < cn ? c + 2 * u : c;    // (a zero weight row makes the clamped read harmless)
+        const float4 d0 = *reinterpret_cast<const float4*>(&dy_s[cc][r0]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&dy_s[cc][r0 + 4]);
         const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
-          for (int j = 0; j < CJ; ++j) acc[r][j] = fmaf(dv[r], wv[j], acc[r][j]);
+          for (int j = 0; j < CJ; ++j) acc[r][j] = fmaf(dv[r], wv[u][j], acc[r][j]);
       }
     }
   }
@@ -209,22 +214,29 @@ __global__ void __launch_bounds__(256) linear_tall_dgrad_kernel(GemmArgs a, int 
   }
 }
 
-// out[n][ci] (+)= sum over chunks of partials[chunk][n][ci]: block = 32 adjacent outputs x 8 interleaved slices of the chunk list
-__global__ void __launch_bounds__(256) linear_tall_fold_kernel(const float* __restrict__ partials, int chunks, int Ci, int N, long long x_sN,
-                                                               int accumulate, float* __restrict__ out) {
-  __shared__ float part[8][32];
+// out[n][ci] (+)= sum over chunks of partials[chunk][n][ci]: block = 32 adjacent outputs x 32 interleaved slices of the chunk list
+// (warp w adds chunks w, w + 32, ...: coalesced 128-byte rows, four loads in flight), folded over the slices in a fixed order
+__global__ void __launch_bounds__(1024) linear_tall_fold_kernel(const float* __restrict__ partials, int chunks, int Ci, int N, long long x_sN,
+                                                                int accumulate, float* __restrict__ out) {
+  __shared__ float part[32][33];
   pdl_prologue();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int o = blockIdx.x * 32 + lane;                 // index into [LT_ROWS][Ci]
   const long long per = (long long)LT_ROWS * Ci;
+  const float* __restrict__ src = partials + o;
   float t = 0.f;
-  for (int c = warp; c < chunks; c += 8) t += __ldcg(partials + c * per + o);
+  int c = warp;
+  for (; c + 96 < chunks; c += 128) {
+    const float v0 = __ldcg(src + c * per), v1 = __ldcg(src + (c + 32) * per), v2 = __ldcg(src + (c + 64) * per), v3 = __ldcg(src + (c + 96) * per);
+    t += v0; t += v1; t += v2; t += v3;
+  }
+  for (; c < chunks; c += 32) t += __ldcg(src + c * per);
   part[warp][lane] = t;
   __syncthreads();
   if (warp == 0) {
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sum += part[k][lane];
+    for (int k = 0; k < 32; ++k) sum += part[k][lane];
     const int n = o / Ci, ci = o - n * Ci;
     if (n < N) {
       float* dst = out + (long long)n * x_sN + ci;
@@ -233,10 +245,10 @@ __global__ void __launch_bounds__(256) linear_tall_fold_kernel(const float* __re
   }
 }
 
-inline int tall_chunk(int Co) {
-  int chunk = ceil_div(Co, 2 * kNumSMs);
+inline int tall_chunk(int Co) {   // ~4 blocks per SM, an even number of output channels per block, 32 .. LT_MAXC
+  int chunk = ceil_div(Co, 4 * kNumSMs);
   chunk += chunk & 1;
-  return chunk < 2 ? 2 : chunk;
+  return chunk < 32 ? 32 : (chunk > LT_MAXC ? LT_MAXC : chunk);
 }
 
 }  // namespace
@@ -261,7 +273,7 @@ int launch_linear_tall(const GemmArgs& a, cudaStream_t stream) {
     case 3: BRE_KLAUNCH((linear_tall_dgrad_kernel<3>), chunks, 256, 0, stream, a, chunk, a.ws); break;
     default: BRE_KLAUNCH((linear_tall_dgrad_kernel<4>), chunks, 256, 0, stream, a, chunk, a.ws); break;
   }
-  BRE_KLAUNCH(linear_tall_fold_kernel, LT_ROWS * Ci / 32, 256, 0, stream, (const float*)a.ws, chunks, Ci, a.g.N, a.x_sN, a.accumulate, a.out);
+  BRE_KLAUNCH(linear_tall_fold_kernel, LT_ROWS * Ci / 32, 1024, 0, stream, (const float*)a.ws, chunks, Ci, a.g.N, a.x_sN, a.accumulate, a.out);
   BRE_CHECK_LAUNCH();
   return 0;
 }

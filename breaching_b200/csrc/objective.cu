@@ -475,13 +475,29 @@ __global__ void __launch_bounds__(256) pixel_step_kernel(StepArgs a, Scalars* sc
 // ---- label leaf of the joint data + label optimisation (optimization_with_label_attack.py:145-189) ----------------------
 // One thread-block cluster per row (cluster_rows.cuh): token models have 50 257 classes per row.
 // q = softmax(label logits) per row: what the closure hands to the task loss (:154)
-__global__ void __launch_bounds__(kRowThreads) row_softmax_kernel(const float* __restrict__ ell, float* __restrict__ q, int C) {
+__global__ void __launch_bounds__(kRowThreads, 2) row_softmax_kernel(const float* __restrict__ ell, float* __restrict__ q, int C) {
   pdl_prologue();
   __shared__ RowReduce ws;
   int c0, c1;
   row_segment(C, c0, c1);
   const float* z = ell + (long long)blockIdx.x * C;
   float* o = q + (long long)blockIdx.x * C;
+  if (seg_fits(C)) {   // segment in registers: one load, one reduction
+    SegCache zc;
+    seg_load(zc, z, c0, c1, -3.402823466e+38f);
+    float m;
+    double sum;
+    seg_softmax_pair(zc, m, sum);
+    row_allreduce_softmax(m, sum, ws, 0);
+    const float inv = (float)(1.0 / sum);
+#pragma unroll
+    for (int k = 0; k < kSegCache; ++k) {
+      const int c = c0 + k * kRowThreads + (int)threadIdx.x;
+      if (c < c1) o[c] = expf(zc.v[k] - m) * inv;
+    }
+    cluster_exit();
+    return;
+  }
   float mx = -3.402823466e+38f;
   for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) mx = fmaxf(mx, z[c]);
   mx = (float)row_allreduce<ROW_MAX>((double)mx, ws, 0);
@@ -493,13 +509,29 @@ __global__ void __launch_bounds__(kRowThreads) row_softmax_kernel(const float* _
 }
 
 // chain d(objective)/dq through the softmax onto the label logits (what autograd does at :162): g <- q * (g - <q, g>)
-__global__ void __launch_bounds__(kRowThreads) softmax_chain_kernel(const float* __restrict__ q, float* __restrict__ g, int C) {
+__global__ void __launch_bounds__(kRowThreads, 2) softmax_chain_kernel(const float* __restrict__ q, float* __restrict__ g, int C) {
   pdl_prologue();
   __shared__ RowReduce ws;
   int c0, c1;
   row_segment(C, c0, c1);
   const float* qq = q + (long long)blockIdx.x * C;
   float* gg = g + (long long)blockIdx.x * C;
+  if (seg_fits(C)) {
+    SegCache qc, gc;
+    seg_load(qc, qq, c0, c1, 0.f);
+    seg_load(gc, gg, c0, c1, 0.f);
+    double part = 0.0;
+#pragma unroll
+    for (int k = 0; k < kSegCache; ++k) part += (double)qc.v[k] * (double)gc.v[k];
+    const float dot = (float)row_allreduce<ROW_SUM>(part, ws, 0);
+#pragma unroll
+    for (int k = 0; k < kSegCache; ++k) {
+      const int c = c0 + k * kRowThreads + (int)threadIdx.x;
+      if (c < c1) gg[c] = qc.v[k] * (gc.v[k] - dot);
+    }
+    cluster_exit();
+    return;
+  }
   double part = 0.0;
   for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) part += (double)qq[c] * (double)gg[c];
   const float dot = (float)row_allreduce<ROW_SUM>(part, ws, 0);

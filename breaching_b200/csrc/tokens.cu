@@ -354,7 +354,7 @@ __device__ __forceinline__ void cluster_softmax_stats(const float* z, int c0, in
   mx_out = mx;
 }
 
-__global__ void __launch_bounds__(kRowThreads) token_ce_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ q, int rows, int V,
+__global__ void __launch_bounds__(kRowThreads, 2) token_ce_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ q, int rows, int V,
                                                                   int Vs, int T, float* p, float* loss_n, float* dlogits) {
   pdl_prologue();
   __shared__ RowReduce ws;
@@ -362,12 +362,40 @@ __global__ void __launch_bounds__(kRowThreads) token_ce_fwd_kernel(const float* 
   int c0, c1;
   row_segment(V, c0, c1);
   const float* z = logits + (long long)row * Vs;   // logits-shaped tensors: row stride Vs >= V (vocabulary padded for the GEMM tiles)
-  float mx, sum;
-  cluster_softmax_stats(z, c0, c1, ws, 0, mx, sum);
   const bool scored = (row % T) != T - 1;
   const float invM = 1.0f / (float)(rows - rows / T);
-  const float lse = mx + logf(sum);
   const float* qn = q + (long long)(row + 1) * V;   // target of the next position (never read for the last position)
+  if (seg_fits(V)) {   // the segment of the logits and of the target row in registers: one load each, two reductions instead of three
+    SegCache zc, qc;
+    seg_load(zc, z, c0, c1, -3.402823466e+38f);
+    if (scored) seg_load(qc, qn, c0, c1, 0.f);
+    float m;
+    double dsum;
+    seg_softmax_pair(zc, m, dsum);
+    row_allreduce_softmax(m, dsum, ws, 0);
+    const float fsum = (float)dsum, lse_c = m + logf(fsum);
+    double lp = 0.0;
+#pragma unroll
+    for (int k = 0; k < kSegCache; ++k) {
+      const int c = c0 + k * kRowThreads + (int)threadIdx.x;
+      if (c >= c1) continue;
+      const float pc = expf(zc.v[k] - m) / fsum;
+      p[(long long)row * Vs + c] = pc;
+      if (scored) {
+        dlogits[(long long)row * Vs + c] = (pc - qc.v[k]) * invM;
+        lp -= (double)qc.v[k] * (double)(zc.v[k] - lse_c);
+      } else {
+        dlogits[(long long)row * Vs + c] = 0.f;
+      }
+    }
+    const double lt = row_allreduce<ROW_SUM>(lp, ws, 2);
+    if (threadIdx.x == 0 && cluster_rank() == 0) loss_n[row] = scored ? (float)(lt * (double)rows * (double)invM) : 0.f;
+    cluster_exit();
+    return;
+  }
+  float mx, sum;
+  cluster_softmax_stats(z, c0, c1, ws, 0, mx, sum);
+  const float lse = mx + logf(sum);
   double lpart = 0.0;
   for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) {
     const float pc = expf(z[c] - mx) / sum;
@@ -385,7 +413,7 @@ __global__ void __launch_bounds__(kRowThreads) token_ce_fwd_kernel(const float* 
   cluster_exit();
 }
 
-__global__ void __launch_bounds__(kRowThreads) token_ce_tan_bwd_kernel(const float* __restrict__ p, const float* __restrict__ zdot, int rows, int V,
+__global__ void __launch_bounds__(kRowThreads, 2) token_ce_tan_bwd_kernel(const float* __restrict__ p, const float* __restrict__ zdot, int rows, int V,
                                                                       int Vs, int T, float* tdl) {
   pdl_prologue();
   __shared__ RowReduce ws;
@@ -394,16 +422,32 @@ __global__ void __launch_bounds__(kRowThreads) token_ce_tan_bwd_kernel(const flo
   row_segment(V, c0, c1);
   const float* pp = p + (long long)row * Vs;
   const float* zz = zdot + (long long)row * Vs;
+  const bool scored = (row % T) != T - 1;
+  const float invM = 1.0f / (float)(rows - rows / T);
+  if (seg_fits(V)) {
+    SegCache pc, zc;
+    seg_load(pc, pp, c0, c1, 0.f);
+    seg_load(zc, zz, c0, c1, 0.f);
+    double pr = 0.0;
+#pragma unroll
+    for (int k = 0; k < kSegCache; ++k) pr += (double)pc.v[k] * (double)zc.v[k];
+    const float dt = (float)row_allreduce<ROW_SUM>(pr, ws, 0);
+#pragma unroll
+    for (int k = 0; k < kSegCache; ++k) {
+      const int c = c0 + k * kRowThreads + (int)threadIdx.x;
+      if (c < c1) tdl[(long long)row * Vs + c] = scored ? pc.v[k] * (zc.v[k] - dt) * invM : 0.f;
+    }
+    cluster_exit();
+    return;
+  }
   double part = 0.0;
   for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) part += (double)pp[c] * (double)zz[c];
   const float dot = (float)row_allreduce<ROW_SUM>(part, ws, 0);
-  const bool scored = (row % T) != T - 1;
-  const float invM = 1.0f / (float)(rows - rows / T);
   for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) tdl[(long long)row * Vs + c] = scored ? pp[c] * (zz[c] - dot) * invM : 0.f;
   cluster_exit();
 }
 
-__global__ void __launch_bounds__(kRowThreads) token_label_grad_kernel(const float* __restrict__ logits, const float* __restrict__ p,
+__global__ void __launch_bounds__(kRowThreads, 2) token_label_grad_kernel(const float* __restrict__ logits, const float* __restrict__ p,
                                                                       const float* __restrict__ zdot, int rows, int V, int Vs, int T,
                                                                       float task_reg, float* __restrict__ out) {
   pdl_prologue();
@@ -420,6 +464,34 @@ __global__ void __launch_bounds__(kRowThreads) token_label_grad_kernel(const flo
   const float* z = logits + src * Vs;
   const float* pp = p + src * Vs;
   const float* zz = zdot + src * Vs;
+  if (seg_fits(V)) {
+    SegCache pc, zc, lc;
+    seg_load(pc, pp, c0, c1, 0.f);
+    seg_load(zc, zz, c0, c1, 0.f);
+    if (task_reg != 0.f) seg_load(lc, z, c0, c1, -3.402823466e+38f);
+    double pr = 0.0;
+#pragma unroll
+    for (int k = 0; k < kSegCache; ++k) pr += (double)pc.v[k] * (double)zc.v[k];
+    const float dt = (float)row_allreduce<ROW_SUM>(pr, ws, 0);
+    float m = 0.f;
+    double dsum = 1.0;
+    if (task_reg != 0.f) {
+      seg_softmax_pair(lc, m, dsum);
+      row_allreduce_softmax(m, dsum, ws, 1);
+    }
+    const float iM = 1.0f / (float)(rows - rows / T);
+    const float lse_c = m + logf((float)dsum);
+#pragma unroll
+    for (int k = 0; k < kSegCache; ++k) {
+      const int c = c0 + k * kRowThreads + (int)threadIdx.x;
+      if (c >= c1) continue;
+      float v = -(zc.v[k] - dt) * iM;
+      if (task_reg != 0.f) v -= task_reg * (lc.v[k] - lse_c) * iM;
+      o[c] = v;
+    }
+    cluster_exit();
+    return;
+  }
   double part = 0.0;
   for (int c = c0 + threadIdx.x; c < c1; c += kRowThreads) part += (double)pp[c] * (double)zz[c];
   const float dot = (float)row_allreduce<ROW_SUM>(part, ws, 0);
