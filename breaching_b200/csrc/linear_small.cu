@@ -5,6 +5,7 @@
 // 7 % of a config-2 iteration in the five head launches).  fp32 throughout (bit-class parity with the fp32 SIMT back end: the
 // same products, summed in a fixed order).
 #include "igemm.cuh"
+#include <type_traits>
 
 namespace bre {
 namespace {
@@ -152,14 +153,24 @@ int launch_nb(const GemmArgs& a, cudaStream_t stream) {
 //      partials in a fixed order.  Same products as the GEMM back ends (the operands are the same arrays), fp32 accumulation.
 constexpr int LT_ROWS = 32, LT_MAXC = 96, LT_PITCH = LT_ROWS + 4;
 
+__device__ __forceinline__ void lt_cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// The weight rows of a chunk are one contiguous block of memory ([Co][Ci] row-major): they are brought into shared memory with 16-byte
+// cp.async granules, every load of the block in flight at once (with register loads the kernel ran as a chain of ~11 dependent HBM
+// round trips per block: 20 / 41 us per launch).  The products then run out of shared memory: per output channel a warp reads CJ
+// conflict-free 128-byte rows and two broadcast 16-byte vectors for 8 CJ fused multiply-adds per lane.
 template <int CJ>   // CJ = Ci / 32
-__global__ void __launch_bounds__(256, (CJ <= 3 ? 4 : 3)) linear_tall_dgrad_kernel(GemmArgs a, int chunk, float* __restrict__ partials) {
-  __shared__ __align__(16) float dy_s[LT_MAXC][LT_PITCH];      // [co][n], rows 16-byte aligned for the 128-bit broadcast reads
-  __shared__ float fold[4][8][CJ * 32];                         // second co-half of every row group, folded at the end
+__global__ void __launch_bounds__(256, 4) linear_tall_dgrad_kernel(GemmArgs a, int chunk, float* __restrict__ partials) {
+  extern __shared__ __align__(16) float lt_smem[];
+  float* w_s = lt_smem;                                                                              // [chunk][Ci]; reused for the final fold
+  float(*dy_s)[LT_PITCH] = reinterpret_cast<float(*)[LT_PITCH]>(lt_smem + LT_MAXC * CJ * 32);        // [co][n], 16-byte aligned rows
   pdl_prologue();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = warp >> 2, r0 = (warp & 3) * 8;              // warps 0-3: even output channels, 4-7: odd; 8 rows each
-  const int Co = a.g.Co, Ci = a.g.Ci, N = a.g.N;
+  const int Co = a.g.Co, N = a.g.N;
+  constexpr int Ci = CJ * 32;
   const int c0 = blockIdx.x * chunk, cn = min(chunk, Co - c0);
   float acc[8][CJ];
 #pragma unroll
@@ -167,42 +178,38 @@ __global__ void __launch_bounds__(256, (CJ <= 3 ? 4 : 3)) linear_tall_dgrad_kern
 #pragma unroll
     for (int j = 0; j < CJ; ++j) acc[r][j] = 0.f;
   for (int s = 0; s < a.nsrc; ++s) {
-    const float* __restrict__ w = a.wgt[s] + (long long)c0 * Ci + lane;
+    const float* __restrict__ wsrc = a.wgt[s] + (long long)c0 * Ci;
     const float* __restrict__ dy = a.act[s] + c0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < chunk * LT_ROWS; i += 256) {   // the whole chunk at once: coalesced along co, transposed into [co][n]
+    __syncthreads();                                             // the previous source has been consumed
+    for (int i = threadIdx.x; i < cn * (Ci / 4); i += 256) lt_cp_async16(w_s + 4 * i, wsrc + 4 * i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = threadIdx.x; i < chunk * LT_ROWS; i += 256) {   // coalesced along co, transposed into [co][n]
       const int n = i / chunk, c = i - n * chunk;
       dy_s[c][n] = (n < N && c < cn) ? __ldg(dy + (long long)n * Co + c) : 0.f;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    // four output channels per trip (c, c + 2, c + 4, c + 6 of this half): 4 CJ independent 128-byte weight loads in flight per
-    // thread, 32 warps per SM -- the kernel is bound by the latency of these loads, not by their volume
-    for (int c = half; c < cn; c += 8) {
-      float wv[4][CJ];
+#pragma unroll 4
+    for (int c = half; c < cn; c += 2) {
+      float wv[CJ];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool ok = c + 2 * u < cn;
+      for (int j = 0; j < CJ; ++j) wv[j] = w_s[c * Ci + 32 * j + lane];
+      const float4 d0 = *reinterpret_cast<const float4*>(&dy_s[c][r0]);
+      const float4 d1 = *reinterpret_cast<const float4*>(&dy_s[c][r0 + 4]);
+      const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-        for (int j = 0; j < CJ; ++j) wv[u][j] = ok ? __ldg(w + (long long)(c + 2 * u) * Ci + 32 * j) : 0.f;
-      }
+      for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int cc = c + 2 * u < cn ? c + 2 * u : c;    // (a zero weight row makes the clamped read harmless)
-        const float4 d0 = *reinterpret_cast<const float4*>(&dy_s[cc][r0]);
-        const float4 d1 = *reinterpret_cast<const float4*>(&dy_s[cc][r0 + 4]);
-        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-          for (int j = 0; j < CJ; ++j) acc[r][j] = fmaf(dv[r], wv[u][j], acc[r][j]);
-      }
+        for (int j = 0; j < CJ; ++j) acc[r][j] = fmaf(dv[r], wv[j], acc[r][j]);
     }
   }
+  __syncthreads();
+  float* fold = w_s;                                             // [4 row groups][8 rows][Ci]: the odd half's sums
   if (half == 1) {
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int j = 0; j < CJ; ++j) fold[warp & 3][r][32 * j + lane] = acc[r][j];
+      for (int j = 0; j < CJ; ++j) fold[((warp & 3) * 8 + r) * Ci + 32 * j + lane] = acc[r][j];
   }
   __syncthreads();
   if (half == 0) {
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(256, (CJ <= 3 ? 4 : 3)) linear_tall_dgrad_kern
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int j = 0; j < CJ; ++j) dst[(r0 + r) * Ci + 32 * j + lane] = acc[r][j] + fold[warp][r][32 * j + lane];
+      for (int j = 0; j < CJ; ++j) dst[(r0 + r) * Ci + 32 * j + lane] = acc[r][j] + fold[(warp * 8 + r) * Ci + 32 * j + lane];
   }
 }
 
@@ -260,6 +267,8 @@ bool linear_tall_supported(const GemmArgs& a) {
   if (!(g.R == 1 && g.S == 1 && g.H == 1 && g.W == 1 && g.Ho == 1 && g.Wo == 1 && g.stride == 1 && g.pad == 0)) return false;
   if (g.N < 1 || g.N > LT_ROWS || g.Ci % 32 != 0 || g.Ci > 128 || g.Co < 8192 || a.x_sC != 1 || a.epi.kind != 0) return false;
   if (a.nsrc < 1 || a.nsrc > 2 || a.ws == nullptr) return false;
+  for (int s = 0; s < a.nsrc; ++s)
+    if ((reinterpret_cast<uintptr_t>(a.wgt[s]) & 15) != 0) return false;   // 16-byte cp.async granules of the weight rows
   const long long need = (long long)ceil_div(g.Co, tall_chunk(g.Co)) * LT_ROWS * g.Ci;
   return need <= (long long)a.ws_tiles * IG_BM * IG_BN;
 }
@@ -267,12 +276,28 @@ bool linear_tall_supported(const GemmArgs& a) {
 int launch_linear_tall(const GemmArgs& a, cudaStream_t stream) {
   const int Co = a.g.Co, Ci = a.g.Ci;
   const int chunk = tall_chunk(Co), chunks = ceil_div(Co, chunk);
+  auto go = [&](auto cj_tag) -> int {
+    constexpr int CJ = decltype(cj_tag)::value;
+    const size_t smem = (size_t)(LT_MAXC * CJ * 32 + LT_MAXC * LT_PITCH) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+      if (cudaFuncSetAttribute(linear_tall_dgrad_kernel<CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        set_error("tall linear dgrad: shared memory opt-in failed");
+        return -2;
+      }
+      attr_done = true;
+    }
+    BRE_KLAUNCH((linear_tall_dgrad_kernel<CJ>), chunks, 256, smem, stream, a, chunk, a.ws);
+    return 0;
+  };
+  int rc = 0;
   switch (Ci / 32) {
-    case 1: BRE_KLAUNCH((linear_tall_dgrad_kernel<1>), chunks, 256, 0, stream, a, chunk, a.ws); break;
-    case 2: BRE_KLAUNCH((linear_tall_dgrad_kernel<2>), chunks, 256, 0, stream, a, chunk, a.ws); break;
-    case 3: BRE_KLAUNCH((linear_tall_dgrad_kernel<3>), chunks, 256, 0, stream, a, chunk, a.ws); break;
-    default: BRE_KLAUNCH((linear_tall_dgrad_kernel<4>), chunks, 256, 0, stream, a, chunk, a.ws); break;
+    case 1: rc = go(std::integral_constant<int, 1>{}); break;
+    case 2: rc = go(std::integral_constant<int, 2>{}); break;
+    case 3: rc = go(std::integral_constant<int, 3>{}); break;
+    default: rc = go(std::integral_constant<int, 4>{}); break;
   }
+  if (rc != 0) return rc;
   BRE_KLAUNCH(linear_tall_fold_kernel, LT_ROWS * Ci / 32, 1024, 0, stream, (const float*)a.ws, chunks, Ci, a.g.N, a.x_sN, a.accumulate, a.out);
   BRE_CHECK_LAUNCH();
   return 0;

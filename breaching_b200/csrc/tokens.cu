@@ -465,28 +465,24 @@ __global__ void __launch_bounds__(kRowThreads, 2) token_label_grad_kernel(const 
   const float* pp = p + src * Vs;
   const float* zz = zdot + src * Vs;
   if (seg_fits(V)) {
-    SegCache pc, zc, lc;
+    // p and z-dot in registers; the logits of the (rare) task-regularised form are streamed (a third cached segment spills)
+    SegCache pc, zc;
     seg_load(pc, pp, c0, c1, 0.f);
     seg_load(zc, zz, c0, c1, 0.f);
-    if (task_reg != 0.f) seg_load(lc, z, c0, c1, -3.402823466e+38f);
     double pr = 0.0;
 #pragma unroll
     for (int k = 0; k < kSegCache; ++k) pr += (double)pc.v[k] * (double)zc.v[k];
     const float dt = (float)row_allreduce<ROW_SUM>(pr, ws, 0);
-    float m = 0.f;
-    double dsum = 1.0;
-    if (task_reg != 0.f) {
-      seg_softmax_pair(lc, m, dsum);
-      row_allreduce_softmax(m, dsum, ws, 1);
-    }
+    float m = 0.f, fsum = 1.f;
+    if (task_reg != 0.f) cluster_softmax_stats(z, c0, c1, ws, 1, m, fsum);
     const float iM = 1.0f / (float)(rows - rows / T);
-    const float lse_c = m + logf((float)dsum);
+    const float lse_c = m + logf(fsum);
 #pragma unroll
     for (int k = 0; k < kSegCache; ++k) {
       const int c = c0 + k * kRowThreads + (int)threadIdx.x;
       if (c >= c1) continue;
       float v = -(zc.v[k] - dt) * iM;
-      if (task_reg != 0.f) v -= task_reg * (lc.v[k] - lse_c) * iM;
+      if (task_reg != 0.f) v -= task_reg * (z[c] - lse_c) * iM;
       o[c] = v;
     }
     cluster_exit();
