@@ -248,12 +248,20 @@ def prepare_for_text_data(rec_models, shared_data, text_strategy="run-embedding"
     return embeddings, embeddings[0]["weight"].shape[1]
 
 
-def _max_similarity(recovered, true):
-    """base_attack.py:126-133 -- note the *squared* norms in the denominator (reference behaviour)."""
-    recovered = recovered - recovered.mean(dim=-1, keepdim=True)
-    true = true - true.mean(dim=-1, keepdim=True)
-    cosim = recovered.matmul(true.T) / recovered.pow(2).sum(dim=-1)[:, None] / true.pow(2).sum(dim=-1)[None, :]
-    return cosim.argmax(dim=1)
+def _max_similarity(recovered, true, subset=None):
+    """base_attack.py:126-133 -- note the *squared* norms in the denominator (reference behaviour).  On the GPU this is
+    one engine kernel (``bre_token_match``); host tensors (the CPU tests of the epilogue) take the formula below."""
+    if recovered.is_cuda:
+        from ..engine import token_match
+
+        return token_match(recovered, true, subset)
+    if subset is not None:
+        true = true[subset, :]
+    centred = recovered - recovered.mean(dim=-1, keepdim=True)
+    vocab = true - true.mean(dim=-1, keepdim=True)
+    scores = centred @ vocab.T
+    scores = scores / centred.square().sum(dim=-1, keepdim=True) / vocab.square().sum(dim=-1)
+    return scores.argmax(dim=1)
 
 
 def postprocess_text_data(reconstructed, embedding_weight, token_recovery):
@@ -268,7 +276,7 @@ def postprocess_text_data(reconstructed, embedding_weight, token_recovery):
         rec = reconstructed["data"]
         base_shape = rec.shape[0:2]
         active = reconstructed["labels"].unique()
-        matches = _max_similarity(rec.reshape(-1, rec.shape[-1]), embedding_weight[active, :])
+        matches = _max_similarity(rec.reshape(-1, rec.shape[-1]), embedding_weight, subset=active)
         tokens = active[matches].view(*base_shape)
     else:
         raise ValueError(f"Invalid token recovery {token_recovery} given.")

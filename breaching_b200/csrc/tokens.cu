@@ -569,9 +569,135 @@ int launch_token_label_grad(const float* logits, const float* p, const float* zd
   return check_launch("token label gradient");
 }
 
+// ---- token recovery (base_attack.py:123-167): nearest vocabulary embedding of every reconstructed position ---------------------------
+// score[n][v] = <r_n - mean r_n, e_v - mean e_v> / |r_n - mean|^2 / |e_v - mean|^2   (squared norms: the reference's formula), token[n] =
+// argmax_v (the smallest v among equal maxima, a NaN score counts as maximal like torch.argmax).  A block keeps the centred
+// reconstructions transposed in shared memory; a warp walks its share of the vocabulary rows: it centres one row cooperatively, then lane
+// n forms the dot product with reconstruction n (conflict-free column reads, broadcast embedding reads).  Stage 2 folds the per-block
+// winners in block order.
+constexpr int TM_THREADS = 256, TM_WARPS = TM_THREADS / 32;
+__device__ __forceinline__ bool tm_better(float s, long long v, float best, long long bi) {
+  if (bi < 0) return true;
+  const bool sn = s != s, bn = best != best;
+  if (sn != bn) return sn;
+  if (!sn && s != best) return s > best;
+  return v < bi;
+}
+__global__ void __launch_bounds__(TM_THREADS) token_match_partial_kernel(const float* __restrict__ rec, const float* __restrict__ emb,
+                                                                        const long long* __restrict__ subset, int rows, int d, int V, int per_block,
+                                                                        float* __restrict__ best_val, long long* __restrict__ best_idx) {
+  extern __shared__ float tm_smem[];
+  float* rc = tm_smem;                              // [d][33]: centred reconstructions of the current group of 32 rows, transposed
+  float* rn = rc + (size_t)d * 33;                  // [32] squared norms
+  float* ev = rn + 32;                              // [TM_WARPS][d] centred embedding row of each warp
+  float* wv = ev + (size_t)TM_WARPS * d;            // [TM_WARPS][32] per-warp winners
+  long long* wi = reinterpret_cast<long long*>(wv + TM_WARPS * 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v0 = blockIdx.x * per_block, v1 = min(V, v0 + per_block);
+  for (int g0 = 0; g0 < rows; g0 += 32) {
+    __syncthreads();
+    for (int n = warp; n < 32; n += TM_WARPS) {     // centre reconstruction g0 + n (one warp per row)
+      const bool ok = g0 + n < rows;
+      float sum = 0.f;
+      for (int k = lane; k < d; k += 32) sum += ok ? rec[(long long)(g0 + n) * d + k] : 0.f;
+      const float mean = warp_sum(sum) / (float)d;
+      float sq = 0.f;
+      for (int k = lane; k < d; k += 32) {
+        const float c = ok ? rec[(long long)(g0 + n) * d + k] - mean : 0.f;
+        rc[k * 33 + n] = c;
+        sq = fmaf(c, c, sq);
+      }
+      sq = warp_sum(sq);
+      if (lane == 0) rn[n] = sq;
+    }
+    __syncthreads();
+    float best = 0.f;
+    long long bi = -1;
+    float* e = ev + (size_t)warp * d;
+    for (int v = v0 + warp; v < v1; v += TM_WARPS) {
+      const float* src = emb + (subset != nullptr ? subset[v] : (long long)v) * d;
+      float sum = 0.f;
+      for (int k = lane; k < d; k += 32) sum += src[k];
+      const float mean = warp_sum(sum) / (float)d;
+      float sq = 0.f;
+      __syncwarp();
+      for (int k = lane; k < d; k += 32) { const float c = src[k] - mean; e[k] = c; sq = fmaf(c, c, sq); }
+      sq = warp_sum(sq);
+      __syncwarp();
+      float dot = 0.f;
+      for (int k = 0; k < d; ++k) dot = fmaf(rc[k * 33 + lane], e[k], dot);
+      const float score = dot / rn[lane] / sq;
+      if (tm_better(score, v, best, bi)) { best = score; bi = v; }
+    }
+    wv[warp * 32 + lane] = best;
+    wi[warp * 32 + lane] = bi;
+    __syncthreads();
+    if (warp == 0 && g0 + lane < rows) {
+      float b = wv[lane];
+      long long i = wi[lane];
+      for (int w = 1; w < TM_WARPS; ++w) {
+        const long long cand = wi[w * 32 + lane];
+        if (cand >= 0 && tm_better(wv[w * 32 + lane], cand, b, i)) { b = wv[w * 32 + lane]; i = cand; }
+      }
+      best_val[(long long)blockIdx.x * rows + g0 + lane] = b;
+      best_idx[(long long)blockIdx.x * rows + g0 + lane] = i;
+    }
+  }
+}
+__global__ void token_match_final_kernel(const float* __restrict__ best_val, const long long* __restrict__ best_idx, int blocks, int rows,
+                                         long long* __restrict__ tokens) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
+  float b = 0.f;
+  long long i = -1;
+  for (int k = 0; k < blocks; ++k) {
+    const long long cand = best_idx[(long long)k * rows + n];
+    if (cand >= 0 && tm_better(best_val[(long long)k * rows + n], cand, b, i)) { b = best_val[(long long)k * rows + n]; i = cand; }
+  }
+  tokens[n] = i;
+}
+
 }  // namespace bre
 
 extern "C" {
+
+// Token recovery: tokens[n] = argmax_v of the reference's centred similarity between rec[n][:] and emb[v][:] (emb rows picked through
+// `subset` [V] when non-null; the returned ids are positions in that list).  All pointers are device pointers.
+int bre_token_match(const float* rec, const float* emb, const int64_t* subset, int32_t rows, int32_t d, int32_t V, int64_t* tokens,
+                    void* stream) {
+  using namespace bre;
+  if (!rec || !emb || !tokens || rows < 1 || d < 1 || V < 1) { set_error("bre_token_match: bad arguments"); return -1; }
+  const size_t smem = ((size_t)d * 33 + 32 + (size_t)TM_WARPS * d + TM_WARPS * 32) * sizeof(float) + (size_t)TM_WARPS * 32 * sizeof(long long) + 8;
+  if (smem > 200 * 1024) { set_error("bre_token_match: embedding too wide for the resident kernel"); return -4; }
+  cudaStream_t s = (cudaStream_t)stream;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(token_match_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      set_error("bre_token_match: shared memory opt-in failed");
+      return -2;
+    }
+    attr_done = true;
+  }
+  int blocks = (V + 63) / 64;
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  const int per_block = (V + blocks - 1) / blocks;
+  blocks = (V + per_block - 1) / per_block;
+  float* best_val = nullptr;
+  long long* best_idx = nullptr;
+  if (cudaMallocAsync((void**)&best_val, sizeof(float) * (size_t)blocks * rows, s) != cudaSuccess ||
+      cudaMallocAsync((void**)&best_idx, sizeof(long long) * (size_t)blocks * rows, s) != cudaSuccess) {
+    set_error("bre_token_match: scratch allocation failed");
+    return -2;
+  }
+  token_match_partial_kernel<<<blocks, TM_THREADS, smem, s>>>(rec, emb, reinterpret_cast<const long long*>(subset), rows, d, V, per_block, best_val,
+                                                             best_idx);
+  token_match_final_kernel<<<(rows + 127) / 128, 128, 0, s>>>(best_val, best_idx, blocks, rows, reinterpret_cast<long long*>(tokens));
+  const cudaError_t err = cudaGetLastError();
+  cudaFreeAsync(best_val, s);
+  cudaFreeAsync(best_idx, s);
+  if (err != cudaSuccess) { set_error(std::string("bre_token_match failed: ") + cudaGetErrorString(err)); return -2; }
+  return 0;
+}
 
 // Stand-alone LayerNorm sweeps over [rows, C] fp32 device tensors (see layernorm_kernel for the meaning of in1..in3 per sweep).
 // sweep 1 additionally writes the parameter gradients when g_gamma / g_beta are non-null.

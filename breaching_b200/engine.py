@@ -81,7 +81,7 @@ EXPORTS = [
     "bre_engine_debug_tensor", "bre_engine_launches_per_iteration", "bre_engine_set_option", "bre_match_reduce",
     "bre_total_variation", "bre_conv_gemm", "bre_last_error", "bre_version",
     "bre_engine_load_soft_labels", "bre_engine_label_gradient", "bre_engine_set_labels",
-    "bre_token_layernorm", "bre_token_attention",
+    "bre_token_layernorm", "bre_token_attention", "bre_token_match",
     "bre_engine_param_gradients", "bre_engine_bn_batch_stats", "bre_engine_forward", "bre_image_mse",
     "bre_engine_begin_joint_trial", "bre_engine_get_joint_labels", "bre_resize_bilinear",
     "bre_engine_set_augmentations", "bre_engine_last_augmentation", "bre_augment_view",
@@ -133,6 +133,7 @@ def load_library(path=None):
     lib.bre_conv_gemm.argtypes = [i32, i32, vp, vp, vp, vp, vp] + [i32] * 9 + [vp]
     lib.bre_token_layernorm.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp, vp, vp]
     lib.bre_token_attention.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.bre_token_match.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.bre_engine_begin_joint_trial.argtypes = [vp, vp, vp, i64, vp, i32]
     lib.bre_engine_get_joint_labels.argtypes = [vp, i32, vp]
     lib.bre_engine_param_gradients.argtypes = [vp, vp, vp, i32, P(vp), i32, P(ctypes.c_double)]
@@ -648,6 +649,23 @@ def token_layernorm(sweep, x, gamma, beta, stats, in1=None, in2=None, in3=None, 
                                      float(eps), rows, C, _ptr(stats), _ptr(out), _ptr(gg), _ptr(gb), ctypes.c_void_p(stream))
     _check(lib, rc, "bre_token_layernorm")
     return (out, gg, gb) if want_param_grad else out
+
+
+def token_match(rec, emb, subset=None):
+    """Nearest vocabulary embedding of every row of ``rec`` [rows, d] under the reference's centred similarity (base_attack.py:126-133);
+    ``subset`` (int64 ids) restricts the candidates and the result indexes into it.  Device tensors; returns int64 [rows]."""
+    lib = load_library()
+    rec = rec.detach().to(torch.float32).contiguous()
+    emb = emb.detach().to(torch.float32).contiguous()
+    if subset is not None:
+        subset = subset.detach().to(torch.int64).contiguous()
+    V = int(subset.numel()) if subset is not None else int(emb.shape[0])
+    out = torch.empty(rec.shape[0], dtype=torch.int64, device=rec.device)
+    stream = torch.cuda.current_stream(rec.device).cuda_stream
+    with torch.cuda.device(rec.device):
+        rc = lib.bre_token_match(_ptr(rec), _ptr(emb), _ptr(subset), int(rec.shape[0]), int(rec.shape[1]), V, _ptr(out), ctypes.c_void_p(stream))
+    _check(lib, rc, "bre_token_match")
+    return out
 
 
 def token_attention(sweep, qkv, B, T, heads, P, Pd, in1=None, in2=None, in3=None):

@@ -252,6 +252,12 @@ int bre_token_layernorm(int32_t sweep, const float* x, const float* in1, const f
 int bre_token_attention(int32_t sweep, const float* qkv, const float* in1, const float* in2, const float* in3, int32_t B, int32_t T,
                         int32_t heads, int32_t dh, float* P, float* Pd, float* out, void* stream);
 
+/* Token recovery of the text attacks (replaces `_postprocess_text_data._max_similarity`, breaching/attacks/base_attack.py:126-133):
+ * tokens[n] = argmax_v <r_n - mean, e_v - mean> / |r_n - mean|^2 / |e_v - mean|^2 over the V rows of emb [*, d] (rows picked through
+ * `subset` [V] when non-NULL; ids are then positions in that list).  rec [rows, d], tokens [rows] int64; device pointers. */
+int bre_token_match(const float* rec, const float* emb, const int64_t* subset, int32_t rows, int32_t d, int32_t V, int64_t* tokens,
+                    void* stream);
+
 /* Implicit-GEMM convolution family, NHWC activations / OHWI weights, fp32:
  * mode 0 fprop  : out[N,Ho,Wo,Co]  = conv(in[N,H,W,Ci], w[Co,R,S,Ci]) (+ conv(in2, w2) when in2 != NULL)
  * mode 1 dgrad  : din[N,H,W,Ci]    = conv^T(dout[N,Ho,Wo,Co], w) (+ conv^T(dout2, w2))

@@ -191,3 +191,40 @@ def test_full_size_config5_closure_on_the_engine(backend):
     assert _relerr(gl[:, :, ::97], fx["raw_grad_l0_sample"]) < tol_g
     assert abs(float(gl.norm()) - fx["raw_grad_l0_norm"]) < tol_g * fx["raw_grad_l0_norm"]
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,d,V,limited", [(32, 96, 50257, False), (7, 16, 50, False), (40, 96, 3000, True)])
+def test_token_recovery_kernel_matches_the_reference_formula(rows, d, V, limited):
+    """bre_token_match against `_postprocess_text_data._max_similarity` (base_attack.py:126-133, squared norms) in float64; half of
+    the rows are exact vocabulary entries plus noise (the case the attack cares about), the rest random."""
+    from breaching_b200 import engine as E
+    from breaching_b200.attacks import host
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(rows * 7 + V)
+    emb = torch.randn(V, d, generator=g)
+    picks = torch.randint(0, V, (rows,), generator=g)
+    rec = torch.randn(rows, d, generator=g)
+    rec[::2] = emb[picks[::2]] + 0.05 * torch.randn(len(picks[::2]), d, generator=g)
+    subset = torch.unique(torch.cat([picks, torch.randint(0, V, (200,), generator=g)])) if limited else None
+
+    def scores(r, e):
+        r = r.double() - r.double().mean(dim=-1, keepdim=True)
+        e = e.double() - e.double().mean(dim=-1, keepdim=True)
+        return r @ e.T / r.pow(2).sum(-1)[:, None] / e.pow(2).sum(-1)[None, :]
+
+    want = scores(rec, emb if subset is None else emb[subset])
+    got = E.token_match(rec.to(dev), emb.to(dev), None if subset is None else subset.to(dev)).cpu()
+    assert got.dtype == torch.int64 and got.shape == (rows,)
+    best = want.max(dim=1)[0]
+    chosen = want[torch.arange(rows), got]
+    assert torch.all(chosen >= best - 1e-6 * best.abs().clamp_min(1e-12)), (chosen, best)
+    if subset is None and d >= 64:
+        assert torch.equal(got[::2], picks[::2])                      # the noisy vocabulary entries are found again
+    # the host-side dispatch (attacks/host.py) gives the same tokens on device tensors as its formula does on host tensors
+    dev_tokens = host._max_similarity(rec.to(dev), emb.to(dev), None if subset is None else subset.to(dev)).cpu()
+    cpu_tokens = host._max_similarity(rec, emb, subset)
+    assert torch.equal(dev_tokens, got)
+    agree = (dev_tokens == cpu_tokens).float().mean().item()
+    assert agree >= 0.95, agree                                       # fp32 near-ties of the random half may flip
