@@ -386,6 +386,7 @@ struct bre_engine {
   }
   int gemm_on(const GemmArgs& a, cudaStream_t st) {
     if (linear_tall_supported(a)) return launch_linear_tall(a, st);
+    if (linear_small_preferred(a)) return launch_linear_small(a, st);
     if (gemm_backend == 1 && !a.force_fp32 && igemm_tc_supported(a)) {
       GemmArgs b = a;
       b.wgt_static = static_weights(a);
@@ -1869,6 +1870,7 @@ int bre_conv_gemm(int32_t mode, int32_t backend, const float* a, const float* w,
     if (!igemm_tc_supported(g)) { set_error("tcgen05 back end does not cover this shape"); return BRE_ERR_UNSUPPORTED; }
     return launch_igemm_tc(g, s);
   }
+  if (backend == 2 && linear_small_preferred(g)) return launch_linear_small(g, s) == 0 ? BRE_OK : BRE_ERR_CUDA;
   if (backend == 2 && igemm_tc_supported(g)) return launch_igemm_tc(g, s);  // the engine's own dispatch rule
   return launch_igemm_simt(g, s);
 }

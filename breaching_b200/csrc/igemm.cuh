@@ -65,6 +65,7 @@ int launch_igemm_simt(const GemmArgs& a, cudaStream_t stream);
 // linear layers on <= 16 rows (the classification head at small batch): dedicated fp32 kernels (linear_small.cu)
 bool linear_small_supported(const GemmArgs& a);
 int launch_linear_small(const GemmArgs& a, cudaStream_t stream);
+bool linear_small_preferred(const GemmArgs& a);   // engine dispatch: small-row linear with a short reduction -> these kernels, not the GEMM
 // dgrad of a linear layer with <= 32 rows, <= 128 inputs and >= 8192 outputs (the token models' decoder): chunked reduction in
 // fp32 registers + a fixed-order fold (linear_small.cu); uses a.ws for the per-chunk partial sums
 bool linear_tall_supported(const GemmArgs& a);

@@ -531,7 +531,7 @@ int launch_igemm_simt(const GemmArgs& a, cudaStream_t stream) {
   if (d.M <= 0 || d.Nc <= 0 || d.K <= 0) { set_error("igemm: empty problem"); return -1; }
   if (a.nsrc < 1 || a.nsrc > 2) { set_error("igemm: bad nsrc"); return -1; }
   static const bool small_linear = [] { const char* e = getenv("BRE_LINEAR_SMALL"); return e ? atoi(e) != 0 : true; }();
-  if (small_linear && linear_small_supported(a)) return launch_linear_small(a, stream);
+  if (small_linear && linear_small_supported(a) && (a.g.N <= 16 || linear_small_preferred(a))) return launch_linear_small(a, stream);
   if (a.mode == GEMM_DGRAD && g.Ci <= 4 && g.Co <= 16 * SC_KCH && g.H <= 65535 && g.N <= 65535 &&
       (size_t)a.nsrc * ((g.R + g.stride - 1) / g.stride) * g.S * g.Co * g.Ci * 4 <= 200 * 1024)
     return launch_dgrad_small_ci(a, stream);

@@ -1,4 +1,4 @@
-// Small-batch linear layers (the classification head at batch 1-16): fprop / dgrad / wgrad of  out[n][co] = sum_k in[n][k] W[co][k]
+// Small-batch linear layers (the classification head at batch 1-16, token-model projections at <= 32 rows): fprop / dgrad / wgrad of  out[n][co] = sum_k in[n][k] W[co][k]
 // with the optional K-concatenated second source of the tangent sweeps.  At these sizes the contraction is a handful of
 // matrix-vector products over a [Co][Ci] weight matrix (ResNet-18 head: 397 x 512 = 0.8 MB): HBM/L2-latency bound, no reuse to
 // tile for -- the 64x64-tile implicit GEMM spent 16 us per launch on a single row of tiles (profiles/launches_r1_summary.txt:
@@ -10,7 +10,7 @@
 namespace bre {
 namespace {
 
-constexpr int LS_MAXN = 16;
+constexpr int LS_MAXN = 32;
 
 // ---- fprop: one warp per output channel, all rows --------------------------------------------------------------------------
 template <int NB>
@@ -315,7 +315,19 @@ int launch_linear_small(const GemmArgs& a, cudaStream_t stream) {
   if (N <= 2) return launch_nb<2>(a, stream);
   if (N <= 4) return launch_nb<4>(a, stream);
   if (N <= 8) return launch_nb<8>(a, stream);
-  return launch_nb<16>(a, stream);
+  if (N <= 16) return launch_nb<16>(a, stream);
+  return launch_nb<32>(a, stream);
+}
+
+// Experiment switch (BRE_LINEAR_SMALL_ROWS=1): send linear layers on <= 32 rows with a short reduction (token models at batch 1:
+// 96 -> 288 / 96 / 1536 projections) to the matrix-vector kernels even where the tcgen05 kernel covers the shape.  Measured on the
+// B200: at 32 rows these kernels are much slower than the 128 x 32-tile GEMM (config 5: 716 vs 1316 it/s) -- 32 accumulators per
+// thread and 32 broadcast loads per weight element are no match for one MMA -- so the default is off.
+bool linear_small_preferred(const GemmArgs& a) {
+  static const int env = [] { const char* e = getenv("BRE_LINEAR_SMALL_ROWS"); return e ? atoi(e) : 0; }();
+  if (!env || a.mode == GEMM_WGRAD || !linear_small_supported(a)) return false;
+  const int K = (a.mode == GEMM_FPROP ? a.g.Ci : a.g.Co) * a.nsrc;
+  return K <= 512;
 }
 
 }  // namespace bre

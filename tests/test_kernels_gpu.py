@@ -200,3 +200,37 @@ def test_tall_linear_dgrad_matches_float64(rows, Ci, Co, dual):
         assert torch.equal(out, again)
         rel = ((out.double() - want).norm() / want.norm()).item()
         assert rel < 2e-6, (backend, rel)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,Ci,Co", [(32, 96, 288), (32, 96, 1536), (20, 96, 96), (32, 1536, 96), (1, 512, 397), (8, 2048, 397)])
+def test_small_row_linear_kernels_match_float64(rows, Ci, Co):
+    """Linear layers on <= 32 rows (classification heads, token-model projections at batch 1) through the engine's dispatch rule
+    (`bre_conv_gemm` backend 2: matrix-vector kernels for short reductions, the GEMM back ends otherwise): fprop / dgrad with one and
+    two sources and wgrad against float64."""
+    from breaching_b200 import engine as E
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(rows + Ci + Co)
+    x, x2 = (torch.randn(rows, Ci, generator=g).to(dev) for _ in range(2))
+    w, w2 = ((torch.randn(Co, Ci, generator=g) / Ci ** 0.5).to(dev) for _ in range(2))
+    dy, dy2 = (torch.randn(rows, Co, generator=g).to(dev) for _ in range(2))
+    geom = (rows, 1, 1, Ci, Co, 1, 1, 1, 0)
+
+    def rel(a, b):
+        return ((a.double() - b).norm() / b.norm()).item()
+
+    for backend, tol in ((0, 2e-6), (2, 2e-3)):   # 2 = engine dispatch: TF32 products where the tcgen05 kernel takes the shape
+        out = torch.empty(rows, Co, device=dev)
+        E.conv_gemm(0, x, w, out, *geom, backend=backend)
+        assert rel(out, x.double() @ w.double().T) < tol, ("fprop", backend)
+        E.conv_gemm(0, x, w, out, *geom, a2=x2, w2=w2, backend=backend)
+        assert rel(out, x.double() @ w.double().T + x2.double() @ w2.double().T) < tol, ("fprop2", backend)
+        din = torch.empty(rows, Ci, device=dev)
+        E.conv_gemm(1, dy, w, din, *geom, backend=backend)
+        assert rel(din, dy.double() @ w.double()) < tol, ("dgrad", backend)
+        E.conv_gemm(1, dy, w, din, *geom, a2=dy2, w2=w2, backend=backend)
+        assert rel(din, dy.double() @ w.double() + dy2.double() @ w2.double()) < tol, ("dgrad2", backend)
+        dw = torch.empty(Co, Ci, device=dev)
+        E.conv_gemm(2, x, dy, dw, *geom, backend=backend)
+        assert rel(dw, dy.double().T @ x.double()) < tol, ("wgrad", backend)
