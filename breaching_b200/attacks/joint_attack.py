@@ -114,9 +114,11 @@ class OptimizationJointAttacker(OptimizationBasedAttacker):
                 continue
             data, _ = self._run_joint_trial(engine, candidate, candidate_labels, stats, trial, dryrun)
             candidate_solutions[trial] = data
+            ts = time.perf_counter()
             q_hard = torch.nn.functional.one_hot(hard_labels, labels.shape[-1]).to(**self.setup)
             engine.load_soft_labels(q_hard.reshape(-1, labels.shape[-1]))
             scores[trial] = engine.score(data.reshape(-1, data.shape[-1], 1, 1), self.cfg.restarts.scoring)
+            clock["trial_score"] = clock.get("trial_score", 0.0) + time.perf_counter() - ts
         clock["trials"], t0 = time.perf_counter() - t0, time.perf_counter()
         optimal_solution = self._select_optimal_reconstruction(candidate_solutions, scores, stats, shape)
         clock["select"], t0 = self.last_select_seconds, time.perf_counter()
@@ -251,7 +253,10 @@ class OptimizationJointAttacker(OptimizationBasedAttacker):
         x = candidate.detach().contiguous()
         if candidate_labels.dim() == 3:      # token models: the engine works on rows = batch * seq_len
             x = x.reshape(-1, x.shape[-1], 1, 1)
+        clock, t0 = self.last_timing, time.perf_counter()
         engine.begin_joint_trial(x, candidate_labels.detach().contiguous(), table)
+        clock["trial_begin"] = clock.get("trial_begin", 0.0) + time.perf_counter() - t0
+        t0 = time.perf_counter()
         T = int(self.cfg.optim.max_iterations)
         total = 1 if dryrun else (T if iterations is None else iterations)
         callback = int(cfg_get(self.cfg.optim, "callback", 0) or 0)
@@ -261,14 +266,19 @@ class OptimizationJointAttacker(OptimizationBasedAttacker):
             engine.run(n)
             done += n
             st = engine.status()                      # one host sync per `callback` iterations
+            if done == 1:
+                clock["trial_first_iteration"] = clock.get("trial_first_iteration", 0.0) + time.perf_counter() - t0
             if st["stopped"]:
                 log.info(f"Recovery loss is non-finite in iteration {st['recorded']}. Cancelling reconstruction!")
                 break
         engine.sync()
+        clock["trial_iterations"] = clock.get("trial_iterations", 0.0) + time.perf_counter() - t0
+        t0 = time.perf_counter()
         stats[f"Trial_{trial}_Val"].extend(engine.history().tolist())
         best = engine.best().reshape(candidate.shape)
         best_l = engine.joint_labels(best=True)
         self._last_joint_state = (engine.candidate().reshape(candidate.shape), engine.joint_labels(best=False))
+        clock["trial_readback"] = clock.get("trial_readback", 0.0) + time.perf_counter() - t0
         return best.detach(), best_l.detach()
 
     def _score_joint(self, engine, candidate, hard_labels):
