@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(TM_THREADS) token_match_partial_kernel(const f
   float* rn = rc + (size_t)d * 33;                  // [32] squared norms
   float* ev = rn + 32;                              // [TM_WARPS][d] centred embedding row of each warp
   float* wv = ev + (size_t)TM_WARPS * d;            // [TM_WARPS][32] per-warp winners
-  long long* wi = reinterpret_cast<long long*>(wv + TM_WARPS * 32);
+  long long* wi = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(wv + TM_WARPS * 32) + 7) & ~(uintptr_t)7);   // (odd d: keep the 8-byte alignment)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int v0 = blockIdx.x * per_block, v1 = min(V, v0 + per_block);
   for (int g0 = 0; g0 < rows; g0 += 32) {
